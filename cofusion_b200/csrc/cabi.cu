@@ -1,0 +1,332 @@
+// cabi.cu -- extern "C" boundary of libcofusion_b200.so (declarations: include/cofusion_b200.h).
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/cofusion_b200.h"
+#include "gn_math.h"
+#include "image_kernels.cuh"
+#include "odometry.cuh"
+#include "tracker_kernels.cuh"
+
+namespace cfb {
+static thread_local char g_err[512] = "";
+int set_error(cudaError_t e, const char* what, const char* file, int line) {
+  snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file,
+           line);
+  return 1000 + (int)e;
+}
+int set_error_msg(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+}  // namespace cfb
+
+using namespace cfb;
+
+#define CK(expr) CFB_CUDA_OK(expr)
+#define REQUIRE(cond, msg) \
+  do {                     \
+    if (!(cond)) return set_error_msg(2, "invalid argument: " msg); \
+  } while (0)
+#define ST(s) ((cudaStream_t)(s))
+
+static_assert(sizeof(cfb_track_stats) == sizeof(cfb::TrackStats), "stats layout");
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char* cfb_last_error(void) { return g_err; }
+int cfb_version(void) { return 100; }
+int cfb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int cfb_upload(void* dst_dev, const void* src_host, size_t bytes, void* stream) {
+  REQUIRE(dst_dev && src_host, "upload");
+  CK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ST(stream)));
+  CK(cudaStreamSynchronize(ST(stream)));
+  return 0;
+}
+int cfb_download(void* dst_host, const void* src_dev, size_t bytes, void* stream) {
+  REQUIRE(dst_host && src_dev, "download");
+  CK(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ST(stream)));
+  CK(cudaStreamSynchronize(ST(stream)));
+  return 0;
+}
+
+int cfb_bilateral_filter(const float* depth, size_t dp, int W, int H, float maxD, float* out, size_t op,
+                         void* stream) {
+  REQUIRE(depth && out && W > 0 && H > 0, "bilateral");
+  CK(launch_bilateral(depth, dp, W, H, maxD, out, op, ST(stream)));
+  return 0;
+}
+int cfb_pyr_down_gauss_f(const float* src, size_t sp, int sw, int sh, float* dst, size_t dp, void* stream) {
+  REQUIRE(src && dst && sw > 1 && sh > 1, "pyr_down_gauss_f");
+  CK(launch_pyr_down_gauss_f(src, sp, sw, sh, dst, dp, ST(stream)));
+  return 0;
+}
+int cfb_pyr_down_uchar_gauss(const uint8_t* src, size_t sp, int sw, int sh, uint8_t* dst, size_t dp,
+                             void* stream) {
+  REQUIRE(src && dst && sw > 1 && sh > 1, "pyr_down_uchar_gauss");
+  CK(launch_pyr_down_uchar(src, sp, sw, sh, dst, dp, ST(stream)));
+  return 0;
+}
+int cfb_create_vmap(float fx, float fy, float cx, float cy, const float* depth, size_t dp, int W, int H,
+                    float* vmap, size_t vp, float cutoff, void* stream) {
+  REQUIRE(depth && vmap && W > 0 && H > 0, "create_vmap");
+  CK(launch_create_vmap(depth, dp, W, H, Intr{fx, fy, cx, cy}, cutoff, vmap, vp, ST(stream)));
+  return 0;
+}
+int cfb_create_nmap(const float* vmap, size_t vp, int W, int H, float* nmap, size_t np, void* stream) {
+  REQUIRE(vmap && nmap && W > 0 && H > 0, "create_nmap");
+  CK(launch_create_nmap(vmap, vp, W, H, nmap, np, ST(stream)));
+  return 0;
+}
+int cfb_tranform_maps(const float* vs, size_t vsp, const float* ns, size_t nsp, int W, int H, const float R[9],
+                      const float t[3], float* vd, size_t vdp, float* nd, size_t ndp, void* stream) {
+  REQUIRE(vs && ns && vd && nd && R && t, "tranform_maps");
+  Mat33 Rm;
+  memcpy(Rm.m, R, sizeof(Rm.m));
+  CK(launch_transform_maps(vs, vsp, ns, nsp, W, H, Rm, t, vd, vdp, nd, ndp, ST(stream)));
+  return 0;
+}
+int cfb_copy_maps(const float* v4, const float* n4, int W, int H, float* vd, size_t vdp, float* nd, size_t ndp,
+                  void* stream) {
+  REQUIRE(v4 && n4 && vd && nd, "copy_maps");
+  CK(launch_copy_maps(v4, n4, W, H, vd, vdp, nd, ndp, ST(stream)));
+  return 0;
+}
+int cfb_resize_vmap(const float* in, size_t ip, int sw, int sh, float* out, size_t op, void* stream) {
+  REQUIRE(in && out && (ip % 8) == 0, "resize_vmap (pitch must be a multiple of 8)");
+  CK(launch_resize_map(in, ip, sw, sh, false, out, op, ST(stream)));
+  return 0;
+}
+int cfb_resize_nmap(const float* in, size_t ip, int sw, int sh, float* out, size_t op, void* stream) {
+  REQUIRE(in && out && (ip % 8) == 0, "resize_nmap (pitch must be a multiple of 8)");
+  CK(launch_resize_map(in, ip, sw, sh, true, out, op, ST(stream)));
+  return 0;
+}
+int cfb_vertices_to_depth(const float* v4, int W, int H, float* dst, size_t dp, float cutOff, void* stream) {
+  REQUIRE(v4 && dst, "vertices_to_depth");
+  CK(launch_vertices_to_depth(v4, W, H, cutOff, dst, dp, ST(stream)));
+  return 0;
+}
+int cfb_image_bgr_to_intensity(const uint8_t* img, size_t ip, int channels, int W, int H, uint8_t* dst, size_t dp,
+                               void* stream) {
+  REQUIRE(img && dst && (channels == 3 || channels == 4), "image_bgr_to_intensity");
+  CK(launch_rgb_to_intensity(img, ip, channels, W, H, dst, dp, ST(stream)));
+  return 0;
+}
+int cfb_compute_derivative_images(const uint8_t* src, size_t sp, int W, int H, int16_t* dx, int16_t* dy, size_t gp,
+                                  void* stream) {
+  REQUIRE(src && dx && dy, "compute_derivative_images");
+  CK(launch_derivative_images(src, sp, W, H, dx, dy, gp, ST(stream)));
+  return 0;
+}
+int cfb_project_to_point_cloud(const float* depth, size_t dp, int W, int H, float fx, float fy, float cx, float cy,
+                               float* cloud3, size_t cp, void* stream) {
+  REQUIRE(depth && cloud3, "project_to_point_cloud");
+  CK(launch_project_to_point_cloud(depth, dp, W, H, Intr{fx, fy, cx, cy}, cloud3, cp, ST(stream)));
+  return 0;
+}
+
+size_t cfb_step_scratch_bytes(void) { return sizeof(StepScratch) + 256; }
+
+// Per-call small device parameter blocks live behind the scratch (after StepScratch).
+static IcpPose* scratch_pose(void* scratch) { return (IcpPose*)((char*)scratch + sizeof(StepScratch)); }
+static RgbWarp* scratch_warp(void* scratch) { return (RgbWarp*)((char*)scratch + sizeof(StepScratch) + 128); }
+static_assert(sizeof(IcpPose) <= 128 && sizeof(RgbWarp) <= 128, "param blocks");
+
+int cfb_icp_step(const float Rcurr[9], const float tcurr[3], const float* vc, size_t vcp, const float* nc,
+                 size_t ncp, const float Rprev_inv[9], const float tprev[3], float fx, float fy, float cx,
+                 float cy, const float* vp, size_t vpp, const float* np, size_t npp, float distThres,
+                 float angleThres, int W, int H, void* scratch, float* A, float* b, float* residual,
+                 float* error_map, size_t error_pitch, void* stream) {
+  REQUIRE(vc && nc && vp && np && scratch && A && b && residual, "icp_step");
+  IcpPose hp;
+  memcpy(hp.Rcurr.m, Rcurr, 36);
+  memcpy(hp.tcurr, tcurr, 12);
+  memcpy(hp.Rprev_inv.m, Rprev_inv, 36);
+  memcpy(hp.tprev, tprev, 12);
+  CK(cudaMemcpyAsync(scratch_pose(scratch), &hp, sizeof(hp), cudaMemcpyHostToDevice, ST(stream)));
+  IcpArgs a;
+  a.vmap_curr = {vc, vcp};
+  a.nmap_curr = {nc, ncp};
+  a.vmap_g_prev = {vp, vpp};
+  a.nmap_g_prev = {np, npp};
+  a.intr = Intr{fx, fy, cx, cy};
+  a.distThres = distThres;
+  a.angleThres = angleThres;
+  a.cols = W;
+  a.rows = H;
+  a.error_map = error_map;
+  a.error_pitch = error_pitch;
+  StepScratch* sc = (StepScratch*)scratch;
+  CK(launch_icp_step(a, scratch_pose(scratch), sc, ST(stream)));
+  float host[32];
+  CK(cudaMemcpyAsync(host, sc->result, sizeof(host), cudaMemcpyDeviceToHost, ST(stream)));
+  CK(cudaStreamSynchronize(ST(stream)));
+  gn::unpack_se3(host, A, b);
+  residual[0] = host[27];
+  residual[1] = host[28];
+  return 0;
+}
+
+int cfb_compute_rgb_residual(float minScale, const int16_t* dIdx, const int16_t* dIdy, size_t gp,
+                             const float* lastDepth, const float* nextDepth, size_t dp, const uint8_t* lastImage,
+                             const uint8_t* nextImage, size_t ip, void* corresImg, void* scratch,
+                             float maxDepthDelta, const float kt[3], const float krkinv[9], int W, int H,
+                             int* sigmaSum, int* count, void* stream) {
+  REQUIRE(dIdx && dIdy && lastDepth && nextDepth && lastImage && nextImage && corresImg && scratch, "rgb_residual");
+  RgbWarp hw;
+  memcpy(hw.krkinv.m, krkinv, 36);
+  memcpy(hw.kt, kt, 12);
+  CK(cudaMemcpyAsync(scratch_warp(scratch), &hw, sizeof(hw), cudaMemcpyHostToDevice, ST(stream)));
+  RgbResidualArgs a;
+  a.minScale = minScale;
+  a.maxDepthDelta = maxDepthDelta;
+  a.dIdx = dIdx;
+  a.dIdy = dIdy;
+  a.grad_pitch = gp;
+  a.lastDepth = lastDepth;
+  a.nextDepth = nextDepth;
+  a.depth_pitch = dp;
+  a.lastImage = lastImage;
+  a.nextImage = nextImage;
+  a.img_pitch = ip;
+  a.corres = (DataTerm*)corresImg;
+  a.cols = W;
+  a.rows = H;
+  StepScratch* sc = (StepScratch*)scratch;
+  CK(launch_rgb_residual(a, scratch_warp(scratch), sc, ST(stream)));
+  int host[2];
+  CK(cudaMemcpyAsync(host, &sc->rgb_count, sizeof(host), cudaMemcpyDeviceToHost, ST(stream)));
+  CK(cudaStreamSynchronize(ST(stream)));
+  *count = host[0];
+  *sigmaSum = host[1];
+  return 0;
+}
+
+int cfb_rgb_step(const void* corresImg, float sigma, const float* cloud3, size_t cp, float fx, float fy,
+                 const int16_t* dIdx, const int16_t* dIdy, size_t gp, float sobelScale, int W, int H,
+                 void* scratch, float* A, float* b, void* stream) {
+  REQUIRE(corresImg && cloud3 && dIdx && dIdy && scratch && A && b, "rgb_step");
+  RgbStepArgs a;
+  a.corres = (const DataTerm*)corresImg;
+  a.cloud = cloud3;
+  a.cloud_pitch = cp;
+  a.dIdx = dIdx;
+  a.dIdy = dIdy;
+  a.grad_pitch = gp;
+  a.fx = fx;
+  a.fy = fy;
+  a.sobelScale = sobelScale;
+  a.cols = W;
+  a.rows = H;
+  StepScratch* sc = (StepScratch*)scratch;
+  CK(launch_rgb_step(a, sigma, sc, ST(stream)));
+  float host[32];
+  CK(cudaMemcpyAsync(host, sc->result, sizeof(host), cudaMemcpyDeviceToHost, ST(stream)));
+  CK(cudaStreamSynchronize(ST(stream)));
+  gn::unpack_se3(host, A, b);
+  return 0;
+}
+
+int cfb_so3_step(const uint8_t* lastImage, const uint8_t* nextImage, size_t ip, const float imageBasis[9],
+                 const float kinv[9], const float krlr[9], int W, int H, void* scratch, float* A, float* b,
+                 float* residual, void* stream) {
+  REQUIRE(lastImage && nextImage && scratch && A && b && residual, "so3_step");
+  So3Args a;
+  a.lastImage = lastImage;
+  a.nextImage = nextImage;
+  a.img_pitch = ip;
+  memcpy(a.imageBasis.m, imageBasis, 36);
+  memcpy(a.kinv.m, kinv, 36);
+  memcpy(a.krlr.m, krlr, 36);
+  a.cols = W;
+  a.rows = H;
+  StepScratch* sc = (StepScratch*)scratch;
+  CK(launch_so3_step(a, sc, ST(stream)));
+  float host[32];
+  CK(cudaMemcpyAsync(host, sc->result, sizeof(host), cudaMemcpyDeviceToHost, ST(stream)));
+  CK(cudaStreamSynchronize(ST(stream)));
+  gn::unpack_so3(host, A, b);
+  residual[0] = host[9];
+  residual[1] = host[10];
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------ RGBDOdometry */
+struct cfb_odom {
+  RGBDOdometry impl;
+  cfb_odom(int w, int h, float cx, float cy, float fx, float fy, float d, float a) : impl(w, h, cx, cy, fx, fy, d, a) {}
+};
+
+int cfb_odom_create(int width, int height, float cx, float cy, float fx, float fy, float distThresh,
+                    float angleThresh, cfb_odom** out) {
+  REQUIRE(out && width >= 32 && height >= 32 && (width % 8) == 0 && (height % 4) == 0,
+          "odom_create (width must be a multiple of 8, height of 4)");
+  *out = nullptr;
+  if (cfb_device_count() <= 0) return set_error_msg(3, "no CUDA device: libcofusion_b200 has no CPU fallback");
+  cfb_odom* o = new (std::nothrow) cfb_odom(width, height, cx, cy, fx, fy, distThresh, angleThresh);
+  if (!o || !o->impl.ok()) {
+    delete o;
+    return set_error_msg(4, "odom_create: device allocation failed");
+  }
+  *out = o;
+  return 0;
+}
+void cfb_odom_destroy(cfb_odom* o) { delete o; }
+
+int cfb_odom_init_icp(cfb_odom* o, const float* const depth_pyr[3], const size_t pitch[3], float cutoff,
+                      void* stream) {
+  REQUIRE(o && depth_pyr && pitch, "odom_init_icp");
+  CK(o->impl.initICP(depth_pyr, pitch, cutoff, ST(stream)));
+  return 0;
+}
+int cfb_odom_init_icp_model(cfb_odom* o, const float* v4, const float* n4, float cutoff, const float pose[16],
+                            void* stream) {
+  REQUIRE(o && v4 && n4 && pose, "odom_init_icp_model");
+  CK(o->impl.initICPModel(v4, n4, cutoff, pose, ST(stream)));
+  return 0;
+}
+int cfb_odom_init_rgb_model(cfb_odom* o, const uint8_t* img, size_t pitch, int channels, void* stream) {
+  REQUIRE(o && img && (channels == 3 || channels == 4), "odom_init_rgb_model");
+  CK(o->impl.initRGBModel(img, pitch, channels, ST(stream)));
+  return 0;
+}
+int cfb_odom_init_rgb(cfb_odom* o, const uint8_t* img, size_t pitch, int channels, void* stream) {
+  REQUIRE(o && img && (channels == 3 || channels == 4), "odom_init_rgb");
+  CK(o->impl.initRGB(img, pitch, channels, ST(stream)));
+  return 0;
+}
+int cfb_odom_init_first_rgb(cfb_odom* o, const uint8_t* img, size_t pitch, int channels, void* stream) {
+  REQUIRE(o && img && (channels == 3 || channels == 4), "odom_init_first_rgb");
+  CK(o->impl.initFirstRGB(img, pitch, channels, ST(stream)));
+  return 0;
+}
+int cfb_odom_get_incremental_transformation(cfb_odom* o, float trans[3], float rot[9], int rgbOnly,
+                                            float icpWeight, int pyramid, int fastOdom, int so3, float* err,
+                                            size_t err_pitch, int force_host_loop, cfb_track_stats* stats_out,
+                                            void* stream) {
+  REQUIRE(o && trans && rot, "odom_get_incremental_transformation");
+  CK(o->impl.getIncrementalTransformation(trans, rot, rgbOnly != 0, icpWeight, pyramid != 0, fastOdom != 0,
+                                          so3 != 0, err, err_pitch, force_host_loop != 0, ST(stream)));
+  if (stats_out) memcpy(stats_out, &o->impl.stats(), sizeof(cfb_track_stats));
+  return 0;
+}
+int cfb_odom_view(cfb_odom* o, int which, int level, const void** dev_ptr, size_t* pitch) {
+  REQUIRE(o && dev_ptr && pitch && level >= 0 && level < 3, "odom_view");
+  *dev_ptr = o->impl.view(which, level, pitch);
+  return *dev_ptr ? 0 : set_error_msg(2, "odom_view: unknown view");
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,370 @@
+// gn_device.cu -- device-resident Gauss-Newton loop of the tracker (RGBDOdometry::deviceLoop).
+//
+// The reference crosses the host<->device boundary >= 60 times per model per frame: each of the 19
+// GN iterations is 3 x (kernel, reduceSum<<<1,1024>>>, cudaDeviceSynchronize, 116-byte D2H) plus a
+// host 6x6 LDLT (RGBDOdometry.cpp:347-461, reduce.cu:474-482).  At 640x480 the per-iteration data
+// (<= 34 MB, L2 resident on B200) moves in a few microseconds, so those crossings ARE the frame
+// time.  Here the whole sequence is enqueued once:
+//     gn_init -> so3_iter x10 -> gn_begin -> [pass1, pass2] x (4+5+10)
+//   pass1 = RGB residual + ICP reduction fused (both only depend on the current pose),
+//   pass2 = RGB Jacobian reduction; its finalising block (the last one to retire) runs the FP64
+//           combine / LDLT / SE(3) update / next-warp computation of gn_math.h in one thread,
+// and the host reads back 12 pose floats + stats once per frame.  SO(3) convergence tests
+// (RGBDOdometry.cpp:285-292) become a device flag that turns the remaining so3 launches into no-ops.
+#include <float.h>
+
+#include "gn_math.h"
+#include "image_kernels.cuh"
+#include "odometry.cuh"
+#include "tracker_device.cuh"
+
+namespace cfb {
+namespace {
+using namespace dev;
+constexpr int kThreads = 256;
+
+#define RET_IF(e)                       \
+  do {                                  \
+    cudaError_t e__ = (e);              \
+    if (e__ != cudaSuccess) return e__; \
+  } while (0)
+
+struct LevelK {  // f32 level intrinsics (CameraModel::operator())
+  float fx, fy, cx, cy;
+};
+
+__device__ void so3_matrices(GNState* g, LevelK k) {
+  double K[9], Kinv[9], KR[9], H[9];
+  gn::make_K(k.fx, k.fy, k.cx, k.cy, K, Kinv);
+  gn::mul3(K, g->resultR, KR);
+  gn::mul3(KR, Kinv, H);
+  for (int q = 0; q < 9; ++q) {
+    g->so3_imageBasis.m[q] = (float)H[q];
+    g->so3_kinv.m[q] = (float)Kinv[q];
+    g->so3_krlr.m[q] = (float)KR[q];
+  }
+}
+
+// ---- gn_init: reset state for a new frame (RGBDOdometry.cpp:224-255, :316-318) ------------------
+__global__ void gn_init_kernel(GNState* g, StepScratch* sc, Mat33 Rprev, float3 tprev, LevelK k_so3) {
+  if (threadIdx.x != 0) return;
+  for (int q = 0; q < 9; ++q) {
+    g->Rprev[q] = Rprev.m[q];
+    g->pose.Rcurr.m[q] = Rprev.m[q];
+    g->resultR[q] = g->lastResultR[q] = (q % 4 == 0) ? 1.0 : 0.0;
+    g->R_lr[q] = (q % 4 == 0) ? 1.f : 0.f;
+  }
+  g->pose.tprev[0] = g->pose.tcurr[0] = tprev.x;
+  g->pose.tprev[1] = g->pose.tcurr[1] = tprev.y;
+  g->pose.tprev[2] = g->pose.tcurr[2] = tprev.z;
+  gn::inverse3f(g->Rprev, g->pose.Rprev_inv.m);
+  g->so3_lastError = FLT_MAX / 2;
+  g->so3_lastCount = FLT_MAX / 2;
+  g->so3_done = 0;
+  TrackStats z = {};
+  g->stats = z;
+  so3_matrices(g, k_so3);
+  sc->rgb_count = 0;
+  sc->rgb_sigma = 0;
+}
+
+// ---- one SO(3) pre-alignment iteration (RGBDOdometry.cpp:257-309) -------------------------------
+__global__ void __launch_bounds__(kThreads)
+so3_iter_kernel(const unsigned char* __restrict__ lastImage, const unsigned char* __restrict__ nextImage,
+                size_t img_pitch, int cols, int rows, LevelK k, GNState* g, StepScratch* sc) {
+  if (g->so3_done) return;  // uniform: set only by a previous launch
+  __shared__ Mat33 M[3];
+  __shared__ float red[(kThreads / 32) * 32];
+  __shared__ float out32[32];
+  for (int i = threadIdx.x; i < 27; i += blockDim.x) ((float*)M)[i] = ((const float*)&g->so3_imageBasis)[i];
+  __syncthreads();
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+  const int N = cols * rows;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += blockDim.x * gridDim.x) {
+    int y = p / cols, x = p - y * cols;
+    so3_pixel(lastImage, nextImage, img_pitch, cols, rows, M[0], M[2], M[1], x, y, acc);
+  }
+  float bt = block_reduce32(acc, red);
+  if (!grid_finalize32(bt, sc->partials, &sc->ticket, red, out32)) return;
+  if (threadIdx.x != 0) return;
+  float jtj[9], jtr[3];
+  gn::unpack_so3(out32, jtj, jtr);
+  TrackStats& st = g->stats;
+  st.so3_iterations++;
+  st.lastSO3Error = sqrtf(out32[9]) / out32[10];
+  st.lastSO3Count = out32[10];
+  if (st.lastSO3Error < g->so3_lastError && fabsf(g->so3_lastError - st.lastSO3Count) < 0.001f) {
+    g->so3_done = 1;
+    return;
+  } else if (st.lastSO3Error > g->so3_lastError + 0.001f) {
+    st.lastSO3Error = g->so3_lastError;
+    st.lastSO3Count = g->so3_lastCount;
+    for (int q = 0; q < 9; ++q) g->resultR[q] = g->lastResultR[q];
+    g->so3_done = 1;
+    return;
+  }
+  g->so3_lastError = st.lastSO3Error;
+  g->so3_lastCount = st.lastSO3Count;
+  for (int q = 0; q < 9; ++q) g->lastResultR[q] = g->resultR[q];
+  double Ad[9], bd[3], xd[3];
+  for (int q = 0; q < 9; ++q) Ad[q] = jtj[q];
+  for (int q = 0; q < 3; ++q) bd[q] = jtr[q];
+  gn::ldlt_solve<3>(Ad, bd, xd);
+  double delta[3] = {(double)(float)xd[0], (double)(float)xd[1], (double)(float)xd[2]};
+  double rotUpdate[9];
+  gn::rodrigues(delta, rotUpdate);
+  float ru[9], nr[9];
+  for (int q = 0; q < 9; ++q) ru[q] = (float)rotUpdate[q];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      nr[r * 3 + c] = ru[r * 3] * g->R_lr[c] + ru[r * 3 + 1] * g->R_lr[3 + c] + ru[r * 3 + 2] * g->R_lr[6 + c];
+  for (int q = 0; q < 9; ++q) {
+    g->R_lr[q] = nr[q];
+    g->resultR[q] = nr[q];
+  }
+  so3_matrices(g, k);
+}
+
+// ---- gn_begin: seed resultRt with the SO(3) result, first warp (RGBDOdometry.cpp:320-328) --------
+__global__ void gn_begin_kernel(GNState* g, int use_so3, LevelK k_first) {
+  if (threadIdx.x != 0) return;
+  for (int q = 0; q < 16; ++q) g->resultRt[q] = (q % 5 == 0) ? 1.0 : 0.0;
+  if (use_so3)
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) g->resultRt[r * 4 + c] = g->resultR[r * 3 + c];
+  double K[9], Kinv[9];
+  gn::make_K(k_first.fx, k_first.fy, k_first.cx, k_first.cy, K, Kinv);
+  gn::pose_to_warp(g->resultRt, K, Kinv, g->warp.krkinv.m, g->warp.kt);
+}
+
+// ---- pass 1: RGB residual + ICP reduction, fused ------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+gn_pass1_kernel(const IcpArgs ia, const RgbResidualArgs ra, GNState* g, StepScratch* sc) {
+  __shared__ IcpPose P;
+  __shared__ RgbWarp Wp;
+  __shared__ float red[(kThreads / 32) * 32];
+  __shared__ float out32[32];
+  __shared__ int scnt[kThreads / 32], ssig[kThreads / 32];
+  for (int i = threadIdx.x; i < (int)(sizeof(IcpPose) / 4); i += blockDim.x) ((float*)&P)[i] = ((const float*)&g->pose)[i];
+  for (int i = threadIdx.x; i < (int)(sizeof(RgbWarp) / 4); i += blockDim.x) ((float*)&Wp)[i] = ((const float*)&g->warp)[i];
+  __syncthreads();
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+  int cnt = 0, sig = 0;
+  const int N = ia.cols * ia.rows;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += blockDim.x * gridDim.x) {
+    int y = p / ia.cols, x = p - y * ia.cols;
+    icp_pixel(ia, P, x, y, acc);
+    DataTerm c;
+    int sq;
+    if (rgb_residual_pixel(ra, Wp, x, y, c, sq)) {
+      cnt += 1;
+      sig += sq;
+    }
+    int4 raw;
+    raw.x = (int)((unsigned short)c.zero.x | ((unsigned)(unsigned short)c.zero.y << 16));
+    raw.y = (int)((unsigned short)c.one.x | ((unsigned)(unsigned short)c.one.y << 16));
+    raw.z = __float_as_int(c.diff);
+    raw.w = c.valid ? 1 : 0;
+    reinterpret_cast<int4*>(ra.corres)[p] = raw;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    sig += __shfl_xor_sync(0xffffffffu, sig, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    scnt[threadIdx.x >> 5] = cnt;
+    ssig[threadIdx.x >> 5] = sig;
+  }
+  float bt = block_reduce32(acc, red);  // contains a __syncthreads
+  if (threadIdx.x == 0) {
+    int c = 0, s = 0;
+    for (int w = 0; w < kThreads / 32; ++w) {
+      c += scnt[w];
+      s += ssig[w];
+    }
+    atomicAdd(&sc->rgb_count, c);
+    atomicAdd(&sc->rgb_sigma, s);
+  }
+  if (grid_finalize32(bt, sc->partials, &sc->ticket, red, out32)) {
+    if (threadIdx.x < 32) g->icp_result[threadIdx.x] = out32[threadIdx.x];
+  }
+}
+
+// ---- pass 2: RGB Jacobian reduction + FP64 GN step in the finalising block -----------------------
+__global__ void __launch_bounds__(kThreads)
+gn_pass2_kernel(const RgbStepArgs a, float icpWeight, LevelK k_next, int is_last, GNState* g, StepScratch* sc) {
+  __shared__ float red[(kThreads / 32) * 32];
+  __shared__ float out32[32];
+  // RGBDOdometry.cpp:373-374
+  const int cnt = sc->rgb_count, sg = sc->rgb_sigma;
+  const float tmpError = (float)(sqrt((double)sg) / (double)cnt);
+  const float sigma = (tmpError == 0.f) ? 1.f : (float)cnt;
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+  const int N = a.cols * a.rows;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < N; p += blockDim.x * gridDim.x) {
+    int4 raw = __ldcg(reinterpret_cast<const int4*>(a.corres) + p);
+    DataTerm c;
+    c.zero = make_short2((short)(raw.x & 0xffff), (short)((unsigned)raw.x >> 16));
+    c.one = make_short2((short)(raw.y & 0xffff), (short)((unsigned)raw.y >> 16));
+    c.diff = __int_as_float(raw.z);
+    c.valid = (raw.w & 0xff) != 0;
+    rgb_step_pixel(a, sigma, c, acc);
+  }
+  float bt = block_reduce32(acc, red);
+  if (!grid_finalize32(bt, sc->partials, &sc->ticket, red, out32)) return;
+  if (threadIdx.x != 0) return;
+  // ---- RGBDOdometry.cpp:412-460 in one thread, FP64
+  TrackStats& st = g->stats;
+  st.lastRGBError = tmpError;
+  st.lastRGBCount = (float)cnt;
+  const float* icp = g->icp_result;
+  st.lastICPError = sqrtf(icp[27]) / icp[28];
+  st.lastICPCount = icp[28];
+  double A_icp[36], b_icp[6], A_rgb[36], b_rgb[6];
+  gn::unpack_se3(icp, A_icp, b_icp);
+  gn::unpack_se3(out32, A_rgb, b_rgb);
+  const double w = icpWeight;
+  for (int q = 0; q < 36; ++q) st.lastA[q] = A_rgb[q] + w * w * A_icp[q];
+  for (int q = 0; q < 6; ++q) st.lastb[q] = b_rgb[q] + w * b_icp[q];
+  double x[6];
+  gn::ldlt_solve<6>(st.lastA, st.lastb, x);
+  gn::update_se3(g->resultRt, x);
+  gn::compose_pose(g->Rprev, g->pose.tprev, g->resultRt, g->pose.Rcurr.m, g->pose.tcurr);
+  sc->rgb_count = 0;
+  sc->rgb_sigma = 0;
+  if (!is_last) {
+    double K[9], Kinv[9];
+    gn::make_K(k_next.fx, k_next.fy, k_next.cx, k_next.cy, K, Kinv);
+    gn::pose_to_warp(g->resultRt, K, Kinv, g->warp.krkinv.m, g->warp.kt);
+  } else {
+    // RGBDOdometry.cpp:464-467: photometric sanity reset
+    float d0 = g->pose.tcurr[0] - g->pose.tprev[0], d1 = g->pose.tcurr[1] - g->pose.tprev[1],
+          d2 = g->pose.tcurr[2] - g->pose.tprev[2];
+    bool reset = sqrtf(d0 * d0 + d1 * d1 + d2 * d2) > 0.3f;
+    for (int q = 0; q < 9; ++q) g->out_rot[q] = reset ? g->Rprev[q] : g->pose.Rcurr.m[q];
+    for (int q = 0; q < 3; ++q) g->out_trans[q] = reset ? g->pose.tprev[q] : g->pose.tcurr[q];
+  }
+}
+
+int grid_for(int N, int per_thread) {
+  int want = (N + kThreads * per_thread - 1) / (kThreads * per_thread);
+  int cap = num_sms() * 4;
+  if (cap > kMaxBlocks) cap = kMaxBlocks;
+  if (want < 1) want = 1;
+  return want < cap ? want : cap;
+}
+
+}  // namespace
+
+cudaError_t RGBDOdometry::deviceLoop(float trans[3], float rot[9], float icpWeight, bool pyramid, bool fastOdom,
+                                     bool so3, float* err, size_t err_pitch, cudaStream_t s) {
+  for (int i = 0; i < NUM_PYRS; i++) {
+    int w = width >> i, h = height >> i;
+    RET_IF(launch_derivative_images(nextImage[i], (size_t)w, w, h, nextdIdx[i], nextdIdy[i], (size_t)w * 2, s));
+    RET_IF(launch_project_to_point_cloud(lastDepth[i], (size_t)w * 4, w, h, intr.level(i), pointClouds[i],
+                                         (size_t)w * 12, s));
+  }
+  auto LK = [&](int l) {
+    Intr k = intr.level(l);
+    return LevelK{k.fx, k.fy, k.cx, k.cy};
+  };
+  Mat33 Rp;
+  memcpy(Rp.m, rot, sizeof(Rp.m));
+  gn_init_kernel<<<1, 32, 0, s>>>(gn, scratch, Rp, make_float3(trans[0], trans[1], trans[2]), LK(2));
+  if (so3) {
+    const int L = 2, w = width >> L, h = height >> L;
+    for (int it = 0; it < 10; ++it)
+      so3_iter_kernel<<<grid_for(w * h, 1), kThreads, 0, s>>>(lastNextImage[L], nextImage[L], (size_t)w, w, h,
+                                                              LK(L), gn, scratch);
+  }
+  int iterations[NUM_PYRS] = {fastOdom ? 3 : 10, pyramid ? 5 : 0, pyramid ? 4 : 0};
+  // schedule of (level) per GN iteration, coarse to fine
+  int sched[32], n = 0;
+  for (int i = NUM_PYRS - 1; i >= 0; --i)
+    for (int j = 0; j < iterations[i]; ++j) sched[n++] = i;
+  gn_begin_kernel<<<1, 32, 0, s>>>(gn, so3 ? 1 : 0, LK(n ? sched[0] : 0));
+  for (int q = 0; q < n; ++q) {
+    const int i = sched[q];
+    const int w = width >> i, h = height >> i;
+    const Intr k = intr.level(i);
+    const size_t p = (size_t)w * 4;
+    IcpArgs ia;
+    ia.vmap_curr = {vmaps_curr_[i], p};
+    ia.nmap_curr = {nmaps_curr_[i], p};
+    ia.vmap_g_prev = {vmaps_g_prev_[i], p};
+    ia.nmap_g_prev = {nmaps_g_prev_[i], p};
+    ia.intr = k;
+    ia.distThres = distThres_;
+    ia.angleThres = angleThres_;
+    ia.cols = w;
+    ia.rows = h;
+    const bool last_of_l0 = (i == 0 && (q + 1 == n || sched[q + 1] != 0));
+    ia.error_map = last_of_l0 ? err : nullptr;
+    ia.error_pitch = err_pitch;
+    RgbResidualArgs ra;
+    ra.minScale = (float)(pow(minimumGradientMagnitudes[i], 2.0) / pow(sobelScale, 2.0));
+    ra.maxDepthDelta = maxDepthDeltaRGB;
+    ra.dIdx = nextdIdx[i];
+    ra.dIdy = nextdIdy[i];
+    ra.grad_pitch = (size_t)w * 2;
+    ra.lastDepth = lastDepth[i];
+    ra.nextDepth = nextDepth[i];
+    ra.depth_pitch = p;
+    ra.lastImage = lastImage[i];
+    ra.nextImage = nextImage[i];
+    ra.img_pitch = (size_t)w;
+    ra.corres = corresImg[i];
+    ra.cols = w;
+    ra.rows = h;
+    RgbStepArgs sa;
+    sa.corres = corresImg[i];
+    sa.cloud = pointClouds[i];
+    sa.cloud_pitch = (size_t)w * 12;
+    sa.dIdx = nextdIdx[i];
+    sa.dIdy = nextdIdy[i];
+    sa.grad_pitch = (size_t)w * 2;
+    sa.fx = k.fx;
+    sa.fy = k.fy;
+    sa.sobelScale = sobelScale;
+    sa.cols = w;
+    sa.rows = h;
+    const int g1 = grid_for(w * h, 2);
+    gn_pass1_kernel<<<g1, kThreads, 0, s>>>(ia, ra, gn, scratch);
+    const bool is_last = (q + 1 == n);
+    gn_pass2_kernel<<<g1, kThreads, 0, s>>>(sa, icpWeight, LK(is_last ? i : sched[q + 1]), is_last ? 1 : 0, gn,
+                                            scratch);
+  }
+  RET_IF(cudaGetLastError());
+  // one small D2H per frame: pose + stats
+  struct Out {
+    float trans[3];
+    float rot[9];
+    TrackStats st;
+  };
+  static_assert(sizeof(Out) <= 2048, "staging");
+  Out* ho = (Out*)((char*)h_pinned + 2048);
+  RET_IF(cudaMemcpyAsync(ho->trans, gn->out_trans, 12 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  RET_IF(cudaMemcpyAsync(&ho->st, &gn->stats, sizeof(TrackStats), cudaMemcpyDeviceToHost, s));
+  RET_IF(cudaStreamSynchronize(s));
+  if (n > 0) {
+    memcpy(trans, ho->trans, sizeof(float) * 3);
+    memcpy(rot, ho->rot, sizeof(float) * 9);
+  }
+  stats_ = ho->st;
+  if (so3)
+    for (int i = 0; i < NUM_PYRS; i++) {
+      unsigned char* t = lastNextImage[i];
+      lastNextImage[i] = nextImage[i];
+      nextImage[i] = t;
+    }
+  return cudaSuccess;
+}
+
+}  // namespace cfb

@@ -1,0 +1,34 @@
+// image_kernels.cuh -- launch wrappers of the image preparation kernels (see image_kernels.cu).
+// All pointers are device pointers, pitches are in bytes, `s` is the stream the launch goes to.
+#pragma once
+#include "cfb_common.cuh"
+
+namespace cfb {
+
+cudaError_t launch_bilateral(const float* depth, size_t dpitch, int W, int H, float maxD, float* out,
+                             size_t opitch, cudaStream_t s);
+cudaError_t launch_pyr_down_gauss_f(const float* src, size_t spitch, int sw, int sh, float* dst,
+                                    size_t dpitch, cudaStream_t s);
+cudaError_t launch_pyr_down_uchar(const unsigned char* src, size_t spitch, int sw, int sh,
+                                  unsigned char* dst, size_t dpitch, cudaStream_t s);
+cudaError_t launch_create_vmap(const float* depth, size_t dpitch, int W, int H, Intr k, float cutoff,
+                               float* vmap, size_t vpitch, cudaStream_t s);
+cudaError_t launch_create_nmap(const float* vmap, size_t vpitch, int W, int H, float* nmap, size_t npitch,
+                               cudaStream_t s);
+cudaError_t launch_copy_maps(const float* v4, const float* n4, int W, int H, float* vmap, size_t vpitch,
+                             float* nmap, size_t npitch, cudaStream_t s);
+cudaError_t launch_resize_map(const float* in, size_t ipitch, int sw, int sh, bool normalize, float* out,
+                              size_t opitch, cudaStream_t s);
+cudaError_t launch_transform_maps(const float* vsrc, size_t vspitch, const float* nsrc, size_t nspitch, int W,
+                                  int H, const Mat33& R, const float t[3], float* vdst, size_t vdpitch,
+                                  float* ndst, size_t ndpitch, cudaStream_t s);
+cudaError_t launch_vertices_to_depth(const float* v4, int W, int H, float cutoff, float* dst, size_t dpitch,
+                                     cudaStream_t s);
+cudaError_t launch_rgb_to_intensity(const unsigned char* rgb, size_t pitch, int channels, int W, int H,
+                                    unsigned char* dst, size_t dpitch, cudaStream_t s);
+cudaError_t launch_derivative_images(const unsigned char* src, size_t spitch, int W, int H, short* dx, short* dy,
+                                     size_t gpitch, cudaStream_t s);
+cudaError_t launch_project_to_point_cloud(const float* depth, size_t dpitch, int W, int H, Intr k, float* cloud,
+                                          size_t cpitch, cudaStream_t s);
+
+}  // namespace cfb

@@ -1,0 +1,105 @@
+// odometry.cuh -- cfb::RGBDOdometry, the host-side mirror of the reference tracker class
+// (Core/Utils/RGBDOdometry.h:31-139): same method names, argument meaning and call order, but
+//   * no GL textures: model predictions arrive as device pointers (AoS float4 maps, u8 image);
+//   * every device buffer is allocated once in the constructor (the reference allocates inside the
+//     hot loop, reduce.cu:958, cudafuncs.cu:525/:581);
+//   * no cudaDeviceSynchronize inside: everything is enqueued on one stream.
+// Two execution paths for getIncrementalTransformation:
+//   HostLoop   - generic (all flag combinations): one fused launch per step, one stream sync + tiny
+//                D2H per step, FP64 GN step on the host (gn_math.h).  Mirrors the reference loop 1:1.
+//   DeviceLoop - default flags (icp && rgb, no early exit): whole SO3 + 19-iteration GN sequence is
+//                enqueued without host involvement; the FP64 GN step runs in the finalising block.
+#pragma once
+#include <vector>
+
+#include "cfb_common.cuh"
+#include "tracker_kernels.cuh"
+
+namespace cfb {
+
+struct TrackStats {  // RGBDOdometry.h:62-70
+  float lastICPError, lastICPCount, lastRGBError, lastRGBCount, lastSO3Error, lastSO3Count;
+  double lastA[36];
+  double lastb[6];
+  int so3_iterations;
+  int pad;
+};
+
+// Device-resident Gauss-Newton state (DeviceLoop).
+struct GNState {
+  double resultRt[16];
+  double resultR[9], lastResultR[9];
+  float R_lr[9];
+  IcpPose pose;
+  float Rprev[9];
+  RgbWarp warp;
+  Mat33 so3_imageBasis, so3_krlr, so3_kinv;
+  float so3_lastError, so3_lastCount;
+  int so3_done;
+  float icp_result[32];
+  float out_trans[3];
+  float out_rot[9];
+  TrackStats stats;
+};
+
+class RGBDOdometry {
+ public:
+  static const int NUM_PYRS = 3;
+  RGBDOdometry(int width, int height, float cx, float cy, float fx, float fy, float distThresh = 0.10f,
+               float angleThresh = 0.34202014332f /* sin(20 deg) */);
+  ~RGBDOdometry();
+  bool ok() const { return ok_; }
+
+  // frame side: Model::generateCUDATextures + initICP(depth pyramid) (RGBDOdometry.cpp:110-118)
+  cudaError_t initICP(const float* const depthPyr[NUM_PYRS], const size_t pitch[NUM_PYRS], float depthCutoff,
+                      cudaStream_t s);
+  // model side (RGBDOdometry.cpp:143-175). v4/n4: device AoS float4 W*H; pose row-major 4x4 (host)
+  cudaError_t initICPModel(const float* v4, const float* n4, float depthCutoff, const float pose[16],
+                           cudaStream_t s);
+  // RGBDOdometry.cpp:196-204 -- both read vmaps_tmp (the model prediction), quirk kept
+  cudaError_t initRGBModel(const unsigned char* img, size_t pitch, int channels, cudaStream_t s);
+  cudaError_t initRGB(const unsigned char* img, size_t pitch, int channels, cudaStream_t s);
+  cudaError_t initFirstRGB(const unsigned char* img, size_t pitch, int channels, cudaStream_t s);
+
+  // RGBDOdometry.cpp:217-477. trans[3], rot[9] (row-major) in/out on the host.
+  // icp_error_map: optional device f32 W*H (pitch bytes) written on the last level-0 iteration.
+  cudaError_t getIncrementalTransformation(float trans[3], float rot[9], bool rgbOnly, float icpWeight,
+                                           bool pyramid, bool fastOdom, bool so3, float* icp_error_map,
+                                           size_t error_pitch, bool force_host_loop, cudaStream_t s);
+  const TrackStats& stats() const { return stats_; }
+
+  // device views (tests / map_view): which as in oracle orc_odom_view
+  const void* view(int which, int level, size_t* pitch) const;
+
+ private:
+  cudaError_t populateRGBDData(const unsigned char* img, size_t pitch, int channels, float* const* destDepths,
+                               unsigned char* const* destImages, cudaStream_t s);
+  cudaError_t hostLoop(float trans[3], float rot[9], bool rgbOnly, float icpWeight, bool pyramid, bool fastOdom,
+                       bool so3, float* err, size_t err_pitch, cudaStream_t s);
+  cudaError_t deviceLoop(float trans[3], float rot[9], float icpWeight, bool pyramid, bool fastOdom, bool so3,
+                         float* err, size_t err_pitch, cudaStream_t s);
+
+  bool ok_ = false;
+  int width, height;
+  Intr intr;
+  float distThres_, angleThres_;
+  float sobelScale, maxDepthDeltaRGB, maxDepthRGB;
+  float minimumGradientMagnitudes[NUM_PYRS];
+
+  // unpitched device buffers (pitch = cols * sizeof(T))
+  float *vmaps_g_prev_[NUM_PYRS], *nmaps_g_prev_[NUM_PYRS], *vmaps_curr_[NUM_PYRS], *nmaps_curr_[NUM_PYRS];
+  float *lastDepth[NUM_PYRS], *nextDepth[NUM_PYRS], *pointClouds[NUM_PYRS];
+  unsigned char *lastImage[NUM_PYRS], *nextImage[NUM_PYRS], *lastNextImage[NUM_PYRS];
+  short *nextdIdx[NUM_PYRS], *nextdIdy[NUM_PYRS];
+  DataTerm* corresImg[NUM_PYRS];
+  float* vmaps_tmp;  // AoS float4 copy of the model prediction
+  StepScratch* scratch;
+  GNState* gn;       // device
+  IcpPose* d_pose;
+  RgbWarp* d_warp;
+  void* h_pinned;    // pinned staging for small H2D/D2H
+  TrackStats stats_;
+  friend struct DeviceLoopAccess;
+};
+
+}  // namespace cfb

@@ -1,0 +1,153 @@
+/*
+ * cofusion_b200.h -- C ABI of the B200-native Co-Fusion hot path (libcofusion_b200.so).
+ *
+ * The reference (martinruenz/co-fusion @ 11b9fef) has no plugin/FFI layer; its seam is C++ source
+ * level.  This header exports both usable cut lines:
+ *
+ *   1. the free-function seam of Core/Cuda/cudafuncs.cuh:64-193 -- one entry point per reference
+ *      function, raw device pointers + pitch in bytes (the layout contract of DeviceArray2D,
+ *      Core/Cuda/containers/kernel_containers.hpp:60-93), host scalars/matrices by value;
+ *   2. the class seam -- cfb_odom_* mirrors RGBDOdometry (Core/Utils/RGBDOdometry.h:31-139);
+ *      cfb_ctx_* / cfb_model_* mirror CoFusion::processFrame's per-frame calls into Model /
+ *      ModelProjection (Core/Model/Model.h:117-157, Core/CoFusion.cpp:171-545) without OpenGL.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a non-zero code; cfb_last_error() gives the text
+ *     (thread-local).  Nothing calls exit() (the reference's cudaSafeCall does, convenience.cuh:74-83).
+ *   - `stream` is a cudaStream_t passed as void*; NULL = the default stream.
+ *   - "planar map" = 3 planes of H rows each ([k*H + y][x] f32), the reference vertex/normal layout
+ *     (Core/Cuda/reduce.cu:287-289).  Pitches must be multiples of 8 bytes.
+ *   - matrices are row-major; poses are 4x4 row-major camera->world.
+ *   - handles own all device memory; callers own host buffers; no allocation after *_create.
+ */
+#ifndef COFUSION_B200_H_
+#define COFUSION_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* cfb_last_error(void);
+int cfb_version(void);
+/* number of CUDA devices visible (0 if none / driver missing) */
+int cfb_device_count(void);
+
+/* DeviceArray::upload / download (Core/Cuda/containers/device_memory.cpp:218-233): synchronous
+ * copies between a host buffer and device memory owned by this module or by the caller. */
+int cfb_upload(void* dst_dev, const void* src_host, size_t bytes, void* stream);
+int cfb_download(void* dst_host, const void* src_dev, size_t bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Seam 1: free functions (device pointers).  Each cites the reference function it replaces.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* CoFusion::filterDepth + depth_bilateral_metric.frag (Core/CoFusion.cpp:567-574) */
+int cfb_bilateral_filter(const float* depth, size_t depth_pitch, int W, int H, float maxD, float* out,
+                         size_t out_pitch, void* stream);
+/* pyrDownGaussF (Core/Cuda/cudafuncs.cu:510-532); dst is (sh/2) x (sw/2) */
+int cfb_pyr_down_gauss_f(const float* src, size_t src_pitch, int sw, int sh, float* dst, size_t dst_pitch,
+                         void* stream);
+/* pyrDownUcharGauss (cudafuncs.cu:566-588) */
+int cfb_pyr_down_uchar_gauss(const uint8_t* src, size_t src_pitch, int sw, int sh, uint8_t* dst,
+                             size_t dst_pitch, void* stream);
+/* createVMap (cudafuncs.cu:136-150); mask/maskID are accepted by the reference but unused (:119) */
+int cfb_create_vmap(float fx, float fy, float cx, float cy, const float* depth, size_t depth_pitch, int W, int H,
+                    float* vmap, size_t vmap_pitch, float depthCutoff, void* stream);
+/* createNMap (cudafuncs.cu:191-205) */
+int cfb_create_nmap(const float* vmap, size_t vmap_pitch, int W, int H, float* nmap, size_t nmap_pitch,
+                    void* stream);
+/* tranformMaps [sic] (cudafuncs.cu:251-269); src may alias dst */
+int cfb_tranform_maps(const float* vmap_src, size_t vs_pitch, const float* nmap_src, size_t ns_pitch, int W, int H,
+                      const float Rmat[9], const float tvec[3], float* vmap_dst, size_t vd_pitch,
+                      float* nmap_dst, size_t nd_pitch, void* stream);
+/* copyMaps (cudafuncs.cu:313-331): AoS float4 W*H -> planar */
+int cfb_copy_maps(const float* vmap_src4, const float* nmap_src4, int W, int H, float* vmap_dst, size_t vd_pitch,
+                  float* nmap_dst, size_t nd_pitch, void* stream);
+/* resizeVMap / resizeNMap (cudafuncs.cu:437-445); output is (sh/2) rows per plane, sw/2 cols */
+int cfb_resize_vmap(const float* in, size_t in_pitch, int sw, int sh, float* out, size_t out_pitch, void* stream);
+int cfb_resize_nmap(const float* in, size_t in_pitch, int sw, int sh, float* out, size_t out_pitch, void* stream);
+/* verticesToDepth (cudafuncs.cu:615-622) */
+int cfb_vertices_to_depth(const float* vmap_src4, int W, int H, float* dst, size_t dst_pitch, float cutOff,
+                          void* stream);
+/* imageBGRToIntensity (cudafuncs.cu:641-653): source is an interleaved u8 image with `channels`
+ * bytes per pixel (3 or 4) instead of a GL-mapped cudaArray */
+int cfb_image_bgr_to_intensity(const uint8_t* img, size_t img_pitch, int channels, int W, int H, uint8_t* dst,
+                               size_t dst_pitch, void* stream);
+/* computeDerivativeImages (cudafuncs.cu:685-715) */
+int cfb_compute_derivative_images(const uint8_t* src, size_t src_pitch, int W, int H, int16_t* dx, int16_t* dy,
+                                  size_t grad_pitch, void* stream);
+/* projectToPointCloud (cudafuncs.cu:738-751): intrinsics are those of `level` already applied by
+ * the caller (fx/2^level ...); cloud is AoS float3 */
+int cfb_project_to_point_cloud(const float* depth, size_t depth_pitch, int W, int H, float fx, float fy, float cx,
+                               float cy, float* cloud3, size_t cloud_pitch, void* stream);
+
+/* Scratch for the reduction steps (the `sum`/`out` DeviceArrays of the reference signatures).
+ * Allocate cfb_step_scratch_bytes() of device memory, zero it once, reuse. */
+size_t cfb_step_scratch_bytes(void);
+
+/* icpStep (Core/Cuda/reduce.cu:425-499).  Outputs on the host: A 6x6, b 6, residual {sum r^2, inliers}.
+ * error_map (device, optional) replaces the cudaSurfaceObject (reduce.cu:301,:325). */
+int cfb_icp_step(const float Rcurr[9], const float tcurr[3], const float* vmap_curr, size_t vc_pitch,
+                 const float* nmap_curr, size_t nc_pitch, const float Rprev_inv[9], const float tprev[3],
+                 float fx, float fy, float cx, float cy, const float* vmap_g_prev, size_t vp_pitch,
+                 const float* nmap_g_prev, size_t np_pitch, float distThres, float angleThres, int W, int H,
+                 void* scratch, float* matrixA_host, float* vectorB_host, float* residual_host,
+                 float* error_map, size_t error_pitch, void* stream);
+/* computeRgbResidual (reduce.cu:893-971). corresImg: device, W*H 16-byte DataTerm, unpitched. */
+int cfb_compute_rgb_residual(float minScale, const int16_t* dIdx, const int16_t* dIdy, size_t grad_pitch,
+                             const float* lastDepth, const float* nextDepth, size_t depth_pitch,
+                             const uint8_t* lastImage, const uint8_t* nextImage, size_t img_pitch,
+                             void* corresImg, void* scratch, float maxDepthDelta, const float kt[3],
+                             const float krkinv[9], int W, int H, int* sigmaSum, int* count, void* stream);
+/* rgbStep (reduce.cu:635-687) */
+int cfb_rgb_step(const void* corresImg, float sigma, const float* cloud3, size_t cloud_pitch, float fx, float fy,
+                 const int16_t* dIdx, const int16_t* dIdy, size_t grad_pitch, float sobelScale, int W, int H,
+                 void* scratch, float* matrixA_host, float* vectorB_host, void* stream);
+/* so3Step (reduce.cu:1118-1176): A 3x3, b 3 */
+int cfb_so3_step(const uint8_t* lastImage, const uint8_t* nextImage, size_t img_pitch, const float imageBasis[9],
+                 const float kinv[9], const float krlr[9], int W, int H, void* scratch, float* matrixA_host,
+                 float* vectorB_host, float* residual_host, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Seam 2a: RGBDOdometry (Core/Utils/RGBDOdometry.h)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cfb_odom cfb_odom;
+
+typedef struct cfb_track_stats { /* RGBDOdometry.h:62-70 */
+  float lastICPError, lastICPCount, lastRGBError, lastRGBCount, lastSO3Error, lastSO3Count;
+  double lastA[36];
+  double lastb[6];
+  int so3_iterations;
+  int pad_;
+} cfb_track_stats;
+
+int cfb_odom_create(int width, int height, float cx, float cy, float fx, float fy, float distThresh,
+                    float angleThresh, cfb_odom** out);
+void cfb_odom_destroy(cfb_odom* o);
+/* initICP(depthPyramid, maskPyramid, depthCutoff) (RGBDOdometry.cpp:110-118): 3 device depth levels */
+int cfb_odom_init_icp(cfb_odom* o, const float* const depth_pyr[3], const size_t pitch[3], float depthCutoff,
+                      void* stream);
+/* initICPModel (RGBDOdometry.cpp:143-175): device AoS float4 vertex/normal predictions, host pose */
+int cfb_odom_init_icp_model(cfb_odom* o, const float* vertices4, const float* normals4, float depthCutoff,
+                            const float modelPose[16], void* stream);
+/* initRGBModel / initRGB / initFirstRGB (RGBDOdometry.cpp:196-215): device interleaved u8 image */
+int cfb_odom_init_rgb_model(cfb_odom* o, const uint8_t* img, size_t pitch, int channels, void* stream);
+int cfb_odom_init_rgb(cfb_odom* o, const uint8_t* img, size_t pitch, int channels, void* stream);
+int cfb_odom_init_first_rgb(cfb_odom* o, const uint8_t* img, size_t pitch, int channels, void* stream);
+/* getIncrementalTransformation (RGBDOdometry.cpp:217-477). trans/rot host in/out.
+ * force_host_loop != 0 selects the generic per-step host loop even for default flags. */
+int cfb_odom_get_incremental_transformation(cfb_odom* o, float trans[3], float rot[9], int rgbOnly,
+                                            float icpWeight, int pyramid, int fastOdom, int so3,
+                                            float* icp_error_map, size_t error_pitch, int force_host_loop,
+                                            cfb_track_stats* stats_out, void* stream);
+/* device views of the internal pyramids. which: 0 vmap_curr 1 nmap_curr 2 vmap_g_prev 3 nmap_g_prev
+ * 4 lastDepth 5 nextDepth 6 lastImage 7 nextImage 8 dIdx 9 dIdy 10 lastNextImage 11 cloud 12 corres */
+int cfb_odom_view(cfb_odom* o, int which, int level, const void** dev_ptr, size_t* pitch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COFUSION_B200_H_ */

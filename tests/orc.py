@@ -1,0 +1,288 @@
+"""ctypes bindings of the oracle (oracle/_build/liboracle.so) and, when present, of the compiled
+reference CUDA sources (oracle/_ref/libcfref.so).  TEST INFRASTRUCTURE -- see oracle/cf_oracle.h."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORC_DIR = os.path.join(ROOT, "oracle")
+ORC_LIB = os.path.join(ORC_DIR, "_build", "liboracle.so")
+REF_LIB = os.path.join(ORC_DIR, "_ref", "libcfref.so")
+
+fp = C.POINTER(C.c_float)
+u8p = C.POINTER(C.c_uint8)
+i16p = C.POINTER(C.c_int16)
+
+
+class OrcTrackStats(C.Structure):
+    _fields_ = [("lastICPError", C.c_float), ("lastICPCount", C.c_float), ("lastRGBError", C.c_float),
+                ("lastRGBCount", C.c_float), ("lastSO3Error", C.c_float), ("lastSO3Count", C.c_float),
+                ("lastA", C.c_double * 36), ("lastb", C.c_double * 6), ("so3_iterations", C.c_int)]
+
+
+_orc = None
+_ref = None
+
+
+def build_oracle():
+    srcs = [os.path.join(ORC_DIR, f) for f in os.listdir(ORC_DIR) if f.endswith((".c", ".h"))]
+    if not os.path.exists(ORC_LIB) or any(os.path.getmtime(s) > os.path.getmtime(ORC_LIB) for s in srcs):
+        subprocess.check_call(["make", "-C", ORC_DIR, "-s"])
+    return ORC_LIB
+
+
+def orc():
+    global _orc
+    if _orc is None:
+        _orc = C.CDLL(build_oracle())
+        _orc.orc_odom_create.restype = C.c_void_p
+        _orc.orc_odom_view.restype = C.c_void_p
+    return _orc
+
+
+def ref():
+    """compiled reference kernels, or None when oracle/_ref was not built"""
+    global _ref
+    if _ref is None and os.path.exists(REF_LIB):
+        orc()
+        _ref = C.CDLL(REF_LIB)
+    return _ref
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def P(a, t=None):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def cf(x):
+    return C.c_float(float(x))
+
+
+# ---------------------------------------------------------------- image preparation
+def bilateral(depth, maxD):
+    H, W = depth.shape
+    out = np.empty((H, W), np.float32)
+    orc().orc_bilateral_filter(P(f32(depth)), W, H, cf(maxD), P(out))
+    return out
+
+
+def pyr_down_f(src, lib=None):
+    H, W = src.shape
+    out = np.empty((H // 2, W // 2), np.float32)
+    (lib or orc()).__getattr__("ref_pyr_down_gauss_f" if lib else "orc_pyr_down_gauss_f")(P(f32(src)), W, H, P(out))
+    return out
+
+
+def pyr_down_u8(src, lib=None):
+    H, W = src.shape
+    out = np.empty((H // 2, W // 2), np.uint8)
+    src = np.ascontiguousarray(src, np.uint8)
+    (lib or orc()).__getattr__("ref_pyr_down_uchar_gauss" if lib else "orc_pyr_down_uchar_gauss")(P(src), W, H, P(out))
+    return out
+
+
+def create_vmap(depth, K, cutoff, lib=None):
+    H, W = depth.shape
+    out = np.empty((3 * H, W), np.float32)
+    fx, fy, cx, cy = K
+    (lib or orc()).__getattr__("ref_create_vmap" if lib else "orc_create_vmap")(
+        P(f32(depth)), W, H, cf(fx), cf(fy), cf(cx), cf(cy), cf(cutoff), P(out))
+    return out
+
+
+def create_nmap(vmap, lib=None):
+    H3, W = vmap.shape
+    out = np.empty((H3, W), np.float32)
+    (lib or orc()).__getattr__("ref_create_nmap" if lib else "orc_create_nmap")(P(f32(vmap)), W, H3 // 3, P(out))
+    return out
+
+
+def copy_maps(v4, n4, lib=None):
+    H, W = v4.shape[:2]
+    v = np.empty((3 * H, W), np.float32)
+    n = np.empty((3 * H, W), np.float32)
+    (lib or orc()).__getattr__("ref_copy_maps" if lib else "orc_copy_maps")(P(f32(v4)), P(f32(n4)), W, H, P(v), P(n))
+    return v, n
+
+
+def resize_map(m, normalize, lib=None):
+    H3, W = m.shape
+    H = H3 // 3
+    out = np.empty((3 * (H // 2), W // 2), np.float32)
+    (lib or orc()).__getattr__("ref_resize_map" if lib else "orc_resize_map")(P(f32(m)), W, H, int(normalize), P(out))
+    return out
+
+
+def transform_maps(v, n, R, t, lib=None):
+    H3, W = v.shape
+    vd = np.empty_like(v)
+    nd = np.empty_like(n)
+    R = f32(R).reshape(9)
+    t = f32(t).reshape(3)
+    (lib or orc()).__getattr__("ref_transform_maps" if lib else "orc_transform_maps")(
+        P(f32(v)), P(f32(n)), W, H3 // 3, P(R), P(t), P(vd), P(nd))
+    return vd, nd
+
+
+def vertices_to_depth(v4, cutoff, lib=None):
+    H, W = v4.shape[:2]
+    out = np.empty((H, W), np.float32)
+    (lib or orc()).__getattr__("ref_vertices_to_depth" if lib else "orc_vertices_to_depth")(P(f32(v4)), W, H, cf(cutoff), P(out))
+    return out
+
+
+def rgb_to_intensity(img):
+    H, W, ch = img.shape
+    out = np.empty((H, W), np.uint8)
+    orc().orc_rgb_to_intensity(P(np.ascontiguousarray(img, np.uint8)), ch, W, H, P(out))
+    return out
+
+
+def derivative_images(img, lib=None):
+    H, W = img.shape
+    dx = np.empty((H, W), np.int16)
+    dy = np.empty((H, W), np.int16)
+    (lib or orc()).__getattr__("ref_derivative_images" if lib else "orc_derivative_images")(
+        P(np.ascontiguousarray(img, np.uint8)), W, H, P(dx), P(dy))
+    return dx, dy
+
+
+def project_cloud(depth, K, lib=None):
+    H, W = depth.shape
+    out = np.empty((H, W * 3), np.float32)
+    fx, fy, cx, cy = K
+    (lib or orc()).__getattr__("ref_project_to_point_cloud" if lib else "orc_project_to_point_cloud")(
+        P(f32(depth)), W, H, cf(fx), cf(fy), cf(cx), cf(cy), P(out))
+    return out
+
+
+# ---------------------------------------------------------------- reduction steps
+def icp_step(Rcurr, tcurr, vc, nc, Rprev_inv, tprev, K, vp, np_, dist, angle, want_error=False, lib=None):
+    H3, W = vc.shape
+    H = H3 // 3
+    A = np.zeros(36, np.float32)
+    b = np.zeros(6, np.float32)
+    res = np.zeros(2, np.float32)
+    fx, fy, cx, cy = K
+    args = [P(f32(Rcurr).reshape(9)), P(f32(tcurr)), P(f32(vc)), P(f32(nc)), P(f32(Rprev_inv).reshape(9)),
+            P(f32(tprev)), cf(fx), cf(fy), cf(cx), cf(cy), P(f32(vp)), P(f32(np_)), cf(dist), cf(angle), W, H,
+            P(A), P(b), P(res)]
+    if lib:
+        lib.ref_icp_step(*args)
+        return A.reshape(6, 6), b, res, None
+    err = np.zeros((H, W), np.float32) if want_error else None
+    orc().orc_icp_step(*args, P(err))
+    return A.reshape(6, 6), b, res, err
+
+
+def rgb_residual(minScale, dIdx, dIdy, lastDepth, nextDepth, lastImage, nextImage, maxDelta, kt, krkinv, lib=None):
+    H, W = lastDepth.shape
+    corres = np.zeros((H, W, 4), np.int32)
+    sigma = C.c_int(0)
+    count = C.c_int(0)
+    (lib or orc()).__getattr__("ref_rgb_residual" if lib else "orc_rgb_residual")(
+        cf(minScale), P(np.ascontiguousarray(dIdx, np.int16)), P(np.ascontiguousarray(dIdy, np.int16)),
+        P(f32(lastDepth)), P(f32(nextDepth)), P(np.ascontiguousarray(lastImage, np.uint8)),
+        P(np.ascontiguousarray(nextImage, np.uint8)), P(corres), cf(maxDelta), P(f32(kt)), P(f32(krkinv).reshape(9)),
+        W, H, C.byref(sigma), C.byref(count))
+    return corres, sigma.value, count.value
+
+
+def rgb_step(corres, sigma, cloud, K, dIdx, dIdy, sobelScale, lib=None):
+    H, W = dIdx.shape
+    A = np.zeros(36, np.float32)
+    b = np.zeros(6, np.float32)
+    fx, fy = K[0], K[1]
+    (lib or orc()).__getattr__("ref_rgb_step" if lib else "orc_rgb_step")(
+        P(np.ascontiguousarray(corres, np.int32)), cf(sigma), P(f32(cloud)), cf(fx), cf(fy),
+        P(np.ascontiguousarray(dIdx, np.int16)), P(np.ascontiguousarray(dIdy, np.int16)), cf(sobelScale), W, H,
+        P(A), P(b))
+    return A.reshape(6, 6), b
+
+
+def so3_step(lastImage, nextImage, imageBasis, kinv, krlr, lib=None):
+    H, W = lastImage.shape
+    A = np.zeros(9, np.float32)
+    b = np.zeros(3, np.float32)
+    res = np.zeros(2, np.float32)
+    (lib or orc()).__getattr__("ref_so3_step" if lib else "orc_so3_step")(
+        P(np.ascontiguousarray(lastImage, np.uint8)), P(np.ascontiguousarray(nextImage, np.uint8)),
+        P(f32(imageBasis).reshape(9)), P(f32(kinv).reshape(9)), P(f32(krlr).reshape(9)), W, H, P(A), P(b), P(res))
+    return A.reshape(3, 3), b, res
+
+
+def corres_valid(corres):
+    """valid flag / fields of a raw DataTerm image (H,W,4) int32"""
+    c = np.ascontiguousarray(corres, np.int32)
+    valid = (c[..., 3] & 0xff) != 0
+    zero_x = (c[..., 0] & 0xffff).astype(np.int16)
+    zero_y = ((c[..., 0] >> 16) & 0xffff).astype(np.int16)
+    diff = c[..., 2].view(np.float32)
+    return valid, zero_x, zero_y, diff
+
+
+# ---------------------------------------------------------------- RGBDOdometry restatement
+class OrcOdometry:
+    VIEW_SHAPE = {0: (3, 4, np.float32), 1: (3, 4, np.float32), 2: (3, 4, np.float32), 3: (3, 4, np.float32),
+                  4: (1, 4, np.float32), 5: (1, 4, np.float32), 6: (1, 1, np.uint8), 7: (1, 1, np.uint8),
+                  8: (1, 2, np.int16), 9: (1, 2, np.int16), 10: (1, 1, np.uint8)}
+
+    def __init__(self, W, H, K, dist=0.10, angle=float(np.sin(np.deg2rad(20.0)))):
+        fx, fy, cx, cy = K
+        self.W, self.H, self.K = W, H, K
+        self.dist, self.angle = dist, angle
+        self.h = C.c_void_p(orc().orc_odom_create(W, H, cf(cx), cf(cy), cf(fx), cf(fy), cf(dist), cf(angle)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            orc().orc_odom_destroy(self.h)
+            self.h = None
+
+    def init_model(self, v4, n4, img, pose):
+        orc().orc_odom_init_model(self.h, P(f32(v4)), P(f32(n4)), P(np.ascontiguousarray(img, np.uint8)),
+                                  img.shape[2], P(f32(pose).reshape(16)))
+
+    def init_frame(self, depth_filtered, rgb, cutoff):
+        orc().orc_odom_init_frame(self.h, P(f32(depth_filtered)), P(np.ascontiguousarray(rgb, np.uint8)),
+                                  rgb.shape[2], cf(cutoff))
+
+    def init_first_rgb(self, rgb):
+        orc().orc_odom_init_first_rgb(self.h, P(np.ascontiguousarray(rgb, np.uint8)), rgb.shape[2])
+
+    def track(self, pose, rgb_only=False, icp_weight=10.0, pyramid=True, fast_odom=False, so3=True,
+              want_error=False, use_ref=False):
+        pose = np.asarray(pose, np.float32)
+        trans = np.ascontiguousarray(pose[:3, 3]).copy()
+        rot = np.ascontiguousarray(pose[:3, :3]).copy()
+        st = OrcTrackStats()
+        err = np.zeros((self.H, self.W), np.float32) if want_error else None
+        extra = {}
+        if use_ref:
+            ms = C.c_double(0)
+            steps = C.c_int(0)
+            ref().ref_odom_track(self.h, P(trans), P(rot), int(rgb_only), cf(icp_weight), int(pyramid),
+                                 int(fast_odom), int(so3), cf(self.dist), cf(self.angle), C.byref(st),
+                                 C.byref(ms), C.byref(steps))
+            extra = {"step_ms": ms.value, "steps": steps.value}
+        else:
+            orc().orc_odom_track(self.h, P(trans), P(rot), int(rgb_only), cf(icp_weight), int(pyramid),
+                                 int(fast_odom), int(so3), P(err), C.byref(st))
+        out = np.eye(4, dtype=np.float32)
+        out[:3, :3] = rot
+        out[:3, 3] = trans
+        return out, st, err, extra
+
+    def view(self, which, level):
+        planes, esz, dt = self.VIEW_SHAPE[which]
+        w, h = self.W >> level, self.H >> level
+        ptr = orc().orc_odom_view(self.h, which, level)
+        n = planes * h * w
+        buf = (C.c_char * (n * esz)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dt).reshape(planes * h, w).copy()
