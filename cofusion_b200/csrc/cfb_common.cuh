@@ -133,7 +133,18 @@ __device__ __forceinline__ bool grid_finalize32(float block_total, float* partia
   if (!is_last) return false;
   __threadfence();
   float s = 0.f;
-  for (unsigned b = warp; b < gridDim.x; b += nw) s += __ldcg(&partials[b * 32 + lane]);
+  {  // independent loads, 4 in flight per warp; fixed summation order
+    unsigned b = warp;
+    for (; b + 3 * nw < gridDim.x; b += 4 * nw) {
+      float p0 = __ldcg(&partials[b * 32 + lane]), p1 = __ldcg(&partials[(b + nw) * 32 + lane]);
+      float p2 = __ldcg(&partials[(b + 2 * nw) * 32 + lane]), p3 = __ldcg(&partials[(b + 3 * nw) * 32 + lane]);
+      s += p0;
+      s += p1;
+      s += p2;
+      s += p3;
+    }
+    for (; b < gridDim.x; b += nw) s += __ldcg(&partials[b * 32 + lane]);
+  }
   __syncthreads();  // smem reuse
   smem[warp * 32 + lane] = s;
   __syncthreads();

@@ -46,17 +46,17 @@ __device__ void so3_matrices(GNState* g, LevelK k) {
 }
 
 // ---- gn_init: reset state for a new frame (RGBDOdometry.cpp:224-255, :316-318) ------------------
-__global__ void gn_init_kernel(GNState* g, StepScratch* sc, Mat33 Rprev, float3 tprev, LevelK k_so3) {
+__global__ void gn_init_kernel(GNState* g, StepScratch* sc, const float* __restrict__ pose_in /* t[3], R[9] */,
+                               LevelK k_so3) {
   if (threadIdx.x != 0) return;
   for (int q = 0; q < 9; ++q) {
-    g->Rprev[q] = Rprev.m[q];
-    g->pose.Rcurr.m[q] = Rprev.m[q];
+    g->Rprev[q] = pose_in[3 + q];
+    g->pose.Rcurr.m[q] = pose_in[3 + q];
     g->resultR[q] = g->lastResultR[q] = (q % 4 == 0) ? 1.0 : 0.0;
     g->R_lr[q] = (q % 4 == 0) ? 1.f : 0.f;
   }
-  g->pose.tprev[0] = g->pose.tcurr[0] = tprev.x;
-  g->pose.tprev[1] = g->pose.tcurr[1] = tprev.y;
-  g->pose.tprev[2] = g->pose.tcurr[2] = tprev.z;
+  for (int q = 0; q < 3; ++q) g->pose.tprev[q] = g->pose.tcurr[q] = pose_in[q];
+  for (int q = 0; q < 12; ++q) g->out_trans[q] = pose_in[q];  // out_trans[3] + out_rot[9] are contiguous
   gn::inverse3f(g->Rprev, g->pose.Rprev_inv.m);
   g->so3_lastError = FLT_MAX / 2;
   g->so3_lastCount = FLT_MAX / 2;
@@ -111,7 +111,7 @@ so3_iter_kernel(const unsigned char* __restrict__ lastImage, const unsigned char
   double Ad[9], bd[3], xd[3];
   for (int q = 0; q < 9; ++q) Ad[q] = jtj[q];
   for (int q = 0; q < 3; ++q) bd[q] = jtr[q];
-  gn::ldlt_solve<3>(Ad, bd, xd);
+  gn::ldlt_solve_unrolled<3>(Ad, bd, xd);
   double delta[3] = {(double)(float)xd[0], (double)(float)xd[1], (double)(float)xd[2]};
   double rotUpdate[9];
   gn::rodrigues(delta, rotUpdate);
@@ -139,9 +139,62 @@ __global__ void gn_begin_kernel(GNState* g, int use_so3, LevelK k_first) {
   gn::pose_to_warp(g->resultRt, K, Kinv, g->warp.krkinv.m, g->warp.kt);
 }
 
+// ---- frame-side photometric preparation, once per level per frame: gradient images
+// (cudafuncs.cu:658-683) + every iteration-invariant gate of RGBResidual::getProducts folded into one
+// byte per pixel: j0 < W-5, i < H-1 (reduce.cu:799), 4x4 window of nextImage > 0 (:803-814),
+// gradient magnitude gate (:823-825), nextDepth not NaN (:832).
+__constant__ float c_sx[9] = {0.52201f, 0.00000f, -0.52201f, 0.79451f, -0.00000f, -0.79451f, 0.52201f, 0.00000f, -0.52201f};
+__constant__ float c_sy[9] = {0.52201f, 0.79451f, 0.52201f, 0.00000f, 0.00000f, 0.00000f, -0.52201f, -0.79451f, -0.52201f};
+__global__ void rgb_prepare_kernel(const unsigned char* __restrict__ img, int W, int H,
+                                   const float* __restrict__ nextDepth, float minScale, short* __restrict__ dx,
+                                   short* __restrict__ dy, unsigned char* __restrict__ cand) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  float dxVal = 0.f, dyVal = 0.f;
+  int k = 8;
+  for (int j = max(y - 1, 0); j <= min(y + 1, H - 1); j++)
+    for (int i = max(x - 1, 0); i <= min(x + 1, W - 1); i++) {
+      float p = (float)__ldg(img + j * W + i);
+      dxVal = __fadd_rn(dxVal, __fmul_rn(p, c_sx[k]));  // no FMA contraction: bit-identical to
+      dyVal = __fadd_rn(dyVal, __fmul_rn(p, c_sy[k]));  // computeDerivativeImages in image_kernels.cu
+      --k;
+    }
+  const short sx = (short)dxVal, sy = (short)dyVal;
+  dx[y * W + x] = sx;
+  dy[y * W + x] = sy;
+  unsigned ok = (x < W - 5 && y < H - 1) ? 1u : 0u;
+  for (int u = max(y - 2, 0); u < min(y + 2, H); u++)
+    for (int v = max(x - 2, 0); v < min(x + 2, W); v++) ok &= (unsigned)(__ldg(img + u * W + v) > 0);
+  const float mTwo = (float)((sx * sx) + (sy * sy));
+  ok &= (unsigned)(mTwo >= minScale);
+  ok &= (unsigned)(!isnan(__ldg(nextDepth + y * W + x)));
+  cand[y * W + x] = (unsigned char)ok;
+}
+
+// RGBResidual::getProducts for a pixel that already passed the invariant gates (reduce.cu:827-853)
+__device__ __forceinline__ bool rgb_residual_cand(const RgbResidualArgs& a, const RgbWarp& Wp, int x, int y,
+                                                  DataTerm& corres, int& sq) {
+  float d1 = __ldg(row_ptr(a.nextDepth, a.depth_pitch, y) + x);
+  const float* k = Wp.krkinv.m;
+  float transformed_d1 = d1 * (k[6] * x + k[7] * y + k[8]) + Wp.kt[2];
+  int u0 = __float2int_rn((d1 * (k[0] * x + k[1] * y + k[2]) + Wp.kt[0]) / transformed_d1);
+  int v0 = __float2int_rn((d1 * (k[3] * x + k[4] * y + k[5]) + Wp.kt[1]) / transformed_d1);
+  if (!(u0 >= 0 && v0 >= 0 && u0 < a.cols && v0 < a.rows)) return false;
+  float d0 = __ldg(row_ptr(a.lastDepth, a.depth_pitch, v0) + u0);
+  unsigned char li = __ldg(row_ptr(a.lastImage, a.img_pitch, v0) + u0);
+  if (!(d0 > 0 && fabsf(transformed_d1 - d0) <= a.maxDepthDelta && li != 0)) return false;
+  corres.zero = make_short2((short)u0, (short)v0);
+  corres.one = make_short2((short)x, (short)y);
+  corres.diff = (float)__ldg(row_ptr(a.nextImage, a.img_pitch, y) + x) - (float)li;
+  corres.valid = true;
+  sq = (int)(corres.diff * corres.diff);
+  return true;
+}
+
 // ---- pass 1: RGB residual + ICP reduction, fused ------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-gn_pass1_kernel(const IcpArgs ia, const RgbResidualArgs ra, GNState* g, StepScratch* sc) {
+gn_pass1_kernel(const IcpArgs ia, const RgbResidualArgs ra, const unsigned char* __restrict__ cand, GNState* g,
+                StepScratch* sc) {
   __shared__ IcpPose P;
   __shared__ RgbWarp Wp;
   __shared__ float red[(kThreads / 32) * 32];
@@ -159,8 +212,12 @@ gn_pass1_kernel(const IcpArgs ia, const RgbResidualArgs ra, GNState* g, StepScra
     int y = p / ia.cols, x = p - y * ia.cols;
     icp_pixel(ia, P, x, y, acc);
     DataTerm c;
+    c.valid = false;
+    c.zero = make_short2(0, 0);
+    c.one = make_short2(0, 0);
+    c.diff = 0.f;
     int sq;
-    if (rgb_residual_pixel(ra, Wp, x, y, c, sq)) {
+    if (__ldg(cand + p) && rgb_residual_cand(ra, Wp, x, y, c, sq)) {
       cnt += 1;
       sig += sq;
     }
@@ -231,31 +288,59 @@ gn_pass2_kernel(const RgbStepArgs a, float icpWeight, LevelK k_next, int is_last
   gn::unpack_se3(icp, A_icp, b_icp);
   gn::unpack_se3(out32, A_rgb, b_rgb);
   const double w = icpWeight;
-  for (int q = 0; q < 36; ++q) st.lastA[q] = A_rgb[q] + w * w * A_icp[q];
-  for (int q = 0; q < 6; ++q) st.lastb[q] = b_rgb[q] + w * b_icp[q];
-  double x[6];
-  gn::ldlt_solve<6>(st.lastA, st.lastb, x);
-  gn::update_se3(g->resultRt, x);
-  gn::compose_pose(g->Rprev, g->pose.tprev, g->resultRt, g->pose.Rcurr.m, g->pose.tcurr);
+  double A[36], bb[6], x[6];
+#pragma unroll
+  for (int q = 0; q < 36; ++q) {
+    A[q] = A_rgb[q] + w * w * A_icp[q];
+    st.lastA[q] = A[q];
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    bb[q] = b_rgb[q] + w * b_icp[q];
+    st.lastb[q] = bb[q];
+  }
+  gn::ldlt_solve_unrolled<6>(A, bb, x);
+  double Rt[16];
+  float Rprev[9], tprev[3], Rcurr[9], tcurr[3];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) Rt[q] = g->resultRt[q];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) Rprev[q] = g->Rprev[q];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) tprev[q] = g->pose.tprev[q];
+  gn::update_se3(Rt, x);
+  gn::compose_pose(Rprev, tprev, Rt, Rcurr, tcurr);
+#pragma unroll
+  for (int q = 0; q < 16; ++q) g->resultRt[q] = Rt[q];
+#pragma unroll
+  for (int q = 0; q < 9; ++q) g->pose.Rcurr.m[q] = Rcurr[q];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) g->pose.tcurr[q] = tcurr[q];
   sc->rgb_count = 0;
   sc->rgb_sigma = 0;
   if (!is_last) {
     double K[9], Kinv[9];
+    float krk[9], kt[3];
     gn::make_K(k_next.fx, k_next.fy, k_next.cx, k_next.cy, K, Kinv);
-    gn::pose_to_warp(g->resultRt, K, Kinv, g->warp.krkinv.m, g->warp.kt);
+    gn::pose_to_warp(Rt, K, Kinv, krk, kt);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) g->warp.krkinv.m[q] = krk[q];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) g->warp.kt[q] = kt[q];
   } else {
     // RGBDOdometry.cpp:464-467: photometric sanity reset
-    float d0 = g->pose.tcurr[0] - g->pose.tprev[0], d1 = g->pose.tcurr[1] - g->pose.tprev[1],
-          d2 = g->pose.tcurr[2] - g->pose.tprev[2];
+    float d0 = tcurr[0] - tprev[0], d1 = tcurr[1] - tprev[1], d2 = tcurr[2] - tprev[2];
     bool reset = sqrtf(d0 * d0 + d1 * d1 + d2 * d2) > 0.3f;
-    for (int q = 0; q < 9; ++q) g->out_rot[q] = reset ? g->Rprev[q] : g->pose.Rcurr.m[q];
-    for (int q = 0; q < 3; ++q) g->out_trans[q] = reset ? g->pose.tprev[q] : g->pose.tcurr[q];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) g->out_rot[q] = reset ? Rprev[q] : Rcurr[q];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) g->out_trans[q] = reset ? tprev[q] : tcurr[q];
   }
 }
 
 int grid_for(int N, int per_thread) {
   int want = (N + kThreads * per_thread - 1) / (kThreads * per_thread);
-  int cap = num_sms() * 4;
+  int cap = num_sms() * 2;
   if (cap > kMaxBlocks) cap = kMaxBlocks;
   if (want < 1) want = 1;
   return want < cap ? want : cap;
@@ -263,11 +348,24 @@ int grid_for(int N, int per_thread) {
 
 }  // namespace
 
-cudaError_t RGBDOdometry::deviceLoop(float trans[3], float rot[9], float icpWeight, bool pyramid, bool fastOdom,
-                                     bool so3, float* err, size_t err_pitch, cudaStream_t s) {
+// Enqueue the whole tracker sequence on `s` (capturable: no host synchronisation inside).
+cudaError_t RGBDOdometry::enqueueDeviceLoop(float icpWeight, bool pyramid, bool fastOdom, bool so3, float* err,
+                                            size_t err_pitch, cudaStream_t s) {
+  struct Out {
+    float trans[3];
+    float rot[9];
+    TrackStats st;
+  };
+  static_assert(sizeof(Out) <= 2048, "staging");
+  float* h_in = (float*)((char*)h_pinned + 1536);
+  Out* ho = (Out*)((char*)h_pinned + 2048);
+  RET_IF(cudaMemcpyAsync(d_pose_in, h_in, 12 * sizeof(float), cudaMemcpyHostToDevice, s));
+  const dim3 b2(32, 8);
   for (int i = 0; i < NUM_PYRS; i++) {
     int w = width >> i, h = height >> i;
-    RET_IF(launch_derivative_images(nextImage[i], (size_t)w, w, h, nextdIdx[i], nextdIdy[i], (size_t)w * 2, s));
+    float minScale = (float)(pow(minimumGradientMagnitudes[i], 2.0) / pow(sobelScale, 2.0));
+    rgb_prepare_kernel<<<dim3((w + 31) / 32, (h + 7) / 8), b2, 0, s>>>(nextImage[i], w, h, nextDepth[i], minScale,
+                                                                         nextdIdx[i], nextdIdy[i], rgbCand[i]);
     RET_IF(launch_project_to_point_cloud(lastDepth[i], (size_t)w * 4, w, h, intr.level(i), pointClouds[i],
                                          (size_t)w * 12, s));
   }
@@ -275,9 +373,7 @@ cudaError_t RGBDOdometry::deviceLoop(float trans[3], float rot[9], float icpWeig
     Intr k = intr.level(l);
     return LevelK{k.fx, k.fy, k.cx, k.cy};
   };
-  Mat33 Rp;
-  memcpy(Rp.m, rot, sizeof(Rp.m));
-  gn_init_kernel<<<1, 32, 0, s>>>(gn, scratch, Rp, make_float3(trans[0], trans[1], trans[2]), LK(2));
+  gn_init_kernel<<<1, 32, 0, s>>>(gn, scratch, d_pose_in, LK(2));
   if (so3) {
     const int L = 2, w = width >> L, h = height >> L;
     for (int it = 0; it < 10; ++it)
@@ -285,8 +381,7 @@ cudaError_t RGBDOdometry::deviceLoop(float trans[3], float rot[9], float icpWeig
                                                               LK(L), gn, scratch);
   }
   int iterations[NUM_PYRS] = {fastOdom ? 3 : 10, pyramid ? 5 : 0, pyramid ? 4 : 0};
-  // schedule of (level) per GN iteration, coarse to fine
-  int sched[32], n = 0;
+  int sched[32], n = 0;  // level of each GN iteration, coarse to fine
   for (int i = NUM_PYRS - 1; i >= 0; --i)
     for (int j = 0; j < iterations[i]; ++j) sched[n++] = i;
   gn_begin_kernel<<<1, 32, 0, s>>>(gn, so3 ? 1 : 0, LK(n ? sched[0] : 0));
@@ -309,7 +404,7 @@ cudaError_t RGBDOdometry::deviceLoop(float trans[3], float rot[9], float icpWeig
     ia.error_map = last_of_l0 ? err : nullptr;
     ia.error_pitch = err_pitch;
     RgbResidualArgs ra;
-    ra.minScale = (float)(pow(minimumGradientMagnitudes[i], 2.0) / pow(sobelScale, 2.0));
+    ra.minScale = 0.f;  // folded into rgbCand
     ra.maxDepthDelta = maxDepthDeltaRGB;
     ra.dIdx = nextdIdx[i];
     ra.dIdy = nextdIdy[i];
@@ -336,34 +431,68 @@ cudaError_t RGBDOdometry::deviceLoop(float trans[3], float rot[9], float icpWeig
     sa.cols = w;
     sa.rows = h;
     const int g1 = grid_for(w * h, 2);
-    gn_pass1_kernel<<<g1, kThreads, 0, s>>>(ia, ra, gn, scratch);
+    gn_pass1_kernel<<<g1, kThreads, 0, s>>>(ia, ra, rgbCand[i], gn, scratch);
     const bool is_last = (q + 1 == n);
     gn_pass2_kernel<<<g1, kThreads, 0, s>>>(sa, icpWeight, LK(is_last ? i : sched[q + 1]), is_last ? 1 : 0, gn,
                                             scratch);
   }
   RET_IF(cudaGetLastError());
   // one small D2H per frame: pose + stats
+  RET_IF(cudaMemcpyAsync(ho->trans, gn->out_trans, 12 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  RET_IF(cudaMemcpyAsync(&ho->st, &gn->stats, sizeof(TrackStats), cudaMemcpyDeviceToHost, s));
+  return cudaSuccess;
+}
+
+cudaError_t RGBDOdometry::deviceLoop(float trans[3], float rot[9], float icpWeight, bool pyramid, bool fastOdom,
+                                     bool so3, float* err, size_t err_pitch, cudaStream_t s) {
   struct Out {
     float trans[3];
     float rot[9];
     TrackStats st;
   };
-  static_assert(sizeof(Out) <= 2048, "staging");
+  float* h_in = (float*)((char*)h_pinned + 1536);
   Out* ho = (Out*)((char*)h_pinned + 2048);
-  RET_IF(cudaMemcpyAsync(ho->trans, gn->out_trans, 12 * sizeof(float), cudaMemcpyDeviceToHost, s));
-  RET_IF(cudaMemcpyAsync(&ho->st, &gn->stats, sizeof(TrackStats), cudaMemcpyDeviceToHost, s));
-  RET_IF(cudaStreamSynchronize(s));
-  if (n > 0) {
-    memcpy(trans, ho->trans, sizeof(float) * 3);
-    memcpy(rot, ho->rot, sizeof(float) * 9);
+  memcpy(h_in, trans, 3 * sizeof(float));
+  memcpy(h_in + 3, rot, 9 * sizeof(float));
+
+  // CUDA graph of the whole sequence (the ~60 launches are otherwise launch-latency bound).  The
+  // legacy default stream cannot be captured: direct launches there.
+  bool launched = false;
+  if (use_graphs_ && s != 0 && s != cudaStreamLegacy) {
+    GraphKey key{parity_, err, err_pitch, icpWeight, pyramid, fastOdom, so3};
+    cudaGraphExec_t exec = nullptr;
+    for (auto& e : graphs_)
+      if (e.key.parity == key.parity && e.key.err == key.err && e.key.err_pitch == key.err_pitch &&
+          e.key.icpWeight == key.icpWeight && e.key.pyramid == key.pyramid && e.key.fastOdom == key.fastOdom &&
+          e.key.so3 == key.so3)
+        exec = e.exec;
+    if (!exec) {
+      cudaGraph_t graph = nullptr;
+      RET_IF(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      cudaError_t ce = enqueueDeviceLoop(icpWeight, pyramid, fastOdom, so3, err, err_pitch, s);
+      cudaError_t ee = cudaStreamEndCapture(s, &graph);
+      if (ce != cudaSuccess) return ce;
+      RET_IF(ee);
+      RET_IF(cudaGraphInstantiate(&exec, graph, 0));
+      cudaGraphDestroy(graph);
+      graphs_.push_back({key, exec});
+    }
+    RET_IF(cudaGraphLaunch(exec, s));
+    launched = true;
   }
+  if (!launched) RET_IF(enqueueDeviceLoop(icpWeight, pyramid, fastOdom, so3, err, err_pitch, s));
+  RET_IF(cudaStreamSynchronize(s));
+  memcpy(trans, ho->trans, sizeof(float) * 3);
+  memcpy(rot, ho->rot, sizeof(float) * 9);
   stats_ = ho->st;
-  if (so3)
+  if (so3) {
     for (int i = 0; i < NUM_PYRS; i++) {
       unsigned char* t = lastNextImage[i];
       lastNextImage[i] = nextImage[i];
       nextImage[i] = t;
     }
+    parity_ ^= 1;
+  }
   return cudaSuccess;
 }
 

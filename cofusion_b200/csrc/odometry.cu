@@ -42,10 +42,10 @@ RGBDOdometry::RGBDOdometry(int w, int h, float cx, float cy, float fx, float fy,
            dalloc(&vmaps_curr_[i], n * 3) && dalloc(&nmaps_curr_[i], n * 3) && dalloc(&lastDepth[i], n) &&
            dalloc(&nextDepth[i], n) && dalloc(&pointClouds[i], n * 3) && dalloc(&lastImage[i], n) &&
            dalloc(&nextImage[i], n) && dalloc(&lastNextImage[i], n) && dalloc(&nextdIdx[i], n) &&
-           dalloc(&nextdIdy[i], n) && dalloc(&corresImg[i], n);
+           dalloc(&nextdIdy[i], n) && dalloc(&corresImg[i], n) && dalloc(&rgbCand[i], n);
   }
   good = good && dalloc(&vmaps_tmp, (size_t)w * h * 4) && dalloc(&scratch, 1) && dalloc(&gn, 1) &&
-         dalloc(&d_pose, 1) && dalloc(&d_warp, 1);
+         dalloc(&d_pose, 1) && dalloc(&d_warp, 1) && dalloc(&d_pose_in, 16);
   good = good && cudaMallocHost(&h_pinned, 4096) == cudaSuccess;
   ok_ = good;
 }
@@ -65,7 +65,10 @@ RGBDOdometry::~RGBDOdometry() {
     cudaFree(nextdIdx[i]);
     cudaFree(nextdIdy[i]);
     cudaFree(corresImg[i]);
+    cudaFree(rgbCand[i]);
   }
+  for (auto& e : graphs_) cudaGraphExecDestroy(e.exec);
+  cudaFree(d_pose_in);
   cudaFree(vmaps_tmp);
   cudaFree(scratch);
   cudaFree(gn);

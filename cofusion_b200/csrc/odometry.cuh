@@ -78,6 +78,8 @@ class RGBDOdometry {
                        bool so3, float* err, size_t err_pitch, cudaStream_t s);
   cudaError_t deviceLoop(float trans[3], float rot[9], float icpWeight, bool pyramid, bool fastOdom, bool so3,
                          float* err, size_t err_pitch, cudaStream_t s);
+  cudaError_t enqueueDeviceLoop(float icpWeight, bool pyramid, bool fastOdom, bool so3, float* err,
+                                size_t err_pitch, cudaStream_t s);
 
   bool ok_ = false;
   int width, height;
@@ -98,6 +100,27 @@ class RGBDOdometry {
   IcpPose* d_pose;
   RgbWarp* d_warp;
   void* h_pinned;    // pinned staging for small H2D/D2H
+  unsigned char* rgbCand[NUM_PYRS];  // iteration-invariant photometric gates, one byte per pixel
+  float* d_pose_in;                  // t[3], R[9] of the incoming pose
+  struct GraphKey {
+    int parity;
+    float* err;
+    size_t err_pitch;
+    float icpWeight;
+    bool pyramid, fastOdom, so3;
+  };
+  struct GraphEntry {
+    GraphKey key;
+    cudaGraphExec_t exec;
+  };
+  std::vector<GraphEntry> graphs_;
+  int parity_ = 0;  // which of the two intensity pyramids currently plays "nextImage"
+  bool use_graphs_ = true;
+
+ public:
+  void setUseGraphs(bool v) { use_graphs_ = v; }
+
+ private:
   TrackStats stats_;
   friend struct DeviceLoopAccess;
 };

@@ -79,12 +79,13 @@ __device__ __forceinline__ bool rgb_residual_pixel(const RgbResidualArgs& a, con
   sq = 0;
   const int cols = a.cols, rows = a.rows;
   if (!(j0 < cols - 5 && i < rows - 1)) return false;
-  bool valid = true;
+  // all 16 loads are issued unconditionally (a short-circuit && would serialise 16 L2 round trips)
+  unsigned nz = 1u;
   for (int u = max(i - 2, 0); u < min(i + 2, rows); u++) {
     const unsigned char* r = row_ptr(a.nextImage, a.img_pitch, u);
-    for (int v = max(j0 - 2, 0); v < min(j0 + 2, cols); v++) valid = valid && (__ldg(r + v) > 0);
+    for (int v = max(j0 - 2, 0); v < min(j0 + 2, cols); v++) nz &= (unsigned)(__ldg(r + v) > 0);
   }
-  if (!valid) return false;
+  if (!nz) return false;
   short valx = __ldg(row_ptr(a.dIdx, a.grad_pitch, i) + j0);
   short valy = __ldg(row_ptr(a.dIdy, a.grad_pitch, i) + j0);
   float mTwo = (float)((valx * valx) + (valy * valy));

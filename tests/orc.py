@@ -241,8 +241,8 @@ class OrcOdometry:
         self.h = C.c_void_p(orc().orc_odom_create(W, H, cf(cx), cf(cy), cf(fx), cf(fy), cf(dist), cf(angle)))
 
     def __del__(self):
-        if getattr(self, "h", None):
-            orc().orc_odom_destroy(self.h)
+        if getattr(self, "h", None) and _orc is not None:
+            _orc.orc_odom_destroy(self.h)
             self.h = None
 
     def init_model(self, v4, n4, img, pose):

