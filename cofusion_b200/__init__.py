@@ -73,9 +73,12 @@ class Odometry:
                                     C.c_float(dist_thresh), C.c_float(angle_thresh), C.byref(self._h)))
 
     def __del__(self):
-        if getattr(self, "_h", None) and self._h.value:
-            lib().cfb_odom_destroy(self._h)
+        if getattr(self, "_h", None) and self._h.value and _lib is not None:
+            _lib.cfb_odom_destroy(self._h)
             self._h = C.c_void_p()
+
+    def set_mode(self, mode):
+        check(lib().cfb_odom_set_mode(self._h, int(mode)))
 
     def init_icp(self, depth_pyr, cutoff):
         ptrs = (C.c_void_p * 3)(*[d.data_ptr() for d in depth_pyr])

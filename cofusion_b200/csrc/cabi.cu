@@ -322,6 +322,16 @@ int cfb_odom_get_incremental_transformation(cfb_odom* o, float trans[3], float r
   if (stats_out) memcpy(stats_out, &o->impl.stats(), sizeof(cfb_track_stats));
   return 0;
 }
+int cfb_odom_set_mode(cfb_odom* o, int mode) {
+  REQUIRE(o && (mode == 0 || mode == 1), "odom_set_mode");
+  o->impl.setMode(mode);
+  return 0;
+}
+int cfb_odom_set_debug_trace(cfb_odom* o, void* dev_u64) {
+  REQUIRE(o, "odom_set_debug_trace");
+  o->impl.setDebugTrace(dev_u64);
+  return 0;
+}
 int cfb_odom_view(cfb_odom* o, int which, int level, const void** dev_ptr, size_t* pitch) {
   REQUIRE(o && dev_ptr && pitch && level >= 0 && level < 3, "odom_view");
   *dev_ptr = o->impl.view(which, level, pitch);

@@ -45,7 +45,8 @@ RGBDOdometry::RGBDOdometry(int w, int h, float cx, float cy, float fx, float fy,
            dalloc(&nextdIdy[i], n) && dalloc(&corresImg[i], n) && dalloc(&rgbCand[i], n);
   }
   good = good && dalloc(&vmaps_tmp, (size_t)w * h * 4) && dalloc(&scratch, 1) && dalloc(&gn, 1) &&
-         dalloc(&d_pose, 1) && dalloc(&d_warp, 1) && dalloc(&d_pose_in, 16);
+         dalloc(&d_pose, 1) && dalloc(&d_warp, 1) && dalloc(&d_pose_in, 16) &&
+         dalloc((unsigned**)&grid_sync_, 64);
   good = good && cudaMallocHost(&h_pinned, 4096) == cudaSuccess;
   ok_ = good;
 }
@@ -69,6 +70,7 @@ RGBDOdometry::~RGBDOdometry() {
   }
   for (auto& e : graphs_) cudaGraphExecDestroy(e.exec);
   cudaFree(d_pose_in);
+  cudaFree(grid_sync_);
   cudaFree(vmaps_tmp);
   cudaFree(scratch);
   cudaFree(gn);

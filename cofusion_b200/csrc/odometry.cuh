@@ -7,8 +7,10 @@
 // Two execution paths for getIncrementalTransformation:
 //   HostLoop   - generic (all flag combinations): one fused launch per step, one stream sync + tiny
 //                D2H per step, FP64 GN step on the host (gn_math.h).  Mirrors the reference loop 1:1.
-//   DeviceLoop - default flags (icp && rgb, no early exit): whole SO3 + 19-iteration GN sequence is
-//                enqueued without host involvement; the FP64 GN step runs in the finalising block.
+//   DeviceLoop - default flags (icp && rgb, no early exit): whole SO3 + 19-iteration GN sequence runs
+//                without host involvement; the FP64 GN step runs on the device.  Two realisations:
+//                mode 0 = ONE persistent cooperative kernel (gn_persistent.cu, default),
+//                mode 1 = one fused kernel per step, captured in a CUDA graph (gn_device.cu).
 #pragma once
 #include <vector>
 
@@ -80,6 +82,8 @@ class RGBDOdometry {
                          float* err, size_t err_pitch, cudaStream_t s);
   cudaError_t enqueueDeviceLoop(float icpWeight, bool pyramid, bool fastOdom, bool so3, float* err,
                                 size_t err_pitch, cudaStream_t s);
+  cudaError_t enqueuePersistent(float icpWeight, bool pyramid, bool fastOdom, bool so3, float* err,
+                                size_t err_pitch, cudaStream_t s);
 
   bool ok_ = false;
   int width, height;
@@ -116,9 +120,16 @@ class RGBDOdometry {
   std::vector<GraphEntry> graphs_;
   int parity_ = 0;  // which of the two intensity pyramids currently plays "nextImage"
   bool use_graphs_ = true;
+  void* grid_sync_ = nullptr;  // software grid barrier state of the persistent kernel
+  void* dbg_trace_ = nullptr;
+  int mode_ = 0;               // 0: one persistent cooperative kernel, 1: per-step kernels (+ CUDA graph)
 
  public:
   void setUseGraphs(bool v) { use_graphs_ = v; }
+  void setMode(int m) { mode_ = m; }
+  // tools only: device buffer of >= 256 u64 receiving a %globaltimer trace of the persistent kernel
+  void setDebugTrace(void* dev_u64) { dbg_trace_ = dev_u64; }
+  int mode() const { return mode_; }
 
  private:
   TrackStats stats_;

@@ -143,6 +143,13 @@ int cfb_odom_get_incremental_transformation(cfb_odom* o, float trans[3], float r
                                             float icpWeight, int pyramid, int fastOdom, int so3,
                                             float* icp_error_map, size_t error_pitch, int force_host_loop,
                                             cfb_track_stats* stats_out, void* stream);
+/* Execution strategy of the default-flag path (no reference equivalent): 0 = one persistent
+ * cooperative kernel for the whole SO(3)+GN optimisation (default), 1 = one fused kernel per step
+ * replayed as a CUDA graph.  Results are identical. */
+int cfb_odom_set_mode(cfb_odom* o, int mode);
+/* Profiling aid: device buffer of >= 256 uint64 that receives a %globaltimer trace of the
+ * persistent kernel's phases (NULL disables). */
+int cfb_odom_set_debug_trace(cfb_odom* o, void* dev_u64);
 /* device views of the internal pyramids. which: 0 vmap_curr 1 nmap_curr 2 vmap_g_prev 3 nmap_g_prev
  * 4 lastDepth 5 nextDepth 6 lastImage 7 nextImage 8 dIdx 9 dIdy 10 lastNextImage 11 cloud 12 corres */
 int cfb_odom_view(cfb_odom* o, int which, int level, const void** dev_ptr, size_t* pitch);

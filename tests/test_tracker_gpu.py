@@ -219,13 +219,15 @@ def _cuda_odometry(gu, case, cutoff=20.0, maxD=5.0):
     return od
 
 
-@pytest.mark.parametrize("host_loop", [False, True], ids=["device_loop", "host_loop"])
-def test_full_tracking_matches_oracle(gu, case, host_loop):
+@pytest.mark.parametrize("variant", ["persistent", "per_step_kernels", "host_loop"])
+def test_full_tracking_matches_oracle(gu, case, variant):
+    host_loop = variant == "host_loop"
     if case["W"] < 160:
         pytest.skip("pyramid needs >= 160x120")
     oo, _ = scenes.oracle_odometry(case)
     # pyramids built by the CUDA init path equal the oracle's
     co = _cuda_odometry(gu, case)
+    co.set_mode(1 if variant == "per_step_kernels" else 0)
     for which, tol in ((0, 0.0), (2, 3e-6), (4, 0.0), (6, 0.0), (7, 0.0), (10, 0.0)):
         for lvl in range(3):
             a, b = co.view(which, lvl), oo.view(which, lvl)
@@ -257,12 +259,14 @@ def test_full_tracking_matches_oracle(gu, case, host_loop):
 
 def test_tracking_is_deterministic_and_flag_variants_agree(gu):
     case = scenes.room_pair(160, 120)
-    outs = []
-    for _ in range(2):
-        co = _cuda_odometry(gu, case)
-        p, st = co.track(case["T0"])
-        outs.append((p.copy(), np.array(st.lastA)))
-    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    for mode in (0, 1):
+        outs = []
+        for _ in range(2):
+            co = _cuda_odometry(gu, case)
+            co.set_mode(mode)
+            p, st = co.track(case["T0"])
+            outs.append((p.copy(), np.array(st.lastA)))
+        assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
     # generic host loop handles the non-default modes like the oracle does
     for kw in (dict(rgb_only=True), dict(icp_weight=100.0), dict(so3=False), dict(fast_odom=True),
                dict(pyramid=False)):

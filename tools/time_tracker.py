@@ -11,17 +11,20 @@ for (W, H) in ((640, 480), (1280, 960)):
     co = _cuda_odometry(gu, case)
     torch.cuda.synchronize()
     side = torch.cuda.Stream()
-    with torch.cuda.stream(side):  # non-default stream -> the device loop runs as one CUDA graph
-        for _ in range(4):
-            co.track(case["T0"])
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        N = 50
-        e0.record()
-        for _ in range(N):
-            p, st = co.track(case["T0"])
-        e1.record(); torch.cuda.synchronize()
-        print("%dx%d device_loop (CUDA graph): %.3f ms/track" % (W, H, e0.elapsed_time(e1) / N), flush=True)
+    for mode, name in ((0, "persistent cooperative kernel"), (1, "per-step kernels, CUDA graph")):
+        co.set_mode(mode)
+        with torch.cuda.stream(side):  # non-default stream -> mode 1 runs as one CUDA graph
+            for _ in range(4):
+                co.track(case["T0"])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            N = 50
+            e0.record()
+            for _ in range(N):
+                p, st = co.track(case["T0"])
+            e1.record(); torch.cuda.synchronize()
+            print("%dx%d device_loop (%s): %.3f ms/track" % (W, H, name, e0.elapsed_time(e1) / N), flush=True)
+    co.set_mode(1)
     for host_loop in (False, True):
         for _ in range(3):
             co.track(case["T0"], force_host_loop=host_loop)
