@@ -135,3 +135,180 @@ class Odometry:
 def _cudart_memcpy_d2h(dst_np, src_ptr):
     check(lib().cfb_download(dst_np.ctypes.data_as(C.c_void_p), C.c_void_p(src_ptr), C.c_size_t(dst_np.nbytes),
                              _stream()))
+
+
+class TrackParams(C.Structure):
+    _fields_ = [("frameToFrameRGB", C.c_int), ("rgbOnly", C.c_int), ("icpWeight", C.c_float), ("pyramid", C.c_int),
+                ("fastOdom", C.c_int), ("so3", C.c_int), ("maxDepthProcessed", C.c_float), ("force_host_loop", C.c_int)]
+
+    @staticmethod
+    def default():  # CoFusion.cpp:51-60 / GUI defaults
+        return TrackParams(0, 0, 10.0, 1, 0, 1, 20.0, 0)
+
+
+class Context:
+    """cfb_ctx_*: per-device frame state (RGB, raw/filtered depth, depth pyramid, mask)."""
+
+    def __init__(self, W, H, K, device=0):
+        fx, fy, cx, cy = K
+        self.W, self.H, self.K = W, H, K
+        self._h = C.c_void_p()
+        check(lib().cfb_ctx_create(device, W, H, C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy),
+                                   C.byref(self._h)))
+        lib().cfb_ctx_stream.restype = C.c_void_p
+        self.stream = lib().cfb_ctx_stream(self._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value and _lib is not None:
+            _lib.cfb_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def upload_frame(self, rgb, depth, mask=None):
+        """host numpy arrays or pinned torch tensors"""
+        def hp(a):
+            if a is None:
+                return C.c_void_p(0)
+            if hasattr(a, "data_ptr"):
+                return C.c_void_p(a.data_ptr())
+            return a.ctypes.data_as(C.c_void_p)
+        check(lib().cfb_ctx_upload_frame(self._h, hp(rgb), hp(depth), hp(mask)))
+
+    def set_frame_device(self, rgb, depth, mask=None):
+        check(lib().cfb_ctx_set_frame_device(self._h, _p(rgb), _p(depth), _p(mask)))
+
+    def preprocess(self, depth_cutoff):
+        check(lib().cfb_ctx_preprocess(self._h, C.c_float(depth_cutoff)))
+
+    def sync(self):
+        check(lib().cfb_ctx_sync(self._h))
+
+    def take_launch_count(self):
+        return lib().cfb_ctx_take_launch_count(self._h)
+
+    def view(self, which):
+        ptr, pitch = C.c_void_p(), C.c_size_t()
+        check(lib().cfb_ctx_view(self._h, which, C.byref(ptr), C.byref(pitch)))
+        W, H = self.W, self.H
+        shp = {0: ((H, W, 3), np.uint8), 1: ((H, W), np.float32), 2: ((H, W), np.float32),
+               3: ((H // 2, W // 2), np.float32), 4: ((H // 4, W // 4), np.float32), 5: ((H, W), np.uint8)}[which]
+        out = np.empty(shp[0], dtype=shp[1])
+        self.sync()
+        check(lib().cfb_download(out.ctypes.data_as(C.c_void_p), ptr, C.c_size_t(out.nbytes), C.c_void_p(self.stream)))
+        return out
+
+
+class Model:
+    """cfb_model_*: Core/Model/Model.h without OpenGL."""
+
+    def __init__(self, ctx, model_id=0, conf_threshold=10.0, max_surfels=1 << 20, enable_fill_in=True):
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        check(lib().cfb_model_create(ctx._h, model_id, C.c_float(conf_threshold), max_surfels, int(enable_fill_in),
+                                     C.byref(self._h)))
+        lib().cfb_model_compute_fusion_weight.restype = C.c_float
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value and _lib is not None:
+            _lib.cfb_model_destroy(self._h)
+            self._h = C.c_void_p()
+
+    @property
+    def pose(self):
+        p = np.zeros(16, np.float32)
+        check(lib().cfb_model_get_pose(self._h, p.ctypes.data_as(c_float_p)))
+        return p.reshape(4, 4)
+
+    def override_pose(self, pose):
+        pp, keep = _f(np.asarray(pose, np.float32).reshape(16))
+        check(lib().cfb_model_override_pose(self._h, pp))
+
+    def set_confidence_threshold(self, v):
+        check(lib().cfb_model_set_confidence_threshold(self._h, C.c_float(v)))
+
+    def set_max_depth(self, v):
+        check(lib().cfb_model_set_max_depth(self._h, C.c_float(v)))
+
+    def set_prediction(self, v4, n4, img):
+        dev = hasattr(v4, "data_ptr")
+        if dev:
+            check(lib().cfb_model_set_prediction(self._h, _p(v4), _p(n4), _p(img), img.shape[2], 1))
+        else:
+            v4 = np.ascontiguousarray(v4, np.float32)
+            n4 = np.ascontiguousarray(n4, np.float32)
+            img = np.ascontiguousarray(img, np.uint8)
+            check(lib().cfb_model_set_prediction(self._h, v4.ctypes.data_as(C.c_void_p), n4.ctypes.data_as(C.c_void_p),
+                                                 img.ctypes.data_as(C.c_void_p), img.shape[2], 0))
+            self.ctx.sync()
+
+    def init_first_rgb(self):
+        check(lib().cfb_model_init_first_rgb(self._h))
+
+    def perform_tracking(self, params=None):
+        params = params or TrackParams.default()
+        pose = np.zeros(16, np.float32)
+        st = TrackStats()
+        check(lib().cfb_model_perform_tracking(self._h, C.byref(params), pose.ctypes.data_as(c_float_p), C.byref(st)))
+        return pose.reshape(4, 4), st
+
+    def odometry_set_mode(self, mode):
+        lib().cfb_model_odometry.restype = C.c_void_p
+        check(lib().cfb_odom_set_mode(C.c_void_p(lib().cfb_model_odometry(self._h)), int(mode)))
+
+    def initialise(self, time, max_depth=20.0):
+        check(lib().cfb_model_initialise(self._h, int(time), C.c_float(max_depth)))
+
+    def predict_indices(self, time, depth_cutoff=20.0, time_delta=200):
+        check(lib().cfb_model_predict_indices(self._h, int(time), C.c_float(depth_cutoff), int(time_delta)))
+
+    def fuse(self, time, depth_cutoff=20.0, weight_multiplier=1.0):
+        check(lib().cfb_model_fuse(self._h, int(time), C.c_float(depth_cutoff), C.c_float(weight_multiplier)))
+
+    def clean(self, time, time_delta=200, depth_cutoff=20.0, outlier_coefficient=3.0):
+        check(lib().cfb_model_clean(self._h, int(time), int(time_delta), C.c_float(depth_cutoff),
+                                    C.c_float(outlier_coefficient)))
+
+    def combined_predict(self, depth_cutoff, time, max_time, time_delta=200):
+        check(lib().cfb_model_combined_predict(self._h, C.c_float(depth_cutoff), int(time), int(max_time),
+                                               int(time_delta)))
+
+    def perform_fill_in(self, frame_to_frame_rgb=False, lost=False):
+        check(lib().cfb_model_perform_fill_in(self._h, int(frame_to_frame_rgb), int(lost)))
+
+    def fusion_weight(self, mult=1.0):
+        return float(lib().cfb_model_compute_fusion_weight(self._h, C.c_float(mult)))
+
+    def download_map(self):
+        n = C.c_uint(0)
+        check(lib().cfb_model_last_count(self._h, C.byref(n)))
+        out = np.zeros((n.value, 12), np.float32)
+        if n.value:
+            check(lib().cfb_model_download_map(self._h, out.ctypes.data_as(c_float_p), C.c_size_t(n.value), C.byref(n)))
+        return out
+
+    def upload_map(self, surfels):
+        s = np.ascontiguousarray(surfels, np.float32)
+        check(lib().cfb_model_upload_map(self._h, s.ctypes.data_as(c_float_p), s.shape[0]))
+
+    def last_count(self):
+        n = C.c_uint(0)
+        check(lib().cfb_model_last_count(self._h, C.byref(n)))
+        return n.value
+
+    VIEWS = {0: (4, np.float32), 1: (4, np.float32), 2: (4, np.uint8), 3: (1, np.float32), 4: (1, np.uint32),
+             5: (4, np.float32), 6: (4, np.float32), 7: (4, np.float32), 8: (4, np.uint8), 9: (4, np.float32),
+             10: (4, np.float32), 11: (1, np.uint16), 12: (4, np.uint8), 13: (4, np.float32), 14: (4, np.float32)}
+
+    def view(self, which, n_unstable=0):
+        ptr, pitch = C.c_void_p(), C.c_size_t()
+        check(lib().cfb_model_view(self._h, which, C.byref(ptr), C.byref(pitch)))
+        W, H = self.ctx.W, self.ctx.H
+        if which == 15:
+            out = np.empty((n_unstable, 12), np.float32)
+        else:
+            ch, dt = self.VIEWS[which]
+            out = np.empty((H, W, ch) if ch > 1 else (H, W), dtype=dt)
+        self.ctx.sync()
+        if out.nbytes:
+            check(lib().cfb_download(out.ctypes.data_as(C.c_void_p), ptr, C.c_size_t(out.nbytes),
+                                     C.c_void_p(self.ctx.stream)))
+        return out

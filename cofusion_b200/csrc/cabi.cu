@@ -8,6 +8,7 @@
 #include "gn_math.h"
 #include "image_kernels.cuh"
 #include "odometry.cuh"
+#include "pipeline.cuh"
 #include "tracker_kernels.cuh"
 
 namespace cfb {
@@ -265,9 +266,11 @@ int cfb_so3_step(const uint8_t* lastImage, const uint8_t* nextImage, size_t ip, 
 
 /* ------------------------------------------------------------------------------ RGBDOdometry */
 struct cfb_odom {
-  RGBDOdometry impl;
-  cfb_odom(int w, int h, float cx, float cy, float fx, float fy, float d, float a) : impl(w, h, cx, cy, fx, fy, d, a) {}
+  RGBDOdometry* p;  // owned unless `borrowed`
+  bool borrowed;
+  RGBDOdometry& impl_ref() { return *p; }
 };
+#define impl impl_ref()
 
 int cfb_odom_create(int width, int height, float cx, float cy, float fx, float fy, float distThresh,
                     float angleThresh, cfb_odom** out) {
@@ -275,15 +278,19 @@ int cfb_odom_create(int width, int height, float cx, float cy, float fx, float f
           "odom_create (width must be a multiple of 8, height of 4)");
   *out = nullptr;
   if (cfb_device_count() <= 0) return set_error_msg(3, "no CUDA device: libcofusion_b200 has no CPU fallback");
-  cfb_odom* o = new (std::nothrow) cfb_odom(width, height, cx, cy, fx, fy, distThresh, angleThresh);
-  if (!o || !o->impl.ok()) {
-    delete o;
+  RGBDOdometry* r = new (std::nothrow) RGBDOdometry(width, height, cx, cy, fx, fy, distThresh, angleThresh);
+  if (!r || !r->ok()) {
+    delete r;
     return set_error_msg(4, "odom_create: device allocation failed");
   }
-  *out = o;
+  *out = new cfb_odom{r, false};
   return 0;
 }
-void cfb_odom_destroy(cfb_odom* o) { delete o; }
+void cfb_odom_destroy(cfb_odom* o) {
+  if (!o) return;
+  if (!o->borrowed) delete o->p;
+  delete o;
+}
 
 int cfb_odom_init_icp(cfb_odom* o, const float* const depth_pyr[3], const size_t pitch[3], float cutoff,
                       void* stream) {
@@ -336,6 +343,212 @@ int cfb_odom_view(cfb_odom* o, int which, int level, const void** dev_ptr, size_
   REQUIRE(o && dev_ptr && pitch && level >= 0 && level < 3, "odom_view");
   *dev_ptr = o->impl.view(which, level, pitch);
   return *dev_ptr ? 0 : set_error_msg(2, "odom_view: unknown view");
+}
+
+#undef impl
+
+/* ------------------------------------------------------------------------------ Context / Model */
+struct cfb_ctx {
+  Context c;
+  cfb_ctx(int d, int w, int h, float fx, float fy, float cx, float cy) : c(d, w, h, fx, fy, cx, cy) {}
+};
+struct cfb_model {
+  Model m;
+  cfb_odom odom_handle;
+  cfb_model(Context* c, unsigned id, float conf, unsigned maxSurfels, bool fillIn)
+      : m(c, id, conf, maxSurfels, fillIn), odom_handle{&m.odom, true} {}
+};
+
+int cfb_ctx_create(int device, int W, int H, float fx, float fy, float cx, float cy, cfb_ctx** out) {
+  REQUIRE(out && W >= 32 && H >= 32 && (W % 8) == 0 && (H % 4) == 0,
+          "ctx_create (W must be a multiple of 8, H of 4)");
+  *out = nullptr;
+  if (cfb_device_count() <= device || device < 0)
+    return set_error_msg(3, "no such CUDA device: libcofusion_b200 has no CPU fallback");
+  cfb_ctx* c = new (std::nothrow) cfb_ctx(device, W, H, fx, fy, cx, cy);
+  if (!c || !c->c.ok()) {
+    delete c;
+    return set_error_msg(4, "ctx_create: device allocation failed");
+  }
+  *out = c;
+  return 0;
+}
+void cfb_ctx_destroy(cfb_ctx* c) { delete c; }
+void* cfb_ctx_stream(cfb_ctx* c) { return c ? (void*)c->c.stream : nullptr; }
+int cfb_ctx_upload_frame(cfb_ctx* c, const uint8_t* rgb, const float* depth, const uint8_t* mask) {
+  REQUIRE(c && rgb && depth, "ctx_upload_frame");
+  CK(c->c.uploadFrame(rgb, depth, mask));
+  return 0;
+}
+int cfb_ctx_set_frame_device(cfb_ctx* c, const uint8_t* rgb, const float* depth, const uint8_t* mask) {
+  REQUIRE(c && rgb && depth, "ctx_set_frame_device");
+  CK(c->c.setFrameDevice(rgb, depth, mask));
+  return 0;
+}
+int cfb_ctx_preprocess(cfb_ctx* c, float depthCutoff) {
+  REQUIRE(c, "ctx_preprocess");
+  CK(c->c.preprocess(depthCutoff));
+  return 0;
+}
+int cfb_ctx_sync(cfb_ctx* c) {
+  REQUIRE(c, "ctx_sync");
+  CK(c->c.sync());
+  return 0;
+}
+int cfb_ctx_view(cfb_ctx* c, int which, const void** dev_ptr, size_t* pitch) {
+  REQUIRE(c && dev_ptr && pitch, "ctx_view");
+  Context& x = c->c;
+  switch (which) {
+    case 0: *dev_ptr = x.rgb; *pitch = (size_t)x.W * 3; break;
+    case 1: *dev_ptr = x.depthRaw; *pitch = (size_t)x.W * 4; break;
+    case 2: *dev_ptr = x.depthFiltered; *pitch = (size_t)x.W * 4; break;
+    case 3: *dev_ptr = x.depthPyr[1]; *pitch = (size_t)(x.W / 2) * 4; break;
+    case 4: *dev_ptr = x.depthPyr[2]; *pitch = (size_t)(x.W / 4) * 4; break;
+    case 5: *dev_ptr = x.mask; *pitch = (size_t)x.W; break;
+    default: return set_error_msg(2, "ctx_view: unknown view");
+  }
+  return 0;
+}
+int cfb_ctx_take_launch_count(cfb_ctx* c) {
+  if (!c) return 0;
+  int n = c->c.launches;
+  c->c.launches = 0;
+  return n;
+}
+
+int cfb_model_create(cfb_ctx* c, unsigned id, float conf, unsigned max_surfels, int enable_fill_in,
+                     cfb_model** out) {
+  REQUIRE(c && out && max_surfels > 0 && id < 256, "model_create");
+  *out = nullptr;
+  cfb_model* m = new (std::nothrow) cfb_model(&c->c, id, conf, max_surfels, enable_fill_in != 0);
+  if (!m || !m->m.ok()) {
+    delete m;
+    return set_error_msg(4, "model_create: device allocation failed");
+  }
+  *out = m;
+  return 0;
+}
+void cfb_model_destroy(cfb_model* m) { delete m; }
+int cfb_model_get_pose(cfb_model* m, float pose[16]) {
+  REQUIRE(m && pose, "model_get_pose");
+  memcpy(pose, m->m.pose, sizeof(float) * 16);
+  return 0;
+}
+int cfb_model_override_pose(cfb_model* m, const float pose[16]) {
+  REQUIRE(m && pose, "model_override_pose");
+  memcpy(m->m.pose, pose, sizeof(float) * 16);
+  memcpy(m->m.lastPose, pose, sizeof(float) * 16);
+  return 0;
+}
+int cfb_model_set_pose_keep_last(cfb_model* m, const float pose[16]) {
+  REQUIRE(m && pose, "model_set_pose_keep_last");
+  memcpy(m->m.pose, pose, sizeof(float) * 16);
+  return 0;
+}
+int cfb_model_set_prediction(cfb_model* m, const float* v4, const float* n4, const uint8_t* img, int channels,
+                             int device_ptrs) {
+  REQUIRE(m && v4 && n4 && img && (channels == 3 || channels == 4), "model_set_prediction");
+  CK(m->m.setPrediction(v4, n4, img, channels, device_ptrs != 0));
+  return 0;
+}
+int cfb_model_init_first_rgb(cfb_model* m) {
+  REQUIRE(m, "model_init_first_rgb");
+  CK(m->m.initFirstRGB());
+  return 0;
+}
+int cfb_model_perform_tracking(cfb_model* m, const cfb_track_params* p, float pose_out[16],
+                               cfb_track_stats* stats_out) {
+  REQUIRE(m && p, "model_perform_tracking");
+  TrackParams tp;
+  static_assert(sizeof(TrackParams) == sizeof(cfb_track_params), "track params layout");
+  memcpy(&tp, p, sizeof(tp));
+  CK(m->m.performTracking(tp));
+  if (pose_out) memcpy(pose_out, m->m.pose, sizeof(float) * 16);
+  if (stats_out) memcpy(stats_out, &m->m.odom.stats(), sizeof(cfb_track_stats));
+  return 0;
+}
+int cfb_model_set_confidence_threshold(cfb_model* m, float v) {
+  REQUIRE(m, "model_set_confidence_threshold");
+  m->m.confidenceThreshold = v;
+  return 0;
+}
+int cfb_model_set_max_depth(cfb_model* m, float d) {
+  REQUIRE(m, "model_set_max_depth");
+  m->m.maxDepth = d;
+  return 0;
+}
+int cfb_model_initialise(cfb_model* m, int time, float maxDepthProcessed) {
+  REQUIRE(m, "model_initialise");
+  CK(m->m.initialise(time, maxDepthProcessed));
+  return 0;
+}
+int cfb_model_predict_indices(cfb_model* m, int time, float depthCutoff, int timeDelta) {
+  REQUIRE(m, "model_predict_indices");
+  CK(m->m.predictIndices(time, depthCutoff, timeDelta));
+  return 0;
+}
+int cfb_model_fuse(cfb_model* m, int time, float depthCutoff, float weightMultiplier) {
+  REQUIRE(m, "model_fuse");
+  CK(m->m.fuse(time, depthCutoff, weightMultiplier));
+  return 0;
+}
+int cfb_model_clean(cfb_model* m, int time, int timeDelta, float depthCutoff, float outlierCoefficient) {
+  REQUIRE(m, "model_clean");
+  CK(m->m.clean(time, timeDelta, depthCutoff, outlierCoefficient));
+  return 0;
+}
+int cfb_model_combined_predict(cfb_model* m, float depthCutoff, int time, int maxTime, int timeDelta) {
+  REQUIRE(m, "model_combined_predict");
+  CK(m->m.combinedPredict(depthCutoff, time, maxTime, timeDelta));
+  return 0;
+}
+int cfb_model_perform_fill_in(cfb_model* m, int frameToFrameRGB, int lost) {
+  REQUIRE(m, "model_perform_fill_in");
+  CK(m->m.performFillIn(frameToFrameRGB != 0, lost != 0));
+  return 0;
+}
+float cfb_model_compute_fusion_weight(cfb_model* m, float weightMultiplier) {
+  return m ? m->m.computeFusionWeight(weightMultiplier) : 0.f;
+}
+int cfb_model_download_map(cfb_model* m, float* dst, size_t cap, unsigned* count_out) {
+  REQUIRE(m, "model_download_map");
+  CK(m->m.downloadMap(dst, cap, count_out));
+  return 0;
+}
+int cfb_model_upload_map(cfb_model* m, const float* src, unsigned count) {
+  REQUIRE(m && (src || !count), "model_upload_map");
+  CK(m->m.uploadMap(src, count));
+  return 0;
+}
+int cfb_model_last_count(cfb_model* m, unsigned* count_out) {
+  REQUIRE(m && count_out, "model_last_count");
+  CK(m->m.lastCount(count_out));
+  return 0;
+}
+cfb_odom* cfb_model_odometry(cfb_model* m) { return m ? &m->odom_handle : nullptr; }
+int cfb_model_view(cfb_model* m, int which, const void** dev_ptr, size_t* pitch) {
+  REQUIRE(m && dev_ptr && pitch, "model_view");
+  const size_t W = (size_t)m->m.ctx->W;
+  switch (which) {
+    case 0: *dev_ptr = m->m.predVertex; *pitch = W * 16; break;
+    case 1: *dev_ptr = m->m.predNormal; *pitch = W * 16; break;
+    case 2: *dev_ptr = m->m.predImage; *pitch = W * 4; break;
+    case 3: *dev_ptr = m->m.icpError; *pitch = W * 4; break;
+    case 4: *dev_ptr = m->m.indexMaps.index; *pitch = W * 4; break;
+    case 5: *dev_ptr = m->m.indexMaps.vertConf; *pitch = W * 16; break;
+    case 6: *dev_ptr = m->m.indexMaps.colorTime; *pitch = W * 16; break;
+    case 7: *dev_ptr = m->m.indexMaps.normRad; *pitch = W * 16; break;
+    case 8: *dev_ptr = m->m.splat.image; *pitch = W * 4; break;
+    case 9: *dev_ptr = m->m.splat.vertexConf; *pitch = W * 16; break;
+    case 10: *dev_ptr = m->m.splat.normalRad; *pitch = W * 16; break;
+    case 11: *dev_ptr = m->m.splat.time; *pitch = W * 2; break;
+    case 12: *dev_ptr = m->m.fill.image; *pitch = W * 4; break;
+    case 13: *dev_ptr = m->m.fill.vertex; *pitch = W * 16; break;
+    case 14: *dev_ptr = m->m.fill.normal; *pitch = W * 16; break;
+    case 15: *dev_ptr = m->m.unstable; *pitch = 48; break;
+    default: return set_error_msg(2, "model_view: unknown view");
+  }
+  return 0;
 }
 
 }  // extern "C"

@@ -1,0 +1,379 @@
+// pipeline.cu -- cfb::Context / cfb::Model (see pipeline.cuh).
+#include "pipeline.cuh"
+
+#include <float.h>
+#include <math.h>
+#include <string.h>
+
+#include "image_kernels.cuh"
+
+namespace cfb {
+
+#define RET_IF(e)                       \
+  do {                                  \
+    cudaError_t e__ = (e);              \
+    if (e__ != cudaSuccess) return e__; \
+  } while (0)
+
+namespace {
+template <class T>
+bool dalloc(T** p, size_t n) {
+  return cudaMalloc((void**)p, n * sizeof(T)) == cudaSuccess && cudaMemset(*p, 0, n * sizeof(T)) == cudaSuccess;
+}
+}  // namespace
+
+Context::Context(int dev, int w, int h, float fx, float fy, float cx, float cy)
+    : device(dev), W(w), H(h), K{fx, fy, cx, cy} {
+  if (cudaSetDevice(dev) != cudaSuccess) return;
+  if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return;
+  const size_t n = (size_t)W * H;
+  bool good = dalloc(&rgb, n * 3) && dalloc(&depthRaw, n) && dalloc(&depthFiltered, n) && dalloc(&mask, n) &&
+              dalloc(&depthPyr[1], n / 4) && dalloc(&depthPyr[2], n / 16);
+  depthPyr[0] = depthFiltered;
+  good = good && cudaMallocHost(&h_rgb, n * 3) == cudaSuccess && cudaMallocHost(&h_depth, n * 4) == cudaSuccess &&
+         cudaMallocHost(&h_mask, n) == cudaSuccess;
+  ok_ = good;
+}
+
+Context::~Context() {
+  cudaFree(rgb);
+  cudaFree(depthRaw);
+  cudaFree(depthFiltered);
+  cudaFree(mask);
+  cudaFree(depthPyr[1]);
+  cudaFree(depthPyr[2]);
+  cudaFreeHost(h_rgb);
+  cudaFreeHost(h_depth);
+  cudaFreeHost(h_mask);
+  if (stream && owns_stream) cudaStreamDestroy(stream);
+}
+
+cudaError_t Context::uploadFrame(const uint8_t* rgb_h, const float* depth_h, const uint8_t* mask_h) {
+  const size_t n = (size_t)W * H;
+  // Pinned callers are copied straight from their buffers; pageable ones are staged through the
+  // context's pinned buffers so that the copy is truly asynchronous either way.
+  cudaPointerAttributes a;
+  auto pinned = [&](const void* p) {
+    return cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeHost;
+  };
+  const uint8_t* r = rgb_h;
+  const float* d = depth_h;
+  if (!pinned(rgb_h)) {
+    cudaGetLastError();
+    memcpy(h_rgb, rgb_h, n * 3);
+    r = h_rgb;
+  }
+  if (!pinned(depth_h)) {
+    cudaGetLastError();
+    memcpy(h_depth, depth_h, n * 4);
+    d = h_depth;
+  }
+  RET_IF(cudaMemcpyAsync(rgb, r, n * 3, cudaMemcpyHostToDevice, stream));
+  RET_IF(cudaMemcpyAsync(depthRaw, d, n * 4, cudaMemcpyHostToDevice, stream));
+  if (mask_h) {
+    const uint8_t* m = mask_h;
+    if (!pinned(mask_h)) {
+      cudaGetLastError();
+      memcpy(h_mask, mask_h, n);
+      m = h_mask;
+    }
+    RET_IF(cudaMemcpyAsync(mask, m, n, cudaMemcpyHostToDevice, stream));
+  } else {
+    // static scene: everything is background (CoFusion.cpp:190-197)
+    RET_IF(cudaMemsetAsync(mask, 0, n, stream));
+  }
+  return cudaSuccess;
+}
+
+cudaError_t Context::setFrameDevice(const uint8_t* rgb_d, const float* depth_d, const uint8_t* mask_d) {
+  const size_t n = (size_t)W * H;
+  RET_IF(cudaMemcpyAsync(rgb, rgb_d, n * 3, cudaMemcpyDeviceToDevice, stream));
+  RET_IF(cudaMemcpyAsync(depthRaw, depth_d, n * 4, cudaMemcpyDeviceToDevice, stream));
+  if (mask_d)
+    RET_IF(cudaMemcpyAsync(mask, mask_d, n, cudaMemcpyDeviceToDevice, stream));
+  else
+    RET_IF(cudaMemsetAsync(mask, 0, n, stream));
+  return cudaSuccess;
+}
+
+cudaError_t Context::preprocess(float depthCutoff) {
+  RET_IF(launch_bilateral(depthRaw, (size_t)W * 4, W, H, depthCutoff, depthFiltered, (size_t)W * 4, stream));
+  RET_IF(launch_pyr_down_gauss_f(depthPyr[0], (size_t)W * 4, W, H, depthPyr[1], (size_t)(W / 2) * 4, stream));
+  RET_IF(launch_pyr_down_gauss_f(depthPyr[1], (size_t)(W / 2) * 4, W / 2, H / 2, depthPyr[2], (size_t)(W / 4) * 4,
+                                 stream));
+  launches += 3;
+  return cudaSuccess;
+}
+
+Model::Model(Context* c, unsigned id_, float conf, unsigned maxSurfels, bool enableFillIn)
+    : ctx(c),
+      id(id_),
+      confidenceThreshold(conf),
+      maxDepth(FLT_MAX),
+      allowsFillIn(enableFillIn),
+      odom(c->W, c->H, c->K.cx, c->K.cy, c->K.fx, c->K.fy),
+      capacity(maxSurfels) {
+  for (int i = 0; i < 16; ++i) pose[i] = lastPose[i] = (i % 5 == 0) ? 1.f : 0.f;
+  const size_t n = (size_t)c->W * c->H;
+  bool good = dalloc(&predVertex, n * 4) && dalloc(&predNormal, n * 4) && dalloc(&predImage, n * 4) &&
+              dalloc(&icpError, n);
+  const size_t scanCap = (size_t)maxSurfels + n;
+  good = good && dalloc(&buf[0], maxSurfels) && dalloc(&buf[1], maxSurfels) && dalloc(&unstable, n) &&
+         dalloc(&candStaging, n) && dalloc(&candBest, n) && dalloc(&winner, maxSurfels) && dalloc(&keys, n) &&
+         dalloc(&indexMaps.index, n) && dalloc(&indexMaps.vertConf, n) && dalloc(&indexMaps.colorTime, n) &&
+         dalloc(&indexMaps.normRad, n) && dalloc(&splat.image, n) && dalloc(&splat.vertexConf, n) &&
+         dalloc(&splat.normalRad, n) && dalloc(&splat.time, n) && dalloc(&fill.image, n) && dalloc(&fill.vertex, n) &&
+         dalloc(&fill.normal, n) && dalloc(&scan.flags, scanCap) && dalloc(&scan.ranks, scanCap) &&
+         dalloc(&scan.blockSums, scanCap / 1024 + 2) && dalloc(&counters, 1);
+  scan.capacity = scanCap;
+  good = good && cudaMallocHost(&h_counters, sizeof(MapCounters)) == cudaSuccess;
+  if (good) memset(h_counters, 0, sizeof(MapCounters));
+  ok_ = good;
+}
+
+Model::~Model() {
+  cudaFree(predVertex);
+  cudaFree(predNormal);
+  cudaFree(predImage);
+  cudaFree(icpError);
+  cudaFree(buf[0]);
+  cudaFree(buf[1]);
+  cudaFree(unstable);
+  cudaFree(candStaging);
+  cudaFree(candBest);
+  cudaFree(winner);
+  cudaFree(keys);
+  cudaFree(indexMaps.index);
+  cudaFree(indexMaps.vertConf);
+  cudaFree(indexMaps.colorTime);
+  cudaFree(indexMaps.normRad);
+  cudaFree(splat.image);
+  cudaFree(splat.vertexConf);
+  cudaFree(splat.normalRad);
+  cudaFree(splat.time);
+  cudaFree(fill.image);
+  cudaFree(fill.vertex);
+  cudaFree(fill.normal);
+  cudaFree(scan.flags);
+  cudaFree(scan.ranks);
+  cudaFree(scan.blockSums);
+  cudaFree(counters);
+  cudaFreeHost(h_counters);
+}
+
+namespace {
+__global__ void rgb_to_rgba_kernel(const uint8_t* __restrict__ src, uchar4* __restrict__ dst, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = make_uchar4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 255);
+}
+}  // namespace
+
+cudaError_t Model::setPrediction(const float* v4, const float* n4, const uint8_t* img, int channels, bool dev) {
+  const size_t n = (size_t)ctx->W * ctx->H;
+  cudaMemcpyKind k = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  RET_IF(cudaMemcpyAsync(predVertex, v4, n * 16, k, ctx->stream));
+  RET_IF(cudaMemcpyAsync(predNormal, n4, n * 16, k, ctx->stream));
+  if (channels == 4) {
+    RET_IF(cudaMemcpyAsync(predImage, img, n * 4, k, ctx->stream));
+  } else {
+    // RGB8 -> RGBA8: staged through the ICP error buffer (4n bytes, rewritten by the next track)
+    RET_IF(cudaMemcpyAsync(icpError, img, n * 3, k, ctx->stream));
+    rgb_to_rgba_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t*)icpError,
+                                                                            (uchar4*)predImage, (int)n);
+    RET_IF(cudaGetLastError());
+  }
+  return cudaSuccess;
+}
+
+cudaError_t Model::initFirstRGB() {
+  return odom.initFirstRGB(ctx->rgb, (size_t)ctx->W * 3, 3, ctx->stream);
+}
+
+namespace {
+void pose_inverse(const float* T, float* Ti) {  // Eigen inverse of a rigid 4x4, f32
+  memset(Ti, 0, 64);
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) Ti[r * 4 + c] = T[c * 4 + r];
+  for (int r = 0; r < 3; ++r) Ti[r * 4 + 3] = -(Ti[r * 4 + 0] * T[3] + Ti[r * 4 + 1] * T[7] + Ti[r * 4 + 2] * T[11]);
+  Ti[15] = 1;
+}
+Pose34 to34(const float* T) {
+  Pose34 p;
+  memcpy(p.m, T, sizeof(p.m));
+  return p;
+}
+}  // namespace
+
+float Model::computeFusionWeight(float weightMultiplier) const {
+  // diff = pose^-1 * lastPose; weight from max(|t|, |log R|) (Model.cpp:391-406, rodrigues2 :816-857
+  // without the SVD re-orthogonalisation)
+  float pinv[16], d[16];
+  pose_inverse(pose, pinv);
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) {
+      float s = 0;
+      for (int k = 0; k < 4; ++k) s += pinv[r * 4 + k] * lastPose[k * 4 + c];
+      d[r * 4 + c] = s;
+    }
+  float tn = sqrtf(d[3] * d[3] + d[7] * d[7] + d[11] * d[11]);
+  double rx = d[9] - d[6], ry = d[2] - d[8], rz = d[4] - d[1];
+  double s = sqrt((rx * rx + ry * ry + rz * rz) * 0.25);
+  double c = ((double)d[0] + d[5] + d[10] - 1) * 0.5;
+  c = c > 1. ? 1. : c < -1. ? -1. : c;
+  double theta = acos(c);
+  if (s < 1e-5) {
+    if (c > 0)
+      rx = ry = rz = 0;
+    else {
+      double t = (d[0] + 1) * 0.5;
+      rx = sqrt(t > 0 ? t : 0);
+      t = (d[5] + 1) * 0.5;
+      ry = sqrt(t > 0 ? t : 0) * (d[1] < 0 ? -1.0 : 1.0);
+      t = (d[10] + 1) * 0.5;
+      rz = sqrt(t > 0 ? t : 0) * (d[2] < 0 ? -1.0 : 1.0);
+      if (fabs(rx) < fabs(ry) && fabs(rx) < fabs(rz) && (d[6] > 0) != (ry * rz > 0)) rz = -rz;
+      theta /= sqrt(rx * rx + ry * ry + rz * rz);
+      rx *= theta;
+      ry *= theta;
+      rz *= theta;
+    }
+  } else {
+    double vth = 1 / (2 * s) * theta;
+    rx *= vth;
+    ry *= vth;
+    rz *= vth;
+  }
+  float rn = sqrtf((float)rx * (float)rx + (float)ry * (float)ry + (float)rz * (float)rz);
+  float weighting = tn > rn ? tn : rn;
+  const float largest = 0.01f, minWeight = 0.5f;
+  if (weighting > largest) weighting = largest;
+  float w = 1.0f - (weighting / largest);
+  return (w > minWeight ? w : minWeight) * weightMultiplier;
+}
+
+cudaError_t Model::initialise(int time, float maxDepthProcessed) {
+  RET_IF(launch_surfel_initialise(geom(), ctx->rgb, ctx->depthRaw, ctx->depthFiltered, time, maxDepthProcessed,
+                                  buf[target], capacity, candStaging, unstable, scan, counters, ctx->stream));
+  const unsigned n = (unsigned)ctx->W * ctx->H;
+  count_ub = n < capacity ? n : capacity;
+  ctx->launches += 12;
+  return cudaSuccess;
+}
+
+cudaError_t Model::predictIndices(int time, float depthCutoff, int timeDelta) {
+  float t_inv[16];
+  pose_inverse(pose, t_inv);
+  ctx->launches += 2;
+  return launch_predict_indices(geom(), buf[target], count_ub, counters, to34(t_inv), time, depthCutoff, timeDelta,
+                                keys, indexMaps, ctx->stream);
+}
+
+cudaError_t Model::fuse(int time, float depthCutoff, float weightMultiplier) {
+  const float md = depthCutoff < maxDepth ? depthCutoff : maxDepth;  // Model.cpp:443
+  ctx->launches += 7;
+  return launch_fuse(geom(), buf[target], count_ub, counters, to34(pose), time, ctx->rgb, ctx->mask, ctx->depthRaw,
+                     ctx->depthFiltered, md, computeFusionWeight(weightMultiplier), id, indexMaps, winner, candStaging,
+                     candBest, unstable, scan, ctx->stream);
+}
+
+cudaError_t Model::clean(int time, int timeDelta, float /*depthCutoff*/, float outlierCoefficient) {
+  float t_inv[16];
+  pose_inverse(pose, t_inv);
+  const unsigned cand_ub = (unsigned)((ctx->W + 1) / 2) * ((ctx->H + 1) / 2);
+  RET_IF(launch_clean(geom(), buf[target], unstable, buf[renderSource], count_ub, cand_ub, capacity, counters,
+                      to34(t_inv), time, confidenceThreshold, timeDelta, ctx->depthFiltered, ctx->mask, id,
+                      outlierCoefficient, indexMaps, scan, ctx->stream));
+  int t = target;
+  target = renderSource;
+  renderSource = t;
+  unsigned ub = count_ub + cand_ub;
+  count_ub = ub < capacity ? ub : capacity;
+  ctx->launches += 6;
+  // refresh the host-side bound with the exact count whenever the stream is next synchronised
+  RET_IF(cudaMemcpyAsync(h_counters, counters, sizeof(MapCounters), cudaMemcpyDeviceToHost, ctx->stream));
+  return cudaSuccess;
+}
+
+cudaError_t Model::combinedPredict(float depthCutoff, int time, int maxTime, int timeDelta) {
+  float t_inv[16];
+  pose_inverse(pose, t_inv);
+  usePrediction = true;
+  ctx->launches += 2;
+  return launch_combined_predict(geom(), buf[target], count_ub, counters, to34(t_inv), depthCutoff, confidenceThreshold,
+                                 time, maxTime, timeDelta, keys, splat, ctx->stream);
+}
+
+cudaError_t Model::performFillIn(bool frameToFrameRGB, bool lost) {
+  if (!allowsFillIn) return cudaSuccess;
+  ctx->launches += 2;
+  return launch_fill_in(geom(), splat, ctx->rgb, ctx->depthFiltered, lost ? 1 : 0, (lost || frameToFrameRGB) ? 1 : 0,
+                        fill, counters, 0.75f, ctx->stream);
+}
+
+cudaError_t Model::downloadMap(float* dst, size_t cap, unsigned* count_out) {
+  RET_IF(cudaMemcpyAsync(h_counters, counters, sizeof(MapCounters), cudaMemcpyDeviceToHost, ctx->stream));
+  RET_IF(cudaStreamSynchronize(ctx->stream));
+  unsigned n = h_counters->count;
+  count_ub = n;
+  if (count_out) *count_out = n;
+  if (dst && n) {
+    if (n > cap) n = (unsigned)cap;
+    RET_IF(cudaMemcpyAsync(dst, buf[target], (size_t)n * sizeof(Surfel), cudaMemcpyDeviceToHost, ctx->stream));
+    RET_IF(cudaStreamSynchronize(ctx->stream));
+  }
+  return cudaSuccess;
+}
+
+cudaError_t Model::uploadMap(const float* src, unsigned count) {
+  if (count > capacity) count = capacity;
+  RET_IF(cudaMemcpyAsync(buf[target], src, (size_t)count * sizeof(Surfel), cudaMemcpyHostToDevice, ctx->stream));
+  MapCounters c = {count, 0, 0, 0};
+  *h_counters = c;
+  RET_IF(cudaMemcpyAsync(counters, h_counters, sizeof(MapCounters), cudaMemcpyHostToDevice, ctx->stream));
+  RET_IF(cudaStreamSynchronize(ctx->stream));
+  count_ub = count;
+  return cudaSuccess;
+}
+
+cudaError_t Model::lastCount(unsigned* out) { return downloadMap(nullptr, 0, out); }
+
+cudaError_t Model::performTracking(const TrackParams& tp) {
+  memcpy(lastPose, pose, sizeof(pose));
+  cudaStream_t s = ctx->stream;
+  if (usePrediction) {
+    // Model::initICP (Model.cpp:350-367): splat prediction, or the fill-in images when
+    // CoFusion::requiresFillIn says so -- selected on the device (no host wait)
+    if (allowsFillIn) {
+      RET_IF(launch_select_prediction(geom(), counters, tp.frameToFrameRGB ? 1 : 0, splat, fill, predVertex, predNormal,
+                                      predImage, s));
+      ctx->launches += 1;
+    } else {
+      const size_t n = (size_t)ctx->W * ctx->H;
+      RET_IF(cudaMemcpyAsync(predVertex, splat.vertexConf, n * 16, cudaMemcpyDeviceToDevice, s));
+      RET_IF(cudaMemcpyAsync(predNormal, splat.normalRad, n * 16, cudaMemcpyDeviceToDevice, s));
+      RET_IF(cudaMemcpyAsync(predImage, splat.image, n * 4, cudaMemcpyDeviceToDevice, s));
+    }
+  }
+  // Model::initICP (Model.cpp:350-367); WARNING initICP* must be called before initRGB*
+  RET_IF(odom.initICPModel(predVertex, predNormal, tp.maxDepthProcessed, pose, s));
+  RET_IF(odom.initRGBModel(predImage, (size_t)ctx->W * 4, 4, s));
+  const float* pyr[3] = {ctx->depthPyr[0], ctx->depthPyr[1], ctx->depthPyr[2]};
+  const size_t pitch[3] = {(size_t)ctx->W * 4, (size_t)(ctx->W / 2) * 4, (size_t)(ctx->W / 4) * 4};
+  RET_IF(odom.initICP(pyr, pitch, tp.maxDepthProcessed, s));
+  RET_IF(odom.initRGB(ctx->rgb, (size_t)ctx->W * 3, 3, s));
+  float trans[3] = {pose[3], pose[7], pose[11]};
+  float rot[9] = {pose[0], pose[1], pose[2], pose[4], pose[5], pose[6], pose[8], pose[9], pose[10]};
+  RET_IF(odom.getIncrementalTransformation(trans, rot, tp.rgbOnly != 0, tp.icpWeight, tp.pyramid != 0,
+                                           tp.fastOdom != 0, tp.so3 != 0, icpError, (size_t)ctx->W * 4,
+                                           tp.force_host_loop != 0, s));
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) pose[r * 4 + c] = rot[r * 3 + c];
+    pose[r * 4 + 3] = trans[r];
+  }
+  // the tracker synchronised the stream: the counters copied after the last clean are exact now
+  if (h_counters->count && h_counters->count < count_ub) count_ub = h_counters->count;
+  ctx->launches += 30;
+  return cudaSuccess;
+}
+
+}  // namespace cfb

@@ -1,0 +1,121 @@
+// pipeline.cuh -- cfb::Context and cfb::Model: the class seam of the reference without OpenGL.
+//
+//   Context  <->  the per-frame shared state of CoFusion (Core/CoFusion.cpp:171-211): RGB, raw and
+//                 bilateral-filtered metric depth, the depth pyramid shared by all models
+//                 (Model::GPUSetup::depth_tmp, Model.h:79-80) and the label mask.
+//   Model    <->  Core/Model/Model.{h,cpp}: pose, tracker (RGBDOdometry frameToModel), prediction
+//                 images (ModelProjection render targets), ICP error map, surfel map.
+// All device memory is allocated at construction; every operation is enqueued on the context's
+// stream; the only host synchronisation per frame is the pose read-back at the end of tracking.
+#pragma once
+#include <stdint.h>
+
+#include "cfb_common.cuh"
+#include "odometry.cuh"
+#include "surfel_kernels.cuh"
+
+namespace cfb {
+
+class Context {
+ public:
+  Context(int device, int W, int H, float fx, float fy, float cx, float cy);
+  ~Context();
+  bool ok() const { return ok_; }
+
+  // CoFusion::processFrame :179-184: upload + bilateral filter.  Host buffers (pinned or pageable).
+  cudaError_t uploadFrame(const uint8_t* rgb_hwc, const float* depth, const uint8_t* mask);
+  // same, inputs already resident in device memory
+  cudaError_t setFrameDevice(const uint8_t* rgb_hwc, const float* depth, const uint8_t* mask);
+  // filterDepth (CoFusion.cpp:567-574) + Model::generateCUDATextures (Model.cpp:319-348)
+  cudaError_t preprocess(float depthCutoff);
+  cudaError_t sync() { return cudaStreamSynchronize(stream); }
+
+  int device, W, H;
+  Intr K;
+  cudaStream_t stream = nullptr;
+  bool owns_stream = true;
+  uint8_t* rgb = nullptr;           // H*W*3
+  float* depthRaw = nullptr;        // metric, 0 = invalid
+  float* depthFiltered = nullptr;   // level 0 of the pyramid
+  float* depthPyr[3] = {nullptr, nullptr, nullptr};
+  uint8_t* mask = nullptr;          // label image (model ids)
+  uint8_t* h_rgb = nullptr;         // pinned staging for pageable callers
+  float* h_depth = nullptr;
+  uint8_t* h_mask = nullptr;
+  int launches = 0;                 // kernels launched since the last reset (bench accounting)
+
+ private:
+  bool ok_ = false;
+};
+
+struct TrackParams {  // arguments of Model::performTracking (Model.h:128-129)
+  int frameToFrameRGB, rgbOnly;
+  float icpWeight;
+  int pyramid, fastOdom, so3;
+  float maxDepthProcessed;
+  int force_host_loop;
+};
+
+class Model {
+ public:
+  Model(Context* ctx, unsigned id, float confidenceThreshold, unsigned maxSurfels, bool enableFillIn);
+  ~Model();
+  bool ok() const { return ok_ && odom.ok(); }
+
+  // Install a model prediction rendered elsewhere (tests; also what combinedPredict produces):
+  // AoS float4 vertex(+conf) / normal(+radius) maps in the camera frame and an RGBA8/RGB8 image.
+  cudaError_t setPrediction(const float* v4, const float* n4, const uint8_t* img, int channels, bool device_ptrs);
+  // RGBDOdometry::initFirstRGB on the current frame (CoFusion.cpp:205)
+  cudaError_t initFirstRGB();
+  // Model::performTracking (Model.cpp:369-389): initICP (:350-367) + getIncrementalTransformation
+  cudaError_t performTracking(const TrackParams& tp);
+
+  // ---- surfel map (Model.cpp / ModelProjection.cpp; kernels in surfel_kernels.cu)
+  cudaError_t initialise(int time, float maxDepthProcessed);                      // Model.cpp:227-272
+  cudaError_t predictIndices(int time, float depthCutoff, int timeDelta);         // Model.h:155-157
+  cudaError_t fuse(int time, float depthCutoff, float weightMultiplier);          // Model.cpp:408-563
+  cudaError_t clean(int time, int timeDelta, float depthCutoff, float outlierCoefficient);  // Model.cpp:565-697
+  cudaError_t combinedPredict(float depthCutoff, int time, int maxTime, int timeDelta);     // Model.h:151-153
+  cudaError_t performFillIn(bool frameToFrameRGB, bool lost);                     // Model.cpp:901-909
+  float computeFusionWeight(float weightMultiplier) const;                        // Model.cpp:391-406
+  // Model::downloadMap (Model.cpp:868-899): synchronises, copies the live surfels to the host
+  cudaError_t downloadMap(float* dst, size_t capacity_surfels, unsigned* count_out);
+  cudaError_t uploadMap(const float* src, unsigned count);
+  cudaError_t lastCount(unsigned* out);  // Model::lastCount (synchronises)
+  const Surfel* surfels() const { return buf[target]; }
+  SurfelGeom geom() const { return SurfelGeom{ctx->W, ctx->H, ctx->K.fx, ctx->K.fy, ctx->K.cx, ctx->K.cy}; }
+
+  Context* ctx;
+  unsigned id;
+  float pose[16], lastPose[16];
+  float confidenceThreshold;
+  float maxDepth;               // per-model depth limit (Model::setMaxDepth)
+  bool allowsFillIn;
+  bool usePrediction = false;   // true once combinedPredict has produced the tracker inputs
+  RGBDOdometry odom;
+  float* predVertex = nullptr;   // W*H float4: what the tracker consumes (selected prediction)
+  float* predNormal = nullptr;   // W*H float4
+  uint8_t* predImage = nullptr;  // W*H*4 RGBA8
+  float* icpError = nullptr;     // W*H f32 (Model::icpError texture)
+
+  unsigned capacity = 0;         // max surfels
+  Surfel* buf[2] = {nullptr, nullptr};
+  int target = 0, renderSource = 1;
+  Surfel* unstable = nullptr;    // newUnstableBuffer (W*H)
+  Surfel* candStaging = nullptr; // per eligible pixel candidate records
+  uint32_t* candBest = nullptr;
+  uint32_t* winner = nullptr;
+  unsigned long long* keys = nullptr;
+  IndexMaps indexMaps{};
+  SplatMaps splat{};
+  FillMaps fill{};
+  ScanScratch scan{};
+  MapCounters* counters = nullptr;   // device
+  MapCounters* h_counters = nullptr; // pinned mirror
+  unsigned count_ub = 0;             // host-side upper bound of counters->count
+
+ private:
+  bool ok_ = false;
+};
+
+}  // namespace cfb

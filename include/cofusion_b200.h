@@ -154,6 +154,88 @@ int cfb_odom_set_debug_trace(cfb_odom* o, void* dev_u64);
  * 4 lastDepth 5 nextDepth 6 lastImage 7 nextImage 8 dIdx 9 dIdy 10 lastNextImage 11 cloud 12 corres */
 int cfb_odom_view(cfb_odom* o, int which, int level, const void** dev_ptr, size_t* pitch);
 
+/* ------------------------------------------------------------------------------------------------
+ * Seam 2b: CoFusion::processFrame's calls into Model / ModelProjection, without OpenGL
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cfb_ctx cfb_ctx;     /* per-device frame state shared by all models (CoFusion textures) */
+typedef struct cfb_model cfb_model; /* Core/Model/Model.h */
+
+/* replaces the Resolution / Intrinsics singletons (Core/Utils/Resolution.h, Intrinsics.h) */
+int cfb_ctx_create(int device, int W, int H, float fx, float fy, float cx, float cy, cfb_ctx** out);
+void cfb_ctx_destroy(cfb_ctx* c);
+/* the CUDA stream every ctx/model call is enqueued on (cudaStream_t) */
+void* cfb_ctx_stream(cfb_ctx* c);
+/* CoFusion::processFrame :179-197: host RGB8 (HxWx3), metric f32 depth, optional u8 label mask
+ * (NULL = everything background).  Asynchronous H2D; pinned host buffers are used in place. */
+int cfb_ctx_upload_frame(cfb_ctx* c, const uint8_t* rgb_hwc, const float* depth, const uint8_t* mask);
+/* same with inputs already in device memory */
+int cfb_ctx_set_frame_device(cfb_ctx* c, const uint8_t* rgb_hwc, const float* depth, const uint8_t* mask);
+/* CoFusion::filterDepth (:567-574) + Model::generateCUDATextures (Model.cpp:319-348) */
+int cfb_ctx_preprocess(cfb_ctx* c, float depthCutoff);
+int cfb_ctx_sync(cfb_ctx* c);
+/* which: 0 rgb(u8x3) 1 depthRaw 2 depthFiltered 3 depthPyr[1] 4 depthPyr[2] 5 mask */
+int cfb_ctx_view(cfb_ctx* c, int which, const void** dev_ptr, size_t* pitch);
+/* kernels launched by ctx/model calls since the last call (bench accounting); resets the counter */
+int cfb_ctx_take_launch_count(cfb_ctx* c);
+
+typedef struct cfb_track_params { /* arguments of Model::performTracking (Model.h:128-129) */
+  int frameToFrameRGB, rgbOnly;
+  float icpWeight;
+  int pyramid, fastOdom, so3;
+  float maxDepthProcessed;
+  int force_host_loop;
+} cfb_track_params;
+
+/* Model::Model (Model.h:100-103).  max_surfels replaces COFUSION_NUM_SURFELS / TEXTURE_DIMENSION^2
+ * (Model.cpp:92-98); enable_fill_in as the reference's enableFillIn (true only for the background). */
+int cfb_model_create(cfb_ctx* c, unsigned id, float confidenceThreshold, unsigned max_surfels, int enable_fill_in,
+                     cfb_model** out);
+void cfb_model_destroy(cfb_model* m);
+int cfb_model_get_pose(cfb_model* m, float pose[16]);
+int cfb_model_override_pose(cfb_model* m, const float pose[16]); /* Model::overridePose (Model.h:218-221) */
+/* pose <- `pose` while lastPose keeps its value: the state Model::performTracking leaves behind
+ * (lastPose = pose; pose = tracked), for callers that track elsewhere (ground-truth / tests) */
+int cfb_model_set_pose_keep_last(cfb_model* m, const float pose[16]);
+/* install prediction images rendered elsewhere (AoS float4 vertex+conf, normal+radius, RGB8/RGBA8) */
+int cfb_model_set_prediction(cfb_model* m, const float* vertices4, const float* normals4, const uint8_t* img,
+                             int channels, int device_ptrs);
+/* RGBDOdometry::initFirstRGB on the current frame (CoFusion.cpp:205) */
+int cfb_model_init_first_rgb(cfb_model* m);
+/* Model::performTracking (Model.cpp:369-389): pose is updated in the model and returned */
+int cfb_model_perform_tracking(cfb_model* m, const cfb_track_params* p, float pose_out[16],
+                               cfb_track_stats* stats_out);
+/* Model::setConfidenceThreshold / setMaxDepth (Model.h:161-165) */
+int cfb_model_set_confidence_threshold(cfb_model* m, float confThresh);
+int cfb_model_set_max_depth(cfb_model* m, float d);
+/* Model::initialise (Model.cpp:227-272) + CoFusion::computeFeedbackBuffers (CoFusion.cpp:161-169):
+ * surfels from the current frame's raw + filtered depth */
+int cfb_model_initialise(cfb_model* m, int time, float maxDepthProcessed);
+/* Model::predictIndices -> ModelProjection::predictIndices (ModelProjection.cpp:105-157) */
+int cfb_model_predict_indices(cfb_model* m, int time, float depthCutoff, int timeDelta);
+/* Model::fuse (Model.cpp:408-563) against the current frame of the context */
+int cfb_model_fuse(cfb_model* m, int time, float depthCutoff, float weightMultiplier);
+/* Model::clean (Model.cpp:565-697); outlierCoefficient = GPUSetup::outlierCoefficient (GUI default 3) */
+int cfb_model_clean(cfb_model* m, int time, int timeDelta, float depthCutoff, float outlierCoefficient);
+/* Model::combinedPredict(ACTIVE) (ModelProjection.cpp:192-273) */
+int cfb_model_combined_predict(cfb_model* m, float depthCutoff, int time, int maxTime, int timeDelta);
+/* Model::performFillIn (Model.cpp:901-909) (+ CoFusion::requiresFillIn evaluated on the device) */
+int cfb_model_perform_fill_in(cfb_model* m, int frameToFrameRGB, int lost);
+/* Model::computeFusionWeight (Model.cpp:391-406) */
+float cfb_model_compute_fusion_weight(cfb_model* m, float weightMultiplier);
+/* Model::downloadMap (Model.cpp:868-899): 12 floats per surfel (pos+conf | colour,0,init,last | normal+radius) */
+int cfb_model_download_map(cfb_model* m, float* dst, size_t capacity_surfels, unsigned* count_out);
+/* test / restore helper: replace the map with `count` host surfels */
+int cfb_model_upload_map(cfb_model* m, const float* src, unsigned count);
+/* Model::lastCount (Model.h:107) */
+int cfb_model_last_count(cfb_model* m, unsigned* count_out);
+/* the model's tracker (frameToModel), e.g. for cfb_odom_view / cfb_odom_set_mode */
+cfb_odom* cfb_model_odometry(cfb_model* m);
+/* which: 0 tracker-input vertex+conf (float4) 1 tracker-input normal+radius (float4) 2 tracker-input
+ * image (RGBA8) 3 ICP error (f32) | index maps: 4 index (u32) 5 vertConf 6 colorTime 7 normRad (float4)
+ * | splat prediction: 8 image (RGBA8) 9 vertexConf 10 normalRad (float4) 11 time (u16)
+ * | fill-in: 12 image 13 vertex 14 normal | 15 new-unstable buffer (48-B surfels) */
+int cfb_model_view(cfb_model* m, int which, const void** dev_ptr, size_t* pitch);
+
 #ifdef __cplusplus
 }
 #endif

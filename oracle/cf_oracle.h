@@ -124,6 +124,50 @@ void orc_odom_dims(const OrcOdometry* o, int* W, int* H, float intr[4]);
  * 7 nextImage 8 dIdx 9 dIdy 10 lastNextImage 11 cloud */
 const void* orc_odom_view(OrcOdometry* o, int which, int level);
 
+/* ---------------------------------------------------------------- surfel map (oracle/surfel.c)
+ * Restatement of the OpenGL predict / fuse / clean stage (Core/Model, Core/Shaders). PARITY UNPINNED
+ * (no GL context, no golden vectors in the reference); frozen GL semantics F1-F6 in surfel.c. */
+typedef struct { /* Core/Shaders/Vertex.cpp:21-43 -- 48 bytes */
+  float pos[4]; /* xyz, confidence */
+  float col[4]; /* colour as 24-bit int in a float, unused, init time, last-update time */
+  float nrm[4]; /* normal xyz, radius */
+} OrcSurfel;
+typedef struct OrcSurfelMap OrcSurfelMap;
+
+OrcSurfelMap* orc_map_create(int W, int H, float fx, float fy, float cx, float cy, unsigned max_surfels);
+void orc_map_destroy(OrcSurfelMap* m);
+unsigned orc_map_count(const OrcSurfelMap* m);
+const OrcSurfel* orc_map_surfels(const OrcSurfelMap* m);
+unsigned orc_map_unstable_count(const OrcSurfelMap* m);
+const OrcSurfel* orc_map_unstable(const OrcSurfelMap* m);
+void orc_map_set_surfels(OrcSurfelMap* m, const OrcSurfel* s, unsigned n);
+/* which: 0 index(u32) 1 vertConf 2 colorTime 3 normRad (float4) 4 image(RGBA8) 5 splat vertexConf
+ * 6 splat normalRad (float4) 7 splat time(u16) 8 fill image 9 fill vertex 10 fill normal */
+const void* orc_map_view(const OrcSurfelMap* m, int which);
+void orc_pose_inverse(const float T[16], float Ti[16]);
+/* Model::initialise via vertex_feedback + init_unstable (Model.cpp:227-272, CoFusion.cpp:161-169) */
+void orc_map_initialise(OrcSurfelMap* m, const uint8_t* rgb, const float* depthRaw, const float* depthFiltered,
+                        int time, float maxDepth);
+/* ModelProjection::predictIndices (ModelProjection.cpp:105-157) */
+void orc_map_predict_indices(OrcSurfelMap* m, const float pose[16], int time, float maxDepth, int timeDelta);
+/* Model::computeFusionWeight (Model.cpp:391-406) */
+float orc_fusion_weight(const float pose[16], const float lastPose[16], float weightMultiplier);
+/* Model::fuse (Model.cpp:408-563); maxDepth = min(depthCutoff, model maxDepth) */
+void orc_map_fuse(OrcSurfelMap* m, const float pose[16], int time, const uint8_t* rgb, const uint8_t* mask,
+                  const float* depthRaw, const float* depthFiltered, float maxDepth, float weighting,
+                  unsigned maskID);
+/* Model::clean (Model.cpp:565-697) */
+void orc_map_clean(OrcSurfelMap* m, const float pose[16], int time, float confThreshold, int timeDelta,
+                   const float* depthFiltered, const uint8_t* mask, unsigned maskID, float outlierCoeff);
+/* ModelProjection::combinedPredict (ModelProjection.cpp:192-273) */
+void orc_map_combined_predict(OrcSurfelMap* m, const float pose[16], float maxDepth, float confThreshold, int time,
+                              int maxTime, int timeDelta);
+/* Model::performFillIn (Model.cpp:901-909) */
+void orc_map_fill_in(OrcSurfelMap* m, const uint8_t* rgb, const float* depthFiltered, int passthrough_geom,
+                     int passthrough_rgb);
+/* CoFusion::requiresFillIn (CoFusion.cpp:547-565) */
+int orc_map_requires_fill_in(const OrcSurfelMap* m, float ratio);
+
 #ifdef __cplusplus
 }
 #endif

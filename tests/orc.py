@@ -286,3 +286,86 @@ class OrcOdometry:
         n = planes * h * w
         buf = (C.c_char * (n * esz)).from_address(ptr)
         return np.frombuffer(buf, dtype=dt).reshape(planes * h, w).copy()
+
+
+# ---------------------------------------------------------------- surfel map restatement
+class OrcMap:
+    VIEWS = {0: (1, np.uint32), 1: (4, np.float32), 2: (4, np.float32), 3: (4, np.float32), 4: (4, np.uint8),
+             5: (4, np.float32), 6: (4, np.float32), 7: (1, np.uint16), 8: (4, np.uint8), 9: (4, np.float32),
+             10: (4, np.float32)}
+
+    def __init__(self, W, H, K, max_surfels=1 << 20):
+        fx, fy, cx, cy = K
+        self.W, self.H, self.K = W, H, K
+        o = orc()
+        o.orc_map_create.restype = C.c_void_p
+        o.orc_map_surfels.restype = C.c_void_p
+        o.orc_map_unstable.restype = C.c_void_p
+        o.orc_map_view.restype = C.c_void_p
+        o.orc_fusion_weight.restype = C.c_float
+        self.h = C.c_void_p(o.orc_map_create(W, H, cf(fx), cf(fy), cf(cx), cf(cy), max_surfels))
+
+    def __del__(self):
+        if getattr(self, "h", None) and _orc is not None:
+            _orc.orc_map_destroy(self.h)
+            self.h = None
+
+    @staticmethod
+    def _u8(a):
+        return P(np.ascontiguousarray(a, np.uint8))
+
+    def initialise(self, rgb, depth_raw, depth_filtered, time, max_depth=20.0):
+        orc().orc_map_initialise(self.h, self._u8(rgb), P(f32(depth_raw)), P(f32(depth_filtered)), int(time), cf(max_depth))
+
+    def predict_indices(self, pose, time, max_depth=20.0, time_delta=200):
+        orc().orc_map_predict_indices(self.h, P(f32(pose).reshape(16)), int(time), cf(max_depth), int(time_delta))
+
+    def fuse(self, pose, time, rgb, mask, depth_raw, depth_filtered, max_depth, weighting, mask_id=0):
+        orc().orc_map_fuse(self.h, P(f32(pose).reshape(16)), int(time), self._u8(rgb), self._u8(mask), P(f32(depth_raw)),
+                           P(f32(depth_filtered)), cf(max_depth), cf(weighting), int(mask_id))
+
+    def clean(self, pose, time, conf_threshold, time_delta, depth_filtered, mask, mask_id=0, outlier_coeff=3.0):
+        orc().orc_map_clean(self.h, P(f32(pose).reshape(16)), int(time), cf(conf_threshold), int(time_delta),
+                            P(f32(depth_filtered)), self._u8(mask), int(mask_id), cf(outlier_coeff))
+
+    def combined_predict(self, pose, max_depth, conf_threshold, time, max_time, time_delta=200):
+        orc().orc_map_combined_predict(self.h, P(f32(pose).reshape(16)), cf(max_depth), cf(conf_threshold), int(time),
+                                       int(max_time), int(time_delta))
+
+    def fill_in(self, rgb, depth_filtered, passthrough_geom=False, passthrough_rgb=False):
+        orc().orc_map_fill_in(self.h, self._u8(rgb), P(f32(depth_filtered)), int(passthrough_geom), int(passthrough_rgb))
+
+    def requires_fill_in(self, ratio=0.75):
+        return bool(orc().orc_map_requires_fill_in(self.h, cf(ratio)))
+
+    @staticmethod
+    def fusion_weight(pose, last_pose, mult=1.0):
+        return float(orc().orc_fusion_weight(P(f32(pose).reshape(16)), P(f32(last_pose).reshape(16)), cf(mult)))
+
+    @property
+    def count(self):
+        return orc().orc_map_count(self.h)
+
+    def surfels(self):
+        n = self.count
+        ptr = orc().orc_map_surfels(self.h)
+        buf = (C.c_char * (n * 48)).from_address(ptr)
+        return np.frombuffer(buf, dtype=np.float32).reshape(n, 12).copy()
+
+    def unstable(self):
+        n = orc().orc_map_unstable_count(self.h)
+        ptr = orc().orc_map_unstable(self.h)
+        buf = (C.c_char * (n * 48)).from_address(ptr)
+        return np.frombuffer(buf, dtype=np.float32).reshape(n, 12).copy()
+
+    def set_surfels(self, s):
+        s = np.ascontiguousarray(s, np.float32)
+        orc().orc_map_set_surfels(self.h, P(s), s.shape[0])
+
+    def view(self, which):
+        ch, dt = self.VIEWS[which]
+        n = self.W * self.H * ch
+        ptr = orc().orc_map_view(self.h, which)
+        buf = (C.c_char * (n * np.dtype(dt).itemsize)).from_address(ptr)
+        a = np.frombuffer(buf, dtype=dt).copy()
+        return a.reshape(self.H, self.W, ch) if ch > 1 else a.reshape(self.H, self.W)
