@@ -312,3 +312,92 @@ class Model:
             check(lib().cfb_download(out.ctypes.data_as(C.c_void_p), ptr, C.c_size_t(out.nbytes),
                                      C.c_void_p(self.ctx.stream)))
         return out
+
+
+class CoFusionParams(C.Structure):
+    _fields_ = [("timeDelta", C.c_int), ("depthCutoff", C.c_float), ("maxDepthProcessed", C.c_float),
+                ("icpWeight", C.c_float), ("pyramid", C.c_int), ("fastOdom", C.c_int), ("so3", C.c_int),
+                ("frameToFrameRGB", C.c_int), ("rgbOnly", C.c_int), ("confGlobalInit", C.c_float),
+                ("confObjectInit", C.c_float), ("outlierCoefficient", C.c_float), ("maxSurfels", C.c_uint)]
+
+    @staticmethod
+    def default(max_surfels=1 << 21):
+        p = CoFusionParams()
+        lib().cfb_cofusion_default_params(C.byref(p))
+        p.maxSurfels = max_surfels
+        return p
+
+
+class _Borrowed:
+    pass
+
+
+class CoFusion:
+    """cfb_cofusion_*: CoFusion::processFrame for the models of one device."""
+
+    def __init__(self, W, H, K, params=None, device=0):
+        fx, fy, cx, cy = K
+        self.W, self.H, self.K = W, H, K
+        self.params = params or CoFusionParams.default()
+        self._h = C.c_void_p()
+        check(lib().cfb_cofusion_create(device, W, H, C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy),
+                                        C.byref(self.params), C.byref(self._h)))
+        lib().cfb_cofusion_model.restype = C.c_void_p
+        lib().cfb_cofusion_ctx.restype = C.c_void_p
+        lib().cfb_ctx_stream.restype = C.c_void_p
+        self.ctx = Context.__new__(Context)
+        self.ctx.W, self.ctx.H, self.ctx.K = W, H, K
+        self.ctx._h = C.c_void_p()  # borrowed: never destroyed from Python
+        self._ctx_h = C.c_void_p(lib().cfb_cofusion_ctx(self._h))
+        self.ctx.stream = lib().cfb_ctx_stream(self._ctx_h)
+        self.ctx.sync = lambda: check(lib().cfb_ctx_sync(self._ctx_h))
+        self.ctx.take_launch_count = lambda: lib().cfb_ctx_take_launch_count(self._ctx_h)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and self._h.value and _lib is not None:
+            _lib.cfb_cofusion_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def process_frame(self, rgb, depth, mask=None, weight_multiplier=1.0):
+        """rgb/depth/mask: host numpy arrays, pinned torch tensors, or CUDA torch tensors"""
+        dev = hasattr(rgb, "is_cuda") and rgb.is_cuda
+
+        def ptr(a):
+            if a is None:
+                return C.c_void_p(0)
+            if hasattr(a, "data_ptr"):
+                return C.c_void_p(a.data_ptr())
+            return a.ctypes.data_as(C.c_void_p)
+        check(lib().cfb_cofusion_process_frame(self._h, ptr(rgb), ptr(depth), ptr(mask), int(dev),
+                                               C.c_float(weight_multiplier)))
+
+    def spawn_object_model(self, model_id, pose=None):
+        pp = None
+        if pose is not None:
+            pa = np.ascontiguousarray(pose, np.float32).reshape(16)
+            pp = pa.ctypes.data_as(c_float_p)
+        check(lib().cfb_cofusion_spawn_object_model(self._h, int(model_id), pp))
+
+    @property
+    def num_models(self):
+        return lib().cfb_cofusion_num_models(self._h)
+
+    @property
+    def tick(self):
+        return lib().cfb_cofusion_tick(self._h)
+
+    def model(self, index=0):
+        m = Model.__new__(Model)
+        m.ctx = self.ctx
+        m._h = C.c_void_p(lib().cfb_cofusion_model(self._h, int(index)))
+        m.__class__ = type("BorrowedModel", (Model,), {"__del__": lambda self_: None})
+        lib().cfb_model_compute_fusion_weight.restype = C.c_float
+        return m
+
+    def pose(self, index=0):
+        return self.model(index).pose
+
+    def last_stats(self, index=0):
+        st = TrackStats()
+        check(lib().cfb_cofusion_last_stats(self._h, int(index), C.byref(st)))
+        return st

@@ -9,6 +9,7 @@
 #include "image_kernels.cuh"
 #include "odometry.cuh"
 #include "pipeline.cuh"
+#include "cofusion.cuh"
 #include "tracker_kernels.cuh"
 
 namespace cfb {
@@ -349,14 +350,21 @@ int cfb_odom_view(cfb_odom* o, int which, int level, const void** dev_ptr, size_
 
 /* ------------------------------------------------------------------------------ Context / Model */
 struct cfb_ctx {
-  Context c;
-  cfb_ctx(int d, int w, int h, float fx, float fy, float cx, float cy) : c(d, w, h, fx, fy, cx, cy) {}
+  Context* owned;
+  Context& c;
+  cfb_ctx(int d, int w, int h, float fx, float fy, float cx, float cy)
+      : owned(new Context(d, w, h, fx, fy, cx, cy)), c(*owned) {}
+  explicit cfb_ctx(Context* b) : owned(nullptr), c(*b) {}
+  ~cfb_ctx() { delete owned; }
 };
 struct cfb_model {
-  Model m;
+  Model* owned;
+  Model& m;
   cfb_odom odom_handle;
   cfb_model(Context* c, unsigned id, float conf, unsigned maxSurfels, bool fillIn)
-      : m(c, id, conf, maxSurfels, fillIn), odom_handle{&m.odom, true} {}
+      : owned(new Model(c, id, conf, maxSurfels, fillIn)), m(*owned), odom_handle{&owned->odom, true} {}
+  explicit cfb_model(Model* b) : owned(nullptr), m(*b), odom_handle{&b->odom, true} {}
+  ~cfb_model() { delete owned; }
 };
 
 int cfb_ctx_create(int device, int W, int H, float fx, float fy, float cx, float cy, cfb_ctx** out) {
@@ -421,6 +429,7 @@ int cfb_model_create(cfb_ctx* c, unsigned id, float conf, unsigned max_surfels, 
   REQUIRE(c && out && max_surfels > 0 && id < 256, "model_create");
   *out = nullptr;
   cfb_model* m = new (std::nothrow) cfb_model(&c->c, id, conf, max_surfels, enable_fill_in != 0);
+
   if (!m || !m->m.ok()) {
     delete m;
     return set_error_msg(4, "model_create: device allocation failed");
@@ -548,6 +557,71 @@ int cfb_model_view(cfb_model* m, int which, const void** dev_ptr, size_t* pitch)
     case 15: *dev_ptr = m->m.unstable; *pitch = 48; break;
     default: return set_error_msg(2, "model_view: unknown view");
   }
+  return 0;
+}
+
+
+/* ------------------------------------------------------------------------------ CoFusion */
+struct cfb_cofusion {
+  CoFusion f;
+  cfb_ctx ctx_handle;
+  std::vector<cfb_model*> model_handles;
+  cfb_cofusion(int d, int w, int h, float fx, float fy, float cx, float cy, const CoFusionParams& p)
+      : f(d, w, h, fx, fy, cx, cy, p), ctx_handle(&f.ctx) {}
+  ~cfb_cofusion() {
+    for (auto* h : model_handles) delete h;
+  }
+  void sync_handles() {
+    while (model_handles.size() < f.numModels()) model_handles.push_back(new cfb_model(f.model(model_handles.size())));
+  }
+};
+
+void cfb_cofusion_default_params(cfb_cofusion_params* p) {
+  if (!p) return;
+  cfb_cofusion_params d = {200, 5.0f, 20.0f, 10.0f, 1, 0, 1, 0, 0, 10.0f, 0.01f, 3.0f, 3072u * 3072u};
+  *p = d;
+}
+int cfb_cofusion_create(int device, int W, int H, float fx, float fy, float cx, float cy,
+                        const cfb_cofusion_params* p, cfb_cofusion** out) {
+  REQUIRE(out && p && W >= 32 && H >= 32 && (W % 8) == 0 && (H % 4) == 0 && p->maxSurfels > 0, "cofusion_create");
+  *out = nullptr;
+  if (cfb_device_count() <= device || device < 0)
+    return set_error_msg(3, "no such CUDA device: libcofusion_b200 has no CPU fallback");
+  static_assert(sizeof(CoFusionParams) == sizeof(cfb_cofusion_params), "params layout");
+  CoFusionParams cp;
+  memcpy(&cp, p, sizeof(cp));
+  cfb_cofusion* f = new (std::nothrow) cfb_cofusion(device, W, H, fx, fy, cx, cy, cp);
+  if (!f || !f->f.ok()) {
+    delete f;
+    return set_error_msg(4, "cofusion_create: device allocation failed");
+  }
+  f->sync_handles();
+  *out = f;
+  return 0;
+}
+void cfb_cofusion_destroy(cfb_cofusion* f) { delete f; }
+int cfb_cofusion_process_frame(cfb_cofusion* f, const uint8_t* rgb, const float* depth, const uint8_t* mask,
+                               int device_ptrs, float weightMultiplier) {
+  REQUIRE(f && rgb && depth, "cofusion_process_frame");
+  CK(f->f.processFrame(rgb, depth, mask, device_ptrs != 0, weightMultiplier));
+  return 0;
+}
+int cfb_cofusion_spawn_object_model(cfb_cofusion* f, unsigned id, const float* initialPose16) {
+  REQUIRE(f && id > 0 && id < 256, "cofusion_spawn_object_model");
+  CK(f->f.spawnObjectModel(id, initialPose16));
+  f->sync_handles();
+  return 0;
+}
+int cfb_cofusion_num_models(cfb_cofusion* f) { return f ? (int)f->f.numModels() : 0; }
+int cfb_cofusion_tick(cfb_cofusion* f) { return f ? f->f.tick() : 0; }
+cfb_model* cfb_cofusion_model(cfb_cofusion* f, int index) {
+  if (!f || index < 0 || (size_t)index >= f->model_handles.size()) return nullptr;
+  return f->model_handles[index];
+}
+cfb_ctx* cfb_cofusion_ctx(cfb_cofusion* f) { return f ? &f->ctx_handle : nullptr; }
+int cfb_cofusion_last_stats(cfb_cofusion* f, int index, cfb_track_stats* out) {
+  REQUIRE(f && out && index >= 0 && (size_t)index < f->f.lastStats.size(), "cofusion_last_stats");
+  memcpy(out, &f->f.lastStats[index], sizeof(cfb_track_stats));
   return 0;
 }
 

@@ -1,0 +1,54 @@
+// cofusion.cuh -- cfb::CoFusion: the per-frame sequencing of CoFusion::processFrame
+// (Core/CoFusion.cpp:171-545) for the models living on one device, GL-free.
+//
+// Kept from the reference: call order (track all -> predict -> indices/fuse/indices/clean -> predict),
+// tick semantics, first-frame initialisation, fill-in for the background model only, external label
+// masks (FrameData::mask).  Not here (out of scope): loop closure, ferns,
+// re-detection, GUI, logging.  Model spawn/deactivate decisions stay with the caller (they are
+// driven by the segmentation result, CoFusion.cpp:243-298).
+#pragma once
+#include <memory>
+#include <vector>
+
+#include "pipeline.cuh"
+
+namespace cfb {
+
+struct CoFusionParams {   // constructor arguments / setters of CoFusion (CoFusion.h:47-66, :130-246)
+  int timeDelta;          // 200 (GUI/MainController.cpp:186; effectively unused while openLoop)
+  float depthCutoff;      // bilateral maxD, GUI default 5 (CoFusion::depthCutoff)
+  float maxDepthProcessed;// 20 (CoFusion.cpp:51)
+  float icpWeight;        // 10
+  int pyramid, fastOdom, so3, frameToFrameRGB, rgbOnly;
+  float confGlobalInit;   // 10  (MainController.cpp:175)
+  float confObjectInit;   // 0.01
+  float outlierCoefficient;  // 3 (GUI/Tools/GUI.h:208)
+  unsigned maxSurfels;    // per model
+};
+
+class CoFusion {
+ public:
+  CoFusion(int device, int W, int H, float fx, float fy, float cx, float cy, const CoFusionParams& p);
+  bool ok() const { return ctx.ok() && !models.empty() && models[0]->ok(); }
+  // CoFusion::processFrame.  Buffers are host pointers (pinned or pageable) unless device_ptrs.
+  // mask == nullptr: static scene, everything labelled background (CoFusion.cpp:190-197).
+  cudaError_t processFrame(const uint8_t* rgb, const float* depth, const uint8_t* mask, bool device_ptrs,
+                           float weightMultiplier);
+  // spawn an object model (CoFusion::spawnObjectModel, CoFusion.cpp:588-597): created empty; it is
+  // initialised by fusing the pixels labelled `id` of the current frame (CoFusion.cpp:265-276)
+  cudaError_t spawnObjectModel(unsigned id, const float* initialPose /* 16 or null = background pose */);
+  Model* model(size_t i) { return i < models.size() ? models[i].get() : nullptr; }
+  size_t numModels() const { return models.size(); }
+  int tick() const { return tick_; }
+  cudaError_t predict();  // CoFusion::predict (CoFusion.cpp:533-545)
+
+  Context ctx;
+  CoFusionParams params;
+  std::vector<std::unique_ptr<Model>> models;
+  std::vector<TrackStats> lastStats;
+
+ private:
+  int tick_ = 1;
+};
+
+}  // namespace cfb

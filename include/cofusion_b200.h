@@ -236,6 +236,38 @@ cfb_odom* cfb_model_odometry(cfb_model* m);
  * | fill-in: 12 image 13 vertex 14 normal | 15 new-unstable buffer (48-B surfels) */
 int cfb_model_view(cfb_model* m, int which, const void** dev_ptr, size_t* pitch);
 
+/* ------------------------------------------------------------------------------------------------
+ * Seam 2c: CoFusion::processFrame (Core/CoFusion.h:67-68, Core/CoFusion.cpp:171-524)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cfb_cofusion cfb_cofusion;
+typedef struct cfb_cofusion_params { /* CoFusion ctor args / setters (CoFusion.h:47-66, :130-246) */
+  int timeDelta;            /* 200 */
+  float depthCutoff;        /* 5   (bilateral maxD) */
+  float maxDepthProcessed;  /* 20  (CoFusion.cpp:51) */
+  float icpWeight;          /* 10 */
+  int pyramid, fastOdom, so3, frameToFrameRGB, rgbOnly; /* 1,0,1,0,0 */
+  float confGlobalInit;     /* 10 */
+  float confObjectInit;     /* 0.01 */
+  float outlierCoefficient; /* 3 */
+  unsigned maxSurfels;      /* per model (reference: 3072^2) */
+} cfb_cofusion_params;
+void cfb_cofusion_default_params(cfb_cofusion_params* p);
+int cfb_cofusion_create(int device, int W, int H, float fx, float fy, float cx, float cy,
+                        const cfb_cofusion_params* p, cfb_cofusion** out);
+void cfb_cofusion_destroy(cfb_cofusion* f);
+/* processFrame(frame, inPose = NULL, weightMultiplier, bootstrap = false).  rgb: HxWx3 u8, depth: HxW
+ * f32 metres, mask: HxW u8 labels or NULL (static scene).  Host buffers unless device_ptrs != 0. */
+int cfb_cofusion_process_frame(cfb_cofusion* f, const uint8_t* rgb, const float* depth, const uint8_t* mask,
+                               int device_ptrs, float weightMultiplier);
+/* CoFusion::spawnObjectModel + the first fuse of the new model (CoFusion.cpp:252-276) */
+int cfb_cofusion_spawn_object_model(cfb_cofusion* f, unsigned id, const float* initialPose16);
+int cfb_cofusion_num_models(cfb_cofusion* f);
+int cfb_cofusion_tick(cfb_cofusion* f);
+/* borrowed handles (owned by the cofusion object) */
+cfb_model* cfb_cofusion_model(cfb_cofusion* f, int index);
+cfb_ctx* cfb_cofusion_ctx(cfb_cofusion* f);
+int cfb_cofusion_last_stats(cfb_cofusion* f, int index, cfb_track_stats* out);
+
 #ifdef __cplusplus
 }
 #endif
