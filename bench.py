@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- RGB-D frames/s of the Co-Fusion per-frame hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank/GPU)
+  python bench.py --impl reference --gpus N --steps K ...  (CPU port of the reference path, rank 0 only)
+
+A "step" is one CoFusion::processFrame of one 640x480 synthetic RGB-D frame (BASELINE.json configs[1]:
+single model, synthetic room sequence): H2D upload, bilateral filter + depth pyramid, model/frame
+pyramids, SO(3) + 19-iteration ICP+RGB Gauss-Newton tracking, predict, index map, fuse, index map,
+clean, predict + fill-in.  `value` is measured with the frames already resident in HBM, `e2e` through
+the same C-ABI call with pinned HOST buffers (H2D of the frame and D2H of the pose inside the timed
+region).  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+W, H = 640, 480
+METRIC = "RGB-D frames/s @640x480 (per-model ICP+fuse)"
+# algorithmic bytes of the tracker's Gauss-Newton loop per model per frame at 640x480
+# = sum over the 10/5/4 iterations of (48 P + 116) ICP + 30 P RGB residual + (32 P + 116) RGB step
+GN_ITERS = ((0, 10), (1, 5), (2, 4))
+
+
+def gn_algorithmic_bytes(w, h):
+    total = 0
+    for lvl, it in GN_ITERS:
+        P = (w >> lvl) * (h >> lvl)
+        total += it * ((48 * P + 116) + 30 * P + (32 * P + 116))
+    return total
+
+
+def make_frames(n):
+    from cofusion_b200 import synth
+    return [(rgb, d) for _, rgb, d, _, _ in synth.room_sequence(n, W, H, synth.K_DEFAULT, noise=True, seed=1234)]
+
+
+def frame_index(step, n):
+    """ping-pong over the rendered frames so that camera motion stays continuous for any step count"""
+    period = 2 * (n - 1)
+    k = step % period
+    return k if k < n else period - k
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 9:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[1]) for s in self.samples)
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for k, nm in enumerate(names):
+                if s[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][2]), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_port_fps(frames, n_frames, warm=2):
+    """The CPU restatement of the same per-frame path (oracle/, single thread) on a bounded sample."""
+    from orc_pipeline import OraclePipeline
+    from cofusion_b200 import synth
+    op = OraclePipeline(W, H, synth.K_DEFAULT, 1 << 21)
+    for t in range(warm):
+        op.process_frame(*frames[frame_index(t, len(frames))])
+    t0 = time.perf_counter()
+    for t in range(warm, warm + n_frames):
+        op.process_frame(*frames[frame_index(t, len(frames))])
+    dt = time.perf_counter() - t0
+    return n_frames / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    frames = make_frames(min(24, args.steps + args.warmup + 2))
+    from orc_pipeline import OraclePipeline
+    from cofusion_b200 import synth
+    op = OraclePipeline(W, H, synth.K_DEFAULT, 1 << 21)
+    for t in range(args.warmup):
+        op.process_frame(*frames[frame_index(t, len(frames))])
+    t0 = time.perf_counter()
+    for t in range(args.warmup, args.warmup + args.steps):
+        op.process_frame(*frames[frame_index(t, len(frames))])
+    dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: single model, 640x480 synthetic room sequence (CPU port of the "
+                                   "reference path: bilateral, pyramids, SO3+ICP+RGB tracking, predict, fuse, clean)",
+                       "parallelism": "1 host thread"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port",
+                             "sample": "%d frames after %d warm-up frames, oracle/ C restatement" % (args.steps, args.warmup)},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="cofusion_b200")
+    ap.add_argument("--cpu-frames", type=int, default=8, help="frames of the cpu_baseline sample (0 = skip)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        # the reference's path on the host cores: steps are a bounded sample
+        args.steps = min(args.steps, 20)
+        args.warmup = min(args.warmup, 3)
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import cofusion_b200 as cfb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    K = cfb.synth.K_DEFAULT
+    n_render = 32
+    frames = make_frames(n_render)
+    P = W * H
+    # packed frame = [rgb u8 3P | depth f32 4P]: the unit the multi-GPU path broadcasts (7P bytes)
+    packed_host = []
+    for rgb, d in frames:
+        buf = torch.empty(7 * P, dtype=torch.uint8).pin_memory()
+        buf[:3 * P] = torch.from_numpy(np.ascontiguousarray(rgb).reshape(-1))
+        buf[3 * P:] = torch.from_numpy(np.ascontiguousarray(d).reshape(-1).view(np.uint8))
+        packed_host.append(buf)
+    packed_dev = [b.cuda() for b in packed_host] if rank == 0 else None
+    recv = torch.empty(7 * P, dtype=torch.uint8, device="cuda")
+
+    def build():
+        params = cfb.CoFusionParams.default(1 << 21)
+        cf = cfb.CoFusion(W, H, K, params, device=local)
+        cfb.lib().cfb_model_odometry.restype = cfb.C.c_void_p
+        odom = cfb.C.c_void_p(cfb.lib().cfb_model_odometry(cf.model(0)._h))
+        cfb.check(cfb.lib().cfb_odom_enable_kernel_timing(odom, 1))
+        return cf, odom
+
+    def step_resident(cf, t):
+        i = frame_index(t, n_render)
+        if world > 1:
+            if rank == 0:
+                recv.copy_(packed_dev[i], non_blocking=True)
+            dist.broadcast(recv, src=0)  # one NCCL broadcast of the packed frame per time step
+            src = recv
+        else:
+            src = packed_dev[i]
+        rgb = src[:3 * P]
+        depth = src[3 * P:].view(torch.float32)
+        cf.process_frame(rgb, depth)
+
+    def step_e2e(cf, t):
+        i = frame_index(t, n_render)
+        if world > 1:
+            if rank == 0:
+                recv.copy_(packed_host[i], non_blocking=True)  # H2D on the root, then NVLink broadcast
+            dist.broadcast(recv, src=0)
+            cf.process_frame(recv[:3 * P], recv[3 * P:].view(torch.float32))
+        else:
+            b = packed_host[i]
+            cf.process_frame(b[:3 * P], b[3 * P:].view(torch.float32))
+
+    def timed(step_fn, sampler=None):
+        cf, odom = build()
+        ext = torch.cuda.ExternalStream(cf.ctx.stream)
+        with torch.cuda.stream(ext):
+            for t in range(args.warmup):
+                step_fn(cf, t)
+            cf.ctx.sync()
+            cf.ctx.take_launch_count()
+            sm, n = cfb.C.c_double(0), cfb.C.c_int(0)
+            cfb.check(cfb.lib().cfb_odom_kernel_timing(odom, cfb.C.byref(sm), cfb.C.byref(n), 1))
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            if sampler:
+                sampler.start()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for t in range(args.warmup, args.warmup + args.steps):
+                step_fn(cf, t)
+            e1.record()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            ms = e0.elapsed_time(e1)
+            if sampler:
+                sampler.stop_flag = True
+        launches = cf.ctx.take_launch_count()
+        cfb.check(cfb.lib().cfb_odom_kernel_timing(odom, cfb.C.byref(sm), cfb.C.byref(n), 0))
+        t_ms = torch.tensor([ms], device="cuda")
+        if world > 1:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)  # max over ranks
+        nsurf = cf.model(0).last_count()
+        return float(t_ms.item()), launches, (sm.value, n.value), nsurf
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, launches, (kms, kn), nsurf = timed(step_resident, sampler)
+    ms_e2e, _, _, _ = timed(step_e2e)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * args.steps / (ms / 1e3)
+    e2e = world * args.steps / (ms_e2e / 1e3)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    alg = gn_algorithmic_bytes(W, H)
+    k_avg_ms = kms / max(kn, 1)
+    achieved = alg / (k_avg_ms * 1e-3) / 1e9 if kn else None
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["gn_persistent_kernel"]["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    cpu = None
+    if args.cpu_frames > 0:
+        fps_cpu, dt = cpu_port_fps(frames, args.cpu_frames)
+        cpu = {"value": fps_cpu, "unit": "frames/s", "cores": 1, "kind": "port",
+               "sample": "%d frames of the same 640x480 room sequence through the oracle/ C restatement "
+                         "(single thread, like the reference's CPU loops), %.1f s" % (args.cpu_frames, dt)}
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: single model, 640x480 synthetic room sequence, full processFrame "
+                               "(bilateral, pyramids, SO3 + 10/5/4-iteration ICP+RGB tracking, predict, fuse, clean)",
+                   "surfels": nsurf, "parallelism": "one model per GPU, frame broadcast over NCCL" if world > 1 else "1 GPU",
+                   "l2": "inputs cycle over %d distinct frames (%.0f MB) + a %.0f MB surfel map; per-step working set "
+                         "is L2 resident by nature of the workload, no flush" % (n_render, n_render * 7 * P / 1e6, nsurf * 96 / 1e6)},
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": 7 * P, "d2h_bytes_per_step": 48 + 376,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "roofline": {"kernel": "gn_persistent_kernel (SO3 + 19 GN iterations of ICP/RGB reductions, 1 launch/frame)",
+                     "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                     "algorithmic_bytes_per_launch": alg, "avg_launch_ms": k_avg_ms, "launches_timed": kn,
+                     "peak_source": peak_src,
+                     "share_of_step": (k_avg_ms / (ms / args.steps)) if kn else None},
+        "cpu_baseline": cpu,
+        "clocks": sampler.summary() if sampler else None,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

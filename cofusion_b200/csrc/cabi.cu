@@ -335,6 +335,16 @@ int cfb_odom_set_mode(cfb_odom* o, int mode) {
   o->impl.setMode(mode);
   return 0;
 }
+int cfb_odom_enable_kernel_timing(cfb_odom* o, int on) {
+  REQUIRE(o, "odom_enable_kernel_timing");
+  o->impl.enableKernelTiming(on != 0);
+  return 0;
+}
+int cfb_odom_kernel_timing(cfb_odom* o, double* sum_ms, int* launches, int reset) {
+  REQUIRE(o, "odom_kernel_timing");
+  o->impl.kernelTiming(sum_ms, launches, reset != 0);
+  return 0;
+}
 int cfb_odom_set_debug_trace(cfb_odom* o, void* dev_u64) {
   REQUIRE(o, "odom_set_debug_trace");
   o->impl.setDebugTrace(dev_u64);

@@ -300,6 +300,7 @@ cudaError_t RGBDOdometry::deviceLoop(float trans[3], float rot[9], float icpWeig
   }
   if (!launched) RET_IF(enqueueDeviceLoop(icpWeight, pyramid, fastOdom, so3, err, err_pitch, s));
   RET_IF(cudaStreamSynchronize(s));
+  if (time_kernel_) kernelTiming(nullptr, nullptr, false);
   memcpy(trans, ho->trans, sizeof(float) * 3);
   memcpy(rot, ho->rot, sizeof(float) * 9);
   stats_ = ho->st;

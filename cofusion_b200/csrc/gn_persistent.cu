@@ -467,7 +467,12 @@ cudaError_t RGBDOdometry::enqueuePersistent(float icpWeight, bool pyramid, bool 
   int grid = num_sms();
   if (grid > kMaxBlocks) grid = kMaxBlocks;
   void* args[] = {(void*)&p};
+  if (time_kernel_) RET_IF(cudaEventRecord(ev_k0_, s));
   RET_IF(cudaLaunchCooperativeKernel((const void*)gn_persistent_kernel, dim3(grid), dim3(kPT), args, 0, s));
+  if (time_kernel_) {
+    RET_IF(cudaEventRecord(ev_k1_, s));
+    ev_pending_ = true;
+  }
   struct Out {
     float trans[3];
     float rot[9];
@@ -477,6 +482,31 @@ cudaError_t RGBDOdometry::enqueuePersistent(float icpWeight, bool pyramid, bool 
   RET_IF(cudaMemcpyAsync(ho->trans, gn->out_trans, 12 * sizeof(float), cudaMemcpyDeviceToHost, s));
   RET_IF(cudaMemcpyAsync(&ho->st, &gn->stats, sizeof(TrackStats), cudaMemcpyDeviceToHost, s));
   return cudaSuccess;
+}
+
+void RGBDOdometry::enableKernelTiming(bool on) {
+  if (on && !ev_k0_) {
+    cudaEventCreate(&ev_k0_);
+    cudaEventCreate(&ev_k1_);
+  }
+  time_kernel_ = on && ev_k0_ && ev_k1_;
+}
+
+void RGBDOdometry::kernelTiming(double* sum_ms, int* launches, bool reset) {
+  if (ev_pending_ && cudaEventSynchronize(ev_k1_) == cudaSuccess) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ev_k0_, ev_k1_) == cudaSuccess) {
+      kernel_ms_sum_ += ms;
+      kernel_launches_++;
+    }
+    ev_pending_ = false;
+  }
+  if (sum_ms) *sum_ms = kernel_ms_sum_;
+  if (launches) *launches = kernel_launches_;
+  if (reset) {
+    kernel_ms_sum_ = 0;
+    kernel_launches_ = 0;
+  }
 }
 
 }  // namespace cfb

@@ -122,6 +122,11 @@ class RGBDOdometry {
   bool use_graphs_ = true;
   void* grid_sync_ = nullptr;  // software grid barrier state of the persistent kernel
   void* dbg_trace_ = nullptr;
+  bool time_kernel_ = false;
+  cudaEvent_t ev_k0_ = nullptr, ev_k1_ = nullptr;
+  bool ev_pending_ = false;
+  double kernel_ms_sum_ = 0;
+  int kernel_launches_ = 0;
   int mode_ = 0;               // 0: one persistent cooperative kernel, 1: per-step kernels (+ CUDA graph)
 
  public:
@@ -129,6 +134,9 @@ class RGBDOdometry {
   void setMode(int m) { mode_ = m; }
   // tools only: device buffer of >= 256 u64 receiving a %globaltimer trace of the persistent kernel
   void setDebugTrace(void* dev_u64) { dbg_trace_ = dev_u64; }
+  // bench: CUDA-event timing of the dominant kernel (the persistent GN kernel) on its own stream
+  void enableKernelTiming(bool on);
+  void kernelTiming(double* sum_ms, int* launches, bool reset);
   int mode() const { return mode_; }
 
  private:

@@ -372,7 +372,7 @@ cudaError_t Model::performTracking(const TrackParams& tp) {
   }
   // the tracker synchronised the stream: the counters copied after the last clean are exact now
   if (h_counters->count && h_counters->count < count_ub) count_ub = h_counters->count;
-  ctx->launches += 30;
+  ctx->launches += 28;  // 8 model pyramid + 6 + 6 RGB-D pyramids + 6 frame maps + prepare + persistent GN
   return cudaSuccess;
 }
 

@@ -147,6 +147,10 @@ int cfb_odom_get_incremental_transformation(cfb_odom* o, float trans[3], float r
  * cooperative kernel for the whole SO(3)+GN optimisation (default), 1 = one fused kernel per step
  * replayed as a CUDA graph.  Results are identical. */
 int cfb_odom_set_mode(cfb_odom* o, int mode);
+/* Measurement aid: CUDA events around the dominant tracker kernel on the stream it is launched on;
+ * cfb_odom_kernel_timing returns the accumulated milliseconds and launch count (optionally resets). */
+int cfb_odom_enable_kernel_timing(cfb_odom* o, int on);
+int cfb_odom_kernel_timing(cfb_odom* o, double* sum_ms, int* launches, int reset);
 /* Profiling aid: device buffer of >= 256 uint64 that receives a %globaltimer trace of the
  * persistent kernel's phases (NULL disables). */
 int cfb_odom_set_debug_trace(cfb_odom* o, void* dev_u64);
