@@ -149,6 +149,7 @@ def main():
     import torch
     import torch.distributed as dist
     import cofusion_b200 as cfb
+    from cofusion_b200 import synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -157,7 +158,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    K = cfb.synth.K_DEFAULT
+    K = synth.K_DEFAULT
     n_render = 32
     frames = make_frames(n_render)
     P = W * H
