@@ -135,8 +135,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=30)
     ap.add_argument("--impl", default="cofusion_b200")
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames of the cpu_baseline sample (0 = skip)")
     args = ap.parse_args()

@@ -250,6 +250,16 @@ class Model:
         check(lib().cfb_model_perform_tracking(self._h, C.byref(params), pose.ctypes.data_as(c_float_p), C.byref(st)))
         return pose.reshape(4, 4), st
 
+    def odometry_view(self, which, level):
+        """numpy copy of one of the tracker's internal pyramid buffers (see cfb_odom_view)"""
+        lib().cfb_model_odometry.restype = C.c_void_p
+        o = Odometry.__new__(Odometry)
+        o.W, o.H, o.K = self.ctx.W, self.ctx.H, self.ctx.K
+        o._h = C.c_void_p(lib().cfb_model_odometry(self._h))
+        o.__class__ = type("BorrowedOdometry", (Odometry,), {"__del__": lambda self_: None})
+        self.ctx.sync()
+        return o.view(which, level)
+
     def odometry_set_mode(self, mode):
         lib().cfb_model_odometry.restype = C.c_void_p
         check(lib().cfb_odom_set_mode(C.c_void_p(lib().cfb_model_odometry(self._h)), int(mode)))
@@ -318,7 +328,8 @@ class CoFusionParams(C.Structure):
     _fields_ = [("timeDelta", C.c_int), ("depthCutoff", C.c_float), ("maxDepthProcessed", C.c_float),
                 ("icpWeight", C.c_float), ("pyramid", C.c_int), ("fastOdom", C.c_int), ("so3", C.c_int),
                 ("frameToFrameRGB", C.c_int), ("rgbOnly", C.c_int), ("confGlobalInit", C.c_float),
-                ("confObjectInit", C.c_float), ("outlierCoefficient", C.c_float), ("maxSurfels", C.c_uint)]
+                ("confObjectInit", C.c_float), ("outlierCoefficient", C.c_float), ("maxSurfels", C.c_uint),
+                ("predictBeforeFuse", C.c_int)]
 
     @staticmethod
     def default(max_surfels=1 << 21):

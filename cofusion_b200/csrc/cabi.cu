@@ -588,7 +588,7 @@ struct cfb_cofusion {
 
 void cfb_cofusion_default_params(cfb_cofusion_params* p) {
   if (!p) return;
-  cfb_cofusion_params d = {200, 5.0f, 20.0f, 10.0f, 1, 0, 1, 0, 0, 10.0f, 0.01f, 3.0f, 3072u * 3072u};
+  cfb_cofusion_params d = {200, 5.0f, 20.0f, 10.0f, 1, 0, 1, 0, 0, 10.0f, 0.01f, 3.0f, 3072u * 3072u, 0};
   *p = d;
 }
 int cfb_cofusion_create(int device, int W, int H, float fx, float fy, float cx, float cy,

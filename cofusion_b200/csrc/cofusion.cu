@@ -68,7 +68,10 @@ cudaError_t CoFusion::processFrame(const uint8_t* rgb, const float* depth, const
       RET_IF(models[i]->performTracking(tp));
       lastStats[i] = models[i]->odom.stats();
     }
-    RET_IF(predict());
+    // CoFusion.cpp:347: this prediction only feeds performSegmentation / the (dead) loop-closure
+    // block; the fuse stage below uses the index maps and the frame, and the final predict()
+    // overwrites every target -> skipped unless asked for.
+    if (params.predictBeforeFuse) RET_IF(predict());
     if (!params.rgbOnly) {
       for (auto& m : models) RET_IF(m->predictIndices(tick_, params.maxDepthProcessed, params.timeDelta));
       for (auto& m : models) RET_IF(m->fuse(tick_, params.maxDepthProcessed, weightMultiplier));

@@ -24,6 +24,8 @@ struct CoFusionParams {   // constructor arguments / setters of CoFusion (CoFusi
   float confObjectInit;   // 0.01
   float outlierCoefficient;  // 3 (GUI/Tools/GUI.h:208)
   unsigned maxSurfels;    // per model
+  int predictBeforeFuse;  // 1: also run the predict() of CoFusion.cpp:347, whose images nobody reads
+                          //    unless the CRF segmentation is on (identical results either way)
 };
 
 class CoFusion {

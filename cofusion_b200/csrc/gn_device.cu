@@ -179,7 +179,7 @@ cudaError_t RGBDOdometry::enqueueDeviceLoop(float icpWeight, bool pyramid, bool 
   for (int i = 0; i < NUM_PYRS; i++) {
     int w = width >> i, h = height >> i;
     float minScale = (float)(pow(minimumGradientMagnitudes[i], 2.0) / pow(sobelScale, 2.0));
-    rgb_prepare_kernel<<<dim3((w + 31) / 32, (h + 7) / 8), b2, 0, s>>>(nextImage[i], w, h, nextDepth[i], minScale,
+    rgb_prepare_kernel<<<dim3((w + 31) / 32, (h + 7) / 8), b2, 0, s>>>(nextImage[i], w, h, (next_is_last_ ? lastDepth[i] : nextDepth[i]), minScale,
                                                                          nextdIdx[i], nextdIdy[i], rgbCand[i]);
     RET_IF(launch_project_to_point_cloud(lastDepth[i], (size_t)w * 4, w, h, intr.level(i), pointClouds[i],
                                          (size_t)w * 12, s));
@@ -225,7 +225,7 @@ cudaError_t RGBDOdometry::enqueueDeviceLoop(float icpWeight, bool pyramid, bool 
     ra.dIdy = nextdIdy[i];
     ra.grad_pitch = (size_t)w * 2;
     ra.lastDepth = lastDepth[i];
-    ra.nextDepth = nextDepth[i];
+    ra.nextDepth = (next_is_last_ ? lastDepth[i] : nextDepth[i]);
     ra.depth_pitch = p;
     ra.lastImage = lastImage[i];
     ra.nextImage = nextImage[i];

@@ -33,15 +33,16 @@ struct LevelData {
   LevelK k;
 };
 
-struct GridSync {
-  unsigned count;
-  unsigned epoch;
+struct GridSync {   // zeroed by rgb_prepare_all_kernel before every launch
+  unsigned arrive;  // monotonic arrival counter of the software grid barrier
+  unsigned pad[31];
+  int counts[32][2];  // per GN iteration: {RGB correspondences, sum of floor(diff^2)} (integer atomics)
 };
 
 struct PersistParams {
   LevelData L[3];
   const unsigned char *so3_last, *so3_next;
-  GNState* g;
+  GNState* g;   // global copy of the final state (pose, stats), written by CTA 0
   StepScratch* sc;
   GridSync* gs;
   const float* pose_in;
@@ -50,7 +51,7 @@ struct PersistParams {
   float distThres, angleThres, maxDepthDelta, sobelScale, icpWeight;
   int use_so3;
   int iters[3];
-  unsigned long long* dbg;  // optional %globaltimer trace (block 0 / finalisers), tools only
+  unsigned long long* dbg;  // optional %globaltimer trace of CTA 0, tools only
 };
 
 __device__ __forceinline__ unsigned long long gtime() {
@@ -68,57 +69,50 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
-// Grid-wide barrier; `fin` runs in every thread of the LAST CTA to arrive, before anyone is released.
-template <class F>
-__device__ __forceinline__ void grid_barrier(GridSync* gs, unsigned& epoch, F&& fin) {
-  __shared__ int s_last;
+// Split software grid barrier on a monotonic counter: arrive() publishes this CTA's global writes,
+// wait(target) blocks until `target` arrivals have been counted.  Work placed between the two calls
+// hides the barrier latency.  No CTA is special: every CTA folds the per-CTA partial sums itself (in
+// the same fixed order -> identical totals everywhere) and runs the FP64 Gauss-Newton step on its own
+// shared-memory copy of the state, so there is no "finaliser -> flag -> everyone re-reads" hop.
+__device__ __forceinline__ void grid_arrive(GridSync* gs) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    unsigned t = atomicAdd(&gs->count, 1u);
-    s_last = (t == gridDim.x - 1);
+    atomicAdd(&gs->arrive, 1u);
+  }
+}
+__device__ __forceinline__ void grid_wait(GridSync* gs, unsigned target) {
+  if (threadIdx.x == 0) {
+    while (ld_acquire(&gs->arrive) < target) __nanosleep(20);
   }
   __syncthreads();
-  if (s_last) {
-    __threadfence();
-    fin();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      gs->count = 0;
-      __threadfence();
-      st_release(&gs->epoch, epoch + 1);
-    }
-  } else if (threadIdx.x == 0) {
-    while (ld_acquire(&gs->epoch) == epoch) __nanosleep(40);
-  }
-  __syncthreads();
-  epoch += 1;
 }
 
-// fixed-order sum of the per-CTA partial rows by all warps of the calling CTA -> out32 (shared)
-__device__ __forceinline__ void sum_partials(const float* partials, float* smem, float* out32) {
+// fixed-order sum of `nsets` consecutive sets of per-CTA partial rows -> out[set*32 + lane] (shared)
+template <int NSETS>
+__device__ __forceinline__ void sum_partials(const float* partials, unsigned rows_per_set, float* smem, float* out) {
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  // all loads of a warp are issued before the first add: one L2 round trip instead of one per row
-  float v[12];
 #pragma unroll
-  for (int k = 0; k < 12; ++k) {
-    const unsigned b = warp + k * nw;
-    v[k] = (b < gridDim.x) ? __ldcg(&partials[b * 32 + lane]) : 0.f;
+  for (int set = 0; set < NSETS; ++set) {
+    const float* base = partials + (size_t)set * rows_per_set * 32;
+    float v[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {  // all loads in flight before the first add
+      const unsigned b = warp + k * nw;
+      v[k] = (b < gridDim.x) ? __ldcg(&base[b * 32 + lane]) : 0.f;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) s += v[k];
+    for (unsigned b = warp + 12 * nw; b < gridDim.x; b += nw) s += __ldcg(&base[b * 32 + lane]);
+    smem[(set * (kPT / 32) + warp) * 32 + lane] = s;
   }
-  float s = 0.f;
-#pragma unroll
-  for (int k = 0; k < 12; ++k) s += v[k];
-  for (unsigned b = warp + 12 * nw; b < gridDim.x; b += nw) s += __ldcg(&partials[b * 32 + lane]);
-  smem[warp * 32 + lane] = s;
   __syncthreads();
-  if (warp == 0) {
+  if (warp < NSETS) {
     float tot = 0.f;
-    for (unsigned w = 0; w < nw; ++w) tot += smem[w * 32 + lane];
-    out32[lane] = tot;
+    for (unsigned w = 0; w < nw; ++w) tot += smem[(warp * (kPT / 32) + w) * 32 + lane];
+    out[warp * 32 + lane] = tot;
   }
   __syncthreads();
 }
@@ -153,64 +147,71 @@ __device__ __forceinline__ void rgb_step_from_depth(const LevelData& L, float si
   accumulate_se3(acc, row, valid);
 }
 
-__global__ void __launch_bounds__(kPT, 1) gn_persistent_kernel(const PersistParams p) {
-  __shared__ float red[(kPT / 32) * 32];
-  __shared__ float out32[32];
-  __shared__ IcpPose P;
-  __shared__ RgbWarp Wp;
-  __shared__ Mat33 M[3];
-  __shared__ int scnt[kPT / 32], ssig[kPT / 32];
-  __shared__ unsigned s_epoch;
-  __shared__ int s_flag;
-
-  GNState* g = p.g;
-  StepScratch* sc = p.sc;
-  if (threadIdx.x == 0) s_epoch = ld_acquire(&p.gs->epoch);
+// block reduce that lets warps without any contribution skip the 31-shuffle transpose
+__device__ __forceinline__ float block_reduce32_sparse(float (&v)[32], bool warp_has_work, float* smem) {
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float t = 0.f;
+  if (warp_has_work) t = warp_transpose_reduce32(v);
+  smem[warp * 32 + lane] = t;
   __syncthreads();
-  unsigned epoch = s_epoch;
+  float s = 0.f;
+  if (warp == 0)
+    for (unsigned w = 0; w < nw; ++w) s += smem[w * 32 + lane];
+  return s;
+}
+
+__global__ void __launch_bounds__(kPT, 1) gn_persistent_kernel(const PersistParams p) {
+  __shared__ float red[2 * (kPT / 32) * 32];
+  __shared__ float out64[64];
+  __shared__ GNState S;  // every CTA keeps (and identically updates) its own copy of the GN state
+  __shared__ int scnt[kPT / 32], ssig[kPT / 32];
+
+  GridSync* gs = p.gs;
+  StepScratch* sc = p.sc;
   const int tid = blockIdx.x * kPT + threadIdx.x, nthreads = gridDim.x * kPT;
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned G = gridDim.x;
+  unsigned barriers = 0;  // barriers completed so far -> target = (barriers + 1) * G
 
   int sched[19], nsched = 0;
   for (int i = 2; i >= 0; --i)
     for (int j = 0; j < p.iters[i] && nsched < 19; ++j) sched[nsched++] = i;
 
   DBG_MARK(0);
-  // ---- barrier 0: state reset by the last CTA (all CTAs have read the epoch by now)
-  grid_barrier(p.gs, epoch, [&] {
-    if (threadIdx.x == 0) {
-      gn_init_serial(g, sc, p.pose_in, p.L[2].k);
-      if (!p.use_so3) gn_begin_serial(g, 0, p.L[nsched ? sched[0] : 0].k);
-    }
-  });
+  if (threadIdx.x == 0) {
+    gn_init_serial(&S, nullptr, p.pose_in, p.L[2].k);
+    if (!p.use_so3) gn_begin_serial(&S, 0, p.L[nsched ? sched[0] : 0].k);
+  }
+  __syncthreads();
+  // partial rows: set s in {0: ICP / SO3, 1: RGB}, double buffered by iteration parity
+  auto prow = [&](int set, int parity) { return sc->partials + (size_t)((parity * 2 + set) * G) * 32; };
 
   DBG_MARK(1);
   // ---- SO(3) pre-alignment on level 2 (RGBDOdometry.cpp:239-310)
   if (p.use_so3) {
     const LevelData& L = p.L[2];
+    const int N = L.w * L.h;
     for (int it = 0; it < 10; ++it) {
-      if (threadIdx.x == 0) s_flag = __ldcg(&g->so3_done);
-      for (int i = threadIdx.x; i < 27; i += kPT) ((float*)M)[i] = __ldcg(((const float*)&g->so3_imageBasis) + i);
-      __syncthreads();
-      if (s_flag) break;  // uniform over the grid: written before the previous barrier released
+      if (S.so3_done) break;  // identical in every CTA
       float acc[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-      const int N = L.w * L.h;
+      bool work = false;
       for (int q = tid; q < N; q += nthreads) {
         int y = q / L.w, x = q - y * L.w;
-        so3_pixel(p.so3_last, p.so3_next, (size_t)L.w, L.w, L.h, M[0], M[2], M[1], x, y, acc);
+        so3_pixel(p.so3_last, p.so3_next, (size_t)L.w, L.w, L.h, S.so3_imageBasis, S.so3_kinv, S.so3_krlr, x, y, acc);
+        work = true;
       }
-      float bt = block_reduce32(acc, red);
-      if (warp == 0) sc->partials[blockIdx.x * 32 + lane] = bt;
-      const int last_it = (it == 9);
-      grid_barrier(p.gs, epoch, [&] {
-        sum_partials(sc->partials, red, out32);
-        if (threadIdx.x == 0) {
-          so3_update_serial(g, out32, L.k);
-          if (g->so3_done || last_it) gn_begin_serial(g, 1, p.L[nsched ? sched[0] : 0].k);
-        }
-      });
+      float bt = block_reduce32_sparse(acc, __any_sync(0xffffffffu, work), red);
+      if (warp == 0) prow(0, it & 1)[blockIdx.x * 32 + lane] = bt;
+      grid_arrive(gs);
+      grid_wait(gs, ++barriers * G);
+      sum_partials<1>(prow(0, it & 1), G, red, out64);
+      if (threadIdx.x == 0) {
+        so3_update_serial(&S, out64, L.k);
+        if (S.so3_done || it == 9) gn_begin_serial(&S, 1, p.L[nsched ? sched[0] : 0].k);
+      }
+      __syncthreads();
     }
   }
 
@@ -221,9 +222,8 @@ __global__ void __launch_bounds__(kPT, 1) gn_persistent_kernel(const PersistPara
     const LevelData& L = p.L[sched[q]];
     const int N = L.w * L.h;
     const bool keep = (N <= nthreads * kMaxPP);  // correspondences stay in registers
-    for (int i = threadIdx.x; i < (int)(sizeof(IcpPose) / 4); i += kPT) ((float*)&P)[i] = __ldcg(((const float*)&g->pose) + i);
-    for (int i = threadIdx.x; i < (int)(sizeof(RgbWarp) / 4); i += kPT) ((float*)&Wp)[i] = __ldcg(((const float*)&g->warp) + i);
-    __syncthreads();
+    const IcpPose& P = S.pose;
+    const RgbWarp& Wp = S.warp;
 
     IcpArgs ia;
     const size_t pitch = (size_t)L.w * 4;
@@ -255,10 +255,7 @@ __global__ void __launch_bounds__(kPT, 1) gn_persistent_kernel(const PersistPara
     ra.cols = L.w;
     ra.rows = L.h;
 
-    // -------- pass 1
-    float acc[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    // -------- phase 1: photometric correspondences (count needed by every CTA before phase 3)
     int cnt = 0, sig = 0;
     unsigned kzero[kMaxPP];
     float kdiff[kMaxPP];
@@ -269,13 +266,11 @@ __global__ void __launch_bounds__(kPT, 1) gn_persistent_kernel(const PersistPara
         const int px = tid + k * nthreads;
         kzero[k] = 0;
         kdiff[k] = 0.f;
-        if (px < N) {
+        if (px < N && __ldg(L.cand + px)) {
           int y = px / L.w, x = px - y * L.w;
-          icp_pixel(ia, P, x, y, acc);
           DataTerm c;
-          c.valid = false;
           int sq;
-          if (__ldg(L.cand + px) && rgb_residual_cand(ra, Wp, x, y, c, sq)) {
+          if (rgb_residual_cand(ra, Wp, x, y, c, sq)) {
             cnt += 1;
             sig += sq;
             kvalid |= 1u << k;
@@ -287,7 +282,6 @@ __global__ void __launch_bounds__(kPT, 1) gn_persistent_kernel(const PersistPara
     } else {
       for (int px = tid; px < N; px += nthreads) {
         int y = px / L.w, x = px - y * L.w;
-        icp_pixel(ia, P, x, y, acc);
         DataTerm c;
         c.valid = false;
         c.zero = make_short2(0, 0);
@@ -299,7 +293,7 @@ __global__ void __launch_bounds__(kPT, 1) gn_persistent_kernel(const PersistPara
         }
         int4 raw;
         raw.x = (int)((unsigned short)c.zero.x | ((unsigned)(unsigned short)c.zero.y << 16));
-        raw.y = (int)((unsigned short)x | ((unsigned)(unsigned short)y << 16));
+        raw.y = 0;
         raw.z = __float_as_int(c.diff);
         raw.w = c.valid ? 1 : 0;
         reinterpret_cast<int4*>(L.corres)[px] = raw;
@@ -314,29 +308,39 @@ __global__ void __launch_bounds__(kPT, 1) gn_persistent_kernel(const PersistPara
       scnt[warp] = cnt;
       ssig[warp] = sig;
     }
-    DBG_MARK(8 + q * 8 + 1);
-    float bt = block_reduce32(acc, red);  // contains __syncthreads
-    if (warp == 0) sc->partials[blockIdx.x * 32 + lane] = bt;
+    __syncthreads();
     if (threadIdx.x == 0) {
       int c = 0, s = 0;
       for (int w = 0; w < kPT / 32; ++w) {
         c += scnt[w];
         s += ssig[w];
       }
-      atomicAdd(&sc->rgb_count, c);  // integer sums commute exactly
-      atomicAdd(&sc->rgb_sigma, s);
+      atomicAdd(&gs->counts[q][0], c);  // integer sums commute exactly
+      atomicAdd(&gs->counts[q][1], s);
     }
+    grid_arrive(gs);  // barrier A: its latency is hidden behind the ICP pass below
+    DBG_MARK(8 + q * 8 + 1);
+
+    // -------- phase 2: ICP rows (independent of the count)
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    bool work = false;
+    for (int px = tid; px < N; px += nthreads) {
+      int y = px / L.w, x = px - y * L.w;
+      icp_pixel(ia, P, x, y, acc);
+      work = true;
+    }
+    float bt = block_reduce32_sparse(acc, __any_sync(0xffffffffu, work), red);
+    if (warp == 0) prow(0, q & 1)[blockIdx.x * 32 + lane] = bt;
     DBG_MARK(8 + q * 8 + 2);
-    grid_barrier(p.gs, epoch, [&] {
-      sum_partials(sc->partials, red, out32);
-      if (threadIdx.x < 32) g->icp_result[threadIdx.x] = out32[threadIdx.x];
-    });
+    grid_wait(gs, ++barriers * G);
     DBG_MARK(8 + q * 8 + 3);
 
-    // -------- pass 2
+    // -------- phase 3: RGB rows weighted with the global count
     if (threadIdx.x == 0) {
-      scnt[0] = __ldcg(&sc->rgb_count);
-      ssig[0] = __ldcg(&sc->rgb_sigma);
+      scnt[0] = __ldcg(&gs->counts[q][0]);
+      ssig[0] = __ldcg(&gs->counts[q][1]);
     }
     __syncthreads();
     const int tot_cnt = scnt[0], tot_sig = ssig[0];
@@ -348,34 +352,44 @@ __global__ void __launch_bounds__(kPT, 1) gn_persistent_kernel(const PersistPara
 #pragma unroll
       for (int k = 0; k < kMaxPP; ++k) {
         const int px = tid + k * nthreads;
-        if (px < N) {
+        if (px < N && ((kvalid >> k) & 1u)) {
           int y = px / L.w, x = px - y * L.w;
-          rgb_step_from_depth(L, sigma, p.sobelScale, (kvalid >> k) & 1u, kzero[k], kdiff[k], x, y, acc);
+          rgb_step_from_depth(L, sigma, p.sobelScale, true, kzero[k], kdiff[k], x, y, acc);
         }
       }
     } else {
       for (int px = tid; px < N; px += nthreads) {
         int4 raw = reinterpret_cast<const int4*>(L.corres)[px];
-        int y = px / L.w, x = px - y * L.w;
-        rgb_step_from_depth(L, sigma, p.sobelScale, (raw.w & 0xff) != 0, (unsigned)raw.x, __int_as_float(raw.z), x, y,
-                            acc);
+        if (raw.w & 0xff) {
+          int y = px / L.w, x = px - y * L.w;
+          rgb_step_from_depth(L, sigma, p.sobelScale, true, (unsigned)raw.x, __int_as_float(raw.z), x, y, acc);
+        }
       }
     }
+    // invalid correspondences contribute nothing to any of the 29 sums (reduce.cu:562-601)
+    bt = block_reduce32_sparse(acc, __any_sync(0xffffffffu, kvalid != 0 || !keep), red);
+    if (warp == 0) prow(1, q & 1)[blockIdx.x * 32 + lane] = bt;
     DBG_MARK(8 + q * 8 + 4);
-    bt = block_reduce32(acc, red);
-    if (warp == 0) sc->partials[blockIdx.x * 32 + lane] = bt;
+    grid_arrive(gs);  // barrier B
+    grid_wait(gs, ++barriers * G);
     DBG_MARK(8 + q * 8 + 5);
+    sum_partials<2>(prow(0, q & 1), G, red, out64);
+    DBG_MARK(8 + q * 8 + 6);
     const int is_last = (q + 1 == nsched);
-    const LevelK k_next = p.L[is_last ? sched[q] : sched[q + 1]].k;
-    grid_barrier(p.gs, epoch, [&] {
-      if (p.dbg && threadIdx.x == 0) p.dbg[8 + q * 8 + 6] = gtime();
-      sum_partials(sc->partials, red, out32);
-      if (threadIdx.x == 0) {
-        if (p.dbg) p.dbg[8 + q * 8 + 7] = gtime();
-        gn_solve_serial(g, sc, out32, p.icpWeight, k_next, is_last, tmpError, tot_cnt);
-        if (p.dbg) p.dbg[200 + q] = gtime();
-      }
-    });
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) S.icp_result[i] = out64[i];
+      gn_solve_serial(&S, nullptr, out64 + 32, p.icpWeight, p.L[is_last ? sched[q] : sched[q + 1]].k, is_last, tmpError,
+                      tot_cnt);
+    }
+    __syncthreads();
+    DBG_MARK(8 + q * 8 + 7);
+  }
+  // ---- CTA 0 publishes pose + stats
+  if (blockIdx.x == 0) {
+    const float* src = (const float*)&S;
+    float* dst = (float*)p.g;
+    for (int i = threadIdx.x; i < (int)(sizeof(GNState) / 4); i += kPT) dst[i] = src[i];
   }
   DBG_MARK(3);
 }
@@ -391,9 +405,11 @@ struct PrepLevel {
 };
 struct PrepParams {
   PrepLevel L[3];
+  unsigned* grid_sync;  // GridSync of the persistent kernel launched next, zeroed here
 };
 __global__ void rgb_prepare_all_kernel(const PrepParams pp) {
   int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < (int)(sizeof(GridSync) / 4)) pp.grid_sync[q] = 0;
 #pragma unroll
   for (int l = 0; l < 3; ++l) {
     const PrepLevel& L = pp.L[l];
@@ -425,7 +441,7 @@ cudaError_t RGBDOdometry::enqueuePersistent(float icpWeight, bool pyramid, bool 
   for (int i = 0; i < NUM_PYRS; ++i) {
     const int w = width >> i, h = height >> i;
     const Intr k = intr.level(i);
-    pp.L[i] = PrepLevel{nextImage[i], nextDepth[i], nextdIdx[i], nextdIdy[i], rgbCand[i], w, h,
+    pp.L[i] = PrepLevel{nextImage[i], (next_is_last_ ? lastDepth[i] : nextDepth[i]), nextdIdx[i], nextdIdy[i], rgbCand[i], w, h,
                         (float)(pow(minimumGradientMagnitudes[i], 2.0) / pow(sobelScale, 2.0))};
     total += w * h;
     LevelData& L = p.L[i];
@@ -434,7 +450,7 @@ cudaError_t RGBDOdometry::enqueuePersistent(float icpWeight, bool pyramid, bool 
     L.vmap_g_prev = vmaps_g_prev_[i];
     L.nmap_g_prev = nmaps_g_prev_[i];
     L.lastDepth = lastDepth[i];
-    L.nextDepth = nextDepth[i];
+    L.nextDepth = (next_is_last_ ? lastDepth[i] : nextDepth[i]);
     L.lastImage = lastImage[i];
     L.nextImage = nextImage[i];
     L.dIdx = nextdIdx[i];
@@ -445,6 +461,7 @@ cudaError_t RGBDOdometry::enqueuePersistent(float icpWeight, bool pyramid, bool 
     L.h = h;
     L.k = LevelK{k.fx, k.fy, k.cx, k.cy};
   }
+  pp.grid_sync = (unsigned*)grid_sync_;
   rgb_prepare_all_kernel<<<(total + 255) / 256, 256, 0, s>>>(pp);
   p.so3_last = lastNextImage[2];
   p.so3_next = nextImage[2];

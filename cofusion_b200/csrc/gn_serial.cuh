@@ -46,8 +46,10 @@ __device__ __forceinline__ void gn_init_serial(GNState* g, StepScratch* sc, cons
   TrackStats z = {};
   g->stats = z;
   so3_matrices(g, k_so3);
-  sc->rgb_count = 0;
-  sc->rgb_sigma = 0;
+  if (sc) {
+    sc->rgb_count = 0;
+    sc->rgb_sigma = 0;
+  }
 }
 
 // host logic of one SO(3) iteration after the reduction (RGBDOdometry.cpp:281-308); sets so3_done
@@ -201,8 +203,10 @@ __device__ __forceinline__ void gn_solve_serial(GNState* g, StepScratch* sc, con
   for (int q = 0; q < 9; ++q) g->pose.Rcurr.m[q] = Rcurr[q];
 #pragma unroll
   for (int q = 0; q < 3; ++q) g->pose.tcurr[q] = tcurr[q];
-  sc->rgb_count = 0;
-  sc->rgb_sigma = 0;
+  if (sc) {
+    sc->rgb_count = 0;
+    sc->rgb_sigma = 0;
+  }
   if (!is_last) {
     double K[9], Kinv[9];
     float krk[9], kt[3];

@@ -279,6 +279,162 @@ __global__ void project_points_kernel(const float* __restrict__ depth, size_t dp
   c[2] = z;
 }
 
+// ================================================================================================
+// Fused pyramid builders used by Model::performTracking (identical arithmetic and operation order
+// as the one-function-per-launch versions above; 28 launches per tracked frame become 10).
+
+// copyMaps + resizeVMap/NMap x2 + tranformMaps x3 + verticesToDepth (RGBDOdometry.cpp:143-175,:179):
+// one thread per level-2 pixel = 4x4 level-0 block.
+struct ModelPyrOut {
+  float *v[3], *n[3];  // planar, unpitched
+  float* depth0;       // lastDepth level 0
+};
+__global__ void model_pyramid_kernel(const float4* __restrict__ v4, const float4* __restrict__ n4, int W, int H,
+                                     Mat33 R, float3 t, float cutoffRGB, ModelPyrOut o) {
+  const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y * blockDim.y + threadIdx.y;
+  const int W2 = W / 4, H2 = H / 4, W1 = W / 2, H1 = H / 2;
+  if (X >= W2 || Y >= H2) return;
+  const float q = qnan();
+  float3 v0[4][4], n0[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int x = 4 * X + i, y = 4 * Y + j;
+      const float4 vs = __ldg(&v4[y * W + x]), ns = __ldg(&n4[y * W + x]);
+      const bool ok = !(vs.z == 0);
+      v0[j][i] = ok ? make_float3(vs.x, vs.y, vs.z) : make_float3(q, q, q);
+      n0[j][i] = ok ? make_float3(ns.x, ns.y, ns.z) : make_float3(q, q, q);
+      o.depth0[y * W + x] = (vs.z > cutoffRGB || vs.z <= 0) ? q : vs.z;
+    }
+  float3 v1[2][2], n1[2][2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float3 a = v0[2 * j][2 * i], b = v0[2 * j][2 * i + 1], c = v0[2 * j + 1][2 * i], d = v0[2 * j + 1][2 * i + 1];
+      v1[j][i] = (isnan(a.x) || isnan(b.x) || isnan(c.x) || isnan(d.x))
+                     ? make_float3(q, q, q)
+                     : make_float3((a.x + b.x + c.x + d.x) / 4, (a.y + b.y + c.y + d.y) / 4, (a.z + b.z + c.z + d.z) / 4);
+      const float3 e = n0[2 * j][2 * i], f = n0[2 * j][2 * i + 1], g = n0[2 * j + 1][2 * i], h = n0[2 * j + 1][2 * i + 1];
+      n1[j][i] = (isnan(e.x) || isnan(f.x) || isnan(g.x) || isnan(h.x))
+                     ? make_float3(q, q, q)
+                     : normalized(make_float3((e.x + f.x + g.x + h.x) / 4, (e.y + f.y + g.y + h.y) / 4,
+                                              (e.z + f.z + g.z + h.z) / 4));
+    }
+  float3 v2, n2;
+  {
+    const float3 a = v1[0][0], b = v1[0][1], c = v1[1][0], d = v1[1][1];
+    v2 = (isnan(a.x) || isnan(b.x) || isnan(c.x) || isnan(d.x))
+             ? make_float3(q, q, q)
+             : make_float3((a.x + b.x + c.x + d.x) / 4, (a.y + b.y + c.y + d.y) / 4, (a.z + b.z + c.z + d.z) / 4);
+    const float3 e = n1[0][0], f = n1[0][1], g = n1[1][0], h = n1[1][1];
+    n2 = (isnan(e.x) || isnan(f.x) || isnan(g.x) || isnan(h.x))
+             ? make_float3(q, q, q)
+             : normalized(make_float3((e.x + f.x + g.x + h.x) / 4, (e.y + f.y + g.y + h.y) / 4, (e.z + f.z + g.z + h.z) / 4));
+  }
+  auto put = [&](float* vp, float* np, int w, int h, int x, int y, float3 v, float3 n) {
+    float3 vd = make_float3(q, q, q), nd = vd;
+    if (!isnan(v.x)) vd = mul(R, v) + t;
+    if (!isnan(n.x)) nd = mul(R, n);
+    vp[y * w + x] = vd.x;
+    vp[(y + h) * w + x] = vd.y;
+    vp[(y + 2 * h) * w + x] = vd.z;
+    np[y * w + x] = nd.x;
+    np[(y + h) * w + x] = nd.y;
+    np[(y + 2 * h) * w + x] = nd.z;
+  };
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) put(o.v[0], o.n[0], W, H, 4 * X + i, 4 * Y + j, v0[j][i], n0[j][i]);
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) put(o.v[1], o.n[1], W1, H1, 2 * X + i, 2 * Y + j, v1[j][i], n1[j][i]);
+  put(o.v[2], o.n[2], W2, H2, X, Y, v2, n2);
+}
+
+// createVMap + createNMap for the three levels in one launch (RGBDOdometry.cpp:110-118)
+struct FrameMapsArgs {
+  const float* depth[3];
+  float *v[3], *n[3];
+  int w[3], h[3];
+  float fx_inv[3], fy_inv[3], cx[3], cy[3];
+  float cutoff;
+};
+__global__ void frame_maps_kernel(const FrameMapsArgs a) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+    const int w = a.w[l], h = a.h[l], n = w * h;
+    if (p < n) {
+      const int v = p / w, u = p - v * w;
+      const float* D = a.depth[l];
+      const float fxi = a.fx_inv[l], fyi = a.fy_inv[l], cx = a.cx[l], cy = a.cy[l];
+      const float q = qnan();
+      auto vert = [&](int uu, int vv, bool& ok) {
+        const float z = __ldg(D + vv * w + uu);
+        ok = (z != 0 && z < a.cutoff);
+        return make_float3(z * ((float)uu - cx) * fxi, z * ((float)vv - cy) * fyi, z);
+      };
+      bool ok00, ok01 = false, ok10 = false;
+      const float3 v00 = vert(u, v, ok00);
+      float* V = a.v[l];
+      V[v * w + u] = ok00 ? v00.x : q;
+      V[(v + h) * w + u] = ok00 ? v00.y : q;
+      V[(v + 2 * h) * w + u] = ok00 ? v00.z : q;
+      float3 r = make_float3(q, q, q);
+      if (!(u == w - 1 || v == h - 1)) {
+        const float3 v01 = vert(u + 1, v, ok01), v10 = vert(u, v + 1, ok10);
+        if (ok00 && ok01 && ok10) r = normalized(cross(v01 - v00, v10 - v00));
+      }
+      float* N = a.n[l];
+      N[v * w + u] = r.x;
+      N[(v + h) * w + u] = r.y;
+      N[(v + 2 * h) * w + u] = r.z;
+      return;
+    }
+    p -= n;
+  }
+}
+
+// imageBGRToIntensity for two images (model prediction RGBA8, frame RGB8) in one launch
+__global__ void intensity2_kernel(const unsigned char* __restrict__ a, int cha, unsigned char* __restrict__ da,
+                                  const unsigned char* __restrict__ b, int chb, unsigned char* __restrict__ db, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned char* p = blockIdx.y ? (b + (size_t)i * chb) : (a + (size_t)i * cha);
+  const float s = __fmaf_rn((float)p[2], 0.587f, __fmaf_rn((float)p[1], 0.299f, __fmul_rn((float)p[0], 0.114f)));
+  (blockIdx.y ? db : da)[i] = (unsigned char)(int)s;
+}
+// pyrDownUcharGauss for two images in one launch
+__global__ void pyr_down_uchar2_kernel(const unsigned char* __restrict__ sa, unsigned char* __restrict__ da,
+                                       const unsigned char* __restrict__ sb, unsigned char* __restrict__ db, int sw,
+                                       int sh) {
+  const int dw = sw / 2, dh = sh / 2;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= dw || y >= dh) return;
+  const unsigned char* src = blockIdx.z ? sb : sa;
+  unsigned char* dst = blockIdx.z ? db : da;
+  const int D = 5;
+  const int tx = min(2 * x - D / 2 + D, sw - 1), ty = min(2 * y - D / 2 + D, sh - 1);
+  float sum = 0.f;
+  int count = 0;
+  for (int cy = max(0, 2 * y - D / 2); cy < ty; ++cy)
+    for (int cx = max(0, 2 * x - D / 2); cx < tx; ++cx) {
+      const unsigned char s = __ldg(src + cy * sw + cx);
+      if (s > 0) {
+        const float w = c_gauss25[(ty - cy - 1) * 5 + (tx - cx - 1)];
+        sum += (float)s * w;
+        count = (int)((float)count + w);
+      }
+    }
+  const float qv = sum / (float)count;
+  const int v = isnan(qv) ? 0 : (int)qv;
+  dst[y * dw + x] = (unsigned char)min(max(v, 0), 255);
+}
+
 }  // namespace
 
 cudaError_t launch_bilateral(const float* depth, size_t dpitch, int W, int H, float maxD, float* out,
@@ -351,6 +507,54 @@ cudaError_t launch_project_to_point_cloud(const float* depth, size_t dpitch, int
                                           size_t cpitch, cudaStream_t s) {
   project_points_kernel<<<grid2d(W, H, kBlock), kBlock, 0, s>>>(depth, dpitch, W, H, 1.0f / k.fx, 1.0f / k.fy, k.cx,
                                                                 k.cy, cloud, cpitch);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_model_pyramid(const float* v4, const float* n4, int W, int H, const Mat33& R, const float t[3],
+                                 float cutoffRGB, float* const v[3], float* const n[3], float* depth0,
+                                 cudaStream_t s) {
+  ModelPyrOut o;
+  for (int i = 0; i < 3; ++i) {
+    o.v[i] = v[i];
+    o.n[i] = n[i];
+  }
+  o.depth0 = depth0;
+  const dim3 b(32, 4);
+  model_pyramid_kernel<<<grid2d(W / 4, H / 4, b), b, 0, s>>>((const float4*)v4, (const float4*)n4, W, H, R,
+                                                            make_float3(t[0], t[1], t[2]), cutoffRGB, o);
+  return cudaGetLastError();
+}
+cudaError_t launch_frame_maps(const float* const depth[3], int W, int H, Intr K, float cutoff, float* const v[3],
+                              float* const n[3], cudaStream_t s) {
+  FrameMapsArgs a;
+  int total = 0;
+  for (int l = 0; l < 3; ++l) {
+    const Intr k = K.level(l);
+    a.depth[l] = depth[l];
+    a.v[l] = v[l];
+    a.n[l] = n[l];
+    a.w[l] = W >> l;
+    a.h[l] = H >> l;
+    a.fx_inv[l] = 1.f / k.fx;
+    a.fy_inv[l] = 1.f / k.fy;
+    a.cx[l] = k.cx;
+    a.cy[l] = k.cy;
+    total += a.w[l] * a.h[l];
+  }
+  a.cutoff = cutoff;
+  frame_maps_kernel<<<(total + 255) / 256, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_intensity2(const unsigned char* a, int cha, unsigned char* da, const unsigned char* b, int chb,
+                              unsigned char* db, int n, cudaStream_t s) {
+  intensity2_kernel<<<dim3((n + 255) / 256, 2), 256, 0, s>>>(a, cha, da, b, chb, db, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_pyr_down_uchar2(const unsigned char* sa, unsigned char* da, const unsigned char* sb,
+                                   unsigned char* db, int sw, int sh, cudaStream_t s) {
+  dim3 g = grid2d(sw / 2, sh / 2, kBlock);
+  g.z = 2;
+  pyr_down_uchar2_kernel<<<g, kBlock, 0, s>>>(sa, da, sb, db, sw, sh);
   return cudaGetLastError();
 }
 

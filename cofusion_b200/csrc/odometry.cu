@@ -46,7 +46,7 @@ RGBDOdometry::RGBDOdometry(int w, int h, float cx, float cy, float fx, float fy,
   }
   good = good && dalloc(&vmaps_tmp, (size_t)w * h * 4) && dalloc(&scratch, 1) && dalloc(&gn, 1) &&
          dalloc(&d_pose, 1) && dalloc(&d_warp, 1) && dalloc(&d_pose_in, 16) &&
-         dalloc((unsigned**)&grid_sync_, 64);
+         dalloc((unsigned**)&grid_sync_, 256);
   good = good && cudaMallocHost(&h_pinned, 4096) == cudaSuccess;
   ok_ = good;
 }
@@ -89,7 +89,7 @@ const void* RGBDOdometry::view(int which, int level, size_t* pitch) const {
     case 2: *pitch = w * 4; return vmaps_g_prev_[level];
     case 3: *pitch = w * 4; return nmaps_g_prev_[level];
     case 4: *pitch = w * 4; return lastDepth[level];
-    case 5: *pitch = w * 4; return nextDepth[level];
+    case 5: *pitch = w * 4; return next_is_last_ ? lastDepth[level] : nextDepth[level];
     case 6: *pitch = w; return lastImage[level];
     case 7: *pitch = w; return nextImage[level];
     case 8: *pitch = w * 2; return nextdIdx[level];
@@ -160,6 +160,7 @@ cudaError_t RGBDOdometry::initRGBModel(const unsigned char* img, size_t pitch, i
   return populateRGBDData(img, pitch, channels, lastDepth, lastImage, s);
 }
 cudaError_t RGBDOdometry::initRGB(const unsigned char* img, size_t pitch, int channels, cudaStream_t s) {
+  next_is_last_ = false;
   return populateRGBDData(img, pitch, channels, nextDepth, nextImage, s);
 }
 cudaError_t RGBDOdometry::initFirstRGB(const unsigned char* img, size_t pitch, int channels, cudaStream_t s) {
@@ -168,6 +169,34 @@ cudaError_t RGBDOdometry::initFirstRGB(const unsigned char* img, size_t pitch, i
     int sw = width >> i, sh = height >> i;
     RET_IF(launch_pyr_down_uchar(lastNextImage[i], (size_t)sw, sw, sh, lastNextImage[i + 1], (size_t)(sw / 2), s));
   }
+  return cudaSuccess;
+}
+
+cudaError_t RGBDOdometry::initAll(const float* v4, const float* n4, const unsigned char* modelImg, int modelCh,
+                                  const float* const depthPyr[NUM_PYRS], const unsigned char* frameImg, int frameCh,
+                                  float depthCutoff, const float pose[16], cudaStream_t s) {
+  if ((width % 4) || (height % 4)) return cudaErrorInvalidValue;
+  Mat33 R;
+  float t[3];
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) R.m[r * 3 + c] = pose[r * 4 + c];
+    t[r] = pose[r * 4 + 3];
+  }
+  // model side: global-frame vertex/normal pyramid + lastDepth level 0
+  RET_IF(launch_model_pyramid(v4, n4, width, height, R, t, maxDepthRGB, vmaps_g_prev_, nmaps_g_prev_, lastDepth[0], s));
+  for (int i = 0; i + 1 < NUM_PYRS; i++) {
+    int sw = width >> i, sh = height >> i;
+    RET_IF(launch_pyr_down_gauss_f(lastDepth[i], (size_t)sw * 4, sw, sh, lastDepth[i + 1], (size_t)(sw / 2) * 4, s));
+  }
+  // quirk kept: initRGB derives nextDepth from the same model prediction (vmaps_tmp) -> it IS
+  // lastDepth; the device loop reads lastDepth for both instead of building a second copy
+  next_is_last_ = true;
+  // frame side
+  RET_IF(launch_frame_maps(depthPyr, width, height, intr, depthCutoff, vmaps_curr_, nmaps_curr_, s));
+  RET_IF(launch_intensity2(modelImg, modelCh, lastImage[0], frameImg, frameCh, nextImage[0], width * height, s));
+  for (int i = 0; i + 1 < NUM_PYRS; i++)
+    RET_IF(launch_pyr_down_uchar2(lastImage[i], lastImage[i + 1], nextImage[i], nextImage[i + 1], width >> i,
+                                  height >> i, s));
   return cudaSuccess;
 }
 
@@ -301,7 +330,7 @@ cudaError_t RGBDOdometry::hostLoop(float trans[3], float rot[9], bool rgbOnly, f
         a.dIdy = nextdIdy[i];
         a.grad_pitch = (size_t)w * 2;
         a.lastDepth = lastDepth[i];
-        a.nextDepth = nextDepth[i];
+        a.nextDepth = next_is_last_ ? lastDepth[i] : nextDepth[i];
         a.depth_pitch = (size_t)w * 4;
         a.lastImage = lastImage[i];
         a.nextImage = nextImage[i];

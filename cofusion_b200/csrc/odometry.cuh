@@ -62,6 +62,12 @@ class RGBDOdometry {
   cudaError_t initRGBModel(const unsigned char* img, size_t pitch, int channels, cudaStream_t s);
   cudaError_t initRGB(const unsigned char* img, size_t pitch, int channels, cudaStream_t s);
   cudaError_t initFirstRGB(const unsigned char* img, size_t pitch, int channels, cudaStream_t s);
+  // initICPModel + initRGBModel + initICP + initRGB in 7 launches instead of 26 (identical results;
+  // exploits that both RGB inits read the same model depth, RGBDOdometry.cpp:179,:196-204).
+  // modelImg: RGBA8/RGB8 prediction image, frameImg: RGB8 frame; depthPyr: unpitched levels.
+  cudaError_t initAll(const float* v4, const float* n4, const unsigned char* modelImg, int modelCh,
+                      const float* const depthPyr[NUM_PYRS], const unsigned char* frameImg, int frameCh,
+                      float depthCutoff, const float pose[16], cudaStream_t s);
 
   // RGBDOdometry.cpp:217-477. trans[3], rot[9] (row-major) in/out on the host.
   // icp_error_map: optional device f32 W*H (pitch bytes) written on the last level-0 iteration.
@@ -127,6 +133,7 @@ class RGBDOdometry {
   bool ev_pending_ = false;
   double kernel_ms_sum_ = 0;
   int kernel_launches_ = 0;
+  bool next_is_last_ = false;  // initAll(): nextDepth pyramid aliases lastDepth (reference quirk)
   int mode_ = 0;               // 0: one persistent cooperative kernel, 1: per-step kernels (+ CUDA graph)
 
  public:

@@ -354,13 +354,9 @@ cudaError_t Model::performTracking(const TrackParams& tp) {
       RET_IF(cudaMemcpyAsync(predImage, splat.image, n * 4, cudaMemcpyDeviceToDevice, s));
     }
   }
-  // Model::initICP (Model.cpp:350-367); WARNING initICP* must be called before initRGB*
-  RET_IF(odom.initICPModel(predVertex, predNormal, tp.maxDepthProcessed, pose, s));
-  RET_IF(odom.initRGBModel(predImage, (size_t)ctx->W * 4, 4, s));
+  // Model::initICP (Model.cpp:350-367): model pyramids first, then the frame's (fused launches)
   const float* pyr[3] = {ctx->depthPyr[0], ctx->depthPyr[1], ctx->depthPyr[2]};
-  const size_t pitch[3] = {(size_t)ctx->W * 4, (size_t)(ctx->W / 2) * 4, (size_t)(ctx->W / 4) * 4};
-  RET_IF(odom.initICP(pyr, pitch, tp.maxDepthProcessed, s));
-  RET_IF(odom.initRGB(ctx->rgb, (size_t)ctx->W * 3, 3, s));
+  RET_IF(odom.initAll(predVertex, predNormal, predImage, 4, pyr, ctx->rgb, 3, tp.maxDepthProcessed, pose, s));
   float trans[3] = {pose[3], pose[7], pose[11]};
   float rot[9] = {pose[0], pose[1], pose[2], pose[4], pose[5], pose[6], pose[8], pose[9], pose[10]};
   RET_IF(odom.getIncrementalTransformation(trans, rot, tp.rgbOnly != 0, tp.icpWeight, tp.pyramid != 0,
@@ -372,7 +368,7 @@ cudaError_t Model::performTracking(const TrackParams& tp) {
   }
   // the tracker synchronised the stream: the counters copied after the last clean are exact now
   if (h_counters->count && h_counters->count < count_ub) count_ub = h_counters->count;
-  ctx->launches += 28;  // 8 model pyramid + 6 + 6 RGB-D pyramids + 6 frame maps + prepare + persistent GN
+  ctx->launches += 9;  // model pyramid, 2 depth levels, frame maps, grey, 2 grey levels, prepare, persistent GN
   return cudaSuccess;
 }
 

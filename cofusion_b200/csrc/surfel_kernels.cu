@@ -460,13 +460,13 @@ __global__ void clean_evaluate_kernel(SurfelGeom g, Surfel* __restrict__ src, Su
         const uint32_t current = __ldg(idx.index + sp);
         if (current > 0U) {
           const float4 vc = __ldg(idx.vertConf + sp);
-          const float4 ct = __ldg(idx.colorTime + sp);
-          const float ddx = vc.x - lp.x, ddy = vc.y - lp.y;
-          if (ct.z < s.col.z && vc.w > confThreshold && vc.z > lp.z && vc.z - lp.z < 0.01f &&
-              sqrtf(ddx * ddx + ddy * ddy) < s.nrm.w * 1.4f)
-            count_++;
-          if (ct.w == ftime && vc.w > confThreshold && vc.z > lp.z && vc.z - lp.z > 0.01f && fabsf(ln.z) > 0.85f)
-            zCount++;
+          // both counters need a confident map surfel BEHIND this one: only then fetch colour/time
+          if (vc.w > confThreshold && vc.z > lp.z) {
+            const float4 ct = __ldg(idx.colorTime + sp);
+            const float ddx = vc.x - lp.x, ddy = vc.y - lp.y;
+            if (ct.z < s.col.z && vc.z - lp.z < 0.01f && sqrtf(ddx * ddx + ddy * ddy) < s.nrm.w * 1.4f) count_++;
+            if (ct.w == ftime && vc.z - lp.z > 0.01f && fabsf(ln.z) > 0.85f) zCount++;
+          }
         }
       }
     for (float si = x_n - stepX; si <= x_n + stepX; si += stepX)

@@ -254,6 +254,8 @@ typedef struct cfb_cofusion_params { /* CoFusion ctor args / setters (CoFusion.h
   float confObjectInit;     /* 0.01 */
   float outlierCoefficient; /* 3 */
   unsigned maxSurfels;      /* per model (reference: 3072^2) */
+  int predictBeforeFuse;    /* 0: skip the predict() of CoFusion.cpp:347 (its images are overwritten by
+                               the final predict() before anything reads them when segmentation is off) */
 } cfb_cofusion_params;
 void cfb_cofusion_default_params(cfb_cofusion_params* p);
 int cfb_cofusion_create(int device, int W, int H, float fx, float fy, float cx, float cy,

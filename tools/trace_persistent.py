@@ -18,6 +18,7 @@ t0 = t[0]
 print("barrier0 %.1f us, so3 %.1f us, gn %.1f us" % ((t[1]-t[0])/1e3, (t[2]-t[1])/1e3, (t[3]-t[2])/1e3))
 for q in range(19):
     b = 8 + q * 8
-    print("it %2d: pass1 %.1f  reduce %.1f  barA %.1f  pass2 %.1f reduce %.1f  barB %.1f (fin-start@%.1f sum %.1f solve %.1f)" % (
+    nxt = t[b + 8] if q < 18 else t[3]
+    print("it %2d: residual+arrive %.1f  icp+reduce %.1f  waitA %.1f  rgbstep+reduce %.1f  barrierB %.1f  sum %.1f  solve %.1f  | total %.1f" % (
         q, (t[b+1]-t[b])/1e3, (t[b+2]-t[b+1])/1e3, (t[b+3]-t[b+2])/1e3, (t[b+4]-t[b+3])/1e3, (t[b+5]-t[b+4])/1e3,
-        ((t[b+8] if q < 18 else t[3]) - t[b+5])/1e3, (t[b+6]-t[b+5])/1e3, (t[b+7]-t[b+6])/1e3, (t[200+q]-t[b+7])/1e3))
+        (t[b+6]-t[b+5])/1e3, (t[b+7]-t[b+6])/1e3, (nxt-t[b])/1e3))
