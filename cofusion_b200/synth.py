@@ -133,10 +133,14 @@ def room_sequence(n_frames=200, W=640, H=480, K=K_DEFAULT, noise=True, seed=1234
     rng = np.random.default_rng(seed) if noise else None
     brng = np.random.default_rng(seed + 1)
     specs = []
+    # boxes start inside the first camera's field of view (1.2-1.9 m in front of it) and drift on
+    # constant-velocity trajectories of 5-20 mm/frame
+    R0 = rot_y(np.pi / 2 + 0.6) @ rot_x(-0.4)
+    t0 = np.array([radius, 0.0, 0.0])
     for b in range(n_boxes):
-        ang = 2 * np.pi * b / max(n_boxes, 1) + 0.3
-        c0 = np.array([1.3 * np.cos(ang), 0.4 * np.sin(2 * ang), 1.1 * np.sin(ang)])
-        hs = brng.uniform(0.15, 0.25, size=3)
+        off = np.array([0.55 * np.cos(2.4 * b + 0.4), 0.32 * np.sin(1.7 * b + 0.9), 1.25 + 0.16 * (b % 4)])
+        c0 = t0 + R0 @ off
+        hs = brng.uniform(0.10, 0.18, size=3)
         vel = brng.uniform(-1, 1, size=3)
         vel = vel / np.linalg.norm(vel) * brng.uniform(0.005, 0.02)
         w = brng.uniform(-0.01, 0.01)

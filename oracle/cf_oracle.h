@@ -168,6 +168,35 @@ void orc_map_fill_in(OrcSurfelMap* m, const uint8_t* rgb, const float* depthFilt
 /* CoFusion::requiresFillIn (CoFusion.cpp:547-565) */
 int orc_map_requires_fill_in(const OrcSurfelMap* m, float ratio);
 
+/* ---------------------------------------------------------------- segmentation (oracle/segment.c)
+ * Restatement of Segmentation::performSegmentationCRF + Slic + ConnectedLabels (Core/Segmentation).
+ * PARITY UNPINNED: gSLICr and densecrf are un-vendored and unpinned; see the header of segment.c for
+ * the published algorithms restated and the frozen choice (exact Gaussian kernels). */
+typedef struct { /* Segmentation.h:123-142 with the GUI defaults of GUI/Tools/GUI.h:212-227 */
+  int crfIterations;
+  float scaleFeaturesRGB, scaleFeaturesDepth, scaleFeaturesPos;
+  float weightAppearance, weightSmoothness;
+  float unaryThresholdNew, unaryKError, unaryWeightError;
+  float maxRelSizeNew, minRelSizeNew;
+} OrcSegParams;
+typedef struct { /* SegmentationResult::ModelData (Segmentation.h:41-67) */
+  unsigned id;
+  unsigned superPixelCount;
+  float avgConfidence, depthMean, depthStd;
+  unsigned short top, right, bottom, left;
+} OrcModelData;
+void orc_seg_default_params(OrcSegParams* p);
+/* gSLICr restatement: labels[H*W] in [0, ceil(W/s)*ceil(H/s)) */
+void orc_slic(const uint8_t* rgb, int W, int H, int spixel_size, int no_iters, float coh_weight, int* labels);
+/* performSegmentationCRF.  icpError[m]: HxW f32 (Model::icpError), vertConf4[m]: HxW float4 splat
+ * vertex+confidence (only .w is read, Segmentation.cpp:187).  md must hold numModels+1 entries.
+ * Returns the number of valid md entries; fullSeg (HxW u8) receives model ids / 255.
+ * Optional outputs (may be NULL): slicLabels (H*W int), unary (N*numLabels, node major), lowMap (N). */
+int orc_segment_crf(const uint8_t* rgb, const float* depth, int W, int H, int numModels, const unsigned char* modelIds,
+                    const float* const* icpError, const float* const* vertConf4, unsigned char nextModelID,
+                    int allowNew, const OrcSegParams* prm, uint8_t* fullSeg, OrcModelData* md, int* hasNewLabel,
+                    int* slicLabelsOut, float* unaryOut, uint8_t* lowMapOut);
+
 #ifdef __cplusplus
 }
 #endif

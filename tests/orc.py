@@ -369,3 +369,56 @@ class OrcMap:
         buf = (C.c_char * (n * np.dtype(dt).itemsize)).from_address(ptr)
         a = np.frombuffer(buf, dtype=dt).copy()
         return a.reshape(self.H, self.W, ch) if ch > 1 else a.reshape(self.H, self.W)
+
+
+# ---------------------------------------------------------------- segmentation restatement
+class OrcSegParams(C.Structure):
+    _fields_ = [("crfIterations", C.c_int), ("scaleFeaturesRGB", C.c_float), ("scaleFeaturesDepth", C.c_float),
+                ("scaleFeaturesPos", C.c_float), ("weightAppearance", C.c_float), ("weightSmoothness", C.c_float),
+                ("unaryThresholdNew", C.c_float), ("unaryKError", C.c_float), ("unaryWeightError", C.c_float),
+                ("maxRelSizeNew", C.c_float), ("minRelSizeNew", C.c_float)]
+
+    @staticmethod
+    def default():
+        p = OrcSegParams()
+        orc().orc_seg_default_params(C.byref(p))
+        return p
+
+
+class OrcModelData(C.Structure):
+    _fields_ = [("id", C.c_uint), ("superPixelCount", C.c_uint), ("avgConfidence", C.c_float),
+                ("depthMean", C.c_float), ("depthStd", C.c_float), ("top", C.c_ushort), ("right", C.c_ushort),
+                ("bottom", C.c_ushort), ("left", C.c_ushort)]
+
+
+def slic(rgb, spixel=16, iters=5, coh=0.6):
+    H, W = rgb.shape[:2]
+    lab = np.zeros((H, W), np.int32)
+    orc().orc_slic(P(np.ascontiguousarray(rgb, np.uint8)), W, H, spixel, iters, cf(coh), P(lab))
+    return lab
+
+
+def segment_crf(rgb, depth, model_ids, icp_errors, vert_confs, next_id, allow_new, params=None):
+    """returns fullSeg (HxW u8), list of ModelData dicts, hasNew, slic labels, unary (N x L), low map"""
+    H, W = depth.shape
+    n = len(model_ids)
+    prm = params or OrcSegParams.default()
+    N = (W // 16) * (H // 16)
+    L = n + (1 if allow_new else 0)
+    icp = [f32(a) for a in icp_errors]
+    vc = [f32(a) for a in vert_confs]
+    icp_p = (C.c_void_p * n)(*[a.ctypes.data for a in icp])
+    vc_p = (C.c_void_p * n)(*[a.ctypes.data for a in vc])
+    ids = np.ascontiguousarray(model_ids, np.uint8)
+    seg = np.zeros((H, W), np.uint8)
+    md = (OrcModelData * (n + 1))()
+    has_new = C.c_int(0)
+    lab = np.zeros((H, W), np.int32)
+    unary = np.zeros((N, L), np.float32)
+    low = np.zeros(N, np.uint8)
+    cnt = orc().orc_segment_crf(P(np.ascontiguousarray(rgb, np.uint8)), P(f32(depth)), W, H, n, P(ids), icp_p, vc_p,
+                                int(next_id), int(allow_new), C.byref(prm), P(seg), md, C.byref(has_new), P(lab),
+                                P(unary), P(low))
+    mds = [dict(id=m.id, superPixelCount=m.superPixelCount, avgConfidence=m.avgConfidence, depthMean=m.depthMean,
+                depthStd=m.depthStd, top=m.top, right=m.right, bottom=m.bottom, left=m.left) for m in md[:cnt]]
+    return seg, mds, bool(has_new.value), lab, unary, low.reshape(H // 16, W // 16)
