@@ -324,12 +324,95 @@ class Model:
         return out
 
 
+class SegParams(C.Structure):  # cfb_seg_params
+    _fields_ = [("crfIterations", C.c_int), ("scaleFeaturesRGB", C.c_float), ("scaleFeaturesDepth", C.c_float),
+                ("scaleFeaturesPos", C.c_float), ("weightAppearance", C.c_float), ("weightSmoothness", C.c_float),
+                ("unaryThresholdNew", C.c_float), ("unaryKError", C.c_float), ("unaryWeightError", C.c_float),
+                ("maxRelSizeNew", C.c_float), ("minRelSizeNew", C.c_float)]
+
+    @staticmethod
+    def default():
+        p = SegParams()
+        lib().cfb_seg_default_params(C.byref(p))
+        return p
+
+
+class ModelData(C.Structure):  # cfb_model_data
+    _fields_ = [("id", C.c_uint), ("superPixelCount", C.c_uint), ("avgConfidence", C.c_float),
+                ("depthMean", C.c_float), ("depthStd", C.c_float), ("top", C.c_ushort), ("right", C.c_ushort),
+                ("bottom", C.c_ushort), ("left", C.c_ushort)]
+
+    def astuple(self):
+        return (self.id, self.superPixelCount, self.avgConfidence, self.depthMean, self.depthStd, self.top,
+                self.right, self.bottom, self.left)
+
+
+SEG_MAX_MODELS = 15
+
+
+class Segmentation:
+    """cfb_segmentation_*: Segmentation::performSegmentationCRF on device buffers (torch CUDA tensors)."""
+
+    def __init__(self, W, H, device=0, _borrowed=None):
+        self.W, self.H, self.N = W, H, (W // 16) * (H // 16)
+        self._owned = _borrowed is None
+        self._h = C.c_void_p()
+        if _borrowed is None:
+            check(lib().cfb_segmentation_create(device, W, H, C.byref(self._h)))
+        else:
+            self._h = _borrowed
+        self.num_labels = 0
+        self.num_models = 0
+
+    def __del__(self):
+        if getattr(self, "_owned", False) and self._h.value and _lib is not None:
+            _lib.cfb_segmentation_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def slic(self, rgb):
+        check(lib().cfb_segmentation_slic(self._h, _p(rgb), _stream()))
+        return self.view(0)
+
+    def perform_crf(self, rgb, depth, model_ids, icp_errors, vert_confs, next_model_id, allow_new, params=None):
+        """All image arguments are CUDA tensors.  Returns (fullSeg u8 HxW tensor, [ModelData], hasNew)."""
+        import torch
+        n = len(model_ids)
+        prm = params or SegParams.default()
+        ids = (C.c_ubyte * n)(*model_ids)
+        icp = (C.c_void_p * n)(*[t.data_ptr() for t in icp_errors])
+        vc = (C.c_void_p * n)(*[t.data_ptr() for t in vert_confs])
+        full = torch.empty((self.H, self.W), dtype=torch.uint8, device=rgb.device)
+        md = (ModelData * (n + 1))()
+        cnt, has_new = C.c_int(0), C.c_int(0)
+        check(lib().cfb_segmentation_perform_crf(self._h, _p(rgb), _p(depth), n, ids, icp, vc,
+                                                 C.c_ubyte(next_model_id), int(bool(allow_new)), C.byref(prm),
+                                                 _p(full), md, C.byref(cnt), C.byref(has_new), _stream()))
+        self.num_models, self.num_labels = n, n + int(bool(allow_new))
+        return full, [md[i] for i in range(cnt.value)], bool(has_new.value)
+
+    def view(self, which):
+        """0 SLIC labels, 1 counts, 2 unary, 3 low-res map, 4 low-res maps, 5 Q (numpy copies)"""
+        ptr, nbytes = C.c_void_p(), C.c_size_t()
+        check(lib().cfb_segmentation_view(self._h, which, C.byref(ptr), C.byref(nbytes)))
+        dt = {0: np.int32, 1: np.uint32, 2: np.float32, 3: np.uint8, 4: np.float32, 5: np.float32}[which]
+        out = np.empty(nbytes.value // np.dtype(dt).itemsize, dt)
+        _cudart_memcpy_d2h(out, ptr.value)
+        if which == 0:
+            return out.reshape(self.H, self.W)
+        if which in (2, 5):
+            return out.reshape(self.N, -1)
+        if which == 4:
+            return out.reshape(-1, self.N)
+        return out
+
+
 class CoFusionParams(C.Structure):
     _fields_ = [("timeDelta", C.c_int), ("depthCutoff", C.c_float), ("maxDepthProcessed", C.c_float),
                 ("icpWeight", C.c_float), ("pyramid", C.c_int), ("fastOdom", C.c_int), ("so3", C.c_int),
                 ("frameToFrameRGB", C.c_int), ("rgbOnly", C.c_int), ("confGlobalInit", C.c_float),
                 ("confObjectInit", C.c_float), ("outlierCoefficient", C.c_float), ("maxSurfels", C.c_uint),
-                ("predictBeforeFuse", C.c_int)]
+                ("predictBeforeFuse", C.c_int), ("enableMultipleModels", C.c_int),
+                ("modelSpawnOffset", C.c_uint), ("seg", SegParams)]
 
     @staticmethod
     def default(max_surfels=1 << 21):
@@ -412,3 +495,19 @@ class CoFusion:
         st = TrackStats()
         check(lib().cfb_cofusion_last_stats(self._h, int(index), C.byref(st)))
         return st
+
+    def last_segmentation(self):
+        """([ModelData], hasNewLabel, spawned_id or -1, deactivated) of the last frame"""
+        md = (ModelData * (SEG_MAX_MODELS + 1))()
+        cnt, hn, sp, de = C.c_int(0), C.c_int(0), C.c_int(-1), C.c_int(0)
+        check(lib().cfb_cofusion_last_segmentation(self._h, md, C.byref(cnt), C.byref(hn), C.byref(sp), C.byref(de)))
+        return [md[i] for i in range(cnt.value)], bool(hn.value), sp.value, de.value
+
+    @property
+    def num_inactive_models(self):
+        return lib().cfb_cofusion_num_inactive_models(self._h)
+
+    def segmentation(self):
+        lib().cfb_cofusion_segmentation.restype = C.c_void_p
+        h = lib().cfb_cofusion_segmentation(self._h)
+        return Segmentation(self.W, self.H, _borrowed=C.c_void_p(h)) if h else None

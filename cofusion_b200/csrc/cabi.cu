@@ -571,6 +571,75 @@ int cfb_model_view(cfb_model* m, int which, const void** dev_ptr, size_t* pitch)
 }
 
 
+/* ------------------------------------------------------------------------------ segmentation */
+struct cfb_segmentation {
+  Segmentation* owned;
+  Segmentation& s;
+  int lastLabels = 0, lastModels = 0;
+  cfb_segmentation(int W, int H) : owned(new Segmentation(W, H)), s(*owned) {}
+  explicit cfb_segmentation(Segmentation* b) : owned(nullptr), s(*b) {}
+  ~cfb_segmentation() { delete owned; }
+};
+void cfb_seg_default_params(cfb_seg_params* p) {
+  static_assert(sizeof(cfb_seg_params) == sizeof(SegParams), "seg params layout");
+  static_assert(sizeof(cfb_model_data) == sizeof(SegModelData), "model data layout");
+  static_assert(CFB_SEG_MAX_MODELS == SegLimits::kMaxModels, "label budget");
+  if (p) seg_default_params((SegParams*)p);
+}
+int cfb_segmentation_create(int device, int W, int H, cfb_segmentation** out) {
+  REQUIRE(out && W >= 32 && H >= 32 && (W % 16) == 0 && (H % 16) == 0, "segmentation_create (W, H multiples of 16)");
+  *out = nullptr;
+  if (cfb_device_count() <= device || device < 0)
+    return set_error_msg(3, "no such CUDA device: libcofusion_b200 has no CPU fallback");
+  CK(cudaSetDevice(device));
+  cfb_segmentation* s = new (std::nothrow) cfb_segmentation(W, H);
+  if (!s || !s->s.ok()) {
+    delete s;
+    return set_error_msg(4, "segmentation_create: device allocation failed");
+  }
+  *out = s;
+  return 0;
+}
+void cfb_segmentation_destroy(cfb_segmentation* s) { delete s; }
+int cfb_segmentation_slic(cfb_segmentation* s, const uint8_t* rgb, void* stream) {
+  REQUIRE(s && rgb, "segmentation_slic");
+  CK(s->s.slic(rgb, ST(stream)));
+  return 0;
+}
+int cfb_segmentation_perform_crf(cfb_segmentation* s, const uint8_t* rgb, const float* depth, int numModels,
+                                 const unsigned char* modelIds, const float* const* icpError,
+                                 const float* const* vertConf4, unsigned char nextModelID, int allowNew,
+                                 const cfb_seg_params* prm, uint8_t* fullSeg, cfb_model_data* md_out, int* md_count,
+                                 int* hasNewLabel, void* stream) {
+  REQUIRE(s && rgb && depth && modelIds && icpError && vertConf4 && prm && fullSeg && md_out && md_count &&
+              hasNewLabel && numModels >= 1 && numModels <= CFB_SEG_MAX_MODELS,
+          "segmentation_perform_crf");
+  SegParams p;
+  memcpy(&p, prm, sizeof(p));
+  bool hn = false;
+  CK(s->s.performSegmentationCRF(rgb, depth, numModels, modelIds, icpError, vertConf4, nextModelID, allowNew != 0, p,
+                                 fullSeg, (SegModelData*)md_out, md_count, &hn, ST(stream)));
+  *hasNewLabel = hn ? 1 : 0;
+  s->lastModels = numModels;
+  s->lastLabels = numModels + (allowNew ? 1 : 0);
+  return 0;
+}
+int cfb_segmentation_view(cfb_segmentation* s, int which, const void** dev_ptr, size_t* bytes) {
+  REQUIRE(s && dev_ptr && bytes, "segmentation_view");
+  const Segmentation& g = s->s;
+  const size_t N = g.N;
+  switch (which) {
+    case 0: *dev_ptr = g.labels; *bytes = (size_t)g.W * g.H * 4; break;
+    case 1: *dev_ptr = g.counts; *bytes = N * 4; break;
+    case 2: *dev_ptr = g.unary; *bytes = N * s->lastLabels * 4; break;
+    case 3: *dev_ptr = g.lowMap; *bytes = N; break;
+    case 4: *dev_ptr = g.low; *bytes = N * (1 + 2 * s->lastModels) * 4; break;
+    case 5: *dev_ptr = g.Q; *bytes = N * s->lastLabels * 4; break;
+    default: return set_error_msg(2, "segmentation_view: unknown view");
+  }
+  return 0;
+}
+
 /* ------------------------------------------------------------------------------ CoFusion */
 struct cfb_cofusion {
   CoFusion f;
@@ -580,20 +649,36 @@ struct cfb_cofusion {
       : f(d, w, h, fx, fy, cx, cy, p), ctx_handle(&f.ctx) {}
   ~cfb_cofusion() {
     for (auto* h : model_handles) delete h;
+    delete seg_handle;
   }
-  void sync_handles() {
-    while (model_handles.size() < f.numModels()) model_handles.push_back(new cfb_model(f.model(model_handles.size())));
+  cfb_segmentation* seg_handle = nullptr;
+  void sync_handles() {  // handle[i] wraps model(i); handles of deactivated models are dropped
+    std::vector<cfb_model*> next;
+    for (size_t i = 0; i < f.numModels(); ++i) {
+      cfb_model* h = nullptr;
+      for (auto*& old : model_handles)
+        if (old && &old->m == f.model(i)) {
+          h = old;
+          old = nullptr;
+        }
+      next.push_back(h ? h : new cfb_model(f.model(i)));
+    }
+    for (auto* old : model_handles) delete old;
+    model_handles.swap(next);
   }
 };
 
 void cfb_cofusion_default_params(cfb_cofusion_params* p) {
   if (!p) return;
-  cfb_cofusion_params d = {200, 5.0f, 20.0f, 10.0f, 1, 0, 1, 0, 0, 10.0f, 0.01f, 3.0f, 3072u * 3072u, 0};
+  cfb_cofusion_params d = {200, 5.0f, 20.0f, 10.0f, 1, 0, 1, 0, 0, 10.0f, 0.01f, 3.0f, 3072u * 3072u, 0, 0, 20u, {}};
+  cfb_seg_default_params(&d.seg);
   *p = d;
 }
 int cfb_cofusion_create(int device, int W, int H, float fx, float fy, float cx, float cy,
                         const cfb_cofusion_params* p, cfb_cofusion** out) {
   REQUIRE(out && p && W >= 32 && H >= 32 && (W % 8) == 0 && (H % 4) == 0 && p->maxSurfels > 0, "cofusion_create");
+  REQUIRE(!p->enableMultipleModels || ((W % 16) == 0 && (H % 16) == 0),
+          "cofusion_create: segmentation needs W, H multiples of 16");
   *out = nullptr;
   if (cfb_device_count() <= device || device < 0)
     return set_error_msg(3, "no such CUDA device: libcofusion_b200 has no CPU fallback");
@@ -614,7 +699,24 @@ int cfb_cofusion_process_frame(cfb_cofusion* f, const uint8_t* rgb, const float*
                                int device_ptrs, float weightMultiplier) {
   REQUIRE(f && rgb && depth, "cofusion_process_frame");
   CK(f->f.processFrame(rgb, depth, mask, device_ptrs != 0, weightMultiplier));
+  if (f->f.params.enableMultipleModels) f->sync_handles();
   return 0;
+}
+int cfb_cofusion_last_segmentation(cfb_cofusion* f, cfb_model_data* md_out, int* md_count, int* hasNewLabel,
+                                   int* spawned_id, int* deactivated) {
+  REQUIRE(f && md_count, "cofusion_last_segmentation");
+  *md_count = (int)f->f.lastModelData.size();
+  if (md_out && *md_count) memcpy(md_out, f->f.lastModelData.data(), sizeof(cfb_model_data) * *md_count);
+  if (hasNewLabel) *hasNewLabel = f->f.lastHasNewLabel ? 1 : 0;
+  if (spawned_id) *spawned_id = f->f.lastSpawnedId;
+  if (deactivated) *deactivated = f->f.lastDeactivated;
+  return 0;
+}
+int cfb_cofusion_num_inactive_models(cfb_cofusion* f) { return f ? (int)f->f.inactiveModels.size() : 0; }
+cfb_segmentation* cfb_cofusion_segmentation(cfb_cofusion* f) {
+  if (!f || !f->f.segmentation) return nullptr;
+  if (!f->seg_handle) f->seg_handle = new cfb_segmentation(f->f.segmentation.get());
+  return f->seg_handle;
 }
 int cfb_cofusion_spawn_object_model(cfb_cofusion* f, unsigned id, const float* initialPose16) {
   REQUIRE(f && id > 0 && id < 256, "cofusion_spawn_object_model");

@@ -1,6 +1,7 @@
 // cofusion.cu -- cfb::CoFusion (see cofusion.cuh).
 #include "cofusion.cuh"
 
+#include <math.h>
 #include <string.h>
 
 namespace cfb {
@@ -17,6 +18,92 @@ CoFusion::CoFusion(int device, int W, int H, float fx, float fy, float cx, float
   // globalModel: id 0, fill-in enabled (CoFusion.cpp:70)
   models.emplace_back(new Model(&ctx, 0, p.confGlobalInit, p.maxSurfels, true));
   lastStats.resize(1);
+  if (p.enableMultipleModels) {
+    segmentation.reset(new Segmentation(W, H));
+    ctx.keepMask = true;  // textures[MASK] persists between frames (CoFusion.cpp:233)
+  }
+}
+
+unsigned char CoFusion::takeNextModelID() {  // CoFusion.cpp:628-645
+  const unsigned char next = nextID_;
+  while (true) {
+    nextID_++;
+    bool occupied = false;
+    for (auto& m : models)
+      if (nextID_ == m->id) occupied = true;
+    if (!occupied) break;
+  }
+  return next;
+}
+
+static float seg_max_depth(const SegModelData& d) {  // getMaxDepth lambda (CoFusion.cpp:228)
+  return (float)((double)d.depthMean + (double)d.depthStd * 1.2);
+}
+
+cudaError_t CoFusion::segmentAndManageModels() {
+  if (!segmentation || !segmentation->ok()) return cudaErrorMemoryAllocation;
+  if (spawnOffset_ < params.modelSpawnOffset) spawnOffset_++;
+  const int n = (int)models.size();
+  if (n > SegLimits::kMaxModels) return cudaErrorInvalidValue;
+  // the label budget of the CRF kernels caps the number of live models (reference: 255)
+  const bool allowNew = spawnOffset_ >= params.modelSpawnOffset && n < SegLimits::kMaxModels;
+  unsigned char ids[SegLimits::kMaxModels];
+  const float* icp[SegLimits::kMaxModels];
+  const float* conf[SegLimits::kMaxModels];
+  std::vector<Model*> owners(n);
+  for (int i = 0; i < n; ++i) {
+    ids[i] = (unsigned char)models[i]->id;
+    icp[i] = models[i]->icpError;
+    conf[i] = (const float*)models[i]->splat.vertexConf;  // Model::downloadVertexConfTexture (Model.h:189)
+    owners[i] = models[i].get();
+  }
+  lastModelData.assign(n + 1, SegModelData{});
+  int cnt = 0;
+  bool hasNew = false;
+  RET_IF(segmentation->performSegmentationCRF(ctx.rgb, ctx.depthRaw, n, ids, icp, conf, nextID_, allowNew, params.seg,
+                                              ctx.mask, lastModelData.data(), &cnt, &hasNew, ctx.stream));
+  ctx.launches += segmentation->launches;
+  lastModelData.resize(cnt);
+  lastHasNewLabel = hasNew;
+  lastSpawnedId = -1;
+  lastDeactivated = 0;
+  std::unique_ptr<Model> newModel;
+  if (hasNew) {  // CoFusion.cpp:243-259, spawnObjectModel :588-597
+    const unsigned char id = takeNextModelID();
+    newModel.reset(new Model(&ctx, id, params.confObjectInit, params.maxSurfels, false));
+    if (!newModel->ok()) return cudaErrorMemoryAllocation;
+    RET_IF(newModel->initFirstRGB());
+    spawnOffset_ = 0;
+    newModel->maxDepth = seg_max_depth(lastModelData.back());
+    lastSpawnedId = id;
+  }
+  for (size_t i = 1; i < models.size(); ++i) models[i]->maxDepth = seg_max_depth(lastModelData[i]);
+  if (hasNew) {  // CoFusion.cpp:265-281
+    RET_IF(newModel->predictIndices(tick_, params.maxDepthProcessed, params.timeDelta));
+    RET_IF(newModel->fuse(tick_, params.maxDepthProcessed, 100.f));
+    RET_IF(newModel->clean(tick_, params.timeDelta, params.maxDepthProcessed, params.outlierCoefficient));
+    models.push_back(std::move(newModel));
+  }
+  for (int k = 0; k < cnt && k < n; ++k) {  // lost models (CoFusion.cpp:284-291); unseenCount is never reset
+    const SegModelData& m = lastModelData[k];
+    if (m.superPixelCount <= 0 && m.id != 0) {
+      for (size_t j = 0; j < models.size(); ++j)
+        if (models[j].get() == owners[k]) {
+          inactiveModels.push_back(std::move(models[j]));
+          models.erase(models.begin() + j);
+          lastDeactivated++;
+          break;
+        }
+    }
+  }
+  // positional indexing into modelData AFTER the list changed, as the reference (CoFusion.cpp:294-298)
+  for (size_t i = 1; i < models.size() && i < lastModelData.size(); ++i) {
+    const float oldConf = models[i]->confidenceThreshold;
+    const float a = lastModelData[i].avgConfidence;
+    models[i]->confidenceThreshold = fminf(fmaxf(oldConf, a), 9.0f);
+  }
+  lastStats.resize(models.size());
+  return cudaSuccess;
 }
 
 cudaError_t CoFusion::spawnObjectModel(unsigned id, const float* initialPose) {
@@ -68,6 +155,7 @@ cudaError_t CoFusion::processFrame(const uint8_t* rgb, const float* depth, const
       RET_IF(models[i]->performTracking(tp));
       lastStats[i] = models[i]->odom.stats();
     }
+    if (params.enableMultipleModels) RET_IF(segmentAndManageModels());
     // CoFusion.cpp:347: this prediction only feeds performSegmentation / the (dead) loop-closure
     // block; the fuse stage below uses the index maps and the frame, and the final predict()
     // overwrites every target -> skipped unless asked for.

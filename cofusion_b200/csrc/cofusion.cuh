@@ -4,13 +4,15 @@
 // Kept from the reference: call order (track all -> predict -> indices/fuse/indices/clean -> predict),
 // tick semantics, first-frame initialisation, fill-in for the background model only, external label
 // masks (FrameData::mask).  Not here (out of scope): loop closure, ferns,
-// re-detection, GUI, logging.  Model spawn/deactivate decisions stay with the caller (they are
-// driven by the segmentation result, CoFusion.cpp:243-298).
+// re-detection, GUI, logging.  With enableMultipleModels the motion segmentation runs after tracking
+// and drives spawn / deactivate exactly as CoFusion.cpp:227-299; without it the caller supplies the
+// label mask (FrameData::mask) and spawns models itself.
 #pragma once
 #include <memory>
 #include <vector>
 
 #include "pipeline.cuh"
+#include "segment_kernels.cuh"
 
 namespace cfb {
 
@@ -25,7 +27,10 @@ struct CoFusionParams {   // constructor arguments / setters of CoFusion (CoFusi
   float outlierCoefficient;  // 3 (GUI/Tools/GUI.h:208)
   unsigned maxSurfels;    // per model
   int predictBeforeFuse;  // 1: also run the predict() of CoFusion.cpp:347, whose images nobody reads
-                          //    unless the CRF segmentation is on (identical results either way)
+                          //    (loop closure is out of scope; identical results either way)
+  int enableMultipleModels;   // 1: run performSegmentationCRF each frame (CoFusion.cpp:227-299)
+  unsigned modelSpawnOffset;  // 20 (CoFusion.h:50): frames between two spawns
+  SegParams seg;              // CRF parameters (GUI defaults)
 };
 
 class CoFusion {
@@ -47,10 +52,22 @@ class CoFusion {
   Context ctx;
   CoFusionParams params;
   std::vector<std::unique_ptr<Model>> models;
+  std::vector<std::unique_ptr<Model>> inactiveModels;  // CoFusion::inactivateModel keeps the data
   std::vector<TrackStats> lastStats;
 
+  // result of the last performSegmentation (CoFusion.cpp:232)
+  std::unique_ptr<Segmentation> segmentation;
+  std::vector<SegModelData> lastModelData;
+  bool lastHasNewLabel = false;
+  int lastSpawnedId = -1;       // id of the model spawned by the last frame, -1 = none
+  int lastDeactivated = 0;      // number of models deactivated by the last frame
+
  private:
+  cudaError_t segmentAndManageModels();  // CoFusion.cpp:227-299
+  unsigned char takeNextModelID();       // getNextModelID(true)
   int tick_ = 1;
+  unsigned spawnOffset_ = 0;
+  unsigned char nextID_ = 1;  // id 0 went to the global model (CoFusion.cpp:70)
 };
 
 }  // namespace cfb

@@ -78,7 +78,7 @@ cudaError_t Context::uploadFrame(const uint8_t* rgb_h, const float* depth_h, con
       m = h_mask;
     }
     RET_IF(cudaMemcpyAsync(mask, m, n, cudaMemcpyHostToDevice, stream));
-  } else {
+  } else if (!keepMask) {
     // static scene: everything is background (CoFusion.cpp:190-197)
     RET_IF(cudaMemsetAsync(mask, 0, n, stream));
   }
@@ -91,7 +91,7 @@ cudaError_t Context::setFrameDevice(const uint8_t* rgb_d, const float* depth_d, 
   RET_IF(cudaMemcpyAsync(depthRaw, depth_d, n * 4, cudaMemcpyDeviceToDevice, stream));
   if (mask_d)
     RET_IF(cudaMemcpyAsync(mask, mask_d, n, cudaMemcpyDeviceToDevice, stream));
-  else
+  else if (!keepMask)
     RET_IF(cudaMemsetAsync(mask, 0, n, stream));
   return cudaSuccess;
 }

@@ -43,6 +43,7 @@ class Context {
   float* h_depth = nullptr;
   uint8_t* h_mask = nullptr;
   int launches = 0;                 // kernels launched since the last reset (bench accounting)
+  bool keepMask = false;            // true: a frame without mask keeps the previous labels (segmentation on)
 
  private:
   bool ok_ = false;

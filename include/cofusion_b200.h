@@ -241,6 +241,48 @@ cfb_odom* cfb_model_odometry(cfb_model* m);
 int cfb_model_view(cfb_model* m, int which, const void** dev_ptr, size_t* pitch);
 
 /* ------------------------------------------------------------------------------------------------
+ * Seam 2b': motion segmentation (Core/Segmentation/Segmentation.h:104-106 performSegmentationCRF,
+ * Core/Segmentation/Slic.h:30-147).  CPU code in the reference (gSLICr + densecrf); here SLIC, the
+ * super-pixel reductions, the CRF mean field, the component post-processing and the label upsampling
+ * all run on the device; only ModelData comes back to the host.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cfb_segmentation cfb_segmentation;
+typedef struct cfb_seg_params { /* Segmentation.h:135-149; defaults = GUI/Tools/GUI.h:212-227 */
+  int crfIterations;
+  float scaleFeaturesRGB, scaleFeaturesDepth, scaleFeaturesPos;
+  float weightAppearance, weightSmoothness;
+  float unaryThresholdNew, unaryKError, unaryWeightError;
+  float maxRelSizeNew, minRelSizeNew;
+} cfb_seg_params;
+typedef struct cfb_model_data { /* SegmentationResult::ModelData (Segmentation.h:41-67) */
+  unsigned id;
+  unsigned superPixelCount;
+  float avgConfidence, depthMean, depthStd;
+  unsigned short top, right, bottom, left;
+} cfb_model_data;
+#define CFB_SEG_MAX_MODELS 15
+void cfb_seg_default_params(cfb_seg_params* p);
+/* W and H must be multiples of 16 (the super-pixel size, Segmentation.cpp:55) */
+int cfb_segmentation_create(int device, int W, int H, cfb_segmentation** out);
+void cfb_segmentation_destroy(cfb_segmentation* s);
+/* Slic::setInputImage + processFrame (Slic.cpp:48-80): rgb HxWx3 u8 (device) -> labels (view 0) */
+int cfb_segmentation_slic(cfb_segmentation* s, const uint8_t* rgb, void* stream);
+/* Segmentation::performSegmentationCRF(models, frame, nextModelID, allowNew).  rgb (HxWx3 u8), depth
+ * (HxW f32, raw metres), icpError[m] (HxW f32, Model::downloadICPErrorTexture), vertConf4[m] (HxW
+ * float4, Model::downloadVertexConfTexture; .w read) and fullSeg (HxW u8 out:
+ * SegmentationResult::fullSegmentation, model ids / 255) are DEVICE pointers; the pointer arrays, ids
+ * and md_out (numModels + 1 entries) live on the host.  Synchronises the stream. */
+int cfb_segmentation_perform_crf(cfb_segmentation* s, const uint8_t* rgb, const float* depth, int numModels,
+                                 const unsigned char* modelIds, const float* const* icpError,
+                                 const float* const* vertConf4, unsigned char nextModelID, int allowNew,
+                                 const cfb_seg_params* prm, uint8_t* fullSeg, cfb_model_data* md_out, int* md_count,
+                                 int* hasNewLabel, void* stream);
+/* device scratch of the last call: 0 SLIC labels (i32 HxW) 1 super-pixel pixel counts (u32 N)
+ * 2 unaries (f32 N x numLabels, node major) 3 low-res label map after post-processing (u8 N)
+ * 4 low-res maps (f32 [1+2*numModels][N]: depth, then icp/conf per model) 5 CRF marginals Q (f32 N x L) */
+int cfb_segmentation_view(cfb_segmentation* s, int which, const void** dev_ptr, size_t* bytes);
+
+/* ------------------------------------------------------------------------------------------------
  * Seam 2c: CoFusion::processFrame (Core/CoFusion.h:67-68, Core/CoFusion.cpp:171-524)
  * ---------------------------------------------------------------------------------------------- */
 typedef struct cfb_cofusion cfb_cofusion;
@@ -255,7 +297,11 @@ typedef struct cfb_cofusion_params { /* CoFusion ctor args / setters (CoFusion.h
   float outlierCoefficient; /* 3 */
   unsigned maxSurfels;      /* per model (reference: 3072^2) */
   int predictBeforeFuse;    /* 0: skip the predict() of CoFusion.cpp:347 (its images are overwritten by
-                               the final predict() before anything reads them when segmentation is off) */
+                               the final predict() before anything reads them without loop closure) */
+  int enableMultipleModels; /* 1: run the motion segmentation after tracking and spawn / deactivate
+                               object models from its result (CoFusion.cpp:227-299) */
+  unsigned modelSpawnOffset;/* 20 (CoFusion.h:50) */
+  cfb_seg_params seg;       /* cfb_seg_default_params */
 } cfb_cofusion_params;
 void cfb_cofusion_default_params(cfb_cofusion_params* p);
 int cfb_cofusion_create(int device, int W, int H, float fx, float fy, float cx, float cy,
@@ -273,6 +319,12 @@ int cfb_cofusion_tick(cfb_cofusion* f);
 cfb_model* cfb_cofusion_model(cfb_cofusion* f, int index);
 cfb_ctx* cfb_cofusion_ctx(cfb_cofusion* f);
 int cfb_cofusion_last_stats(cfb_cofusion* f, int index, cfb_track_stats* out);
+/* SegmentationResult of the last frame (enableMultipleModels): up to CFB_SEG_MAX_MODELS+1 entries.
+ * spawned_id: id of the model spawned by the last frame or -1; deactivated: models lost by it. */
+int cfb_cofusion_last_segmentation(cfb_cofusion* f, cfb_model_data* md_out, int* md_count, int* hasNewLabel,
+                                   int* spawned_id, int* deactivated);
+int cfb_cofusion_num_inactive_models(cfb_cofusion* f);
+cfb_segmentation* cfb_cofusion_segmentation(cfb_cofusion* f); /* borrowed; NULL when segmentation is off */
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,8 @@
  *     updates Q <- softmax(-unary - sum_k compat_k * K_k Q) with Gaussian kernels K_k; the library
  *     evaluates K Q approximately on a permutohedral lattice.  FROZEN CHOICE: this restatement
  *     evaluates the kernel product EXACTLY, k(i,j) = exp(-|f_i - f_j|^2 / 2) including j = i, with the
- *     library's symmetric normalisation n_i = 1/sqrt(sum_j k(i,j) + 1e-20), out = n .* K (n .* Q).
+ *     library's symmetric normalisation n_i = 1/sqrt(sum_j k(i,j) + 1e-20), out = n .* K (n .* Q);
+ *     the float sums over j use the fixed order documented at butterfly32() below.
  *     With 1200 super-pixels that is a 1200 x 1200 kernel -- cheaper than building a lattice and
  *     free of its (order dependent) approximation error.  Labels are therefore bit-exact only
  *     against this restatement, not against a densecrf build (hard part 6).
@@ -242,6 +243,22 @@ static void exp_and_normalize(float* out, const float* in, int L, int N) { /* De
     for (int l = 0; l < L; ++l) out[i * L + l] = out[i * L + l] / sum;
   }
 }
+/* FROZEN SUMMATION ORDER of the kernel products (the lattice of the library has its own, unrelated
+ * order): 128 partial sums, partial k owning j = k, k+128, ... in ascending j; each group of 32
+ * partials is combined by an xor butterfly (distance 16, 8, 4, 2, 1) and the four group sums as
+ * (s0 + s1) + (s2 + s3).  It is the order four 32-wide warps produce naturally. */
+static float butterfly32(float* v) {
+  for (int o = 16; o > 0; o >>= 1) {
+    float nv[32];
+    for (int k = 0; k < 32; ++k) nv[k] = v[k] + v[k ^ o];
+    memcpy(v, nv, sizeof(nv));
+  }
+  return v[0];
+}
+static float combine128(float* part) {
+  float s0 = butterfly32(part), s1 = butterfly32(part + 32), s2 = butterfly32(part + 64), s3 = butterfly32(part + 96);
+  return (s0 + s1) + (s2 + s3);
+}
 /* K (N x N, row-major), norm (N): out = norm .* (K (norm .* Q)); Q, out are N x L (node major) */
 static void kernel_apply(const float* K, const float* norm, const float* Q, int N, int L, float* out) {
   float* nq = (float*)malloc(sizeof(float) * N * L);
@@ -249,15 +266,17 @@ static void kernel_apply(const float* K, const float* norm, const float* Q, int 
     for (int l = 0; l < L; ++l) nq[i * L + l] = norm[i] * Q[i * L + l];
   for (int i = 0; i < N; ++i)
     for (int l = 0; l < L; ++l) {
-      float s = 0;
-      for (int j = 0; j < N; ++j) s += K[(size_t)i * N + j] * nq[j * L + l];
-      out[i * L + l] = norm[i] * s;
+      float part[128];
+      memset(part, 0, sizeof(part));
+      for (int j = 0; j < N; ++j) part[j & 127] += K[(size_t)i * N + j] * nq[j * L + l];
+      out[i * L + l] = norm[i] * combine128(part);
     }
   free(nq);
 }
 static void build_kernel(const float* feat, int D, int N, float* K, float* norm) {
   for (int i = 0; i < N; ++i) {
-    float rs = 0;
+    float part[128];
+    memset(part, 0, sizeof(part));
     for (int j = 0; j < N; ++j) {
       float d2 = 0;
       for (int k = 0; k < D; ++k) {
@@ -266,9 +285,9 @@ static void build_kernel(const float* feat, int D, int N, float* K, float* norm)
       }
       float v = orc_expf(-0.5f * d2);
       K[(size_t)i * N + j] = v;
-      rs += v;
+      part[j & 127] += v;
     }
-    norm[i] = 1.0f / sqrtf(rs + 1e-20f);
+    norm[i] = 1.0f / sqrtf(combine128(part) + 1e-20f);
   }
 }
 
