@@ -225,6 +225,12 @@ class Model:
     def set_confidence_threshold(self, v):
         check(lib().cfb_model_set_confidence_threshold(self._h, C.c_float(v)))
 
+    def info(self):
+        """(id, confidence threshold, max depth)"""
+        i, c, d = C.c_uint(0), C.c_float(0), C.c_float(0)
+        check(lib().cfb_model_get_info(self._h, C.byref(i), C.byref(c), C.byref(d)))
+        return i.value, c.value, d.value
+
     def set_max_depth(self, v):
         check(lib().cfb_model_set_max_depth(self._h, C.c_float(v)))
 
@@ -441,8 +447,9 @@ class CoFusion:
         lib().cfb_ctx_stream.restype = C.c_void_p
         self.ctx = Context.__new__(Context)
         self.ctx.W, self.ctx.H, self.ctx.K = W, H, K
-        self.ctx._h = C.c_void_p()  # borrowed: never destroyed from Python
         self._ctx_h = C.c_void_p(lib().cfb_cofusion_ctx(self._h))
+        self.ctx._h = self._ctx_h  # borrowed (BorrowedContext has no __del__): never destroyed from Python
+        self.ctx.__class__ = type("BorrowedContext", (Context,), {"__del__": lambda self_: None})
         self.ctx.stream = lib().cfb_ctx_stream(self._ctx_h)
         self.ctx.sync = lambda: check(lib().cfb_ctx_sync(self._ctx_h))
         self.ctx.take_launch_count = lambda: lib().cfb_ctx_take_launch_count(self._ctx_h)
@@ -495,6 +502,10 @@ class CoFusion:
         st = TrackStats()
         check(lib().cfb_cofusion_last_stats(self._h, int(index), C.byref(st)))
         return st
+
+    def ctx_view_mask(self):
+        """textures[MASK]: the label image the fuse / clean stage of the last frame used (HxW u8)"""
+        return self.ctx.view(5)
 
     def last_segmentation(self):
         """([ModelData], hasNewLabel, spawned_id or -1, deactivated) of the last frame"""

@@ -491,6 +491,13 @@ int cfb_model_set_confidence_threshold(cfb_model* m, float v) {
   m->m.confidenceThreshold = v;
   return 0;
 }
+int cfb_model_get_info(cfb_model* m, unsigned* id, float* confThresh, float* maxDepth) {
+  REQUIRE(m, "model_get_info");
+  if (id) *id = m->m.id;
+  if (confThresh) *confThresh = m->m.confidenceThreshold;
+  if (maxDepth) *maxDepth = m->m.maxDepth;
+  return 0;
+}
 int cfb_model_set_max_depth(cfb_model* m, float d) {
   REQUIRE(m, "model_set_max_depth");
   m->m.maxDepth = d;

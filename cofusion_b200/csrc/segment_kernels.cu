@@ -11,6 +11,8 @@
 // approximates the same product (frozen choice shared with the oracle).
 #include "segment_kernels.cuh"
 
+#include <stdlib.h>
+
 #include "detmath.cuh"
 
 namespace cfb {
@@ -23,7 +25,7 @@ constexpr int kSp = 16;  // super-pixel size (Segmentation.cpp:55)
 // staged in shared memory once.  The centre update of the previous iteration is folded into the
 // prologue (sum / count from the integer accumulators of the previous launch -- exact, order free)
 // and this launch accumulates the sums the next one needs: 6 launches instead of 1 + 6 + 5 + 1.
-__global__ void __launch_bounds__(256) slic_iter_kernel(const uint8_t* __restrict__ rgb, int W, int H, int mx, int my,
+__global__ void __launch_bounds__(128) slic_iter_kernel(const uint8_t* __restrict__ rgb, int W, int H, int mx, int my,
                                                         int it, const int* __restrict__ sums_prev,
                                                         const float* __restrict__ ctr_prev, float* __restrict__ ctr_cur,
                                                         int* __restrict__ sums_cur, float coh_weight, float max_xy_dist,
@@ -62,37 +64,43 @@ __global__ void __launch_bounds__(256) slic_iter_kernel(const uint8_t* __restric
   }
   if (tid < 54) (&sacc[0][0])[tid] = 0;
   __syncthreads();
-  const int x = cx * kSp + threadIdx.x, y = cy * kSp + threadIdx.y;
-  const uint8_t* p = rgb + (y * W + x) * 3;
-  const int q0 = p[0], q1 = p[1], q2 = p[2];
-  const float p0 = (float)q0, p1 = (float)q1, p2 = (float)q2;
-  int best = 4;
-  float dist = 999999.9999f;
+  // 16 x 8 threads, two pixels each (rows ty and ty + 8): 16 CTAs fit one SM, so the 1200 cells of a
+  // VGA frame are a single wave
 #pragma unroll
-  for (int c = 0; c < 9; ++c) {  // same visiting order as gSLICr: rows -1..1, columns -1..1
-    if (sv[c] >= 0) {
-      const float dcolor = (p0 - sc[c][2]) * (p0 - sc[c][2]) + (p1 - sc[c][3]) * (p1 - sc[c][3]) +
-                           (p2 - sc[c][4]) * (p2 - sc[c][4]);
-      const float dxy = ((float)x - sc[c][0]) * ((float)x - sc[c][0]) + ((float)y - sc[c][1]) * ((float)y - sc[c][1]);
-      const float cdist = sqrtf(dcolor * max_color_dist + coh_weight * dxy * max_xy_dist);
-      if (cdist < dist) {
-        dist = cdist;
-        best = c;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int x = cx * kSp + threadIdx.x, y = cy * kSp + threadIdx.y + 8 * pass;
+    const uint8_t* p = rgb + (y * W + x) * 3;
+    const int q0 = p[0], q1 = p[1], q2 = p[2];
+    const float p0 = (float)q0, p1 = (float)q1, p2 = (float)q2;
+    int best = 4;
+    float dist = 999999.9999f;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {  // same visiting order as gSLICr: rows -1..1, columns -1..1
+      if (sv[c] >= 0) {
+        const float dcolor = (p0 - sc[c][2]) * (p0 - sc[c][2]) + (p1 - sc[c][3]) * (p1 - sc[c][3]) +
+                             (p2 - sc[c][4]) * (p2 - sc[c][4]);
+        const float dxy =
+            ((float)x - sc[c][0]) * ((float)x - sc[c][0]) + ((float)y - sc[c][1]) * ((float)y - sc[c][1]);
+        const float cdist = sqrtf(dcolor * max_color_dist + coh_weight * dxy * max_xy_dist);
+        if (cdist < dist) {
+          dist = cdist;
+          best = c;
+        }
       }
     }
-  }
-  labels[y * W + x] = sv[best];
-  // integer sums of this assignment, warp-aggregated per chosen centre
-  const unsigned peers = __match_any_sync(0xffffffffu, best);
-  const int sx = __reduce_add_sync(peers, x), sy = __reduce_add_sync(peers, y), s0 = __reduce_add_sync(peers, q0),
-            s1 = __reduce_add_sync(peers, q1), s2 = __reduce_add_sync(peers, q2);
-  if ((int)(threadIdx.x + 16 * (threadIdx.y & 1)) == __ffs(peers) - 1) {
-    atomicAdd(&sacc[best][0], sx);
-    atomicAdd(&sacc[best][1], sy);
-    atomicAdd(&sacc[best][2], s0);
-    atomicAdd(&sacc[best][3], s1);
-    atomicAdd(&sacc[best][4], s2);
-    atomicAdd(&sacc[best][5], __popc(peers));
+    labels[y * W + x] = sv[best];
+    // integer sums of this assignment, warp-aggregated per chosen centre
+    const unsigned peers = __match_any_sync(0xffffffffu, best);
+    const int sx = __reduce_add_sync(peers, x), sy = __reduce_add_sync(peers, y), s0 = __reduce_add_sync(peers, q0),
+              s1 = __reduce_add_sync(peers, q1), s2 = __reduce_add_sync(peers, q2);
+    if ((tid & 31) == __ffs(peers) - 1) {
+      atomicAdd(&sacc[best][0], sx);
+      atomicAdd(&sacc[best][1], sy);
+      atomicAdd(&sacc[best][2], s0);
+      atomicAdd(&sacc[best][3], s1);
+      atomicAdd(&sacc[best][4], s2);
+      atomicAdd(&sacc[best][5], __popc(peers));
+    }
   }
   __syncthreads();
   if (tid < 54) {
@@ -346,10 +354,11 @@ __global__ void __launch_bounds__(1024) seg_lowres_kernel(const SegState st, con
 }
 
 // ------------------------------------------------------------------------------- dense CRF
-// Exact Gaussian kernels over the N super-pixels, evaluated ON THE FLY: k2(i,j) is a table lookup by
-// grid offset, k6(i,j) = exp(-|f6_i - f6_j|^2 / 2) costs ~40 instructions -- cheaper than streaming two
-// N x N matrices (11.5 MB) out of L2 ten times, and nothing is stored.  Four warps per node; the sum
-// over j follows the oracle's frozen order: 128 partial sums (partial k owns j = k, k+128, ...), an xor
+// Exact Gaussian kernels over the N super-pixels: k2(i,j) is a table lookup by grid offset,
+// k6(i,j) = exp(-|f6_i - f6_j|^2 / 2).  Both N x N matrices are built once per frame (11.5 MB at
+// 640x480, L2 resident) and streamed by the ten mean-field iterations, which then cost ~20
+// instructions per pair instead of ~75.  Four warps per node; the sum over j follows the oracle's
+// frozen order: 128 partial sums (partial k owns j = k, k+128, ...), an xor
 // butterfly inside each group of 32, then (s0 + s1) + (s2 + s3).
 struct CrfNode {  // 32-byte record per super-pixel: appearance features + grid position
   float f[6];
@@ -388,7 +397,8 @@ __device__ __forceinline__ void crf_pair(const CrfNode& r, const CrfNode& q, con
 }
 constexpr int kCrfRowsPerCta = 2;  // 8 warps: 2 nodes x 4 warps
 __global__ void __launch_bounds__(256) crf_norm_kernel(const CrfNode* __restrict__ nodes, const float* __restrict__ T2,
-                                                       int N, int mx, float* __restrict__ n2, float* __restrict__ n6) {
+                                                       int N, int mx, float* __restrict__ K2, float* __restrict__ K6,
+                                                       float* __restrict__ n2, float* __restrict__ n6) {
   __shared__ float sh[kCrfRowsPerCta][4][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, row = warp >> 2, part = warp & 3;
   const int i = blockIdx.x * kCrfRowsPerCta + row;
@@ -400,6 +410,8 @@ __global__ void __launch_bounds__(256) crf_norm_kernel(const CrfNode* __restrict
       const CrfNode q = load_node(nodes, j);
       float k2, k6;
       crf_pair(r, q, T2, mx, k2, k6);
+      K2[(size_t)i * N + j] = k2;
+      K6[(size_t)i * N + j] = k6;
       rs2 += k2;
       rs6 += k6;
     }
@@ -457,8 +469,8 @@ __global__ void __launch_bounds__(256) crf_init_kernel(const float* __restrict__
 }
 // one mean-field iteration: t1 = -unary - (-w2 * n2_i * sum_j K2_ij nq2_jl) - (-w6 * n6_i * sum_j K6_ij nq6_jl)
 template <int LP>
-__global__ void __launch_bounds__(256) crf_iter_kernel(const float* __restrict__ unary, const CrfNode* __restrict__ nodes,
-                                                       const float* __restrict__ T2, int mx, const float* __restrict__ n2,
+__global__ void __launch_bounds__(256) crf_iter_kernel(const float* __restrict__ unary, const float* __restrict__ K2,
+                                                       const float* __restrict__ K6, const float* __restrict__ n2,
                                                        const float* __restrict__ n6, const float* __restrict__ nq2in,
                                                        const float* __restrict__ nq6in, int N, int L, float w2, float w6,
                                                        float* __restrict__ Q, float* __restrict__ nq2out,
@@ -467,15 +479,14 @@ __global__ void __launch_bounds__(256) crf_iter_kernel(const float* __restrict__
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, row = warp >> 2, part = warp & 3;
   const int i = blockIdx.x * kCrfRowsPerCta + row;
   if (i < N) {
-    const CrfNode r = load_node(nodes, i);
+    const float* __restrict__ k2r = K2 + (size_t)i * N;
+    const float* __restrict__ k6r = K6 + (size_t)i * N;
     float a2[LP], a6[LP];
 #pragma unroll
     for (int l = 0; l < LP; ++l) a2[l] = a6[l] = 0.f;
-#pragma unroll 2
+#pragma unroll 4
     for (int j = part * 32 + lane; j < N; j += 128) {
-      const CrfNode q = load_node(nodes, j);
-      float k2, k6;
-      crf_pair(r, q, T2, mx, k2, k6);
+      const float k2 = __ldg(k2r + j), k6 = __ldg(k6r + j);
 #pragma unroll
       for (int l = 0; l < LP; ++l)
         if (l < L) {
@@ -654,10 +665,13 @@ __global__ void __launch_bounds__(1024) seg_post_kernel(const SegState st, const
         next[tail[lab]] = c;
       tail[lab] = c;
     }
-    int firstLabel = -1;
-    for (int lab = 0; lab < 256 && firstLabel < 0; ++lab)
-      if (head[lab] >= 0) firstLabel = lab;
-    for (int lab = 0; lab < 256; ++lab) {  // onlyKeepLargest: earlier component wins ties
+    // the labels present are a subset of the L model ids: the first entry of the std::map is the
+    // smallest id present
+    int firstLabel = 256;
+    for (int m = 0; m < L; ++m)
+      if (head[smd[m].id] >= 0 && (int)smd[m].id < firstLabel) firstLabel = (int)smd[m].id;
+    for (int m = 0; m < L; ++m) {  // onlyKeepLargest: earlier component wins ties
+      const int lab = (int)smd[m].id;
       if (lab == firstLabel || head[lab] < 0) continue;
       int cur = head[lab];
       for (int c2 = next[cur]; c2 >= 0;) {
@@ -802,7 +816,7 @@ Segmentation::Segmentation(int W_, int H_) : W(W_), H(H_) {
          dalloc(&slicSums, (size_t)6 * N * 6) && dalloc(&counts, N) && dalloc(&dcounts, N) &&
          dalloc(&sums, (size_t)kMaxMaps * N) && dalloc(&low, (size_t)kMaxMaps * N) &&
          dalloc(&unary, (size_t)N * Lmax) && dalloc(&T2, (size_t)N) && dalloc(&f6, (size_t)N * 8) &&
-         dalloc(&n2, N) && dalloc(&n6, N) &&
+         dalloc(&K2, (size_t)N * N) && dalloc(&K6, (size_t)N * N) && dalloc(&n2, N) && dalloc(&n6, N) &&
          dalloc(&Q, (size_t)N * Lmax) && dalloc(&nq2, (size_t)2 * N * Lmax) && dalloc(&nq6, (size_t)2 * N * Lmax) &&
          dalloc(&lowMap, N) && dalloc(&md, Lmax) && dalloc(&hdr, 1) && dalloc(&depthRange, 1);
   good = good && cudaMallocHost(&h_out, sizeof(SegResultHeader) + Lmax * sizeof(SegModelData)) == cudaSuccess;
@@ -812,10 +826,12 @@ Segmentation::Segmentation(int W_, int H_) : W(W_), H(H_) {
 }
 
 Segmentation::~Segmentation() {
-  void* ptrs[] = {labels, centers, slicSums, counts, dcounts, sums, low, unary,     T2, f6,
-                  n2,     n6,      Q,        nq2,    nq6,     lowMap, md, hdr,  depthRange};
+  void* ptrs[] = {labels, centers, slicSums, counts, dcounts, sums, low, unary, T2, f6,  K2,
+                  K6,     n2,      n6,       Q,      nq2,     nq6,  lowMap, md, hdr, depthRange};
   for (void* p : ptrs) cudaFree(p);
   cudaFreeHost(h_out);
+  if (graphExec_) cudaGraphExecDestroy((cudaGraphExec_t)graphExec_);
+  free(graphKey_);
 }
 
 cudaError_t Segmentation::slic(const uint8_t* rgb, cudaStream_t s) {
@@ -824,7 +840,7 @@ cudaError_t Segmentation::slic(const uint8_t* rgb, cudaStream_t s) {
   max_color_dist *= max_color_dist;
   max_xy_dist *= max_xy_dist;
   RET_IF(cudaMemsetAsync(slicSums, 0, sizeof(int) * 6 * N * 6, s));
-  const dim3 b(kSp, kSp), g(mx, my);
+  const dim3 b(kSp, kSp / 2), g(mx, my);
   for (int it = 0; it <= 5; ++it) {  // no_iters = 5 (Slic.cpp:39): 6 assignments, 5 centre updates
     const int* prev = it ? slicSums + (size_t)(it - 1) * N * 6 : nullptr;
     slic_iter_kernel<<<g, b, 0, s>>>(rgb, W, H, mx, my, it, prev, centers + (size_t)((it + 1) & 1) * N * 5,
@@ -842,19 +858,18 @@ void launch_crf(const Segmentation& g, int L, const SegParams& prm, cudaStream_t
   crf_init_kernel<LP><<<cdiv(N, 256), 256, 0, s>>>(g.unary, N, L, g.n2, g.n6, g.Q, g.nq2, g.nq6);
   for (int it = 0; it < prm.crfIterations; ++it) {
     const size_t in = (size_t)(it & 1) * half, out = (size_t)((it + 1) & 1) * half;
-    crf_iter_kernel<LP><<<cdiv(N, kCrfRowsPerCta), 256, 0, s>>>(g.unary, (const CrfNode*)g.f6, g.T2, g.mx, g.n2, g.n6, g.nq2 + in, g.nq6 + in, N, L,
+    crf_iter_kernel<LP><<<cdiv(N, kCrfRowsPerCta), 256, 0, s>>>(g.unary, g.K2, g.K6, g.n2, g.n6, g.nq2 + in, g.nq6 + in, N, L,
                                                    prm.weightSmoothness, prm.weightAppearance, g.Q, g.nq2 + out,
                                                    g.nq6 + out);
   }
 }
 }  // namespace
 
-cudaError_t Segmentation::performSegmentationCRF(const uint8_t* rgb, const float* depth, int numModels,
-                                                 const unsigned char* modelIds, const float* const* icpError,
-                                                 const float* const* vertConf4, unsigned char nextModelID,
-                                                 bool allowNew, const SegParams& prm, uint8_t* fullSeg,
-                                                 SegModelData* md_host, int* md_count, bool* hasNew, cudaStream_t s) {
-  if (numModels < 1 || numModels > SegLimits::kMaxModels) return cudaErrorInvalidValue;
+// Everything one performSegmentationCRF enqueues: 1 memset, 6 + 5 + crfIterations kernels, 2 copies.
+cudaError_t Segmentation::enqueue(const uint8_t* rgb, const float* depth, int numModels, const unsigned char* modelIds,
+                                  const float* const* icpError, const float* const* vertConf4,
+                                  unsigned char nextModelID, bool allowNew, const SegParams& prm, uint8_t* fullSeg,
+                                  cudaStream_t s) {
   RET_IF(slic(rgb, s));
   SegState st;
   st.W = W;
@@ -865,6 +880,7 @@ cudaError_t Segmentation::performSegmentationCRF(const uint8_t* rgb, const float
   st.numModels = numModels;
   st.allowNew = allowNew ? 1 : 0;
   st.numLabels = numModels + st.allowNew;
+  for (int m = 0; m <= SegLimits::kMaxModels; ++m) st.modelIds[m] = 0;
   for (int m = 0; m < numModels; ++m) st.modelIds[m] = modelIds[m];
   st.modelIds[numModels] = nextModelID;
   st.nextModelID = nextModelID;
@@ -882,7 +898,7 @@ cudaError_t Segmentation::performSegmentationCRF(const uint8_t* rgb, const float
   spixel_sum_kernel<<<dim3(cdiv(N, 8), a.nmaps), 256, 0, s>>>(a, labels, W, H, mx, my, sums, dcounts);
   seg_lowres_kernel<<<1, 1024, 0, s>>>(st, labels, finalSums, dcounts, sums, low, counts, unary, md, depthRange, rgb,
                                        T2, f6);
-  crf_norm_kernel<<<cdiv(N, kCrfRowsPerCta), 256, 0, s>>>((const CrfNode*)f6, T2, N, mx, n2, n6);
+  crf_norm_kernel<<<cdiv(N, kCrfRowsPerCta), 256, 0, s>>>((const CrfNode*)f6, T2, N, mx, K2, K6, n2, n6);
   if (L <= 2)
     launch_crf<2>(*this, L, prm, s);
   else if (L <= 4)
@@ -898,7 +914,77 @@ cudaError_t Segmentation::performSegmentationCRF(const uint8_t* rgb, const float
   SegModelData* hm = (SegModelData*)((char*)h_out + sizeof(SegResultHeader));
   RET_IF(cudaMemcpyAsync(hh, hdr, sizeof(SegResultHeader), cudaMemcpyDeviceToHost, s));
   RET_IF(cudaMemcpyAsync(hm, md, sizeof(SegModelData) * L, cudaMemcpyDeviceToHost, s));
+  return cudaSuccess;
+}
+
+namespace {
+struct GraphKey {  // every argument baked into the captured launches
+  const void *rgb, *depth, *fullSeg;
+  const void* maps[2 * SegLimits::kMaxModels];
+  unsigned char ids[SegLimits::kMaxModels + 1];
+  int numModels, allowNew;
+  SegParams prm;
+};
+bool same_key(const GraphKey& a, const GraphKey& b) {
+  if (a.rgb != b.rgb || a.depth != b.depth || a.fullSeg != b.fullSeg || a.numModels != b.numModels ||
+      a.allowNew != b.allowNew || memcmp(&a.prm, &b.prm, sizeof(SegParams)) != 0)
+    return false;
+  for (int m = 0; m < a.numModels; ++m)
+    if (a.maps[2 * m] != b.maps[2 * m] || a.maps[2 * m + 1] != b.maps[2 * m + 1] || a.ids[m] != b.ids[m]) return false;
+  return a.ids[a.numModels] == b.ids[b.numModels];
+}
+}  // namespace
+
+cudaError_t Segmentation::performSegmentationCRF(const uint8_t* rgb, const float* depth, int numModels,
+                                                 const unsigned char* modelIds, const float* const* icpError,
+                                                 const float* const* vertConf4, unsigned char nextModelID,
+                                                 bool allowNew, const SegParams& prm, uint8_t* fullSeg,
+                                                 SegModelData* md_host, int* md_count, bool* hasNew, cudaStream_t s) {
+  if (numModels < 1 || numModels > SegLimits::kMaxModels) return cudaErrorInvalidValue;
+  // The launch sequence only changes when a model is spawned / lost or a parameter moves: replay it as
+  // a CUDA graph (the legacy default stream cannot be captured -> plain launches there).
+  bool launched = false;
+  if (useGraph && s != nullptr && s != cudaStreamLegacy && s != cudaStreamPerThread) {
+    GraphKey k;
+    memset(&k, 0, sizeof(k));
+    k.rgb = rgb;
+    k.depth = depth;
+    k.fullSeg = fullSeg;
+    k.numModels = numModels;
+    k.allowNew = allowNew ? 1 : 0;
+    k.prm = prm;
+    for (int m = 0; m < numModels; ++m) {
+      k.maps[2 * m] = icpError[m];
+      k.maps[2 * m + 1] = vertConf4[m];
+      k.ids[m] = modelIds[m];
+    }
+    k.ids[numModels] = nextModelID;
+    GraphKey* cached = (GraphKey*)graphKey_;
+    if (!graphExec_ || !cached || !same_key(*cached, k)) {
+      if (graphExec_) cudaGraphExecDestroy((cudaGraphExec_t)graphExec_);
+      graphExec_ = nullptr;
+      cudaGraph_t graph = nullptr;
+      RET_IF(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      const cudaError_t ce =
+          enqueue(rgb, depth, numModels, modelIds, icpError, vertConf4, nextModelID, allowNew, prm, fullSeg, s);
+      const cudaError_t ee = cudaStreamEndCapture(s, &graph);
+      if (ce != cudaSuccess) return ce;
+      RET_IF(ee);
+      cudaGraphExec_t exec = nullptr;
+      RET_IF(cudaGraphInstantiate(&exec, graph, 0));
+      cudaGraphDestroy(graph);
+      graphExec_ = exec;
+      if (!cached) graphKey_ = cached = (GraphKey*)malloc(sizeof(GraphKey));
+      *cached = k;
+    }
+    RET_IF(cudaGraphLaunch((cudaGraphExec_t)graphExec_, s));
+    launched = true;
+  }
+  if (!launched)
+    RET_IF(enqueue(rgb, depth, numModels, modelIds, icpError, vertConf4, nextModelID, allowNew, prm, fullSeg, s));
   RET_IF(cudaStreamSynchronize(s));
+  const SegResultHeader* hh = (const SegResultHeader*)h_out;
+  const SegModelData* hm = (const SegModelData*)((const char*)h_out + sizeof(SegResultHeader));
   if (md_count) *md_count = hh->numModelData;
   if (hasNew) *hasNew = hh->hasNewLabel != 0;
   if (md_host) memcpy(md_host, hm, sizeof(SegModelData) * hh->numModelData);

@@ -52,7 +52,8 @@ class Segmentation {
                                      bool* hasNew, cudaStream_t s);
 
   int W, H, mx, my, N;
-  int launches = 0;  // kernels launched by the last performSegmentationCRF
+  int launches = 0;      // kernels launched by the last performSegmentationCRF
+  bool useGraph = true;  // replay the launch sequence as a CUDA graph on capturable streams
   // device scratch (public: the tests read labels / unary / lowMap through the C ABI)
   int* labels = nullptr;
   float* centers = nullptr;  // [2][N][5] ping-pong
@@ -62,6 +63,7 @@ class Segmentation {
   float *low = nullptr;      // low-res maps [maps][N]: depth, then icp / conf per model
   float *unary = nullptr, *f6 = nullptr;  // unaries [N][L]; node records [N][8] (6 features + x, y)
   float *T2 = nullptr;                    // smoothness kernel by grid offset [my][mx]
+  float *K2 = nullptr, *K6 = nullptr;      // Gaussian kernels [N][N], rebuilt every frame
   float *n2 = nullptr, *n6 = nullptr, *Q = nullptr;
   float *nq2 = nullptr, *nq6 = nullptr;  // [2][N][Lmax] ping-pong
   uint8_t* lowMap = nullptr;
@@ -71,7 +73,12 @@ class Segmentation {
   void* h_out = nullptr;
 
  private:
+  cudaError_t enqueue(const uint8_t* rgb, const float* depth, int numModels, const unsigned char* modelIds,
+                      const float* const* icpError, const float* const* vertConf4, unsigned char nextModelID,
+                      bool allowNew, const SegParams& prm, uint8_t* fullSeg, cudaStream_t s);
   bool ok_ = false;
+  void* graphExec_ = nullptr;  // cudaGraphExec_t of the cached launch sequence
+  void* graphKey_ = nullptr;   // the arguments it was captured with
 };
 
 }  // namespace cfb

@@ -128,7 +128,7 @@ def plane_sequence(n_frames=64, W=640, H=480, K=K_DEFAULT):
 
 
 def room_sequence(n_frames=200, W=640, H=480, K=K_DEFAULT, noise=True, seed=1234, n_boxes=0,
-                  deg_per_frame=1.0, radius=0.5):
+                  deg_per_frame=1.0, radius=0.5, box_speed=1.0, box_start=0):
     """Config 2 (n_boxes=0) / 3 (n_boxes=4) / 4 (n_boxes=8): camera on a 0.5 m orbit, 1 deg/frame."""
     rng = np.random.default_rng(seed) if noise else None
     brng = np.random.default_rng(seed + 1)
@@ -151,7 +151,8 @@ def room_sequence(n_frames=200, W=640, H=480, K=K_DEFAULT, noise=True, seed=1234
         # look across the room towards a corner, pitched so that floor/ceiling + walls are in view:
         # a single visible wall would make point-to-plane ICP rank deficient
         T = make_pose(rot_y(-a + np.pi / 2 + 0.6) @ rot_x(-0.4 + 0.1 * np.sin(2 * a)), t)
-        boxes = [(c0 + vel * i, hs, rot_y(w * i)) for (c0, hs, vel, w) in specs]
+        bi = max(i - box_start, 0)  # the boxes stand still until frame `box_start`
+        boxes = [(c0 + vel * box_speed * bi, hs, rot_y(w * bi)) for (c0, hs, vel, w) in specs]
         rgb, depth, ids = render_room(T, W, H, K, boxes=boxes, noise_rng=rng)
         yield i * 33, rgb, depth, T, ids
 

@@ -211,6 +211,8 @@ int cfb_model_perform_tracking(cfb_model* m, const cfb_track_params* p, float po
 /* Model::setConfidenceThreshold / setMaxDepth (Model.h:161-165) */
 int cfb_model_set_confidence_threshold(cfb_model* m, float confThresh);
 int cfb_model_set_max_depth(cfb_model* m, float d);
+/* Model::getID / getConfidenceThreshold / getMaxDepth (Model.h:160-166) */
+int cfb_model_get_info(cfb_model* m, unsigned* id, float* confThresh, float* maxDepth);
 /* Model::initialise (Model.cpp:227-272) + CoFusion::computeFeedbackBuffers (CoFusion.cpp:161-169):
  * surfels from the current frame's raw + filtered depth */
 int cfb_model_initialise(cfb_model* m, int time, float maxDepthProcessed);

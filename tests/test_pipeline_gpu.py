@@ -67,3 +67,65 @@ def test_static_plane_config0_drift():
         assert np.abs(pg - po).max() < 1e-4, (t, pg, po)
     step_err = [np.abs(res[t][0] - res[t][2]).max() for t in range(len(res))]
     assert max(step_err) < 6e-3 * len(res), step_err
+
+
+def test_multi_model_segmentation_sequence():
+    """enableMultipleModels: tracking of every model -> motion segmentation -> spawn / lose object
+    models -> fuse / clean per label (CoFusion.cpp:171-524, :227-299) against the oracle pipeline.
+    A box starts to move in frame 4; within 10 frames the scenario spawns two object models and
+    deactivates one.  Label decisions are discrete, the inputs (poses, ICP error) agree to ~1e-6:
+    the model lists and ModelData must match, masks may differ in a handful of border super-pixels.
+    (Longer runs are not compared frame by frame: a 20-super-pixel object is a chaotic system -- one
+    border super-pixel flipping label changes which pixels fuse, and the two pipelines drift apart.)"""
+    import cofusion_b200 as cfb
+    import orc
+    from orc_pipeline import OracleCoFusion
+    W, H, frames = 320, 240, 10
+    K = scenes.scaled_K(W)
+    seq = list(synth.room_sequence(frames, W, H, K, noise=True, n_boxes=1, box_speed=4.0, box_start=4))
+    p = cfb.CoFusionParams.default(1 << 18)
+    p.confGlobalInit = 1.5
+    p.enableMultipleModels = 1
+    p.modelSpawnOffset = 2
+    p.seg.unaryWeightError = 150.0
+    p.seg.unaryThresholdNew = 3.5
+    op_prm = orc.OrcSegParams.default()
+    op_prm.unaryWeightError = 150.0
+    op_prm.unaryThresholdNew = 3.5
+    cf = cfb.CoFusion(W, H, K, p)
+    op = OracleCoFusion(W, H, K, max_surfels=1 << 18, conf_global=1.5, spawn_offset=2, seg_params=op_prm)
+    spawned, lost = [], 0
+    for t in range(frames):
+        rgb, d = np.ascontiguousarray(seq[t][1]), np.ascontiguousarray(seq[t][2])
+        cf.process_frame(rgb, d)
+        op.process_frame(rgb, d)
+        ids_g = [cf.model(i).info()[0] for i in range(cf.num_models)]
+        ids_o = [m.id for m in op.models]
+        assert ids_g == ids_o, (t, ids_g, ids_o)
+        if t == 0:
+            continue
+        mds_g, new_g, spawn_g, lost_g = cf.last_segmentation()
+        mds_o, new_o, spawn_o, lost_o = op.last_seg
+        assert (new_g, spawn_g, lost_g) == (new_o, spawn_o, lost_o), t
+        assert len(mds_g) == len(mds_o)
+        for a, b in zip(mds_g, mds_o):
+            assert a.id == b["id"] and abs(int(a.superPixelCount) - int(b["superPixelCount"])) <= 2, (t, a.astuple(), b)
+            assert abs(a.avgConfidence - b["avgConfidence"]) < 1e-3 and abs(a.depthMean - b["depthMean"]) < 2e-2
+        mask_g = cf.ctx_view_mask()
+        assert (mask_g != op.mask).mean() < 0.01, (t, (mask_g != op.mask).mean())
+        for i, m in enumerate(op.models):
+            gm = cf.model(i)
+            # north_star tolerance (1e-4) for the camera; an object of a few hundred surfels has an
+            # ill-conditioned 6x6 system (cond ~3e3 here) that amplifies the 1e-7 input differences
+            # between the two pipelines: its bound scales with the condition number
+            cond = np.linalg.cond(np.array(m.stats.lastA).reshape(6, 6)) if m.stats else 1.0
+            tol = 1e-4 if i == 0 else max(1e-4, 1e-7 * cond)
+            assert np.abs(gm.pose - m.pose).max() < tol, (t, i, m.map.count, cond, gm.pose, m.pose)
+            gid, gconf, gmax = gm.info()
+            assert abs(gconf - float(m.conf)) < 1e-3 and (gmax == float(m.max_depth) or abs(gmax - float(m.max_depth)) < 2e-2)
+            ng, no = gm.last_count(), m.map.count
+            assert abs(ng - no) <= max(8, 0.02 * no), (t, i, ng, no)
+        if spawn_g >= 0:
+            spawned.append(spawn_g)
+        lost += lost_g
+    assert spawned == [1, 2] and lost == 1 and cf.num_inactive_models == 1

@@ -97,3 +97,17 @@ def test_default_params_match_oracle():
     op, gp = orc.OrcSegParams.default(), cfb.SegParams.default()
     for name, _ in cfb.SegParams._fields_:
         assert getattr(op, name) == getattr(gp, name), name
+
+
+def test_graph_replay_on_a_side_stream_matches():
+    """On a capturable stream the launch sequence is replayed as a CUDA graph; results must not change,
+    also when the arguments change between calls (graph re-capture)."""
+    import torch
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        c = seg_cases.room_case(320, 240)
+        for _ in range(2):
+            _check(c)
+        _check(c, allow_new=False)
+        _check(seg_cases.two_model_case(320, 240))
+    torch.cuda.synchronize()

@@ -7,6 +7,8 @@ import torch
 import cofusion_b200 as cfb
 import seg_cases
 
+side = torch.cuda.Stream()
+torch.cuda.set_stream(side)  # a capturable stream: the launch sequence is replayed as a CUDA graph
 for name, c in (("1 model", seg_cases.room_case()), ("2 models", seg_cases.two_model_case())):
     H, W = c["depth"].shape
     seg = cfb.Segmentation(W, H)
