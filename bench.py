@@ -204,8 +204,28 @@ def main():
             b = packed_host[i]
             cf.process_frame(b[:3 * P], b[3 * P:].view(torch.float32))
 
+    keep = []  # the pipelines (and their streams) outlive every torch tensor that was used on them
+
+    def shutdown():
+        # torch's caching allocators record events on the streams a block was used on when it is freed:
+        # free the frame buffers while the library streams are still alive, then the pipelines, then NCCL
+        nonlocal packed_dev, recv
+        torch.cuda.synchronize()
+        packed_host.clear()
+        packed_dev = None
+        recv = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        keep.clear()
+        gc.collect()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+
     def timed(step_fn, sampler=None):
         cf, odom = build()
+        keep.append(cf)
         ext = torch.cuda.ExternalStream(cf.ctx.stream)
         with torch.cuda.stream(ext):
             for t in range(args.warmup):
@@ -242,8 +262,7 @@ def main():
     ms, launches, (kms, kn), nsurf = timed(step_resident, sampler)
     ms_e2e, _, _, _ = timed(step_e2e)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown()
         return
 
     value = world * args.steps / (ms / 1e3)
@@ -291,8 +310,7 @@ def main():
         "clocks": sampler.summary() if sampler else None,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 if __name__ == "__main__":

@@ -20,7 +20,6 @@ namespace {
 using namespace dev;
 
 constexpr int kPT = 512;   // threads per CTA, one CTA per SM
-constexpr int kMaxPP = 6;  // pixels per thread whose correspondences stay in registers
 
 struct LevelData {
   const float *vmap_curr, *nmap_curr, *vmap_g_prev, *nmap_g_prev;
@@ -63,6 +62,28 @@ __device__ __forceinline__ unsigned long long gtime() {
   do {                                                                       \
     if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[(slot)] = gtime(); \
   } while (0)
+
+// All shared state lives in ONE dynamic allocation with a fixed layout, so that the (deliberately
+// not inlined: one copy of the FP64 solve instead of five) phase functions can re-derive typed
+// shared-memory references from `extern __shared__` -- LDS/STS with immediate offsets instead of
+// generic loads through pointers, and no local-memory copy of the kernel parameters.
+enum StagePlane { SP_VX, SP_VY, SP_VZ, SP_NX, SP_NY, SP_NZ, SP_D1, SP_SOB, SP_FLAGS, SP_ZERO, SP_DIFF, SP_D0, SP_COUNT };
+constexpr int kStagePP = 5;  // 640x480 on 148 x 512 threads: ceil(307200 / 75776)
+constexpr unsigned kNoCorr = 0xffffffffu;
+struct Smem {
+  float stage[SP_COUNT * kStagePP * kPT];
+  float red[2 * (kPT / 32) * 32];
+  float out64[64];
+  GNState S;  // every CTA keeps (and identically updates) its own copy of the GN state
+  int scnt[kPT / 32], ssig[kPT / 32];
+  PersistParams prm;
+  int sched[20];
+  int nsched;
+};
+#define SMEM_REF()                                                \
+  extern __shared__ __align__(16) unsigned char dyn_smem_raw[]; \
+  Smem& sm = *reinterpret_cast<Smem*>(dyn_smem_raw);              \
+  const PersistParams& p = sm.prm
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   unsigned v;
@@ -160,234 +181,469 @@ __device__ __forceinline__ float block_reduce32_sparse(float (&v)[32], bool warp
   return s;
 }
 
-__global__ void __launch_bounds__(kPT, 1) gn_persistent_kernel(const PersistParams p) {
-  __shared__ float red[2 * (kPT / 32) * 32];
-  __shared__ float out64[64];
-  __shared__ GNState S;  // every CTA keeps (and identically updates) its own copy of the GN state
-  __shared__ int scnt[kPT / 32], ssig[kPT / 32];
+// ---------------------------------------------------------------------------------------------
+// Per-level staging.  The pixels a thread owns (tid + k * nthreads) do not change within a level, and
+// half of what an iteration reads about them does not change either: the current-frame vertex and
+// normal, nextDepth / nextImage / Sobel of the photometric term, the candidate gate.  They are loaded
+// ONCE per level into shared memory (plane-major [plane][k][thread], conflict free); an iteration
+// then only issues the pose-dependent gathers (model vertex / normal, lastDepth / lastImage), all of a
+// thread's pixels in flight together, and the RGB Jacobian pass touches no global memory at all.
+struct LevelCtx {  // everything the phases of one level need, built once per level
+  IcpArgs ia;
+  RgbResidualArgs ra;
+};
 
+__device__ __forceinline__ void make_level_ctx(const PersistParams& p, const LevelData& L, LevelCtx& c) {
+  const size_t pitch = (size_t)L.w * 4;
+  c.ia.vmap_curr = {L.vmap_curr, pitch};
+  c.ia.nmap_curr = {L.nmap_curr, pitch};
+  c.ia.vmap_g_prev = {L.vmap_g_prev, pitch};
+  c.ia.nmap_g_prev = {L.nmap_g_prev, pitch};
+  c.ia.intr = Intr{L.k.fx, L.k.fy, L.k.cx, L.k.cy};
+  c.ia.distThres = p.distThres;
+  c.ia.angleThres = p.angleThres;
+  c.ia.cols = L.w;
+  c.ia.rows = L.h;
+  c.ia.error_map = nullptr;
+  c.ia.error_pitch = p.err_pitch;
+  c.ra.minScale = 0.f;
+  c.ra.maxDepthDelta = p.maxDepthDelta;
+  c.ra.dIdx = L.dIdx;
+  c.ra.dIdy = L.dIdy;
+  c.ra.grad_pitch = (size_t)L.w * 2;
+  c.ra.lastDepth = L.lastDepth;
+  c.ra.nextDepth = L.nextDepth;
+  c.ra.depth_pitch = pitch;
+  c.ra.lastImage = L.lastImage;
+  c.ra.nextImage = L.nextImage;
+  c.ra.img_pitch = (size_t)L.w;
+  c.ra.corres = L.corres;
+  c.ra.cols = L.w;
+  c.ra.rows = L.h;
+}
+
+// the common tail of a GN iteration: barrier B, fixed-order fold of the partial rows, FP64 solve
+__device__ __noinline__ void finish_iteration(unsigned& barriers, int q, float tmpError, int tot_cnt) {
+  SMEM_REF();
   GridSync* gs = p.gs;
   StepScratch* sc = p.sc;
-  const int tid = blockIdx.x * kPT + threadIdx.x, nthreads = gridDim.x * kPT;
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nsched = sm.nsched;
+  const int* sched = sm.sched;
   const unsigned G = gridDim.x;
-  unsigned barriers = 0;  // barriers completed so far -> target = (barriers + 1) * G
-
-  int sched[19], nsched = 0;
-  for (int i = 2; i >= 0; --i)
-    for (int j = 0; j < p.iters[i] && nsched < 19; ++j) sched[nsched++] = i;
-
-  DBG_MARK(0);
+  grid_arrive(gs);  // barrier B
+  grid_wait(gs, ++barriers * G);
+  DBG_MARK(8 + q * 8 + 5);
+  const float* rows = sc->partials + (size_t)(((q & 1) * 2) * G) * 32;
+  sum_partials<2>(rows, G, sm.red, sm.out64);
+  DBG_MARK(8 + q * 8 + 6);
+  const int is_last = (q + 1 == nsched);
   if (threadIdx.x == 0) {
-    gn_init_serial(&S, nullptr, p.pose_in, p.L[2].k);
-    if (!p.use_so3) gn_begin_serial(&S, 0, p.L[nsched ? sched[0] : 0].k);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) sm.S.icp_result[i] = sm.out64[i];
+    gn_solve_serial(&sm.S, nullptr, sm.out64 + 32, p.icpWeight, p.L[is_last ? sched[q] : sched[q + 1]].k, is_last,
+                    tmpError, tot_cnt);
   }
   __syncthreads();
-  // partial rows: set s in {0: ICP / SO3, 1: RGB}, double buffered by iteration parity
-  auto prow = [&](int set, int parity) { return sc->partials + (size_t)((parity * 2 + set) * G) * 32; };
+  DBG_MARK(8 + q * 8 + 7);
+}
 
-  DBG_MARK(1);
-  // ---- SO(3) pre-alignment on level 2 (RGBDOdometry.cpp:239-310)
-  if (p.use_so3) {
-    const LevelData& L = p.L[2];
-    const int N = L.w * L.h;
-    for (int it = 0; it < 10; ++it) {
-      if (S.so3_done) break;  // identical in every CTA
-      float acc[32];
+// publish the integer photometric count / sigma of this CTA, then arrive at barrier A
+__device__ __forceinline__ void publish_counts(int q, int cnt, int sig) {
+  SMEM_REF();
+  GridSync* gs = p.gs;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-      bool work = false;
-      for (int q = tid; q < N; q += nthreads) {
-        int y = q / L.w, x = q - y * L.w;
-        so3_pixel(p.so3_last, p.so3_next, (size_t)L.w, L.w, L.h, S.so3_imageBasis, S.so3_kinv, S.so3_krlr, x, y, acc);
-        work = true;
-      }
-      float bt = block_reduce32_sparse(acc, __any_sync(0xffffffffu, work), red);
-      if (warp == 0) prow(0, it & 1)[blockIdx.x * 32 + lane] = bt;
-      grid_arrive(gs);
-      grid_wait(gs, ++barriers * G);
-      sum_partials<1>(prow(0, it & 1), G, red, out64);
-      if (threadIdx.x == 0) {
-        so3_update_serial(&S, out64, L.k);
-        if (S.so3_done || it == 9) gn_begin_serial(&S, 1, p.L[nsched ? sched[0] : 0].k);
-      }
-      __syncthreads();
-    }
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    sig += __shfl_xor_sync(0xffffffffu, sig, o);
   }
+  if (lane == 0) {
+    sm.scnt[warp] = cnt;
+    sm.ssig[warp] = sig;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int c = 0, s = 0;
+    for (int w = 0; w < kPT / 32; ++w) {
+      c += sm.scnt[w];
+      s += sm.ssig[w];
+    }
+    atomicAdd(&gs->counts[q][0], c);  // integer sums commute exactly
+    atomicAdd(&gs->counts[q][1], s);
+  }
+  grid_arrive(gs);  // barrier A: its latency is hidden behind the ICP pass
+}
 
-  DBG_MARK(2);
-  // ---- Gauss-Newton iterations, coarse to fine (RGBDOdometry.cpp:331-461)
-  for (int q = 0; q < nsched; ++q) {
+__device__ __forceinline__ float fetch_sigma(int q, float* tmpError, int* tot) {
+  SMEM_REF();
+  GridSync* gs = p.gs;
+  if (threadIdx.x == 0) {
+    sm.scnt[0] = __ldcg(&gs->counts[q][0]);
+    sm.ssig[0] = __ldcg(&gs->counts[q][1]);
+  }
+  __syncthreads();
+  const int tot_cnt = sm.scnt[0], tot_sig = sm.ssig[0];
+  *tot = tot_cnt;
+  return rgb_sigma_from_counts(tot_cnt, tot_sig, tmpError);
+}
+
+template <int PP>
+__device__ __noinline__ void run_level_staged(int lvl, int q0, int nit, unsigned& barriers) {
+  SMEM_REF();
+  GridSync* gs = p.gs;
+  StepScratch* sc = p.sc;
+  const LevelData& L = p.L[lvl];
+  const int N = L.w * L.h, W = L.w;
+  const int tid = blockIdx.x * kPT + threadIdx.x, nthreads = gridDim.x * kPT;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, G = gridDim.x;
+  auto at = [&](int plane, int k) -> float& { return sm.stage[(plane * PP + k) * kPT + threadIdx.x]; };
+  auto prow = [&](int set, int parity) { return sc->partials + (size_t)((parity * 2 + set) * G) * 32; };
+  LevelCtx c;
+  make_level_ctx(p, L, c);
+  const GNState& S = sm.S;
+
+  // ---- stage the iteration-invariant inputs of this thread's pixels
+  bool any_px = false;
+#pragma unroll
+  for (int k = 0; k < PP; ++k) {
+    const int px = tid + k * nthreads;
+    unsigned flags = 0;
+    if (px < N) {
+      any_px = true;
+      const int y = px / W, x = px - y * W;
+      at(SP_VX, k) = ldplane(c.ia.vmap_curr, y, x);
+      at(SP_VY, k) = ldplane(c.ia.vmap_curr, y + L.h, x);
+      at(SP_VZ, k) = ldplane(c.ia.vmap_curr, y + 2 * L.h, x);
+      at(SP_NX, k) = ldplane(c.ia.nmap_curr, y, x);
+      at(SP_NY, k) = ldplane(c.ia.nmap_curr, y + L.h, x);
+      at(SP_NZ, k) = ldplane(c.ia.nmap_curr, y + 2 * L.h, x);
+      at(SP_D1, k) = __ldg(L.nextDepth + px);
+      const unsigned sob = (unsigned)(unsigned short)__ldg(L.dIdx + px) | ((unsigned)(unsigned short)__ldg(L.dIdy + px) << 16);
+      at(SP_SOB, k) = __uint_as_float(sob);
+      flags = 0x10000u | (__ldg(L.cand + px) ? 1u : 0u) | ((unsigned)__ldg(L.nextImage + px) << 8);
+    }
+    at(SP_FLAGS, k) = __uint_as_float(flags);
+  }
+  const bool warp_work = __any_sync(0xffffffffu, any_px);
+
+  for (int it = 0; it < nit; ++it) {
+    const int q = q0 + it;
     DBG_MARK(8 + q * 8 + 0);
-    const LevelData& L = p.L[sched[q]];
-    const int N = L.w * L.h;
-    const bool keep = (N <= nthreads * kMaxPP);  // correspondences stay in registers
     const IcpPose& P = S.pose;
     const RgbWarp& Wp = S.warp;
+    const bool last_of_l0 = (lvl == 0 && it + 1 == nit);
+    float* const error_map = last_of_l0 ? p.err : nullptr;
 
-    IcpArgs ia;
-    const size_t pitch = (size_t)L.w * 4;
-    ia.vmap_curr = {L.vmap_curr, pitch};
-    ia.nmap_curr = {L.nmap_curr, pitch};
-    ia.vmap_g_prev = {L.vmap_g_prev, pitch};
-    ia.nmap_g_prev = {L.nmap_g_prev, pitch};
-    ia.intr = Intr{L.k.fx, L.k.fy, L.k.cx, L.k.cy};
-    ia.distThres = p.distThres;
-    ia.angleThres = p.angleThres;
-    ia.cols = L.w;
-    ia.rows = L.h;
-    const bool last_of_l0 = (sched[q] == 0 && (q + 1 == nsched || sched[q + 1] != 0));
-    ia.error_map = last_of_l0 ? p.err : nullptr;
-    ia.error_pitch = p.err_pitch;
-    RgbResidualArgs ra;
-    ra.minScale = 0.f;
-    ra.maxDepthDelta = p.maxDepthDelta;
-    ra.dIdx = L.dIdx;
-    ra.dIdy = L.dIdy;
-    ra.grad_pitch = (size_t)L.w * 2;
-    ra.lastDepth = L.lastDepth;
-    ra.nextDepth = L.nextDepth;
-    ra.depth_pitch = pitch;
-    ra.lastImage = L.lastImage;
-    ra.nextImage = L.nextImage;
-    ra.img_pitch = (size_t)L.w;
-    ra.corres = L.corres;
-    ra.cols = L.w;
-    ra.rows = L.h;
-
-    // -------- phase 1: photometric correspondences (count needed by every CTA before phase 3)
+    // -------- phase 1: photometric correspondences; all gathers of the thread in flight together
     int cnt = 0, sig = 0;
-    unsigned kzero[kMaxPP];
-    float kdiff[kMaxPP];
-    unsigned kvalid = 0;
-    if (keep) {
+    {
+      int u0[PP], v0[PP];
+      float td1[PP];
+      bool ok[PP];
 #pragma unroll
-      for (int k = 0; k < kMaxPP; ++k) {
-        const int px = tid + k * nthreads;
-        kzero[k] = 0;
-        kdiff[k] = 0.f;
-        if (px < N && __ldg(L.cand + px)) {
-          int y = px / L.w, x = px - y * L.w;
-          DataTerm c;
-          int sq;
-          if (rgb_residual_cand(ra, Wp, x, y, c, sq)) {
-            cnt += 1;
-            sig += sq;
-            kvalid |= 1u << k;
-            kzero[k] = (unsigned)(unsigned short)c.zero.x | ((unsigned)(unsigned short)c.zero.y << 16);
-            kdiff[k] = c.diff;
-          }
+      for (int k = 0; k < PP; ++k) {
+        const unsigned flags = __float_as_uint(at(SP_FLAGS, k));
+        ok[k] = (flags & 1u) != 0;
+        u0[k] = v0[k] = 0;
+        td1[k] = 0.f;
+        if (ok[k]) {
+          const int px = tid + k * nthreads, y = px / W, x = px - y * W;
+          const float d1 = at(SP_D1, k);
+          const float* kk = Wp.krkinv.m;
+          td1[k] = d1 * (kk[6] * x + kk[7] * y + kk[8]) + Wp.kt[2];
+          u0[k] = __float2int_rn((d1 * (kk[0] * x + kk[1] * y + kk[2]) + Wp.kt[0]) / td1[k]);
+          v0[k] = __float2int_rn((d1 * (kk[3] * x + kk[4] * y + kk[5]) + Wp.kt[1]) / td1[k]);
+          ok[k] = (u0[k] >= 0 && v0[k] >= 0 && u0[k] < W && v0[k] < L.h);
         }
       }
-    } else {
-      for (int px = tid; px < N; px += nthreads) {
-        int y = px / L.w, x = px - y * L.w;
-        DataTerm c;
-        c.valid = false;
-        c.zero = make_short2(0, 0);
-        c.diff = 0.f;
-        int sq;
-        if (__ldg(L.cand + px) && rgb_residual_cand(ra, Wp, x, y, c, sq)) {
+      float d0[PP];
+      unsigned char li[PP];
+#pragma unroll
+      for (int k = 0; k < PP; ++k) {
+        d0[k] = ok[k] ? __ldg(L.lastDepth + v0[k] * W + u0[k]) : 0.f;
+        li[k] = ok[k] ? __ldg(L.lastImage + v0[k] * W + u0[k]) : (unsigned char)0;
+      }
+#pragma unroll
+      for (int k = 0; k < PP; ++k) {
+        unsigned zero = kNoCorr;
+        if (ok[k] && d0[k] > 0 && fabsf(td1[k] - d0[k]) <= p.maxDepthDelta && li[k] != 0) {
+          const unsigned flags = __float_as_uint(at(SP_FLAGS, k));
+          const float diff = (float)((flags >> 8) & 0xffu) - (float)li[k];
           cnt += 1;
-          sig += sq;
+          sig += (int)(diff * diff);  // float -> int truncation, reduce.cu:851
+          zero = (unsigned)(unsigned short)u0[k] | ((unsigned)(unsigned short)v0[k] << 16);
+          at(SP_DIFF, k) = diff;
+          at(SP_D0, k) = d0[k];
         }
-        int4 raw;
-        raw.x = (int)((unsigned short)c.zero.x | ((unsigned)(unsigned short)c.zero.y << 16));
-        raw.y = 0;
-        raw.z = __float_as_int(c.diff);
-        raw.w = c.valid ? 1 : 0;
-        reinterpret_cast<int4*>(L.corres)[px] = raw;
+        at(SP_ZERO, k) = __uint_as_float(zero);
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-      sig += __shfl_xor_sync(0xffffffffu, sig, o);
-    }
-    if (lane == 0) {
-      scnt[warp] = cnt;
-      ssig[warp] = sig;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int c = 0, s = 0;
-      for (int w = 0; w < kPT / 32; ++w) {
-        c += scnt[w];
-        s += ssig[w];
-      }
-      atomicAdd(&gs->counts[q][0], c);  // integer sums commute exactly
-      atomicAdd(&gs->counts[q][1], s);
-    }
-    grid_arrive(gs);  // barrier A: its latency is hidden behind the ICP pass below
+    publish_counts(q, cnt, sig);
     DBG_MARK(8 + q * 8 + 1);
 
     // -------- phase 2: ICP rows (independent of the count)
     float acc[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-    bool work = false;
-    for (int px = tid; px < N; px += nthreads) {
-      int y = px / L.w, x = px - y * L.w;
-      icp_pixel(ia, P, x, y, acc);
-      work = true;
+    {
+      const float3 tcurr = make_float3(P.tcurr[0], P.tcurr[1], P.tcurr[2]);
+      const float3 tprev = make_float3(P.tprev[0], P.tprev[1], P.tprev[2]);
+      int ux[PP], uy[PP];
+      bool ok[PP];
+#pragma unroll
+      for (int k = 0; k < PP; ++k) {
+        const int px = tid + k * nthreads;
+        ok[k] = false;
+        ux[k] = uy[k] = 0;
+        if (px < N) {
+          const float3 vcurr = make_float3(at(SP_VX, k), at(SP_VY, k), at(SP_VZ, k));
+          const float3 vcurr_g = mul(P.Rcurr, vcurr) + tcurr;
+          const float3 vcurr_cp = mul(P.Rprev_inv, vcurr_g - tprev);
+          ux[k] = __float2int_rn(vcurr_cp.x * c.ia.intr.fx / vcurr_cp.z + c.ia.intr.cx);
+          uy[k] = __float2int_rn(vcurr_cp.y * c.ia.intr.fy / vcurr_cp.z + c.ia.intr.cy);
+          ok[k] = !(ux[k] < 0 || uy[k] < 0 || ux[k] >= W || uy[k] >= L.h || vcurr_cp.z < 0);
+          if (!ok[k] && error_map) {
+            const int y = px / W, x = px - y * W;
+            row_ptr(error_map, p.err_pitch, y)[x] = 0.0f;
+          }
+        }
+      }
+      float3 vp[PP], np[PP];
+#pragma unroll
+      for (int k = 0; k < PP; ++k) {
+        vp[k] = np[k] = make_float3(0.f, 0.f, 0.f);
+        if (ok[k]) {
+          vp[k] = make_float3(ldplane(c.ia.vmap_g_prev, uy[k], ux[k]), ldplane(c.ia.vmap_g_prev, uy[k] + L.h, ux[k]),
+                              ldplane(c.ia.vmap_g_prev, uy[k] + 2 * L.h, ux[k]));
+          np[k] = make_float3(ldplane(c.ia.nmap_g_prev, uy[k], ux[k]), ldplane(c.ia.nmap_g_prev, uy[k] + L.h, ux[k]),
+                              ldplane(c.ia.nmap_g_prev, uy[k] + 2 * L.h, ux[k]));
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < PP; ++k) {
+        if (!ok[k]) continue;
+        const float3 vcurr = make_float3(at(SP_VX, k), at(SP_VY, k), at(SP_VZ, k));
+        const float3 ncurr = make_float3(at(SP_NX, k), at(SP_NY, k), at(SP_NZ, k));
+        const float3 vcurr_g = mul(P.Rcurr, vcurr) + tcurr;
+        const float3 vcurr_cp = mul(P.Rprev_inv, vcurr_g - tprev);
+        const float3 ncurr_g = mul(P.Rcurr, ncurr);
+        const float dist = norm(vp[k] - vcurr_g);
+        const float sine = norm(cross(ncurr_g, np[k]));
+        if (error_map) {
+          const int px = tid + k * nthreads, y = px / W, x = px - y * W;
+          row_ptr(error_map, p.err_pitch, y)[x] = isfinite(dist) ? dist : 0.0f;
+        }
+        const bool found = (sine < p.angleThres && dist <= p.distThres && !isnan(ncurr.x) && !isnan(np[k].x));
+        if (found) {
+          const float3 d_cp = mul(P.Rprev_inv, vp[k] - tprev);
+          const float3 n_cp = mul(P.Rprev_inv, np[k]);
+          const float3 cr = cross(vcurr_cp, n_cp);
+          const float row[7] = {n_cp.x, n_cp.y, n_cp.z, cr.x, cr.y, cr.z, dot(n_cp, vcurr_cp - d_cp)};
+          accumulate_se3(acc, row, true);
+        }
+      }
     }
-    float bt = block_reduce32_sparse(acc, __any_sync(0xffffffffu, work), red);
+    float bt = block_reduce32_sparse(acc, warp_work, sm.red);
     if (warp == 0) prow(0, q & 1)[blockIdx.x * 32 + lane] = bt;
     DBG_MARK(8 + q * 8 + 2);
     grid_wait(gs, ++barriers * G);
     DBG_MARK(8 + q * 8 + 3);
 
-    // -------- phase 3: RGB rows weighted with the global count
-    if (threadIdx.x == 0) {
-      scnt[0] = __ldcg(&gs->counts[q][0]);
-      ssig[0] = __ldcg(&gs->counts[q][1]);
-    }
-    __syncthreads();
-    const int tot_cnt = scnt[0], tot_sig = ssig[0];
+    // -------- phase 3: RGB rows weighted with the global count -- shared memory only
     float tmpError;
-    const float sigma = rgb_sigma_from_counts(tot_cnt, tot_sig, &tmpError);
+    int tot_cnt;
+    const float sigma = fetch_sigma(q, &tmpError, &tot_cnt);
 #pragma unroll
     for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-    if (keep) {
+    bool any_valid = false;
 #pragma unroll
-      for (int k = 0; k < kMaxPP; ++k) {
-        const int px = tid + k * nthreads;
-        if (px < N && ((kvalid >> k) & 1u)) {
-          int y = px / L.w, x = px - y * L.w;
-          rgb_step_from_depth(L, sigma, p.sobelScale, true, kzero[k], kdiff[k], x, y, acc);
-        }
-      }
-    } else {
-      for (int px = tid; px < N; px += nthreads) {
-        int4 raw = reinterpret_cast<const int4*>(L.corres)[px];
-        if (raw.w & 0xff) {
-          int y = px / L.w, x = px - y * L.w;
-          rgb_step_from_depth(L, sigma, p.sobelScale, true, (unsigned)raw.x, __int_as_float(raw.z), x, y, acc);
-        }
-      }
+    for (int k = 0; k < PP; ++k) {
+      const unsigned zero = __float_as_uint(at(SP_ZERO, k));
+      if (zero == kNoCorr) continue;
+      any_valid = true;
+      const float diff = at(SP_DIFF, k), z = at(SP_D0, k);
+      const unsigned sob = __float_as_uint(at(SP_SOB, k));
+      float w = sigma + fabsf(diff);
+      w = w > 1.19209290E-07F ? 1.0f / w : 1.0f;
+      if (sigma == -1.f) w = 1.f;
+      const int zx = (int)(zero & 0xffff), zy = (int)(zero >> 16);
+      const float invFx = 1.0f / L.k.fx, invFy = 1.0f / L.k.fy;
+      const float3 Pt = make_float3(((float)zx - L.k.cx) * z * invFx, ((float)zy - L.k.cy) * z * invFy, z);
+      const float invz = (float)(1.0 / (double)Pt.z);
+      const float dI_dx_val = w * p.sobelScale * (float)(short)(sob & 0xffff);
+      const float dI_dy_val = w * p.sobelScale * (float)(short)(sob >> 16);
+      const float v0 = dI_dx_val * L.k.fx * invz;
+      const float v1 = dI_dy_val * L.k.fy * invz;
+      const float v2 = -(v0 * Pt.x + v1 * Pt.y) * invz;
+      const float row[7] = {v0, v1, v2, -Pt.z * v1 + Pt.y * v2, Pt.z * v0 - Pt.x * v2, -Pt.y * v0 + Pt.x * v1, -w * diff};
+      accumulate_se3(acc, row, true);
     }
     // invalid correspondences contribute nothing to any of the 29 sums (reduce.cu:562-601)
-    bt = block_reduce32_sparse(acc, __any_sync(0xffffffffu, kvalid != 0 || !keep), red);
+    bt = block_reduce32_sparse(acc, __any_sync(0xffffffffu, any_valid), sm.red);
     if (warp == 0) prow(1, q & 1)[blockIdx.x * 32 + lane] = bt;
     DBG_MARK(8 + q * 8 + 4);
-    grid_arrive(gs);  // barrier B
-    grid_wait(gs, ++barriers * G);
-    DBG_MARK(8 + q * 8 + 5);
-    sum_partials<2>(prow(0, q & 1), G, red, out64);
-    DBG_MARK(8 + q * 8 + 6);
-    const int is_last = (q + 1 == nsched);
-    if (threadIdx.x == 0) {
+    finish_iteration(barriers, q, tmpError, tot_cnt);
+  }
+}
+
+// any image size: correspondences round-trip through the DataTerm image, nothing is staged
+__device__ __noinline__ void run_level_generic(int lvl, int q0, int nit, unsigned& barriers) {
+  SMEM_REF();
+  GridSync* gs = p.gs;
+  StepScratch* sc = p.sc;
+  const LevelData& L = p.L[lvl];
+  const int N = L.w * L.h;
+  const int tid = blockIdx.x * kPT + threadIdx.x, nthreads = gridDim.x * kPT;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, G = gridDim.x;
+  auto prow = [&](int set, int parity) { return sc->partials + (size_t)((parity * 2 + set) * G) * 32; };
+  LevelCtx c;
+  make_level_ctx(p, L, c);
+  const GNState& S = sm.S;
+  for (int it = 0; it < nit; ++it) {
+    const int q = q0 + it;
+    DBG_MARK(8 + q * 8 + 0);
+    const IcpPose& P = S.pose;
+    const RgbWarp& Wp = S.warp;
+    c.ia.error_map = (lvl == 0 && it + 1 == nit) ? p.err : nullptr;
+    int cnt = 0, sig = 0;
+    for (int px = tid; px < N; px += nthreads) {
+      int y = px / L.w, x = px - y * L.w;
+      DataTerm ct;
+      ct.valid = false;
+      ct.zero = make_short2(0, 0);
+      ct.diff = 0.f;
+      int sq;
+      if (__ldg(L.cand + px) && rgb_residual_cand(c.ra, Wp, x, y, ct, sq)) {
+        cnt += 1;
+        sig += sq;
+      }
+      int4 raw;
+      raw.x = (int)((unsigned short)ct.zero.x | ((unsigned)(unsigned short)ct.zero.y << 16));
+      raw.y = 0;
+      raw.z = __float_as_int(ct.diff);
+      raw.w = ct.valid ? 1 : 0;
+      reinterpret_cast<int4*>(L.corres)[px] = raw;
+    }
+    publish_counts(q, cnt, sig);
+    DBG_MARK(8 + q * 8 + 1);
+    float acc[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) S.icp_result[i] = out64[i];
-      gn_solve_serial(&S, nullptr, out64 + 32, p.icpWeight, p.L[is_last ? sched[q] : sched[q + 1]].k, is_last, tmpError,
-                      tot_cnt);
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    bool work = false;
+    for (int px = tid; px < N; px += nthreads) {
+      int y = px / L.w, x = px - y * L.w;
+      icp_pixel(c.ia, P, x, y, acc);
+      work = true;
+    }
+    float bt = block_reduce32_sparse(acc, __any_sync(0xffffffffu, work), sm.red);
+    if (warp == 0) prow(0, q & 1)[blockIdx.x * 32 + lane] = bt;
+    DBG_MARK(8 + q * 8 + 2);
+    grid_wait(gs, ++barriers * G);
+    DBG_MARK(8 + q * 8 + 3);
+    float tmpError;
+    int tot_cnt;
+    const float sigma = fetch_sigma(q, &tmpError, &tot_cnt);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    for (int px = tid; px < N; px += nthreads) {
+      int4 raw = reinterpret_cast<const int4*>(L.corres)[px];
+      if (raw.w & 0xff) {
+        int y = px / L.w, x = px - y * L.w;
+        rgb_step_from_depth(L, sigma, p.sobelScale, true, (unsigned)raw.x, __int_as_float(raw.z), x, y, acc);
+      }
+    }
+    bt = block_reduce32_sparse(acc, true, sm.red);
+    if (warp == 0) prow(1, q & 1)[blockIdx.x * 32 + lane] = bt;
+    DBG_MARK(8 + q * 8 + 4);
+    finish_iteration(barriers, q, tmpError, tot_cnt);
+  }
+}
+
+// SO(3) pre-alignment on level 2 (RGBDOdometry.cpp:239-310)
+__device__ __noinline__ void run_so3(unsigned& barriers) {
+  SMEM_REF();
+  GridSync* gs = p.gs;
+  StepScratch* sc = p.sc;
+  GNState& S = sm.S;
+  const int tid = blockIdx.x * kPT + threadIdx.x, nthreads = gridDim.x * kPT;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, G = gridDim.x;
+  auto prow = [&](int set, int parity) { return sc->partials + (size_t)((parity * 2 + set) * G) * 32; };
+  const LevelData& L = p.L[2];
+  const int N = L.w * L.h;
+  for (int it = 0; it < 10; ++it) {
+    if (S.so3_done) break;  // identical in every CTA
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    bool work = false;
+    for (int q = tid; q < N; q += nthreads) {
+      int y = q / L.w, x = q - y * L.w;
+      so3_pixel(p.so3_last, p.so3_next, (size_t)L.w, L.w, L.h, S.so3_imageBasis, S.so3_kinv, S.so3_krlr, x, y, acc);
+      work = true;
+    }
+    float bt = block_reduce32_sparse(acc, __any_sync(0xffffffffu, work), sm.red);
+    if (warp == 0) prow(0, it & 1)[blockIdx.x * 32 + lane] = bt;
+    grid_arrive(gs);
+    grid_wait(gs, ++barriers * G);
+    sum_partials<1>(prow(0, it & 1), G, sm.red, sm.out64);
+    if (threadIdx.x == 0) {
+      so3_update_serial(&S, sm.out64, L.k);
+      if (S.so3_done || it == 9) gn_begin_serial(&S, 1, p.L[sm.nsched ? sm.sched[0] : 0].k);
     }
     __syncthreads();
-    DBG_MARK(8 + q * 8 + 7);
+  }
+}
+
+__global__ void __launch_bounds__(kPT, 1) gn_persistent_kernel(const PersistParams kp) {
+  extern __shared__ __align__(16) unsigned char dyn_smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(dyn_smem_raw);
+  {  // parameters -> shared memory (the phase functions are not inlined)
+    const int* src = reinterpret_cast<const int*>(&kp);
+    int* dst = reinterpret_cast<int*>(&sm.prm);
+    for (int i = threadIdx.x; i < (int)(sizeof(PersistParams) / 4); i += kPT) dst[i] = src[i];
+  }
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int i = 2; i >= 0; --i)
+      for (int j = 0; j < kp.iters[i] && n < 19; ++j) sm.sched[n++] = i;
+    sm.nsched = n;
+  }
+  __syncthreads();
+  const PersistParams& p = sm.prm;
+  const int nthreads = gridDim.x * kPT;
+  unsigned barriers = 0;  // barriers completed so far -> target = (barriers + 1) * G
+  const int nsched = sm.nsched;
+
+  DBG_MARK(0);
+  if (threadIdx.x == 0) {
+    gn_init_serial(&sm.S, nullptr, p.pose_in, p.L[2].k);
+    if (!p.use_so3) gn_begin_serial(&sm.S, 0, p.L[nsched ? sm.sched[0] : 0].k);
+  }
+  __syncthreads();
+  DBG_MARK(1);
+  if (p.use_so3) run_so3(barriers);
+
+  DBG_MARK(2);
+  // ---- Gauss-Newton iterations, coarse to fine (RGBDOdometry.cpp:331-461)
+  int q0 = 0;
+  for (int lvl = 2; lvl >= 0; --lvl) {
+    int nit = p.iters[lvl];
+    if (q0 + nit > nsched) nit = nsched - q0;
+    if (nit <= 0) continue;
+    const int need = (p.L[lvl].w * p.L[lvl].h + nthreads - 1) / nthreads;
+    if (need <= 1)
+      run_level_staged<1>(lvl, q0, nit, barriers);
+    else if (need <= 2)
+      run_level_staged<2>(lvl, q0, nit, barriers);
+    else if (need <= kStagePP)
+      run_level_staged<kStagePP>(lvl, q0, nit, barriers);
+    else
+      run_level_generic(lvl, q0, nit, barriers);
+    q0 += nit;
   }
   // ---- CTA 0 publishes pose + stats
   if (blockIdx.x == 0) {
-    const float* src = (const float*)&S;
+    const float* src = (const float*)&sm.S;
     float* dst = (float*)p.g;
     for (int i = threadIdx.x; i < (int)(sizeof(GNState) / 4); i += kPT) dst[i] = src[i];
   }
@@ -485,7 +741,13 @@ cudaError_t RGBDOdometry::enqueuePersistent(float icpWeight, bool pyramid, bool 
   if (grid > kMaxBlocks) grid = kMaxBlocks;
   void* args[] = {(void*)&p};
   if (time_kernel_) RET_IF(cudaEventRecord(ev_k0_, s));
-  RET_IF(cudaLaunchCooperativeKernel((const void*)gn_persistent_kernel, dim3(grid), dim3(kPT), args, 0, s));
+  const size_t stage_bytes = sizeof(Smem);
+  static bool attr_set = false;  // per process; the attribute is per function, identical for every device
+  if (!attr_set) {
+    RET_IF(cudaFuncSetAttribute(gn_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
+    attr_set = true;
+  }
+  RET_IF(cudaLaunchCooperativeKernel((const void*)gn_persistent_kernel, dim3(grid), dim3(kPT), args, stage_bytes, s));
   if (time_kernel_) {
     RET_IF(cudaEventRecord(ev_k1_, s));
     ev_pending_ = true;
