@@ -104,6 +104,20 @@ def cpu_port_fps(frames, n_frames, warm=2):
     return n_frames / dt, dt
 
 
+def cpu_segmentation_ms(frames, reps=3):
+    """The part of the path that is CPU code in the reference (SLIC + dense CRF + components,
+    Core/Segmentation): oracle/segment.c on one host core, one model + the "new" label, 640x480."""
+    import orc
+    rgb, d = frames[3]
+    icp = np.full((H, W), 0.002, np.float32)
+    vc = np.zeros((H, W, 4), np.float32)
+    vc[..., 3] = 10.0
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        orc.segment_crf(rgb, d, [0], [icp], [vc], 1, True)
+    return 1e3 * (time.perf_counter() - t0) / reps
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -287,7 +301,8 @@ def main():
         fps_cpu, dt = cpu_port_fps(frames, args.cpu_frames)
         cpu = {"value": fps_cpu, "unit": "frames/s", "cores": 1, "kind": "port",
                "sample": "%d frames of the same 640x480 room sequence through the oracle/ C restatement "
-                         "(single thread, like the reference's CPU loops), %.1f s" % (args.cpu_frames, dt)}
+                         "(single thread, like the reference's CPU loops), %.1f s" % (args.cpu_frames, dt),
+               "segmentation_ms_per_frame": cpu_segmentation_ms(frames)}
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -314,6 +314,12 @@ class Model:
              5: (4, np.float32), 6: (4, np.float32), 7: (4, np.float32), 8: (4, np.uint8), 9: (4, np.float32),
              10: (4, np.float32), 11: (1, np.uint16), 12: (4, np.uint8), 13: (4, np.float32), 14: (4, np.float32)}
 
+    def view_ptr(self, which):
+        """raw device pointer of a model buffer (see cfb_model_view)"""
+        ptr, pitch = C.c_void_p(), C.c_size_t()
+        check(lib().cfb_model_view(self._h, which, C.byref(ptr), C.byref(pitch)))
+        return ptr.value
+
     def view(self, which, n_unstable=0):
         ptr, pitch = C.c_void_p(), C.c_size_t()
         check(lib().cfb_model_view(self._h, which, C.byref(ptr), C.byref(pitch)))
@@ -385,8 +391,9 @@ class Segmentation:
         n = len(model_ids)
         prm = params or SegParams.default()
         ids = (C.c_ubyte * n)(*model_ids)
-        icp = (C.c_void_p * n)(*[t.data_ptr() for t in icp_errors])
-        vc = (C.c_void_p * n)(*[t.data_ptr() for t in vert_confs])
+        dp = lambda t: t.data_ptr() if hasattr(t, "data_ptr") else int(t)  # tensors or raw device pointers
+        icp = (C.c_void_p * n)(*[dp(t) for t in icp_errors])
+        vc = (C.c_void_p * n)(*[dp(t) for t in vert_confs])
         full = torch.empty((self.H, self.W), dtype=torch.uint8, device=rgb.device)
         md = (ModelData * (n + 1))()
         cnt, has_new = C.c_int(0), C.c_int(0)

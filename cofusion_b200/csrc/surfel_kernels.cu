@@ -452,31 +452,61 @@ __global__ void clean_evaluate_kernel(SurfelGeom g, Surfel* __restrict__ src, Su
   float avgViolation = 0;
   const float ftime = (float)time;
   if (ftime - s.col.w < (float)timeDelta && lp.z > 0 && x > 0 && y > 0 && x < cols && y < rows) {
+    // The shader walks a (nominally 4x4) window with float loop counters; the trip counts are whatever
+    // the float accumulation gives (4 or 5).  Enumerate the texels first, then issue the loads of all
+    // of them together: 3 dependent round trips (index -> vertex -> colour/time) instead of up to 48.
+    constexpr int kMaxTap = 5;  // 4 nominal steps, +1 when the accumulated counter lands just below the bound
+    int tx[kMaxTap], ty[kMaxTap], nx = 0, ny = 0;
     for (float si = x_n - (scale * indexXStep * windowMultiplier); si < x_n + (scale * indexXStep * windowMultiplier);
          si += indexXStep)
-      for (float sj = y_n - (scale * indexYStep * windowMultiplier);
-           sj < y_n + (scale * indexYStep * windowMultiplier); sj += indexYStep) {
-        const int sp = texel(sj, H) * W + texel(si, W);
-        const uint32_t current = __ldg(idx.index + sp);
-        if (current > 0U) {
-          const float4 vc = __ldg(idx.vertConf + sp);
-          // both counters need a confident map surfel BEHIND this one: only then fetch colour/time
-          if (vc.w > confThreshold && vc.z > lp.z) {
-            const float4 ct = __ldg(idx.colorTime + sp);
-            const float ddx = vc.x - lp.x, ddy = vc.y - lp.y;
-            if (ct.z < s.col.z && vc.z - lp.z < 0.01f && sqrtf(ddx * ddx + ddy * ddy) < s.nrm.w * 1.4f) count_++;
-            if (ct.w == ftime && vc.z - lp.z > 0.01f && fabsf(ln.z) > 0.85f) zCount++;
+      if (nx < kMaxTap) tx[nx++] = texel(si, W);
+    for (float sj = y_n - (scale * indexYStep * windowMultiplier); sj < y_n + (scale * indexYStep * windowMultiplier);
+         sj += indexYStep)
+      if (ny < kMaxTap) ty[ny++] = texel(sj, H);
+    uint32_t cur[kMaxTap][kMaxTap];
+#pragma unroll
+    for (int a = 0; a < kMaxTap; ++a)
+#pragma unroll
+      for (int b = 0; b < kMaxTap; ++b) cur[a][b] = (a < nx && b < ny) ? __ldg(idx.index + ty[b] * W + tx[a]) : 0U;
+#pragma unroll
+    for (int a = 0; a < kMaxTap; ++a) {
+      float4 vcs[kMaxTap];
+#pragma unroll
+      for (int b = 0; b < kMaxTap; ++b)
+        vcs[b] = cur[a][b] > 0U ? __ldg(idx.vertConf + ty[b] * W + tx[a]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int b = 0; b < kMaxTap; ++b) {
+        const float4 vc = vcs[b];
+        // both counters need a confident map surfel BEHIND this one: only then fetch colour/time
+        if (cur[a][b] > 0U && vc.w > confThreshold && vc.z > lp.z) {
+          const float4 ct = __ldg(idx.colorTime + ty[b] * W + tx[a]);
+          const float ddx = vc.x - lp.x, ddy = vc.y - lp.y;
+          if (ct.z < s.col.z && vc.z - lp.z < 0.01f && sqrtf(ddx * ddx + ddy * ddy) < s.nrm.w * 1.4f) count_++;
+          if (ct.w == ftime && vc.z - lp.z > 0.01f && fabsf(ln.z) > 0.85f) zCount++;
+        }
+      }
+    }
+    float dd[3][3];
+    int nsx = 0, nsy = 0, sx[3], sy[3];
+    for (float si = x_n - stepX; si <= x_n + stepX; si += stepX)
+      if (nsx < 3) sx[nsx++] = texel(si, W);
+    for (float sj = y_n - stepY; sj <= y_n + stepY; sj += stepY)
+      if (nsy < 3) sy[nsy++] = texel(sj, H);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) dd[a][b] = (a < nsx && b < nsy) ? __ldg(depthFiltered + sy[b] * W + sx[a]) : 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)  // same visiting order as the shader: si outer, sj inner (the float sum is ordered)
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+        if (a < nsx && b < nsy) {
+          const float d = dd[a][b] - lp.z;
+          if (d > 0.03f) {
+            violationCount++;
+            avgViolation += d;
           }
         }
-      }
-    for (float si = x_n - stepX; si <= x_n + stepX; si += stepX)
-      for (float sj = y_n - stepY; sj <= y_n + stepY; sj += stepY) {
-        const float d = __ldg(depthFiltered + texel(sj, H) * W + texel(si, W)) - lp.z;
-        if (d > 0.03f) {
-          violationCount++;
-          avgViolation += d;
-        }
-      }
   }
   if (count_ > 8 || zCount > 4) test = 0;
   if (s.col.w == -2.f) s.col.w = ftime;
