@@ -2,7 +2,10 @@
 #include "cofusion.cuh"
 
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 namespace cfb {
 
@@ -131,8 +134,41 @@ cudaError_t CoFusion::predict() {
   return cudaSuccess;
 }
 
+// Optional timeline (tools only, CFB_TIMELINE=1): device time between four points of a frame and the
+// host time spent enqueueing each section, averaged over 200 frames and printed to stderr.
+namespace {
+struct Timeline {
+  bool on = false, init = false;
+  cudaEvent_t ev[2][4];
+  double host[4] = {0, 0, 0, 0}, devms[4] = {0, 0, 0, 0};
+  double hprev = 0;
+  int frames = 0, cur = 0;
+  static double now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  }
+};
+Timeline g_tl;
+}  // namespace
+
 cudaError_t CoFusion::processFrame(const uint8_t* rgb, const float* depth, const uint8_t* mask, bool device_ptrs,
                                    float weightMultiplier) {
+  Timeline& tl = g_tl;
+  if (!tl.init) {
+    tl.init = true;
+    tl.on = getenv("CFB_TIMELINE") != nullptr;
+    if (tl.on)
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 4; ++b) cudaEventCreate(&tl.ev[a][b]);
+  }
+  double h[4] = {0, 0, 0, 0};
+  auto mark = [&](int k) {
+    if (!tl.on) return;
+    h[k] = Timeline::now();
+    cudaEventRecord(tl.ev[tl.cur][k], ctx.stream);
+  };
+  mark(0);
   if (device_ptrs)
     RET_IF(ctx.setFrameDevice(rgb, depth, mask));
   else
@@ -151,10 +187,12 @@ cudaError_t CoFusion::processFrame(const uint8_t* rgb, const float* depth, const
     tp.so3 = params.so3;
     tp.maxDepthProcessed = params.maxDepthProcessed;
     tp.force_host_loop = 0;
+    mark(1);
     for (size_t i = 0; i < models.size(); ++i) {
       RET_IF(models[i]->performTracking(tp));
       lastStats[i] = models[i]->odom.stats();
     }
+    mark(2);
     if (params.enableMultipleModels) RET_IF(segmentAndManageModels());
     // CoFusion.cpp:347: this prediction only feeds performSegmentation / the (dead) loop-closure
     // block; the fuse stage below uses the index maps and the frame, and the final predict()
@@ -170,6 +208,33 @@ cudaError_t CoFusion::processFrame(const uint8_t* rgb, const float* depth, const
   }
   RET_IF(predict());
   tick_++;
+  mark(3);
+  if (tl.on && tick_ > 3) {
+    // the previous frame's events are complete by now (this frame synchronised after them)
+    const int prev = tl.cur ^ 1;
+    if (tl.frames > 0 || true) {
+      float ms;
+      if (tl.hprev > 0) {
+        for (int k = 0; k < 3; ++k)
+          if (cudaEventElapsedTime(&ms, tl.ev[prev][k], tl.ev[prev][k + 1]) == cudaSuccess) tl.devms[k] += ms;
+        if (cudaEventElapsedTime(&ms, tl.ev[prev][3], tl.ev[tl.cur][0]) == cudaSuccess) tl.devms[3] += ms;
+        tl.host[3] += h[0] - tl.hprev;
+        tl.frames++;
+      }
+      for (int k = 0; k < 3; ++k) tl.host[k] += h[k + 1] - h[k];
+    }
+    tl.hprev = h[3];
+    if (tl.frames == 200) {
+      fprintf(stderr,
+              "[cfb timeline, ms] device: start->track %.3f  track(+sync) %.3f  fuse..predict %.3f  frame gap %.3f | "
+              "host: pre %.3f  track+sync %.3f  post %.3f  between calls %.3f\n",
+              tl.devms[0] / 200, tl.devms[1] / 200, tl.devms[2] / 200, tl.devms[3] / 200, tl.host[0] / 200,
+              tl.host[1] / 200, tl.host[2] / 200, tl.host[3] / 200);
+      tl.frames = 0;
+      for (int k = 0; k < 4; ++k) tl.devms[k] = tl.host[k] = 0;
+    }
+  }
+  if (tl.on) tl.cur ^= 1;
   return cudaSuccess;
 }
 

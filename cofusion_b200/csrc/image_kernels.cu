@@ -30,11 +30,15 @@ const dim3 kBlock(32, 8);
 // 32x8 tile + 6-pixel halo staged in shared memory: each input texel is read from L2/HBM once per
 // tile instead of 169 times.
 constexpr int BR = 6;
-__global__ void bilateral_kernel(const float* __restrict__ depth, size_t dpitch, int W, int H, float maxD,
-                                 float* __restrict__ out, size_t opitch) {
-  __shared__ float tile[8 + 2 * BR][32 + 2 * BR + 1];
-  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
-  for (int ty = threadIdx.y; ty < 8 + 2 * BR; ty += 8)
+// Rows per thread.  Measured on B200 (VGA): 1 row/thread 78 us (1200 CTAs on 1184 resident slots: the
+// last 16 run as a short second wave), 3 rows/thread 160 us -- the kernel lives on occupancy (64
+// warps/SM hide the exp() dependency chains), so the single-row shape stays.
+constexpr int BROWS = 1;
+__global__ void __launch_bounds__(256) bilateral_kernel(const float* __restrict__ depth, size_t dpitch, int W, int H,
+                                                        float maxD, float* __restrict__ out, size_t opitch) {
+  __shared__ float tile[8 * BROWS + 2 * BR][32 + 2 * BR + 1];
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8 * BROWS;
+  for (int ty = threadIdx.y; ty < 8 * BROWS + 2 * BR; ty += 8)
     for (int tx = threadIdx.x; tx < 32 + 2 * BR; tx += 32) {
       int gx = x0 + tx - BR, gy = y0 + ty - BR;
       float v = 0.f;
@@ -42,29 +46,52 @@ __global__ void bilateral_kernel(const float* __restrict__ depth, size_t dpitch,
       tile[ty][tx] = v;
     }
   __syncthreads();
-  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-  if (x >= W || y >= H) return;
-  const float value = tile[threadIdx.y + BR][threadIdx.x + BR];
-  float res = 0.f;
-  if (!(value > maxD || value < 0.3f)) {
-    const float sigma_space2_inv_half = 0.024691358f;
-    const float sigma_color2_inv_half = 555.556f;
-    const int D = 2 * BR + 1;
-    int tx = min(x - D / 2 + D, W), ty = min(y - D / 2 + D, H);
-    float sum1 = 0.f, sum2 = 0.f;
-    for (int cy = max(y - D / 2, 0); cy < ty; ++cy)
-      for (int cx = max(x - D / 2, 0); cx < tx; ++cx) {
-        float tmp = tile[cy - y0 + BR][cx - x0 + BR];
-        float dx = (float)x - (float)cx, dy = (float)y - (float)cy;
-        float space2 = dx * dx + dy * dy;
-        float color2 = (value - tmp) * (value - tmp);
-        float weight = det_expf(-(space2 * sigma_space2_inv_half + color2 * sigma_color2_inv_half));
-        sum1 += tmp * weight;
-        sum2 += weight;
+  const int x = x0 + threadIdx.x;
+  if (x >= W) return;
+#pragma unroll 1
+  for (int k = 0; k < BROWS; ++k) {
+    const int ly = threadIdx.y + 8 * k, y = y0 + ly;
+    if (y >= H) return;
+    const float value = tile[ly + BR][threadIdx.x + BR];
+    float res = 0.f;
+    if (!(value > maxD || value < 0.3f)) {
+      const float sigma_space2_inv_half = 0.024691358f;
+      const float sigma_color2_inv_half = 555.556f;
+      const int D = 2 * BR + 1;
+      float sum1 = 0.f, sum2 = 0.f;
+      if (x >= BR && x + BR < W && y >= BR && y + BR < H) {
+        // interior (97 % of a VGA frame): the window is the full 13x13, so the loops unroll completely
+        // and the spatial term (float)x - (float)cx = -ox (exact) folds into one constant per tap; same
+        // taps, same order, same roundings as the clamped loop below
+#pragma unroll
+        for (int oy = -BR; oy <= BR; ++oy)
+#pragma unroll
+          for (int ox = -BR; ox <= BR; ++ox) {
+            const float tmp = tile[ly + BR + oy][threadIdx.x + BR + ox];
+            const float dx = (float)(-ox), dy = (float)(-oy);
+            const float space2 = dx * dx + dy * dy;
+            const float color2 = (value - tmp) * (value - tmp);
+            const float weight = det_expf(-(space2 * sigma_space2_inv_half + color2 * sigma_color2_inv_half));
+            sum1 += tmp * weight;
+            sum2 += weight;
+          }
+      } else {
+        int tx = min(x - D / 2 + D, W), ty = min(y - D / 2 + D, H);
+        for (int cy = max(y - D / 2, 0); cy < ty; ++cy)
+          for (int cx = max(x - D / 2, 0); cx < tx; ++cx) {
+            float tmp = tile[cy - y0 + BR][cx - x0 + BR];
+            float dx = (float)x - (float)cx, dy = (float)y - (float)cy;
+            float space2 = dx * dx + dy * dy;
+            float color2 = (value - tmp) * (value - tmp);
+            float weight = det_expf(-(space2 * sigma_space2_inv_half + color2 * sigma_color2_inv_half));
+            sum1 += tmp * weight;
+            sum2 += weight;
+          }
       }
-    res = sum1 / sum2;
+      res = sum1 / sum2;
+    }
+    row_ptr(out, opitch, y)[x] = res;
   }
-  row_ptr(out, opitch, y)[x] = res;
 }
 
 // ---- a2: 5x5 Gaussian 2x downsample of f32 depth skipping NaN (cudafuncs.cu:333-364) -----------
@@ -439,7 +466,7 @@ __global__ void pyr_down_uchar2_kernel(const unsigned char* __restrict__ sa, uns
 
 cudaError_t launch_bilateral(const float* depth, size_t dpitch, int W, int H, float maxD, float* out,
                              size_t opitch, cudaStream_t s) {
-  bilateral_kernel<<<grid2d(W, H, kBlock), kBlock, 0, s>>>(depth, dpitch, W, H, maxD, out, opitch);
+  bilateral_kernel<<<dim3((W + 31) / 32, (H + 8 * BROWS - 1) / (8 * BROWS)), kBlock, 0, s>>>(depth, dpitch, W, H, maxD, out, opitch);
   return cudaGetLastError();
 }
 cudaError_t launch_pyr_down_gauss_f(const float* src, size_t spitch, int sw, int sh, float* dst,

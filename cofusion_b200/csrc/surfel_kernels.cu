@@ -463,22 +463,46 @@ __global__ void clean_evaluate_kernel(SurfelGeom g, Surfel* __restrict__ src, Su
     for (float sj = y_n - (scale * indexYStep * windowMultiplier); sj < y_n + (scale * indexYStep * windowMultiplier);
          sj += indexYStep)
       if (ny < kMaxTap) ty[ny++] = texel(sj, H);
+    // the counters advance by HALF a texel: consecutive taps often name the same texel.  A repeated
+    // column / row reuses the values already loaded (it is still counted once per tap, as the shader does).
+    bool dupx[kMaxTap], dupy[kMaxTap];
+#pragma unroll
+    for (int a = 0; a < kMaxTap; ++a) {
+      dupx[a] = a > 0 && a < nx && tx[a] == tx[a - 1];
+      dupy[a] = a > 0 && a < ny && ty[a] == ty[a - 1];
+    }
     uint32_t cur[kMaxTap][kMaxTap];
 #pragma unroll
     for (int a = 0; a < kMaxTap; ++a)
 #pragma unroll
-      for (int b = 0; b < kMaxTap; ++b) cur[a][b] = (a < nx && b < ny) ? __ldg(idx.index + ty[b] * W + tx[a]) : 0U;
+      for (int b = 0; b < kMaxTap; ++b)
+        cur[a][b] = (a < nx && b < ny && !dupx[a] && !dupy[b]) ? __ldg(idx.index + ty[b] * W + tx[a]) : 0U;
+#pragma unroll
+    for (int a = 0; a < kMaxTap; ++a)
+#pragma unroll
+      for (int b = 0; b < kMaxTap; ++b) {
+        if (b > 0 && dupy[b]) cur[a][b] = cur[a][b - 1];
+        if (a > 0 && dupx[a]) cur[a][b] = cur[a - 1][b];
+      }
+    float4 vprev[kMaxTap];
 #pragma unroll
     for (int a = 0; a < kMaxTap; ++a) {
       float4 vcs[kMaxTap];
 #pragma unroll
       for (int b = 0; b < kMaxTap; ++b)
-        vcs[b] = cur[a][b] > 0U ? __ldg(idx.vertConf + ty[b] * W + tx[a]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        vcs[b] = (cur[a][b] > 0U && !dupx[a] && !dupy[b]) ? __ldg(idx.vertConf + ty[b] * W + tx[a])
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int b = 0; b < kMaxTap; ++b) {
+        if (b > 0 && dupy[b]) vcs[b] = vcs[b - 1];
+        if (a > 0 && dupx[a]) vcs[b] = vprev[b];
+      }
+#pragma unroll
+      for (int b = 0; b < kMaxTap; ++b) {
+        vprev[b] = vcs[b];
         const float4 vc = vcs[b];
         // both counters need a confident map surfel BEHIND this one: only then fetch colour/time
-        if (cur[a][b] > 0U && vc.w > confThreshold && vc.z > lp.z) {
+        if (a < nx && b < ny && cur[a][b] > 0U && vc.w > confThreshold && vc.z > lp.z) {
           const float4 ct = __ldg(idx.colorTime + ty[b] * W + tx[a]);
           const float ddx = vc.x - lp.x, ddy = vc.y - lp.y;
           if (ct.z < s.col.z && vc.z - lp.z < 0.01f && sqrtf(ddx * ddx + ddy * ddy) < s.nrm.w * 1.4f) count_++;

@@ -230,7 +230,7 @@ static int connected_labels(const uint8_t* in, int rows, int cols, int* comp, Co
 }
 
 /* ---------------------------------------------------------------- dense CRF (exact kernels) */
-static void exp_and_normalize(float* out, const float* in, int L, int N) { /* DenseCRF::expAndNormalize */
+ORC_FMA_CLONES static void exp_and_normalize(float* out, const float* in, int L, int N) { /* DenseCRF::expAndNormalize */
   for (int i = 0; i < N; ++i) {
     float mx = in[i * L];
     for (int l = 1; l < L; ++l) mx = in[i * L + l] > mx ? in[i * L + l] : mx;
@@ -273,7 +273,7 @@ static void kernel_apply(const float* K, const float* norm, const float* Q, int 
     }
   free(nq);
 }
-static void build_kernel(const float* feat, int D, int N, float* K, float* norm) {
+ORC_FMA_CLONES static void build_kernel(const float* feat, int D, int N, float* K, float* norm) {
   for (int i = 0; i < N; ++i) {
     float part[128];
     memset(part, 0, sizeof(part));

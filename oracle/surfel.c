@@ -163,7 +163,7 @@ static inline float get_radius(float depth, float norm_z, float inv_fx, float in
   return radius_n;
 }
 /* surfels.glsl:36-46 */
-static inline float confidence(float x, float y, float cx, float cy, float weighting) {
+ORC_FMA_CLONES static float confidence(float x, float y, float cx, float cy, float weighting) {
   const float maxRadDist = 400, twoSigmaSquared = 0.72f;
   float px = x - cx, py = y - cy;
   float radialDist = sqrtf(px * px + py * py) / maxRadDist;

@@ -62,7 +62,7 @@ static inline f3 mul33(const float* m, f3 a) {
 
 /* Core/Shaders/depth_bilateral_metric.frag:30-76 (via CoFusion::filterDepth, CoFusion.cpp:567-574).
  * Frozen GL semantics: nearest sampling, tap (cx,cy) reads texel (cx,cy); exp() = orc_expf. */
-void orc_bilateral_filter(const float* depth, int W, int H, float maxD, float* out) {
+ORC_FMA_CLONES void orc_bilateral_filter(const float* depth, int W, int H, float maxD, float* out) {
   const float sigma_space2_inv_half = 0.024691358f;
   const float sigma_color2_inv_half = 555.556f;
   const int R = 6, D = R * 2 + 1;
