@@ -177,14 +177,14 @@ __device__ __forceinline__ void gn_solve_serial(GNState* g, StepScratch* sc, con
   const double w = icpWeight;
   double A[36], bb[6], x[6];
 #pragma unroll
-  for (int q = 0; q < 36; ++q) {
-    A[q] = A_rgb[q] + w * w * A_icp[q];
-    st.lastA[q] = A[q];
-  }
+  for (int q = 0; q < 36; ++q) A[q] = A_rgb[q] + w * w * A_icp[q];
 #pragma unroll
-  for (int q = 0; q < 6; ++q) {
-    bb[q] = b_rgb[q] + w * b_icp[q];
-    st.lastb[q] = bb[q];
+  for (int q = 0; q < 6; ++q) bb[q] = b_rgb[q] + w * b_icp[q];
+  if (is_last || sc) {  // lastA / lastb are only reported for the final iteration (RGBDOdometry.h:62-70);
+#pragma unroll         // the multi-kernel path (sc != nullptr) keeps them current for the per-step tests
+    for (int q = 0; q < 36; ++q) st.lastA[q] = A[q];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) st.lastb[q] = bb[q];
   }
   gn::ldlt_solve_unrolled<6>(A, bb, x);
   double Rt[16];
