@@ -184,7 +184,13 @@ def main():
         buf[3 * P:] = torch.from_numpy(np.ascontiguousarray(d).reshape(-1).view(np.uint8))
         packed_host.append(buf)
     packed_dev = [b.cuda() for b in packed_host] if rank == 0 else None
-    recv = torch.empty(7 * P, dtype=torch.uint8, device="cuda")
+    # N > 1: the frame travels on a torch-owned stream (H2D / D2D into a double-buffered receive buffer, then
+    # ONE NCCL broadcast); the pipeline's own stream only waits on an event.  NCCL and torch's allocator
+    # never see the library's stream.
+    recv = [torch.empty(7 * P, dtype=torch.uint8, device="cuda") for _ in range(2)] if world > 1 else None
+    comm = torch.cuda.Stream() if world > 1 else None
+    ev_ready = [torch.cuda.Event() for _ in range(2)]
+    ev_consumed = [torch.cuda.Event() for _ in range(2)]
 
     def build():
         params = cfb.CoFusionParams.default(1 << 21)
@@ -194,29 +200,30 @@ def main():
         cfb.check(cfb.lib().cfb_odom_enable_kernel_timing(odom, 1))
         return cf, odom
 
-    def step_resident(cf, t):
-        i = frame_index(t, n_render)
-        if world > 1:
+    def step_broadcast(cf, ext, t, source):
+        """root copies frame t into the receive buffer, all ranks broadcast, the pipeline consumes it"""
+        i, k = frame_index(t, n_render), t & 1
+        with torch.cuda.stream(comm):
+            comm.wait_event(ev_consumed[k])  # the frame that used this buffer two steps ago is done with it
             if rank == 0:
-                recv.copy_(packed_dev[i], non_blocking=True)
-            dist.broadcast(recv, src=0)  # one NCCL broadcast of the packed frame per time step
-            src = recv
-        else:
-            src = packed_dev[i]
-        rgb = src[:3 * P]
-        depth = src[3 * P:].view(torch.float32)
-        cf.process_frame(rgb, depth)
+                recv[k].copy_(source[i], non_blocking=True)
+            dist.broadcast(recv[k], src=0)  # one NCCL broadcast of the packed frame per time step
+            ev_ready[k].record(comm)
+        ext.wait_event(ev_ready[k])
+        cf.process_frame(recv[k][:3 * P], recv[k][3 * P:].view(torch.float32))
+        ev_consumed[k].record(ext)
 
-    def step_e2e(cf, t):
-        i = frame_index(t, n_render)
+    def step_resident(cf, ext, t):
         if world > 1:
-            if rank == 0:
-                recv.copy_(packed_host[i], non_blocking=True)  # H2D on the root, then NVLink broadcast
-            dist.broadcast(recv, src=0)
-            cf.process_frame(recv[:3 * P], recv[3 * P:].view(torch.float32))
-        else:
-            b = packed_host[i]
-            cf.process_frame(b[:3 * P], b[3 * P:].view(torch.float32))
+            return step_broadcast(cf, ext, t, packed_dev)
+        src = packed_dev[frame_index(t, n_render)]
+        cf.process_frame(src[:3 * P], src[3 * P:].view(torch.float32))
+
+    def step_e2e(cf, ext, t):
+        if world > 1:
+            return step_broadcast(cf, ext, t, packed_host)  # H2D on the root, then NVLink broadcast
+        b = packed_host[frame_index(t, n_render)]
+        cf.process_frame(b[:3 * P], b[3 * P:].view(torch.float32))
 
     keep = []  # the pipelines (and their streams) outlive every torch tensor that was used on them
 
@@ -225,6 +232,8 @@ def main():
         # free the frame buffers while the library streams are still alive, then the pipelines, then NCCL
         nonlocal packed_dev, recv
         torch.cuda.synchronize()
+        ev_ready.clear()
+        ev_consumed.clear()
         packed_host.clear()
         packed_dev = None
         recv = None
@@ -240,36 +249,37 @@ def main():
     def timed(step_fn, sampler=None):
         cf, odom = build()
         keep.append(cf)
-        ext = torch.cuda.ExternalStream(cf.ctx.stream)
-        with torch.cuda.stream(ext):
-            for t in range(args.warmup):
-                step_fn(cf, t)
-            cf.ctx.sync()
-            cf.ctx.take_launch_count()
-            sm, n = cfb.C.c_double(0), cfb.C.c_int(0)
-            cfb.check(cfb.lib().cfb_odom_kernel_timing(odom, cfb.C.byref(sm), cfb.C.byref(n), 1))
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            if sampler:
-                sampler.start()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for t in range(args.warmup, args.warmup + args.steps):
-                step_fn(cf, t)
-            e1.record()
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            ms = e0.elapsed_time(e1)
-            if sampler:
-                sampler.stop_flag = True
+        ext = torch.cuda.ExternalStream(cf.ctx.stream)  # only used to record / wait on events
+        for t in range(args.warmup):
+            step_fn(cf, ext, t)
+        cf.ctx.sync()
+        cf.ctx.take_launch_count()
+        sm, n = cfb.C.c_double(0), cfb.C.c_int(0)
+        cfb.check(cfb.lib().cfb_odom_kernel_timing(odom, cfb.C.byref(sm), cfb.C.byref(n), 1))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for t in range(args.warmup, args.warmup + args.steps):
+            step_fn(cf, ext, t)
+        e1.record(ext)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        if sampler:
+            sampler.stop_flag = True
         launches = cf.ctx.take_launch_count()
         cfb.check(cfb.lib().cfb_odom_kernel_timing(odom, cfb.C.byref(sm), cfb.C.byref(n), 0))
         t_ms = torch.tensor([ms], device="cuda")
         if world > 1:
             dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)  # max over ranks
         nsurf = cf.model(0).last_count()
+        del e0, e1, ext
         return float(t_ms.item()), launches, (sm.value, n.value), nsurf
 
     sampler = ClockSampler(local) if rank == 0 else None
