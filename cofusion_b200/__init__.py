@@ -521,6 +521,9 @@ class CoFusion:
         check(lib().cfb_cofusion_last_segmentation(self._h, md, C.byref(cnt), C.byref(hn), C.byref(sp), C.byref(de)))
         return [md[i] for i in range(cnt.value)], bool(hn.value), sp.value, de.value
 
+    def set_batched_tracking(self, on):
+        check(lib().cfb_cofusion_set_batched_tracking(self._h, int(bool(on))))
+
     @property
     def num_inactive_models(self):
         return lib().cfb_cofusion_num_inactive_models(self._h)

@@ -720,6 +720,11 @@ int cfb_cofusion_last_segmentation(cfb_cofusion* f, cfb_model_data* md_out, int*
   return 0;
 }
 int cfb_cofusion_num_inactive_models(cfb_cofusion* f) { return f ? (int)f->f.inactiveModels.size() : 0; }
+int cfb_cofusion_set_batched_tracking(cfb_cofusion* f, int on) {
+  REQUIRE(f, "cofusion_set_batched_tracking");
+  f->f.batchedTracking = on != 0;
+  return 0;
+}
 cfb_segmentation* cfb_cofusion_segmentation(cfb_cofusion* f) {
   if (!f || !f->f.segmentation) return nullptr;
   if (!f->seg_handle) f->seg_handle = new cfb_segmentation(f->f.segmentation.get());

@@ -188,9 +188,15 @@ cudaError_t CoFusion::processFrame(const uint8_t* rgb, const float* depth, const
     tp.maxDepthProcessed = params.maxDepthProcessed;
     tp.force_host_loop = 0;
     mark(1);
-    for (size_t i = 0; i < models.size(); ++i) {
-      RET_IF(models[i]->performTracking(tp));
-      lastStats[i] = models[i]->odom.stats();
+    {
+      std::vector<Model*> ms;
+      for (auto& m : models) ms.push_back(m.get());
+      if (batchedTracking) {
+        RET_IF(trackModels(&ctx, ms.data(), (int)ms.size(), tp));
+      } else {
+        for (Model* m : ms) RET_IF(m->performTracking(tp));
+      }
+      for (size_t i = 0; i < models.size(); ++i) lastStats[i] = models[i]->odom.stats();
     }
     mark(2);
     if (params.enableMultipleModels) RET_IF(segmentAndManageModels());

@@ -49,6 +49,7 @@ class CoFusion {
   int tick() const { return tick_; }
   cudaError_t predict();  // CoFusion::predict (CoFusion.cpp:533-545)
 
+  bool batchedTracking = true;  // track all models of a frame in one persistent launch (gn_batched.cu)
   Context ctx;
   CoFusionParams params;
   std::vector<std::unique_ptr<Model>> models;

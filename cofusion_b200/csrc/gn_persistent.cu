@@ -689,19 +689,29 @@ __global__ void rgb_prepare_all_kernel(const PrepParams pp) {
     if (e__ != cudaSuccess) return e__; \
   } while (0)
 
+cudaError_t RGBDOdometry::enqueuePrepare(cudaStream_t s) {
+  PrepParams pp;
+  int total = 0;
+  for (int i = 0; i < NUM_PYRS; ++i) {
+    const int w = width >> i, h = height >> i;
+    pp.L[i] = PrepLevel{nextImage[i], (next_is_last_ ? lastDepth[i] : nextDepth[i]), nextdIdx[i], nextdIdy[i], rgbCand[i], w, h,
+                        (float)(pow(minimumGradientMagnitudes[i], 2.0) / pow(sobelScale, 2.0))};
+    total += w * h;
+  }
+  pp.grid_sync = (unsigned*)grid_sync_;
+  rgb_prepare_all_kernel<<<(total + 255) / 256, 256, 0, s>>>(pp);
+  return cudaGetLastError();
+}
+
 cudaError_t RGBDOdometry::enqueuePersistent(float icpWeight, bool pyramid, bool fastOdom, bool so3, float* err,
                                             size_t err_pitch, cudaStream_t s) {
   float* h_in = (float*)((char*)h_pinned + 1536);
   RET_IF(cudaMemcpyAsync(d_pose_in, h_in, 12 * sizeof(float), cudaMemcpyHostToDevice, s));
-  PrepParams pp;
+  RET_IF(enqueuePrepare(s));
   PersistParams p;
-  int total = 0;
   for (int i = 0; i < NUM_PYRS; ++i) {
     const int w = width >> i, h = height >> i;
     const Intr k = intr.level(i);
-    pp.L[i] = PrepLevel{nextImage[i], (next_is_last_ ? lastDepth[i] : nextDepth[i]), nextdIdx[i], nextdIdy[i], rgbCand[i], w, h,
-                        (float)(pow(minimumGradientMagnitudes[i], 2.0) / pow(sobelScale, 2.0))};
-    total += w * h;
     LevelData& L = p.L[i];
     L.vmap_curr = vmaps_curr_[i];
     L.nmap_curr = nmaps_curr_[i];
@@ -719,8 +729,6 @@ cudaError_t RGBDOdometry::enqueuePersistent(float icpWeight, bool pyramid, bool 
     L.h = h;
     L.k = LevelK{k.fx, k.fy, k.cx, k.cy};
   }
-  pp.grid_sync = (unsigned*)grid_sync_;
-  rgb_prepare_all_kernel<<<(total + 255) / 256, 256, 0, s>>>(pp);
   p.so3_last = lastNextImage[2];
   p.so3_next = nextImage[2];
   p.g = gn;

@@ -76,6 +76,16 @@ class RGBDOdometry {
                                            size_t error_pitch, bool force_host_loop, cudaStream_t s);
   const TrackStats& stats() const { return stats_; }
 
+  // ---- several models of one frame in ONE persistent launch (gn_batched.cu).  Every object had
+  // initAll() called for the same frame on stream s.  trans / rot: n x 3 / n x 9 host arrays (in/out),
+  // err: n device error maps (or null), scratch: batchScratchBytes() of zero-initialised device memory.
+  static const int kMaxBatch = 5;
+  static size_t batchScratchBytes();
+  bool canBatch(int n) const;
+  static cudaError_t trackBatched(RGBDOdometry* const* od, int n, float (*trans)[3], float (*rot)[9], float icpWeight,
+                                  bool pyramid, bool fastOdom, bool so3, float* const* err, size_t err_pitch,
+                                  void* scratch, cudaStream_t s);
+
   // device views (tests / map_view): which as in oracle orc_odom_view
   const void* view(int which, int level, size_t* pitch) const;
 
@@ -90,6 +100,7 @@ class RGBDOdometry {
                                 size_t err_pitch, cudaStream_t s);
   cudaError_t enqueuePersistent(float icpWeight, bool pyramid, bool fastOdom, bool so3, float* err,
                                 size_t err_pitch, cudaStream_t s);
+  cudaError_t enqueuePrepare(cudaStream_t s);  // Sobel images + photometric candidate gates, 3 levels, 1 launch
 
   bool ok_ = false;
   int width, height;

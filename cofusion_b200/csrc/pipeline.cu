@@ -45,6 +45,7 @@ Context::~Context() {
   cudaFreeHost(h_rgb);
   cudaFreeHost(h_depth);
   cudaFreeHost(h_mask);
+  cudaFree(batchScratch);
   if (stream && owns_stream) cudaStreamDestroy(stream);
 }
 
@@ -337,7 +338,7 @@ cudaError_t Model::uploadMap(const float* src, unsigned count) {
 
 cudaError_t Model::lastCount(unsigned* out) { return downloadMap(nullptr, 0, out); }
 
-cudaError_t Model::performTracking(const TrackParams& tp) {
+cudaError_t Model::prepareTracking(const TrackParams& tp) {
   memcpy(lastPose, pose, sizeof(pose));
   cudaStream_t s = ctx->stream;
   if (usePrediction) {
@@ -357,18 +358,68 @@ cudaError_t Model::performTracking(const TrackParams& tp) {
   // Model::initICP (Model.cpp:350-367): model pyramids first, then the frame's (fused launches)
   const float* pyr[3] = {ctx->depthPyr[0], ctx->depthPyr[1], ctx->depthPyr[2]};
   RET_IF(odom.initAll(predVertex, predNormal, predImage, 4, pyr, ctx->rgb, 3, tp.maxDepthProcessed, pose, s));
-  float trans[3] = {pose[3], pose[7], pose[11]};
-  float rot[9] = {pose[0], pose[1], pose[2], pose[4], pose[5], pose[6], pose[8], pose[9], pose[10]};
-  RET_IF(odom.getIncrementalTransformation(trans, rot, tp.rgbOnly != 0, tp.icpWeight, tp.pyramid != 0,
-                                           tp.fastOdom != 0, tp.so3 != 0, icpError, (size_t)ctx->W * 4,
-                                           tp.force_host_loop != 0, s));
+  ctx->launches += 7;  // model pyramid, 2 depth levels, frame maps, grey, 2 grey levels
+  return cudaSuccess;
+}
+
+void Model::finishTracking(const float trans[3], const float rot[9]) {
   for (int r = 0; r < 3; ++r) {
     for (int c = 0; c < 3; ++c) pose[r * 4 + c] = rot[r * 3 + c];
     pose[r * 4 + 3] = trans[r];
   }
   // the tracker synchronised the stream: the counters copied after the last clean are exact now
   if (h_counters->count && h_counters->count < count_ub) count_ub = h_counters->count;
-  ctx->launches += 9;  // model pyramid, 2 depth levels, frame maps, grey, 2 grey levels, prepare, persistent GN
+}
+
+cudaError_t Model::performTracking(const TrackParams& tp) {
+  RET_IF(prepareTracking(tp));
+  float trans[3] = {pose[3], pose[7], pose[11]};
+  float rot[9] = {pose[0], pose[1], pose[2], pose[4], pose[5], pose[6], pose[8], pose[9], pose[10]};
+  RET_IF(odom.getIncrementalTransformation(trans, rot, tp.rgbOnly != 0, tp.icpWeight, tp.pyramid != 0,
+                                           tp.fastOdom != 0, tp.so3 != 0, icpError, (size_t)ctx->W * 4,
+                                           tp.force_host_loop != 0, ctx->stream));
+  finishTracking(trans, rot);
+  ctx->launches += 2;  // prepare, persistent GN
+  return cudaSuccess;
+}
+
+cudaError_t trackModels(Context* ctx, Model* const* models, int n, const TrackParams& tp) {
+  const bool icp = !tp.rgbOnly && tp.icpWeight > 0, rgb = tp.rgbOnly || tp.icpWeight < 100;
+  int i = 0;
+  while (i < n) {
+    int nb = n - i;
+    if (nb > RGBDOdometry::kMaxBatch) nb = RGBDOdometry::kMaxBatch;
+    if (nb == RGBDOdometry::kMaxBatch + 0 && n - i - nb == 1) nb -= 1;  // never leave a single model for the last batch
+    const bool batch = nb >= 2 && icp && rgb && !tp.force_host_loop && models[i]->odom.canBatch(nb);
+    if (!batch) {
+      RET_IF(models[i]->performTracking(tp));
+      i += 1;
+      continue;
+    }
+    if (!ctx->batchScratch) {
+      RET_IF(cudaMalloc(&ctx->batchScratch, RGBDOdometry::batchScratchBytes()));
+      RET_IF(cudaMemsetAsync(ctx->batchScratch, 0, RGBDOdometry::batchScratchBytes(), ctx->stream));
+    }
+    RGBDOdometry* od[RGBDOdometry::kMaxBatch];
+    float trans[RGBDOdometry::kMaxBatch][3], rot[RGBDOdometry::kMaxBatch][9];
+    float* err[RGBDOdometry::kMaxBatch];
+    for (int k = 0; k < nb; ++k) {
+      Model* m = models[i + k];
+      RET_IF(m->prepareTracking(tp));
+      od[k] = &m->odom;
+      err[k] = m->icpError;
+      const float* P = m->pose;
+      const float t[3] = {P[3], P[7], P[11]};
+      const float r[9] = {P[0], P[1], P[2], P[4], P[5], P[6], P[8], P[9], P[10]};
+      memcpy(trans[k], t, sizeof(t));
+      memcpy(rot[k], r, sizeof(r));
+    }
+    RET_IF(RGBDOdometry::trackBatched(od, nb, trans, rot, tp.icpWeight, tp.pyramid != 0, tp.fastOdom != 0, tp.so3 != 0, err,
+                                      (size_t)ctx->W * 4, ctx->batchScratch, ctx->stream));
+    for (int k = 0; k < nb; ++k) models[i + k]->finishTracking(trans[k], rot[k]);
+    ctx->launches += nb + 1;  // one prepare per model + ONE persistent GN launch
+    i += nb;
+  }
   return cudaSuccess;
 }
 

@@ -44,10 +44,17 @@ class Context {
   uint8_t* h_mask = nullptr;
   int launches = 0;                 // kernels launched since the last reset (bench accounting)
   bool keepMask = false;            // true: a frame without mask keeps the previous labels (segmentation on)
+  void* batchScratch = nullptr;     // RGBDOdometry::batchScratchBytes(), allocated on first multi-model frame
 
  private:
   bool ok_ = false;
 };
+
+class Model;
+struct TrackParams;
+// `for (auto model : models) model->performTracking(...)` (CoFusion.cpp:213-218): one persistent launch for
+// up to RGBDOdometry::kMaxBatch models when the tracker mode allows it, the per-model path otherwise
+cudaError_t trackModels(Context* ctx, Model* const* models, int n, const TrackParams& tp);
 
 struct TrackParams {  // arguments of Model::performTracking (Model.h:128-129)
   int frameToFrameRGB, rgbOnly;
@@ -70,6 +77,10 @@ class Model {
   cudaError_t initFirstRGB();
   // Model::performTracking (Model.cpp:369-389): initICP (:350-367) + getIncrementalTransformation
   cudaError_t performTracking(const TrackParams& tp);
+  // the two halves of performTracking, for the batched tracker (trackModels): everything up to the
+  // optimisation (prediction selection + pyramids), and the pose update after it
+  cudaError_t prepareTracking(const TrackParams& tp);
+  void finishTracking(const float trans[3], const float rot[9]);
 
   // ---- surfel map (Model.cpp / ModelProjection.cpp; kernels in surfel_kernels.cu)
   cudaError_t initialise(int time, float maxDepthProcessed);                      // Model.cpp:227-272

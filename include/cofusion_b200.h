@@ -326,6 +326,10 @@ int cfb_cofusion_last_stats(cfb_cofusion* f, int index, cfb_track_stats* out);
 int cfb_cofusion_last_segmentation(cfb_cofusion* f, cfb_model_data* md_out, int* md_count, int* hasNewLabel,
                                    int* spawned_id, int* deactivated);
 int cfb_cofusion_num_inactive_models(cfb_cofusion* f);
+/* 1 (default): all models of a frame are tracked by ONE persistent kernel launch (<= 5 per launch);
+ * 0: one launch per model, as the reference's `for (auto model : models) performTracking` loop.
+ * Results are bit-identical either way. */
+int cfb_cofusion_set_batched_tracking(cfb_cofusion* f, int on);
 cfb_segmentation* cfb_cofusion_segmentation(cfb_cofusion* f); /* borrowed; NULL when segmentation is off */
 
 #ifdef __cplusplus

@@ -43,6 +43,9 @@ with torch.cuda.stream(ext):
     for k in range(1, NB + 1):
         cf.spawn_object_model(k)
     models = [cf.model(i) for i in range(cf.num_models)]
+    cfb.lib().cfb_model_odometry.restype = cfb.C.c_void_p
+    odom0 = cfb.C.c_void_p(cfb.lib().cfb_model_odometry(models[0]._h))
+    cfb.check(cfb.lib().cfb_odom_enable_kernel_timing(odom0, 1))
     ids = [m.info()[0] for m in models]
     icp = [m.view_ptr(3) for m in models]
     vconf = [m.view_ptr(9) for m in models]
@@ -57,6 +60,7 @@ with torch.cuda.stream(ext):
         step(t)
     cf.ctx.sync()
     cf.ctx.take_launch_count()
+    cfb.check(cfb.lib().cfb_odom_kernel_timing(odom0, None, None, 1))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for t in range(2 + args.warmup, 2 + args.warmup + args.steps):
@@ -65,6 +69,8 @@ with torch.cuda.stream(ext):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
 launches = cf.ctx.take_launch_count() + (0 if args.no_seg else args.steps * 21)
+ksum, kn = cfb.C.c_double(0), cfb.C.c_int(0)
+cfb.check(cfb.lib().cfb_odom_kernel_timing(odom0, cfb.C.byref(ksum), cfb.C.byref(kn), 0))
 counts = [m.last_count() for m in models]
 
 # CPU baseline: the segmentation alone through the oracle (1 core), same inputs
@@ -80,7 +86,9 @@ cpu_ms = (time.perf_counter() - t0) / reps * 1e3
 print(json.dumps({
     "metric": "RGB-D frames/s @640x480, 4 tracked objects + background on 1 GPU, CRF segmentation on",
     "value": args.steps / (ms / 1e3), "unit": "frames/s", "ms_per_step": ms / args.steps, "steps": args.steps,
-    "warmup": args.warmup, "models": len(models), "surfels_per_model": counts, "gpu_launches": launches,
+    "warmup": args.warmup, "models": len(models),
+    "tracker_kernel_ms": (ksum.value / kn.value) if kn.value else None,
+    "tracker": "one persistent launch for all 5 models (gn_batched.cu)", "surfels_per_model": counts, "gpu_launches": launches,
     "segmentation": "off" if args.no_seg else "6 labels, 10 mean-field iterations, every frame",
     "cpu_baseline_segmentation": {"ms_per_frame": cpu_ms, "cores": 1, "kind": "port",
                                   "sample": "%d calls of oracle/segment.c on one frame with the same 5 models" % reps},
