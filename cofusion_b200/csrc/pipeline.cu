@@ -27,30 +27,52 @@ Context::Context(int dev, int w, int h, float fx, float fy, float cx, float cy)
   if (cudaSetDevice(dev) != cudaSuccess) return;
   if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return;
   const size_t n = (size_t)W * H;
-  bool good = dalloc(&rgb, n * 3) && dalloc(&depthRaw, n) && dalloc(&depthFiltered, n) && dalloc(&mask, n) &&
-              dalloc(&depthPyr[1], n / 4) && dalloc(&depthPyr[2], n / 16);
+  bool good = dalloc(&rgbBuf[0], n * 3) && dalloc(&rgbBuf[1], n * 3) && dalloc(&depthBuf[0], n) && dalloc(&depthBuf[1], n) &&
+              dalloc(&depthFiltered, n) && dalloc(&mask, n) && dalloc(&depthPyr[1], n / 4) && dalloc(&depthPyr[2], n / 16);
+  rgb = rgbBuf[0];
+  depthRaw = depthBuf[0];
   depthPyr[0] = depthFiltered;
-  good = good && cudaMallocHost(&h_rgb, n * 3) == cudaSuccess && cudaMallocHost(&h_depth, n * 4) == cudaSuccess &&
-         cudaMallocHost(&h_mask, n) == cudaSuccess;
+  for (int k = 0; k < 2; ++k)
+    good = good && cudaMallocHost(&h_rgbBuf[k], n * 3) == cudaSuccess && cudaMallocHost(&h_depthBuf[k], n * 4) == cudaSuccess &&
+           cudaEventCreateWithFlags(&evCopied[k], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&evBufferFree[k], cudaEventDisableTiming) == cudaSuccess;
+  h_rgb = h_rgbBuf[0];
+  h_depth = h_depthBuf[0];
+  good = good && cudaMallocHost(&h_mask, n) == cudaSuccess &&
+         cudaStreamCreateWithFlags(&copyStream, cudaStreamNonBlocking) == cudaSuccess;
   ok_ = good;
 }
 
 Context::~Context() {
-  cudaFree(rgb);
-  cudaFree(depthRaw);
+  if (stream) cudaStreamSynchronize(stream);
+  if (copyStream) cudaStreamSynchronize(copyStream);
+  for (int k = 0; k < 2; ++k) {
+    cudaFree(rgbBuf[k]);
+    cudaFree(depthBuf[k]);
+    cudaFreeHost(h_rgbBuf[k]);
+    cudaFreeHost(h_depthBuf[k]);
+    if (evCopied[k]) cudaEventDestroy(evCopied[k]);
+    if (evBufferFree[k]) cudaEventDestroy(evBufferFree[k]);
+  }
   cudaFree(depthFiltered);
   cudaFree(mask);
   cudaFree(depthPyr[1]);
   cudaFree(depthPyr[2]);
-  cudaFreeHost(h_rgb);
-  cudaFreeHost(h_depth);
   cudaFreeHost(h_mask);
   cudaFree(batchScratch);
+  if (copyStream) cudaStreamDestroy(copyStream);
   if (stream && owns_stream) cudaStreamDestroy(stream);
 }
 
 cudaError_t Context::uploadFrame(const uint8_t* rgb_h, const float* depth_h, const uint8_t* mask_h) {
   const size_t n = (size_t)W * H;
+  // everything enqueued so far on the pipeline stream (the whole previous frame) is what still reads the
+  // current buffers: they may be overwritten once that point is reached
+  RET_IF(cudaEventRecord(evBufferFree[cur], stream));
+  cur ^= 1;
+  rgb = rgbBuf[cur];
+  depthRaw = depthBuf[cur];
+  RET_IF(cudaStreamWaitEvent(copyStream, evBufferFree[cur], 0));  // the frame before the previous one
   // Pinned callers are copied straight from their buffers; pageable ones are staged through the
   // context's pinned buffers so that the copy is truly asynchronous either way.
   cudaPointerAttributes a;
@@ -59,22 +81,28 @@ cudaError_t Context::uploadFrame(const uint8_t* rgb_h, const float* depth_h, con
   };
   const uint8_t* r = rgb_h;
   const float* d = depth_h;
-  if (!pinned(rgb_h)) {
+  const bool pr = pinned(rgb_h), pd = pinned(depth_h);
+  if (!pr || !pd) {
     cudaGetLastError();
-    memcpy(h_rgb, rgb_h, n * 3);
-    r = h_rgb;
+    RET_IF(cudaEventSynchronize(evCopied[cur]));  // the staging buffers' previous transfer (two frames ago) is done
   }
-  if (!pinned(depth_h)) {
-    cudaGetLastError();
-    memcpy(h_depth, depth_h, n * 4);
-    d = h_depth;
+  if (!pr) {
+    memcpy(h_rgbBuf[cur], rgb_h, n * 3);
+    r = h_rgbBuf[cur];
   }
-  RET_IF(cudaMemcpyAsync(rgb, r, n * 3, cudaMemcpyHostToDevice, stream));
-  RET_IF(cudaMemcpyAsync(depthRaw, d, n * 4, cudaMemcpyHostToDevice, stream));
+  if (!pd) {
+    memcpy(h_depthBuf[cur], depth_h, n * 4);
+    d = h_depthBuf[cur];
+  }
+  RET_IF(cudaMemcpyAsync(rgb, r, n * 3, cudaMemcpyHostToDevice, copyStream));
+  RET_IF(cudaMemcpyAsync(depthRaw, d, n * 4, cudaMemcpyHostToDevice, copyStream));
+  RET_IF(cudaEventRecord(evCopied[cur], copyStream));
+  RET_IF(cudaStreamWaitEvent(stream, evCopied[cur], 0));
   if (mask_h) {
     const uint8_t* m = mask_h;
     if (!pinned(mask_h)) {
       cudaGetLastError();
+      RET_IF(cudaStreamSynchronize(stream));  // single staging buffer for the (small, optional) label image
       memcpy(h_mask, mask_h, n);
       m = h_mask;
     }

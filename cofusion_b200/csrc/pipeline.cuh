@@ -34,8 +34,17 @@ class Context {
   Intr K;
   cudaStream_t stream = nullptr;
   bool owns_stream = true;
-  uint8_t* rgb = nullptr;           // H*W*3
-  float* depthRaw = nullptr;        // metric, 0 = invalid
+  uint8_t* rgb = nullptr;           // H*W*3 -- the buffer of the CURRENT frame (one of rgbBuf[])
+  float* depthRaw = nullptr;        // metric, 0 = invalid (one of depthBuf[])
+  // uploadFrame() double-buffers the inputs and copies on its own stream: the H2D transfer of frame
+  // t+1 overlaps the fuse / clean / predict kernels of frame t (the copy engine is otherwise idle)
+  uint8_t* rgbBuf[2] = {nullptr, nullptr};
+  float* depthBuf[2] = {nullptr, nullptr};
+  uint8_t* h_rgbBuf[2] = {nullptr, nullptr};
+  float* h_depthBuf[2] = {nullptr, nullptr};
+  int cur = 0;
+  cudaStream_t copyStream = nullptr;
+  cudaEvent_t evCopied[2] = {nullptr, nullptr}, evBufferFree[2] = {nullptr, nullptr};
   float* depthFiltered = nullptr;   // level 0 of the pyramid
   float* depthPyr[3] = {nullptr, nullptr, nullptr};
   uint8_t* mask = nullptr;          // label image (model ids)

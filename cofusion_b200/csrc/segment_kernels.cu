@@ -830,8 +830,10 @@ Segmentation::~Segmentation() {
                   K6,     n2,      n6,       Q,      nq2,     nq6,  lowMap, md, hdr, depthRange};
   for (void* p : ptrs) cudaFree(p);
   cudaFreeHost(h_out);
-  if (graphExec_) cudaGraphExecDestroy((cudaGraphExec_t)graphExec_);
-  free(graphKey_);
+  for (int i = 0; i < kGraphSlots; ++i) {
+    if (graphExec_[i]) cudaGraphExecDestroy((cudaGraphExec_t)graphExec_[i]);
+    free(graphKey_[i]);
+  }
 }
 
 cudaError_t Segmentation::slic(const uint8_t* rgb, cudaStream_t s) {
@@ -959,10 +961,15 @@ cudaError_t Segmentation::performSegmentationCRF(const uint8_t* rgb, const float
       k.ids[m] = modelIds[m];
     }
     k.ids[numModels] = nextModelID;
-    GraphKey* cached = (GraphKey*)graphKey_;
-    if (!graphExec_ || !cached || !same_key(*cached, k)) {
-      if (graphExec_) cudaGraphExecDestroy((cudaGraphExec_t)graphExec_);
-      graphExec_ = nullptr;
+    // a few cached graphs: the frame buffers of a context alternate (double-buffered upload)
+    int slot = -1;
+    for (int i = 0; i < kGraphSlots; ++i)
+      if (graphExec_[i] && graphKey_[i] && same_key(*(GraphKey*)graphKey_[i], k)) slot = i;
+    if (slot < 0) {
+      slot = graphNext_;
+      graphNext_ = (graphNext_ + 1) % kGraphSlots;
+      if (graphExec_[slot]) cudaGraphExecDestroy((cudaGraphExec_t)graphExec_[slot]);
+      graphExec_[slot] = nullptr;
       cudaGraph_t graph = nullptr;
       RET_IF(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
       const cudaError_t ce =
@@ -973,11 +980,11 @@ cudaError_t Segmentation::performSegmentationCRF(const uint8_t* rgb, const float
       cudaGraphExec_t exec = nullptr;
       RET_IF(cudaGraphInstantiate(&exec, graph, 0));
       cudaGraphDestroy(graph);
-      graphExec_ = exec;
-      if (!cached) graphKey_ = cached = (GraphKey*)malloc(sizeof(GraphKey));
-      *cached = k;
+      graphExec_[slot] = exec;
+      if (!graphKey_[slot]) graphKey_[slot] = malloc(sizeof(GraphKey));
+      *(GraphKey*)graphKey_[slot] = k;
     }
-    RET_IF(cudaGraphLaunch((cudaGraphExec_t)graphExec_, s));
+    RET_IF(cudaGraphLaunch((cudaGraphExec_t)graphExec_[slot], s));
     launched = true;
   }
   if (!launched)

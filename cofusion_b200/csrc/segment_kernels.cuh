@@ -77,8 +77,10 @@ class Segmentation {
                       const float* const* icpError, const float* const* vertConf4, unsigned char nextModelID,
                       bool allowNew, const SegParams& prm, uint8_t* fullSeg, cudaStream_t s);
   bool ok_ = false;
-  void* graphExec_ = nullptr;  // cudaGraphExec_t of the cached launch sequence
-  void* graphKey_ = nullptr;   // the arguments it was captured with
+  static constexpr int kGraphSlots = 4;
+  void* graphExec_[kGraphSlots] = {nullptr, nullptr, nullptr, nullptr};  // cudaGraphExec_t of cached launch sequences
+  void* graphKey_[kGraphSlots] = {nullptr, nullptr, nullptr, nullptr};   // the arguments each was captured with
+  int graphNext_ = 0;
 };
 
 }  // namespace cfb
