@@ -603,10 +603,14 @@ cudaError_t RGBDOdometry::trackBatched(RGBDOdometry* const* od, int n, float (*t
   RET_IF(cudaMemsetAsync(p.gs, 0, sizeof(BatchSync), s));
   int grid = num_sms();
   if (grid > kMaxBlocks) grid = kMaxBlocks;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RET_IF(cudaFuncSetAttribute(gn_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BSmem)));
-    attr_set = true;
+  {  // the opt-in to > 48 KB of dynamic shared memory is per device: once per device and process
+    static bool attr_set[64] = {};
+    int dev = 0;
+    RET_IF(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      RET_IF(cudaFuncSetAttribute(gn_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BSmem)));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
   }
   void* args[] = {(void*)&p};
   if (f.time_kernel_) RET_IF(cudaEventRecord(f.ev_k0_, s));

@@ -752,10 +752,14 @@ cudaError_t RGBDOdometry::enqueuePersistent(float icpWeight, bool pyramid, bool 
   void* args[] = {(void*)&p};
   if (time_kernel_) RET_IF(cudaEventRecord(ev_k0_, s));
   const size_t stage_bytes = sizeof(Smem);
-  static bool attr_set = false;  // per process; the attribute is per function, identical for every device
-  if (!attr_set) {
-    RET_IF(cudaFuncSetAttribute(gn_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
-    attr_set = true;
+  {  // the opt-in to > 48 KB of dynamic shared memory is per device: once per device and process
+    static bool attr_set[64] = {};
+    int dev = 0;
+    RET_IF(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      RET_IF(cudaFuncSetAttribute(gn_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
   }
   RET_IF(cudaLaunchCooperativeKernel((const void*)gn_persistent_kernel, dim3(grid), dim3(kPT), args, stage_bytes, s));
   if (time_kernel_) {

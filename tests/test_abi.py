@@ -48,3 +48,32 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".cu", ".cuh", ".h", ".py", ".cpp")):
                 src = open(os.path.join(dp, f), errors="ignore").read()
                 assert not bad.search(src), f
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """The Python harness mirrors the C structs by hand: compile the header with gcc and compare sizes
+    and the offsets of the last members, so that a drifted field is caught without a GPU."""
+    import ctypes as C
+    import subprocess
+    import cofusion_b200 as cfb
+    src = tmp_path / "sizes.c"
+    src.write_text('''
+#include <stddef.h>
+#include <stdio.h>
+#include "cofusion_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(cfb_track_stats), sizeof(cfb_track_params),
+         sizeof(cfb_seg_params), sizeof(cfb_model_data), sizeof(cfb_cofusion_params),
+         offsetof(cfb_cofusion_params, seg), offsetof(cfb_cofusion_params, modelSpawnOffset),
+         offsetof(cfb_model_data, left), offsetof(cfb_track_stats, so3_iterations));
+  return 0;
+}
+''')
+    exe = tmp_path / "sizes"
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    want = [C.sizeof(cfb.TrackStats), C.sizeof(cfb.TrackParams), C.sizeof(cfb.SegParams), C.sizeof(cfb.ModelData),
+            C.sizeof(cfb.CoFusionParams), cfb.CoFusionParams.seg.offset, cfb.CoFusionParams.modelSpawnOffset.offset,
+            cfb.ModelData.left.offset, cfb.TrackStats.so3_iterations.offset]
+    assert got == want, (got, want)
