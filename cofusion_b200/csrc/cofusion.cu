@@ -218,16 +218,14 @@ cudaError_t CoFusion::processFrame(const uint8_t* rgb, const float* depth, const
   if (tl.on && tick_ > 3) {
     // the previous frame's events are complete by now (this frame synchronised after them)
     const int prev = tl.cur ^ 1;
-    if (tl.frames > 0 || true) {
-      float ms;
-      if (tl.hprev > 0) {
-        for (int k = 0; k < 3; ++k)
-          if (cudaEventElapsedTime(&ms, tl.ev[prev][k], tl.ev[prev][k + 1]) == cudaSuccess) tl.devms[k] += ms;
-        if (cudaEventElapsedTime(&ms, tl.ev[prev][3], tl.ev[tl.cur][0]) == cudaSuccess) tl.devms[3] += ms;
-        tl.host[3] += h[0] - tl.hprev;
-        tl.frames++;
-      }
+    float ms;
+    if (tl.hprev > 0) {
+      for (int k = 0; k < 3; ++k)
+        if (cudaEventElapsedTime(&ms, tl.ev[prev][k], tl.ev[prev][k + 1]) == cudaSuccess) tl.devms[k] += ms;
+      if (cudaEventElapsedTime(&ms, tl.ev[prev][3], tl.ev[tl.cur][0]) == cudaSuccess) tl.devms[3] += ms;
+      tl.host[3] += h[0] - tl.hprev;
       for (int k = 0; k < 3; ++k) tl.host[k] += h[k + 1] - h[k];
+      tl.frames++;
     }
     tl.hprev = h[3];
     if (tl.frames == 200) {
