@@ -104,17 +104,20 @@ def cpu_port_fps(frames, n_frames, warm=2):
     return n_frames / dt, dt
 
 
-def cpu_segmentation_ms(frames, reps=3):
+def cpu_segmentation_ms(frames, reps=3, n_models=1):
     """The part of the path that is CPU code in the reference (SLIC + dense CRF + components,
-    Core/Segmentation): oracle/segment.c on one host core, one model + the "new" label, 640x480."""
+    Core/Segmentation): oracle/segment.c on one host core, n models + the "new" label, 640x480."""
     import orc
     rgb, d = frames[3]
-    icp = np.full((H, W), 0.002, np.float32)
-    vc = np.zeros((H, W, 4), np.float32)
-    vc[..., 3] = 10.0
+    icp = [np.full((H, W), 0.002 * (m + 1), np.float32) for m in range(n_models)]
+    vcs = []
+    for m in range(n_models):
+        vc = np.zeros((H, W, 4), np.float32)
+        vc[..., 3] = 10.0 if m == 0 else 1.0
+        vcs.append(vc)
     t0 = time.perf_counter()
     for _ in range(reps):
-        orc.segment_crf(rgb, d, [0], [icp], [vc], 1, True)
+        orc.segment_crf(rgb, d, list(range(n_models)), icp, vcs, n_models, True)
     return 1e3 * (time.perf_counter() - t0) / reps
 
 
@@ -312,7 +315,8 @@ def main():
         cpu = {"value": fps_cpu, "unit": "frames/s", "cores": 1, "kind": "port",
                "sample": "%d frames of the same 640x480 room sequence through the oracle/ C restatement "
                          "(single thread, like the reference's CPU loops), %.1f s" % (args.cpu_frames, dt),
-               "segmentation_ms_per_frame": cpu_segmentation_ms(frames)}
+               "segmentation_ms_per_frame": cpu_segmentation_ms(frames),
+               "segmentation_ms_per_frame_5_models": cpu_segmentation_ms(frames, reps=2, n_models=5)}
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -5,8 +5,8 @@ segmentation runs over all five models' ICP-error / confidence maps (6 labels in
 the model set stable over an arbitrarily long timed region, the objects are spawned once from the
 renderer's label image (FrameData::mask path, Segmentation.cpp:61-119) and the fuse/clean stage keeps
 using those labels; the segmentation result of every frame is computed (and timed) but not fed back.
-Prints one JSON line; the CPU figure is the oracle's segmentation alone (the part that is CPU code in
-the reference) on one host core.
+Prints one JSON line.  (The CPU figure for the same segmentation -- the part that is CPU code in the
+reference -- is part of bench.py's cpu_baseline: `segmentation_ms_per_frame`, 1 and 5 models.)
 
   python tools/bench_objects.py [--steps K] [--warmup W]
 """
@@ -73,16 +73,6 @@ ksum, kn = cfb.C.c_double(0), cfb.C.c_int(0)
 cfb.check(cfb.lib().cfb_odom_kernel_timing(odom0, cfb.C.byref(ksum), cfb.C.byref(kn), 0))
 counts = [m.last_count() for m in models]
 
-# CPU baseline: the segmentation alone through the oracle (1 core), same inputs
-import orc
-_, rgb_h, d_h, _, _ = seq[5]
-icp_h = [m.view(3) for m in models]
-vc_h = [m.view(9) for m in models]
-t0 = time.perf_counter()
-reps = 3
-for _ in range(reps):
-    orc.segment_crf(rgb_h, d_h, ids, icp_h, vc_h, NB + 1, True)
-cpu_ms = (time.perf_counter() - t0) / reps * 1e3
 print(json.dumps({
     "metric": "RGB-D frames/s @640x480, 4 tracked objects + background on 1 GPU, CRF segmentation on",
     "value": args.steps / (ms / 1e3), "unit": "frames/s", "ms_per_step": ms / args.steps, "steps": args.steps,
@@ -90,6 +80,4 @@ print(json.dumps({
     "tracker_kernel_ms": (ksum.value / kn.value) if kn.value else None,
     "tracker": "one persistent launch for all 5 models (gn_batched.cu)", "surfels_per_model": counts, "gpu_launches": launches,
     "segmentation": "off" if args.no_seg else "6 labels, 10 mean-field iterations, every frame",
-    "cpu_baseline_segmentation": {"ms_per_frame": cpu_ms, "cores": 1, "kind": "port",
-                                  "sample": "%d calls of oracle/segment.c on one frame with the same 5 models" % reps},
     "data": "synthetic room + 4 moving boxes, labels from the renderer (external mask path)"}))
