@@ -121,6 +121,31 @@ def cpu_segmentation_ms(frames, reps=3, n_models=1):
     return 1e3 * (time.perf_counter() - t0) / reps
 
 
+def reference_cuda_tracker():
+    """SURVEY.md 8(d) "reference timed beside it" (1): the reference's OWN tracker kernels (oracle/_ref =
+    Core/Cuda/reduce.cu + cudafuncs.cu compiled as they are for sm_100a) driven through the call sequence of
+    RGBDOdometry::getIncrementalTransformation on one 640x480 frame pair of the same sequence, on this GPU.
+    Timed inside the reference driver around the step calls only (no pyramid building).  Part of the
+    cpu_baseline / reference leg: never on the product path."""
+    try:
+        import orc
+        import scenes
+        if orc.ref() is None:
+            return None
+        case = scenes.room_pair(W, H)
+        best, steps = None, 0
+        for _ in range(3):
+            oo, _ = scenes.oracle_odometry(case)
+            _, _, _, extra = oo.track(case["T0"], use_ref=True)
+            best = extra["step_ms"] if best is None else min(best, extra["step_ms"])
+            steps = extra["steps"]
+        return {"tracker_ms_per_frame": best, "launch_sync_steps": steps, "kind": "reference",
+                "what": "icpStep / computeRgbResidual / rgbStep / so3Step of the reference, reference launch "
+                        "configuration and per-step synchronisation; compare with roofline.avg_launch_ms"}
+    except Exception as e:  # the reference kernels are optional evidence, never a reason to fail the bench
+        return {"unavailable": repr(e)[:200]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -336,6 +361,7 @@ def main():
                      "peak_source": peak_src,
                      "share_of_step": (k_avg_ms / (ms / args.steps)) if kn else None},
         "cpu_baseline": cpu,
+        "reference_cuda": reference_cuda_tracker() if (world == 1 and args.cpu_frames > 0) else None,
         "clocks": sampler.summary() if sampler else None,
     }
     print(json.dumps(line), flush=True)
