@@ -1,17 +1,19 @@
 // gn_persistent.cu -- the whole tracker optimisation (SO(3) pre-alignment + 3-level ICP/RGB
 // Gauss-Newton) as ONE persistent cooperative kernel: one CTA per SM, grid-wide barriers in
-// software, the FP64 Gauss-Newton step executed by the last CTA to reach each barrier.
+// software, the FP64 Gauss-Newton step executed redundantly by every CTA on its own copy of the state.
 //
 // Why (measured on B200, profiles/): at 640x480 a GN iteration touches <= 34 MB that sits in the
-// 126 MB L2, so the work of an iteration is 3-8 us while every separate reduction kernel costs
-// ~9 us of launch + prologue + last-block election latency; the 48-launch graph version spends
+// 126 MB L2, so the work of an iteration is a few microseconds while every separate reduction kernel
+// costs ~9 us of launch + prologue + last-block election latency; the 48-launch graph version spends
 // two thirds of its 0.58 ms in those fixed costs.  Inside one kernel an iteration is
-//     pass1 (ICP rows + RGB correspondences) -> barrier A -> pass2 (RGB rows) -> barrier B (+solve)
-// and the photometric correspondences of a pixel never leave the registers of the thread that owns
-// it (the reference round-trips a 16-byte DataTerm image through memory, reduce.cu:862 / :524).
+//     residual -> arrive A -> ICP rows -> wait A -> RGB rows -> barrier B -> fold partial rows -> solve
+// with the iteration-invariant inputs of a thread's pixels staged in shared memory once per level and
+// the photometric correspondences of a pixel never leaving the SM (the reference round-trips a
+// 16-byte DataTerm image through memory, reduce.cu:862 / :524).
 //
 // Arithmetic is the same per-pixel code as the stand-alone steps (tracker_device.cuh); sums are
 // folded in a fixed order (per-CTA partials, then CTA order) -> bit-reproducible run to run.
+// gn_batched.cu is the same kernel over several models of one frame.
 #include "gn_serial.cuh"
 #include "image_kernels.cuh"
 
