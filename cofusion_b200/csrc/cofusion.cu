@@ -177,6 +177,9 @@ cudaError_t CoFusion::processFrame(const uint8_t* rgb, const float* depth, const
   if (tick_ == 1) {
     RET_IF(models[0]->initialise(tick_, params.maxDepthProcessed));
     RET_IF(models[0]->initFirstRGB());
+    // every later frame synchronises on its tracker (after the upload); the first one has none, and the
+    // contract is that host buffers may be reused once the call returns
+    if (!device_ptrs) RET_IF(cudaStreamSynchronize(ctx.copyStream));
   } else {
     TrackParams tp;
     tp.frameToFrameRGB = params.frameToFrameRGB;
