@@ -596,6 +596,9 @@ __device__ __noinline__ void run_so3(unsigned& barriers) {
     }
     __syncthreads();
   }
+  // the Gauss-Newton loop reuses the partial rows (parity 0 first): no CTA may still be folding SO(3) rows
+  grid_arrive(gs);
+  grid_wait(gs, ++barriers * G);
 }
 
 __global__ void __launch_bounds__(kPT, 1) gn_persistent_kernel(const PersistParams kp) {
