@@ -274,8 +274,14 @@ cudaError_t RGBDOdometry::deviceLoop(float trans[3], float rot[9], float icpWeig
   // legacy default stream cannot be captured: direct launches there.
   bool launched = false;
   if (mode_ == 0) {
-    RET_IF(enqueuePersistent(icpWeight, pyramid, fastOdom, so3, err, err_pitch, s));
-    launched = true;
+    if (!tiled_scratch_) {
+      RET_IF(cudaMalloc(&tiled_scratch_, tiledScratchBytes()));
+      RET_IF(cudaMemsetAsync(tiled_scratch_, 0, tiledScratchBytes(), s));
+    }
+    RGBDOdometry* od[1] = {this};
+    float* errs[1] = {err};
+    return trackTiled(od, 1, (float(*)[3])trans, (float(*)[9])rot, icpWeight, pyramid, fastOdom, so3, errs, err_pitch,
+                      tiled_scratch_, s);
   } else if (use_graphs_ && s != 0 && s != cudaStreamLegacy) {
     GraphKey key{parity_, err, err_pitch, icpWeight, pyramid, fastOdom, so3};
     cudaGraphExec_t exec = nullptr;

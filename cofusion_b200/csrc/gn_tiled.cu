@@ -1,0 +1,1566 @@
+// gn_tiled.cu -- the tracker optimisation (SO(3) pre-alignment + 3-level ICP/RGB Gauss-Newton,
+// Core/Utils/RGBDOdometry.cpp:217-477 over Core/Cuda/reduce.cu) of ALL models of a frame
+// (`for (auto model : models) model->performTracking(...)`, Core/CoFusion.cpp:213-218) as ONE persistent
+// cooperative kernel, organised around 2-D image tiles that live in shared memory.
+//
+// Layout of the work
+//   * The image of every pyramid level is cut into the same gx x gy grid of tiles, one tile per CTA
+//     (one CTA per SM, 576 threads).  A CTA owns its tile for the whole launch.
+//   * Frame side (current vertex / normal map, Sobel images, grey image, and for the camera model the
+//     warped-depth plane and the photometric candidate gate): the tile of EVERY level is fetched once,
+//     at kernel start, by TMA (cp.async.bulk.tensor + mbarrier; 3-D tensor maps over the planar
+//     pyramids) -- the copies of the finer levels land while the coarser levels iterate.
+//   * Model side (global-frame vertex / normal prediction, lastDepth, lastImage): projective data
+//     association maps pixel (x, y) to a pixel a few columns away, coherently over a tile.  At the
+//     start of a level the CTA measures the mean displacement of its tile under the current pose
+//     estimate and fetches ONE window (tile + halo, shifted by that displacement) by TMA.  A Gauss-
+//     Newton iteration then touches shared memory only; an association that leaves the window falls
+//     back to the same values in global memory (identical results, only slower).
+//   * Object models (m >= 1) cover a few percent of the image: they share the frame tiles and read their
+//     own prediction from global memory (x plane first, the other five only where the object is).
+//   * Levels whose tiles do not fit (1280x960 level 0) run the same code on global memory.
+//
+// One Gauss-Newton iteration
+//     photometric correspondences -> red.add.u64 {arrived, count, sum floor(diff^2)} (barrier A, no fence:
+//     the payload IS the atomic) -> ICP rows (hides A) -> RGB rows weighted with the global count ->
+//     every CTA publishes its 58 partial sums as 20 x 16-byte packets {3 sums, tag} -> every CTA polls
+//     the packets of all CTAs (the tag makes the data its own flag: no barrier, no fence, one L2 round
+//     trip), folds them in a fixed order and runs the FP64 Gauss-Newton step on its own copy of the
+//     state, spread over the lanes of a warp (warp m solves model m).
+// Sums are folded in a fixed order (thread -> warp -> CTA -> grid): bit-reproducible run to run.
+// Per-pixel arithmetic: SURVEY.md Appendix A1-A5 (tracker_device.cuh holds the stand-alone form).
+#include <cuda.h>  // CUtensorMap + enums only; the encoder is fetched through cudaGetDriverEntryPoint
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "gn_serial.cuh"
+#include "image_kernels.cuh"
+
+namespace cfb {
+namespace {
+using namespace dev;
+
+constexpr int kT = 576;               // threads per CTA, one CTA per SM
+constexpr int kNW = kT / 32;          // 18 warps
+constexpr int kPP = 4;                // pixels per thread of a shared-memory tile
+constexpr int kMaxM = RGBDOdometry::kMaxBatch;
+constexpr int kChunks = 20;           // 16-byte packets per (CTA, model, GN iteration): 58 sums
+constexpr int kGroups = kT / kChunks; // 28 thread groups share the rows of the fold
+constexpr int kSo3Chunks = 4;         // 11 sums
+constexpr int kSo3Groups = 36;
+constexpr unsigned kNoCorr = 0xffffffffu;
+constexpr int kMaxRounds = 32;        // 10 SO(3) + 19 GN reduction rounds
+
+struct MLevel {  // per model, per level
+  const float *vmap_g_prev, *nmap_g_prev, *lastDepth, *nextDepth;
+  const unsigned char *lastImage, *cand;
+  const CUtensorMap *tm_d1, *tm_cand, *tm_pv, *tm_pn, *tm_ld, *tm_li;  // camera model (m == 0) only
+};
+struct MParams {
+  MLevel L[3];
+  const unsigned char *so3_last, *so3_next;
+  GNState* g;
+  const float* pose_in;
+  float* err;
+};
+struct FLevel {  // frame side + tile plan of one level
+  const float *vmap_curr, *nmap_curr;
+  const unsigned char* nextImage;
+  const short *dIdx, *dIdy;
+  const CUtensorMap *tm_v, *tm_n, *tm_dx, *tm_dy, *tm_img;
+  int w, h;
+  LevelK k;
+  int tw, th;      // tile size in pixels
+  int rw, npx;     // row width of the pixel enumeration (tw rounded up to 4) and rw * th
+  int staged;      // 0: global memory, 1: shared-memory tiles filled by TMA, 2: filled by the threads
+  int bws, bwb;    // row pitch (elements) of the s16 / u8 frame tiles
+  int ww, wh;      // model window (pixels); ww is a multiple of 16
+  unsigned o_v, o_n, o_dx, o_dy, o_img, o_d1, o_cand;  // byte offsets into dynamic shared memory
+  unsigned o_pv, o_pn, o_ld, o_li;
+  unsigned frame_bytes, win_bytes;  // TMA transaction sizes
+};
+struct TParams {
+  MParams M[kMaxM];
+  FLevel F[3];
+  int nmodels, gx, gy;
+  float4* rows;              // [2][G][nmodels][kChunks] packets
+  unsigned long long* acnt;  // [kMaxRounds][kMaxM] barrier-A words, zero before the launch
+  unsigned epoch;            // launch counter: tags never repeat, the packet buffer is never cleared
+  size_t err_pitch;
+  float distThres, angleThres, maxDepthDelta, sobelScale, icpWeight;
+  int use_so3;
+  int iters[3];
+  unsigned o_wrow, o_part, o_out, o_corr;
+  unsigned long long* dbg;
+};
+
+// per level, per CTA: everything the pixel phases address, derived once per level (kept in shared memory:
+// the phase functions are separate register-allocation units and read it with uniform LDS)
+struct LvCtx {
+  int W, H, x0, y0, tw, th, rw, npx, bws, bwb;
+  float fx, fy, cx, cy;
+  const float *sV, *sN, *sD1;  // frame tiles (f32 planes of npx elements)
+  const short *sDX, *sDY;
+  const unsigned char *sIMG, *sCAND;
+  const float *sPV, *sPN, *sLD;  // model window of the camera model (planes of ww * wh elements)
+  const unsigned char* sLI;
+  int ww, wh, wn, wx0, wy0;
+  unsigned* corrZ;  // [kPP][kT] packed correspondence of the camera model
+  float* corrD;     // [kPP][kT] depth of the matched point
+};
+
+static_assert(sizeof(TParams) <= 4000, "kernel parameter block");
+
+struct TFixed {  // fixed head of the dynamic shared memory
+  TParams prm;
+  LvCtx lv;
+  GNState S[kMaxM];  // every CTA keeps (and identically updates) its own copy of every model's state
+  double K[3][9], Kinv[3][9];
+  double solveA[kMaxM][42];
+  unsigned long long bar_frame[3], bar_win;
+  int cntw[kMaxM][kNW], sigw[kMaxM][kNW];
+  int tot[kMaxM][2];
+  float tmpErr[kMaxM];
+  int winacc[3];
+  int win_x0, win_y0;
+  int sched[20];
+  int nsched;
+};
+
+#define TSMEM()                                                   \
+  extern __shared__ __align__(128) unsigned char dyn_smem_raw[]; \
+  TFixed& sm = *reinterpret_cast<TFixed*>(dyn_smem_raw);          \
+  const TParams& p = sm.prm
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define DBG_MARK(slot)                                                       \
+  do {                                                                       \
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[(slot)] = gtime(); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ unsigned smem_u32(const void* q) { return (unsigned)__cvta_generic_to_shared(q); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2,
+                                            unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ float4 ld_packet(const float4* q) {  // one 16-byte access, never cached in L1
+  float4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(q) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_packet(float4* q, float4 v) {
+  asm volatile("st.relaxed.gpu.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_u64_relaxed(const unsigned long long* q) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(q) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_add_u64(unsigned long long* q, unsigned long long v) {
+  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(q), "l"(v) : "memory");
+}
+
+// correspondence of one pixel packed into 32 bits: u0 (11) | v0 (11) | diff + 256 (10).  diff is the
+// difference of two 8-bit intensities, an integer in [-255, 255]: lossless for images below 2048 x 2048.
+__device__ __forceinline__ unsigned pack_corr(int u0, int v0, float diff) {
+  return (unsigned)u0 | ((unsigned)v0 << 11) | ((unsigned)((int)diff + 256) << 22);
+}
+
+__device__ __forceinline__ void make_lvctx(int lvl) {  // one thread
+  TSMEM();
+  LvCtx& c = sm.lv;
+  const FLevel& F = p.F[lvl];
+  const int bx = blockIdx.x % p.gx, by = blockIdx.x / p.gx;
+  c.W = F.w;
+  c.H = F.h;
+  c.tw = F.tw;
+  c.th = F.th;
+  c.x0 = bx * F.tw;
+  c.y0 = by * F.th;
+  c.rw = F.rw;
+  c.npx = F.npx;
+  c.bws = F.bws;
+  c.bwb = F.bwb;
+  c.fx = F.k.fx;
+  c.fy = F.k.fy;
+  c.cx = F.k.cx;
+  c.cy = F.k.cy;
+  unsigned char* base = dyn_smem_raw;
+  c.sV = (const float*)(base + F.o_v);
+  c.sN = (const float*)(base + F.o_n);
+  c.sD1 = (const float*)(base + F.o_d1);
+  c.sDX = (const short*)(base + F.o_dx);
+  c.sDY = (const short*)(base + F.o_dy);
+  c.sIMG = base + F.o_img;
+  c.sCAND = base + F.o_cand;
+  c.sPV = (const float*)(base + F.o_pv);
+  c.sPN = (const float*)(base + F.o_pn);
+  c.sLD = (const float*)(base + F.o_ld);
+  c.sLI = base + F.o_li;
+  c.ww = F.ww;
+  c.wh = F.wh;
+  c.wn = F.ww * F.wh;
+  c.wx0 = sm.win_x0;
+  c.wy0 = sm.win_y0;
+  c.corrZ = (unsigned*)(base + p.o_corr);
+  c.corrD = (float*)(base + p.o_corr + kPP * kT * 4);
+}
+
+// pixel i of the tile enumeration -> local / image coordinates; false for padding and image borders
+__device__ __forceinline__ bool tile_pixel(const LvCtx& c, int i, int& lx, int& ly, int& x, int& y) {
+  ly = i / c.rw;
+  lx = i - ly * c.rw;
+  x = c.x0 + lx;
+  y = c.y0 + ly;
+  return lx < c.tw && x < c.W && y < c.H;
+}
+
+// ------------------------------------------------------------------------------------------ phase 1
+// RGBResidual::getProducts for a candidate pixel (reduce.cu:827-853).  FS: frame tiles in shared
+// memory, MS: this model's window in shared memory.  Returns validity, fills u0 / v0 / diff / d0.
+template <bool FS, bool MS>
+__device__ __forceinline__ bool residual_pixel(const LvCtx& c, const MLevel& L, const RgbWarp& Wp, float maxDepthDelta,
+                                               int i, int lx, int ly, int x, int y, const unsigned char* nextImage,
+                                               int& u0, int& v0, float& diff, float& d0) {
+  bool cand;
+  float d1;
+  if (MS) {
+    cand = c.sCAND[ly * c.bwb + lx] != 0;
+    d1 = c.sD1[i];
+  } else {
+    cand = __ldg(L.cand + y * c.W + x) != 0;
+    d1 = cand ? __ldg(L.nextDepth + y * c.W + x) : 0.f;
+  }
+  if (!cand) return false;
+  const float* kk = Wp.krkinv.m;
+  const float td1 = d1 * (kk[6] * x + kk[7] * y + kk[8]) + Wp.kt[2];
+  u0 = __float2int_rn((d1 * (kk[0] * x + kk[1] * y + kk[2]) + Wp.kt[0]) / td1);
+  v0 = __float2int_rn((d1 * (kk[3] * x + kk[4] * y + kk[5]) + Wp.kt[1]) / td1);
+  if (!(u0 >= 0 && v0 >= 0 && u0 < c.W && v0 < c.H)) return false;
+  unsigned char li;
+  const int wu = u0 - c.wx0, wv = v0 - c.wy0;
+  if (MS && (unsigned)wu < (unsigned)c.ww && (unsigned)wv < (unsigned)c.wh) {
+    d0 = c.sLD[wv * c.ww + wu];
+    li = c.sLI[wv * c.ww + wu];
+  } else {
+    d0 = __ldg(L.lastDepth + v0 * c.W + u0);
+    li = __ldg(L.lastImage + v0 * c.W + u0);
+  }
+  if (!(d0 > 0 && fabsf(td1 - d0) <= maxDepthDelta && li != 0)) return false;
+  const unsigned char ni = FS ? c.sIMG[ly * c.bwb + lx] : __ldg(nextImage + y * c.W + x);
+  diff = (float)ni - (float)li;
+  return true;
+}
+
+template <bool FS, bool MS>
+__device__ __noinline__ void phase1(int lvl, int m) {
+  TSMEM();
+  const LvCtx& c = sm.lv;
+  const MLevel& L = p.M[m].L[lvl];
+  const RgbWarp& Wp = sm.S[m].warp;
+  const unsigned char* nextImage = p.F[lvl].nextImage;
+  int cnt = 0, sig = 0;
+  int k = 0;
+#pragma unroll 2
+  for (int i = threadIdx.x; i < c.npx; i += kT, ++k) {
+    int lx, ly, x, y, u0, v0;
+    float diff, d0;
+    unsigned zero = kNoCorr;
+    if (tile_pixel(c, i, lx, ly, x, y) && residual_pixel<FS, MS>(c, L, Wp, p.maxDepthDelta, i, lx, ly, x, y, nextImage, u0, v0, diff, d0)) {
+      cnt += 1;
+      sig += (int)(diff * diff);  // float -> int truncation, reduce.cu:851
+      if (MS) {
+        zero = pack_corr(u0, v0, diff);
+        c.corrD[k * kT + threadIdx.x] = d0;
+      }
+    }
+    if (MS) c.corrZ[k * kT + threadIdx.x] = zero;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    sig += __shfl_xor_sync(0xffffffffu, sig, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sm.cntw[m][threadIdx.x >> 5] = cnt;
+    sm.sigw[m][threadIdx.x >> 5] = sig;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ phase 2
+__device__ __forceinline__ void store_warp_row(int m, int set, bool any, float (&acc)[32]) {
+  TSMEM();
+  float* wrow = (float*)(dyn_smem_raw + p.o_wrow) + ((size_t)(m * 2 + set) * kNW + (threadIdx.x >> 5)) * 32;
+  // a warp without any contribution adds exact zeros: skip its 31-shuffle transpose
+  wrow[threadIdx.x & 31] = __any_sync(0xffffffffu, any) ? warp_transpose_reduce32(acc) : 0.f;
+}
+
+__device__ __forceinline__ void icp_found_row(const IcpPose& P, float3 tprev, float3 vcurr_cp, float3 vp, float3 np,
+                                              float (&acc)[32]) {
+  const float3 d_cp = mul(P.Rprev_inv, vp - tprev);
+  const float3 n_cp = mul(P.Rprev_inv, np);
+  const float3 cr = cross(vcurr_cp, n_cp);
+  const float row[7] = {n_cp.x, n_cp.y, n_cp.z, cr.x, cr.y, cr.z, dot(n_cp, vcurr_cp - d_cp)};
+  accumulate_se3(acc, row, true);
+}
+
+template <bool FS, bool MS>
+__device__ __noinline__ void phase2(int lvl, int m, float* error_map) {
+  TSMEM();
+  const LvCtx& c = sm.lv;
+  const MLevel& L = p.M[m].L[lvl];
+  const FLevel& F = p.F[lvl];
+  const IcpPose& P = sm.S[m].pose;
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+  const float3 tcurr = make_float3(P.tcurr[0], P.tcurr[1], P.tcurr[2]);
+  const float3 tprev = make_float3(P.tprev[0], P.tprev[1], P.tprev[2]);
+  const int HW = c.W * c.H;
+  bool any = false;
+#pragma unroll 2
+  for (int i = threadIdx.x; i < c.npx; i += kT) {
+    int lx, ly, x, y;
+    if (!tile_pixel(c, i, lx, ly, x, y)) continue;
+    float3 vcurr;
+    vcurr.x = FS ? c.sV[i] : __ldg(F.vmap_curr + y * c.W + x);
+    float* const err = error_map ? row_ptr(error_map, p.err_pitch, y) + x : nullptr;
+    // an invalid vertex has NaN in x: every coordinate of vcurr_g is NaN, dist is NaN -> no
+    // correspondence, error 0 (same outcome as running the arithmetic, without the gathers)
+    if (isnan(vcurr.x)) {
+      if (err) *err = 0.0f;
+      continue;
+    }
+    vcurr.y = FS ? c.sV[c.npx + i] : __ldg(F.vmap_curr + HW + y * c.W + x);
+    vcurr.z = FS ? c.sV[2 * c.npx + i] : __ldg(F.vmap_curr + 2 * HW + y * c.W + x);
+    const float3 vcurr_g = mul(P.Rcurr, vcurr) + tcurr;
+    const float3 vcurr_cp = mul(P.Rprev_inv, vcurr_g - tprev);
+    const int ux = __float2int_rn(vcurr_cp.x * c.fx / vcurr_cp.z + c.cx);
+    const int uy = __float2int_rn(vcurr_cp.y * c.fy / vcurr_cp.z + c.cy);
+    if (ux < 0 || uy < 0 || ux >= c.W || uy >= c.H || vcurr_cp.z < 0) {
+      if (err) *err = 0.0f;
+      continue;
+    }
+    float3 vp, np;
+    const int wu = ux - c.wx0, wv = uy - c.wy0;
+    if (MS && (unsigned)wu < (unsigned)c.ww && (unsigned)wv < (unsigned)c.wh) {
+      const int j = wv * c.ww + wu;
+      vp = make_float3(c.sPV[j], c.sPV[c.wn + j], c.sPV[2 * c.wn + j]);
+      np = make_float3(c.sPN[j], c.sPN[c.wn + j], c.sPN[2 * c.wn + j]);
+    } else {
+      const int j = uy * c.W + ux;
+      vp.x = __ldg(L.vmap_g_prev + j);
+      // An object model predicts a few percent of the image; everywhere else its vertex map is NaN.
+      // A NaN in the x plane makes dist NaN whatever the other five planes hold.
+      if (isnan(vp.x)) {
+        if (err) *err = 0.0f;
+        continue;
+      }
+      vp.y = __ldg(L.vmap_g_prev + HW + j);
+      vp.z = __ldg(L.vmap_g_prev + 2 * HW + j);
+      np = make_float3(__ldg(L.nmap_g_prev + j), __ldg(L.nmap_g_prev + HW + j), __ldg(L.nmap_g_prev + 2 * HW + j));
+    }
+    float3 ncurr;
+    if (FS)
+      ncurr = make_float3(c.sN[i], c.sN[c.npx + i], c.sN[2 * c.npx + i]);
+    else
+      ncurr = make_float3(__ldg(F.nmap_curr + y * c.W + x), __ldg(F.nmap_curr + HW + y * c.W + x),
+                          __ldg(F.nmap_curr + 2 * HW + y * c.W + x));
+    const float3 ncurr_g = mul(P.Rcurr, ncurr);
+    const float dist = norm(vp - vcurr_g);
+    const float sine = norm(cross(ncurr_g, np));
+    if (err) *err = isfinite(dist) ? dist : 0.0f;
+    if (sine < p.angleThres && dist <= p.distThres && !isnan(ncurr.x) && !isnan(np.x)) {
+      any = true;
+      icp_found_row(P, tprev, vcurr_cp, vp, np, acc);
+    }
+  }
+  store_warp_row(m, 0, any, acc);
+}
+
+// ------------------------------------------------------------------------------------------ phase 3
+__device__ __forceinline__ void rgb_row(const LvCtx& c, float sigma, float sobelScale, int zx, int zy, float z, float diff,
+                                        short sdx, short sdy, float (&acc)[32]) {
+  float w = sigma + fabsf(diff);
+  w = w > 1.19209290E-07F ? 1.0f / w : 1.0f;
+  if (sigma == -1.f) w = 1.f;
+  const float invFx = 1.0f / c.fx, invFy = 1.0f / c.fy;
+  const float3 Pt = make_float3(((float)zx - c.cx) * z * invFx, ((float)zy - c.cy) * z * invFy, z);
+  const float invz = (float)(1.0 / (double)Pt.z);
+  const float dI_dx_val = w * sobelScale * (float)sdx;
+  const float dI_dy_val = w * sobelScale * (float)sdy;
+  const float v0 = dI_dx_val * c.fx * invz;
+  const float v1 = dI_dy_val * c.fy * invz;
+  const float v2 = -(v0 * Pt.x + v1 * Pt.y) * invz;
+  const float row[7] = {v0, v1, v2, -Pt.z * v1 + Pt.y * v2, Pt.z * v0 - Pt.x * v2, -Pt.y * v0 + Pt.x * v1, -w * diff};
+  accumulate_se3(acc, row, true);
+}
+
+template <bool FS, bool MS>
+__device__ __noinline__ void phase3(int lvl, int m, float sigma) {
+  TSMEM();
+  const LvCtx& c = sm.lv;
+  const FLevel& F = p.F[lvl];
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+  bool any = false;
+  int k = 0;
+#pragma unroll 2
+  for (int i = threadIdx.x; i < c.npx; i += kT, ++k) {
+    if (MS) {  // the correspondences of phase 1 never left the SM
+      const unsigned zero = c.corrZ[k * kT + threadIdx.x];
+      if (zero == kNoCorr) continue;
+      const int ly = i / c.rw, lx = i - ly * c.rw;
+      any = true;
+      rgb_row(c, sigma, p.sobelScale, (int)(zero & 0x7ffu), (int)((zero >> 11) & 0x7ffu), c.corrD[k * kT + threadIdx.x],
+              (float)((int)(zero >> 22) - 256), c.sDX[ly * c.bws + lx], c.sDY[ly * c.bws + lx], acc);
+    } else {  // recomputed: the same decisions and values as phase 1
+      int lx, ly, x, y, u0, v0;
+      float diff, d0;
+      if (!tile_pixel(c, i, lx, ly, x, y)) continue;
+      if (!residual_pixel<FS, false>(c, p.M[m].L[lvl], sm.S[m].warp, p.maxDepthDelta, i, lx, ly, x, y, F.nextImage, u0, v0, diff, d0))
+        continue;
+      any = true;
+      const short sdx = FS ? c.sDX[ly * c.bws + lx] : __ldg(F.dIdx + y * c.W + x);
+      const short sdy = FS ? c.sDY[ly * c.bws + lx] : __ldg(F.dIdy + y * c.W + x);
+      rgb_row(c, sigma, p.sobelScale, u0, v0, d0, diff, sdx, sdy, acc);
+    }
+  }
+  store_warp_row(m, 1, any, acc);
+}
+
+// ------------------------------------------------------------------------- publish / fold / barrier A
+// warp rows -> this CTA's packets of model m: packet c holds sums 3c..3c+2 of [set 0 (29), set 1 (29)]
+template <int NCH>
+__device__ __forceinline__ void publish_rows(int m, int par, unsigned tag) {
+  TSMEM();
+  const float* wrow = (const float*)(dyn_smem_raw + p.o_wrow) + (size_t)m * 2 * kNW * 32;
+  const int c = threadIdx.x - m * NCH;  // caller guarantees 0 <= c < NCH
+  float v[3];
+#pragma unroll
+  for (int e = 0; e < 3; ++e) {
+    const int j = 3 * c + e;
+    float s = 0.f;
+    if (NCH == kSo3Chunks ? (j < 11) : (j < 58)) {
+      const int set = (NCH == kSo3Chunks) ? 0 : (j >= 29 ? 1 : 0), idx = j - 29 * set;
+      const float* r = wrow + set * kNW * 32 + idx;
+#pragma unroll
+      for (int w = 0; w < kNW; ++w) s += r[w * 32];  // warp order
+    }
+    v[e] = s;
+  }
+  float4* dst = p.rows + ((size_t)(par * gridDim.x + blockIdx.x) * p.nmodels + m) * kChunks + c;
+  st_packet(dst, make_float4(v[0], v[1], v[2], __uint_as_float(tag)));
+}
+
+// poll the packets of every CTA for model m, fold them in a fixed order into out[m][0..3*NCH)
+template <int NCH, int NGRP>
+__device__ __forceinline__ void fold_rows(int m, int par, unsigned tag) {
+  TSMEM();
+  constexpr int JMAX = 6;
+  float4* part = (float4*)(dyn_smem_raw + p.o_part);
+  float* out = (float*)(dyn_smem_raw + p.o_out) + m * 64;
+  const int G = gridDim.x;
+  const int t = threadIdx.x;
+  if (t < NGRP * NCH) {
+    const int c = t % NCH, b0 = t / NCH;
+    const float4* base = p.rows + ((size_t)par * G * p.nmodels + m) * kChunks + c;
+    const size_t stride = (size_t)p.nmodels * kChunks;
+    float3 s = make_float3(0.f, 0.f, 0.f);
+    for (int bb = b0; bb < G; bb += NGRP * JMAX) {
+      float4 v[JMAX];
+      unsigned pend = 0;
+#pragma unroll
+      for (int j = 0; j < JMAX; ++j)
+        if (bb + j * NGRP < G) pend |= 1u << j;
+      while (pend) {
+#pragma unroll
+        for (int j = 0; j < JMAX; ++j)
+          if (pend & (1u << j)) v[j] = ld_packet(base + (size_t)(bb + j * NGRP) * stride);
+#pragma unroll
+        for (int j = 0; j < JMAX; ++j)
+          if ((pend & (1u << j)) && __float_as_uint(v[j].w) == tag) pend &= ~(1u << j);
+      }
+#pragma unroll
+      for (int j = 0; j < JMAX; ++j)
+        if (bb + j * NGRP < G) {
+          s.x += v[j].x;
+          s.y += v[j].y;
+          s.z += v[j].z;
+        }
+    }
+    part[b0 * NCH + c] = make_float4(s.x, s.y, s.z, 0.f);
+  }
+  __syncthreads();
+  if (t < NCH * 3) {
+    const int c = t / 3, e = t - 3 * c;
+    const float* q = (const float*)(part + c) + e;
+    float tot = 0.f;
+#pragma unroll 4
+    for (int g = 0; g < NGRP; ++g) tot += q[g * NCH * 4];
+    out[t] = tot;
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------- FP64 Gauss-Newton step, one warp
+// lower-triangular LDL^T of the 6x6 normal equations in registers (every lane runs it redundantly: no
+// exchange, and the pose update that follows is spread over the lanes)
+__device__ __forceinline__ void ldlt6_lower(double (&A)[21], double (&b)[6], double (&x)[6]) {
+#define LA(i, j) A[(i) * ((i) + 1) / 2 + (j)]
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double d = LA(k, k);
+    const double inv = (d != 0.0) ? 1.0 / d : 0.0;
+    double l[6];
+#pragma unroll
+    for (int i = k + 1; i < 6; ++i) l[i] = LA(i, k) * inv;
+#pragma unroll
+    for (int i = k + 1; i < 6; ++i)
+#pragma unroll
+      for (int j = k + 1; j <= i; ++j) LA(i, j) -= l[i] * LA(j, k);
+#pragma unroll
+    for (int i = k + 1; i < 6; ++i) LA(i, k) = l[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < i; ++j) b[i] -= LA(i, j) * b[j];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) b[i] = (LA(i, i) != 0.0) ? b[i] / LA(i, i) : 0.0;
+#pragma unroll
+  for (int i = 5; i >= 0; --i)
+#pragma unroll
+    for (int j = i + 1; j < 6; ++j) b[i] -= LA(j, i) * b[j];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) x[i] = b[i];
+#undef LA
+}
+
+// RGBDOdometry.cpp:412-460 (+ :464-467 on the last iteration) by the 32 lanes of one warp
+__device__ __noinline__ void gn_solve_warp(int m, int lvl_next, int is_last, float tmpError, int cnt) {
+  TSMEM();
+  GNState* g = &sm.S[m];
+  const float* out = (const float*)(dyn_smem_raw + p.o_out) + m * 64;  // [0..28] ICP sums, [29..57] RGB sums
+  double* sA = sm.solveA[m];
+  const int lane = threadIdx.x & 31;
+  const double w = p.icpWeight;
+  // 1. normal equations: lane l combines packed sum l (order aa..ag, bb..bg, ..., fg; types.cuh:101-112)
+  if (lane < 27) {
+    int i = 0, rem = lane;
+    while (rem >= 7 - i) {
+      rem -= 7 - i;
+      ++i;
+    }
+    const int j = i + rem;
+    const double icp = (double)out[lane], rgb = (double)out[29 + lane];
+    if (j == 6) {
+      sA[36 + i] = rgb + w * icp;
+    } else {
+      const double v = rgb + w * w * icp;
+      sA[i * 6 + j] = v;
+      sA[j * 6 + i] = v;
+    }
+  }
+  if (lane == 27) {
+    TrackStats& st = g->stats;
+    st.lastRGBError = tmpError;
+    st.lastRGBCount = (float)cnt;
+    st.lastICPError = sqrtf(out[27]) / out[28];
+    st.lastICPCount = out[28];
+  }
+  __syncwarp();
+  if (is_last) {  // lastA / lastb are reported for the final iteration (RGBDOdometry.h:62-70)
+    for (int q = lane; q < 42; q += 32) (q < 36 ? g->stats.lastA[q] : g->stats.lastb[q - 36]) = sA[q];
+  }
+  // 2. solve (redundantly in every lane)
+  double A[21], b[6], x[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+#pragma unroll
+    for (int j = 0; j <= i; ++j) A[i * (i + 1) / 2 + j] = sA[i * 6 + j];
+    b[i] = sA[36 + i];
+  }
+  ldlt6_lower(A, b, x);
+  // 3. resultRt <- [exp(x[3..5]) | x[0..2]] * resultRt: lane (r, c) owns one element of the top 3 rows
+  double Rm[9];
+  {
+    const double rv[3] = {x[3], x[4], x[5]};
+    gn::rodrigues(rv, Rm);
+  }
+  double nrt = 0.0;
+  if (lane < 12) {
+    const int r = lane >> 2, c = lane & 3;
+    const double* Rt = g->resultRt;
+    nrt = Rm[r * 3] * Rt[c] + Rm[r * 3 + 1] * Rt[4 + c] + Rm[r * 3 + 2] * Rt[8 + c] + x[r] * Rt[12 + c];
+  }
+  __syncwarp();
+  if (lane < 12) g->resultRt[lane] = nrt;
+  __syncwarp();
+  double Rt[12];
+#pragma unroll
+  for (int q = 0; q < 12; ++q) Rt[q] = g->resultRt[q];
+  // 4a. lanes 0..11: [Rcurr|tcurr] = [Rprev|tprev] * (f32 resultRt)^-1 (gn::compose_pose)
+  if (lane < 12) {
+    float Ro[9], to[3], ti[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) Ro[r * 3 + c] = (float)Rt[r * 4 + c];
+      to[r] = (float)Rt[r * 4 + 3];
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) ti[r] = -(Ro[r] * to[0] + Ro[3 + r] * to[1] + Ro[6 + r] * to[2]);
+    const float* Rp = g->Rprev;
+    const float* tp = g->pose.tprev;
+    float val;
+    if (lane < 9) {
+      const int r = lane / 3, c = lane - 3 * r;
+      val = Rp[r * 3] * Ro[c * 3] + Rp[r * 3 + 1] * Ro[c * 3 + 1] + Rp[r * 3 + 2] * Ro[c * 3 + 2];
+    } else {
+      const int r = lane - 9;
+      val = Rp[r * 3] * ti[0] + Rp[r * 3 + 1] * ti[1] + Rp[r * 3 + 2] * ti[2] + tp[r];
+    }
+    if (lane < 9)
+      g->pose.Rcurr.m[lane] = val;
+    else
+      g->pose.tcurr[lane - 9] = val;
+    if (is_last) {  // RGBDOdometry.cpp:464-467: photometric sanity reset, decided on the translation
+      const float tc0 = __shfl_sync(0xfffu, val, 9), tc1 = __shfl_sync(0xfffu, val, 10), tc2 = __shfl_sync(0xfffu, val, 11);
+      const float d0 = tc0 - tp[0], d1 = tc1 - tp[1], d2 = tc2 - tp[2];
+      const bool reset = sqrtf(d0 * d0 + d1 * d1 + d2 * d2) > 0.3f;
+      if (lane < 9)
+        g->out_rot[lane] = reset ? Rp[lane] : val;
+      else
+        g->out_trans[lane - 9] = reset ? tp[lane - 9] : val;
+    }
+  } else if (lane >= 16 && lane < 28 && !is_last) {
+    // 4b. lanes 16..27: warp of the next iteration, krkinv = K R' K^-1, kt = K t' with [R'|t'] = resultRt^-1
+    const int e = lane - 16;
+    const double* K = sm.K[lvl_next];
+    const double* Kinv = sm.Kinv[lvl_next];
+    double R[9], tt[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) R[i * 3 + j] = Rt[j * 4 + i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) tt[i] = -(R[i * 3] * Rt[3] + R[i * 3 + 1] * Rt[7] + R[i * 3 + 2] * Rt[11]);
+    if (e < 9) {
+      const int i = e / 3, j = e - 3 * i;
+      double tmp[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) tmp[k] = K[i * 3] * R[k] + K[i * 3 + 1] * R[3 + k] + K[i * 3 + 2] * R[6 + k];
+      g->warp.krkinv.m[e] = (float)(tmp[0] * Kinv[j] + tmp[1] * Kinv[3 + j] + tmp[2] * Kinv[6 + j]);
+    } else {
+      const int i = e - 9;
+      g->warp.kt[i] = (float)(K[i * 3] * tt[0] + K[i * 3 + 1] * tt[1] + K[i * 3 + 2] * tt[2]);
+    }
+  }
+  __syncwarp();
+}
+
+// H = K R K^-1 etc. of the SO(3) step (gn_serial.cuh: so3_matrices), lane e < 9 owns element e
+__device__ __forceinline__ void so3_matrices_warp(GNState* g) {
+  TSMEM();
+  const int lane = threadIdx.x & 31;
+  if (lane < 9) {
+    const double* K = sm.K[2];
+    const double* Kinv = sm.Kinv[2];
+    const double* R = g->resultR;
+    const int i = lane / 3, j = lane - 3 * i;
+    double kr[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) kr[k] = K[i * 3] * R[k] + K[i * 3 + 1] * R[3 + k] + K[i * 3 + 2] * R[6 + k];
+    g->so3_imageBasis.m[lane] = (float)(kr[0] * Kinv[j] + kr[1] * Kinv[3 + j] + kr[2] * Kinv[6 + j]);
+    g->so3_kinv.m[lane] = (float)Kinv[lane];
+    g->so3_krlr.m[lane] = (float)kr[j];
+  }
+  __syncwarp();
+}
+
+// RGBDOdometry.cpp:320-328: seed resultRt with the SO(3) rotation, first photometric warp
+__device__ __forceinline__ void gn_begin_warp(GNState* g, int use_so3, int lvl_first) {
+  TSMEM();
+  const int lane = threadIdx.x & 31;
+  if (lane < 16) {
+    const int r = lane >> 2, c = lane & 3;
+    double v = (r == c) ? 1.0 : 0.0;
+    if (use_so3 && r < 3 && c < 3) v = g->resultR[r * 3 + c];
+    g->resultRt[lane] = v;
+  }
+  __syncwarp();
+  if (lane < 12) {  // translation of resultRt is zero: krkinv = K R^T K^-1, kt = 0
+    const double* K = sm.K[lvl_first];
+    const double* Kinv = sm.Kinv[lvl_first];
+    const double* Rt = g->resultRt;
+    if (lane < 9) {
+      const int i = lane / 3, j = lane - 3 * i;
+      double tmp[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) tmp[k] = K[i * 3] * Rt[k * 4] + K[i * 3 + 1] * Rt[k * 4 + 1] + K[i * 3 + 2] * Rt[k * 4 + 2];
+      g->warp.krkinv.m[lane] = (float)(tmp[0] * Kinv[j] + tmp[1] * Kinv[3 + j] + tmp[2] * Kinv[6 + j]);
+    } else {
+      g->warp.kt[lane - 9] = 0.f;
+    }
+  }
+  __syncwarp();
+}
+
+// host logic of one SO(3) iteration after the reduction (RGBDOdometry.cpp:281-308) by one warp
+__device__ __noinline__ void so3_update_warp(int m, int it) {
+  TSMEM();
+  GNState* g = &sm.S[m];
+  const float* out = (const float*)(dyn_smem_raw + p.o_out) + m * 64;
+  const int lane = threadIdx.x & 31;
+  TrackStats& st = g->stats;
+  const float err = sqrtf(out[9]) / out[10], count = out[10];
+  const float lastError = g->so3_lastError, lastCount = g->so3_lastCount;
+  int done = 0;
+  if (err < lastError && fabsf(lastError - count) < 0.001f) {
+    done = 1;
+    if (lane == 0) {
+      st.lastSO3Error = err;
+      st.lastSO3Count = count;
+    }
+  } else if (err > lastError + 0.001f) {
+    done = 1;
+    if (lane == 0) {
+      st.lastSO3Error = lastError;
+      st.lastSO3Count = lastCount;
+    }
+    if (lane < 9) g->resultR[lane] = g->lastResultR[lane];
+  }
+  if (lane == 0) st.so3_iterations++;
+  if (!done) {
+    float jtj[9], jtr[3];
+    gn::unpack_so3(out, jtj, jtr);
+    double Ad[9], bd[3], xd[3];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) Ad[q] = jtj[q];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) bd[q] = jtr[q];
+    gn::ldlt_solve_unrolled<3>(Ad, bd, xd);
+    const double delta[3] = {(double)(float)xd[0], (double)(float)xd[1], (double)(float)xd[2]};
+    double rotUpdate[9];
+    gn::rodrigues(delta, rotUpdate);
+    float nr = 0.f;
+    if (lane < 9) {
+      const int r = lane / 3, c = lane - 3 * r;
+      nr = (float)rotUpdate[r * 3] * g->R_lr[c] + (float)rotUpdate[r * 3 + 1] * g->R_lr[3 + c] +
+           (float)rotUpdate[r * 3 + 2] * g->R_lr[6 + c];
+    }
+    __syncwarp();
+    if (lane < 9) {
+      g->lastResultR[lane] = g->resultR[lane];
+      g->R_lr[lane] = nr;
+      g->resultR[lane] = nr;
+    }
+    if (lane == 0) {
+      st.lastSO3Error = err;
+      st.lastSO3Count = count;
+      g->so3_lastError = err;
+      g->so3_lastCount = count;
+    }
+    __syncwarp();
+    so3_matrices_warp(g);
+  }
+  __syncwarp();
+  if (done || it == 9) {
+    if (lane == 0) g->so3_done = 1;
+    gn_begin_warp(g, 1, sm.nsched ? sm.sched[0] : 0);
+  }
+  __syncwarp();
+}
+
+// reset the state of model m for a new frame (RGBDOdometry.cpp:224-255, :316-318) by one warp
+__device__ __forceinline__ void gn_init_warp(int m) {
+  TSMEM();
+  GNState* g = &sm.S[m];
+  const float* pose_in = p.M[m].pose_in;
+  const int lane = threadIdx.x & 31;
+  if (lane < 9) {
+    const float r = __ldg(pose_in + 3 + lane);
+    g->Rprev[lane] = r;
+    g->pose.Rcurr.m[lane] = r;
+    g->out_rot[lane] = r;
+    const double id = (lane % 4 == 0) ? 1.0 : 0.0;
+    g->resultR[lane] = id;
+    g->lastResultR[lane] = id;
+    g->R_lr[lane] = (float)id;
+  } else if (lane < 12) {
+    const float t = __ldg(pose_in + lane - 9);
+    g->pose.tprev[lane - 9] = t;
+    g->pose.tcurr[lane - 9] = t;
+    g->out_trans[lane - 9] = t;
+  } else if (lane == 12) {
+    g->so3_lastError = FLT_MAX / 2;
+    g->so3_lastCount = FLT_MAX / 2;
+    g->so3_done = 0;
+    TrackStats z = {};
+    g->stats = z;
+  } else if (lane >= 16) {  // resultRt row 3 = (0, 0, 0, 1); the top rows are set by gn_begin_warp
+    const int q = lane - 16;
+    g->resultRt[q] = (q % 5 == 0) ? 1.0 : 0.0;
+  }
+  __syncwarp();
+  if (lane == 0) gn::inverse3f(g->Rprev, g->pose.Rprev_inv.m);
+  so3_matrices_warp(g);
+}
+
+// --------------------------------------------------------------------------------- level set-up
+// cooperative fill of a shared-memory box from a planar image (zero outside): staged == 2
+template <class T>
+__device__ __forceinline__ void fill_box(T* dst, const T* src, int W, int H, int x0, int y0, int bw, int bh) {
+  for (int i = threadIdx.x; i < bw * bh; i += kT) {
+    const int ly = i / bw, lx = i - ly * bw, x = x0 + lx, y = y0 + ly;
+    dst[i] = (x >= 0 && y >= 0 && x < W && y < H) ? __ldg(src + (size_t)y * W + x) : (T)0;
+  }
+}
+
+__device__ __forceinline__ void issue_frame_tma(int lvl) {  // one thread
+  TSMEM();
+  const FLevel& F = p.F[lvl];
+  const MLevel& L = p.M[0].L[lvl];
+  const int x0 = (blockIdx.x % p.gx) * F.tw, y0 = (blockIdx.x / p.gx) * F.th;
+  unsigned char* base = dyn_smem_raw;
+  unsigned long long* bar = &sm.bar_frame[lvl];
+  mbar_expect_tx(bar, F.frame_bytes);
+  tma_load_3d(base + F.o_v, F.tm_v, x0, y0, 0, bar);
+  tma_load_3d(base + F.o_n, F.tm_n, x0, y0, 0, bar);
+  tma_load_2d(base + F.o_dx, F.tm_dx, x0, y0, bar);
+  tma_load_2d(base + F.o_dy, F.tm_dy, x0, y0, bar);
+  tma_load_2d(base + F.o_img, F.tm_img, x0, y0, bar);
+  tma_load_2d(base + F.o_d1, L.tm_d1, x0, y0, bar);
+  tma_load_2d(base + F.o_cand, L.tm_cand, x0, y0, bar);
+}
+
+__device__ __noinline__ void level_begin(int lvl, unsigned& win_phase) {
+  TSMEM();
+  const FLevel& F = p.F[lvl];
+  if (!F.staged) {
+    if (threadIdx.x == 0) make_lvctx(lvl);
+    __syncthreads();
+    return;
+  }
+  const MLevel& L = p.M[0].L[lvl];
+  unsigned char* base = dyn_smem_raw;
+  const int x0 = (blockIdx.x % p.gx) * F.tw, y0 = (blockIdx.x / p.gx) * F.th;
+  if (F.staged == 1) {
+    mbar_wait(&sm.bar_frame[lvl], 0);
+  } else {
+    const size_t hw = (size_t)F.w * F.h;
+    for (int k = 0; k < 3; ++k) {
+      fill_box((float*)(base + F.o_v) + k * F.npx, F.vmap_curr + k * hw, F.w, F.h, x0, y0, F.rw, F.th);
+      fill_box((float*)(base + F.o_n) + k * F.npx, F.nmap_curr + k * hw, F.w, F.h, x0, y0, F.rw, F.th);
+    }
+    fill_box((short*)(base + F.o_dx), F.dIdx, F.w, F.h, x0, y0, F.bws, F.th);
+    fill_box((short*)(base + F.o_dy), F.dIdy, F.w, F.h, x0, y0, F.bws, F.th);
+    fill_box(base + F.o_img, F.nextImage, F.w, F.h, x0, y0, F.bwb, F.th);
+    fill_box((float*)(base + F.o_d1), L.nextDepth, F.w, F.h, x0, y0, F.rw, F.th);
+    fill_box(base + F.o_cand, L.cand, F.w, F.h, x0, y0, F.bwb, F.th);
+  }
+  if (threadIdx.x < 3) sm.winacc[threadIdx.x] = 0;
+  __syncthreads();
+  // mean displacement of the tile's photometric candidates under the current estimate of the camera model
+  {
+    const RgbWarp& Wp = sm.S[0].warp;
+    const float* kk = Wp.krkinv.m;
+    const float* sD1 = (const float*)(base + F.o_d1);
+    const unsigned char* sC = base + F.o_cand;
+    int sx = 0, sy = 0, n = 0;
+    for (int i = threadIdx.x; i < F.npx; i += kT) {
+      const int ly = i / F.rw, lx = i - ly * F.rw, x = x0 + lx, y = y0 + ly;
+      if (lx < F.tw && x < F.w && y < F.h && sC[ly * F.bwb + lx]) {
+        const float d1 = sD1[i];
+        const float td1 = d1 * (kk[6] * x + kk[7] * y + kk[8]) + Wp.kt[2];
+        const int u0 = __float2int_rn((d1 * (kk[0] * x + kk[1] * y + kk[2]) + Wp.kt[0]) / td1);
+        const int v0 = __float2int_rn((d1 * (kk[3] * x + kk[4] * y + kk[5]) + Wp.kt[1]) / td1);
+        const int dx = u0 - x, dy = v0 - y;
+        if (abs(dx) < 64 && abs(dy) < 64) {
+          sx += dx;
+          sy += dy;
+          n += 1;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sx += __shfl_xor_sync(0xffffffffu, sx, o);
+      sy += __shfl_xor_sync(0xffffffffu, sy, o);
+      n += __shfl_xor_sync(0xffffffffu, n, o);
+    }
+    if ((threadIdx.x & 31) == 0 && n) {
+      atomicAdd(&sm.winacc[0], sx);
+      atomicAdd(&sm.winacc[1], sy);
+      atomicAdd(&sm.winacc[2], n);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int n = sm.winacc[2];
+    const int mx = n ? __float2int_rn((float)sm.winacc[0] / (float)n) : 0;
+    const int my = n ? __float2int_rn((float)sm.winacc[1] / (float)n) : 0;
+    const int wx0 = x0 + mx - (F.ww - F.tw) / 2, wy0 = y0 + my - (F.wh - F.th) / 2;
+    sm.win_x0 = wx0;
+    sm.win_y0 = wy0;
+    make_lvctx(lvl);
+    if (F.staged == 1) {
+      // the window region was read by the previous level through the generic proxy
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&sm.bar_win, F.win_bytes);
+      tma_load_3d(base + F.o_pv, L.tm_pv, wx0, wy0, 0, &sm.bar_win);
+      tma_load_3d(base + F.o_pn, L.tm_pn, wx0, wy0, 0, &sm.bar_win);
+      tma_load_2d(base + F.o_ld, L.tm_ld, wx0, wy0, &sm.bar_win);
+      tma_load_2d(base + F.o_li, L.tm_li, wx0, wy0, &sm.bar_win);
+    }
+  }
+  __syncthreads();
+  if (F.staged == 1) {
+    mbar_wait(&sm.bar_win, win_phase);
+    win_phase ^= 1u;
+  } else {
+    const int wx0 = sm.win_x0, wy0 = sm.win_y0, wn = F.ww * F.wh;
+    const size_t hw = (size_t)F.w * F.h;
+    for (int k = 0; k < 3; ++k) {
+      fill_box((float*)(base + F.o_pv) + k * wn, L.vmap_g_prev + k * hw, F.w, F.h, wx0, wy0, F.ww, F.wh);
+      fill_box((float*)(base + F.o_pn) + k * wn, L.nmap_g_prev + k * hw, F.w, F.h, wx0, wy0, F.ww, F.wh);
+    }
+    fill_box((float*)(base + F.o_ld), L.lastDepth, F.w, F.h, wx0, wy0, F.ww, F.wh);
+    fill_box(base + F.o_li, L.lastImage, F.w, F.h, wx0, wy0, F.ww, F.wh);
+    __syncthreads();
+  }
+}
+
+// --------------------------------------------------------------------------------- the iterations
+__device__ __noinline__ void run_level(int lvl, int q0, int nit, unsigned round0) {
+  TSMEM();
+  const int NM = p.nmodels, G = gridDim.x;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool FS = p.F[lvl].staged != 0;
+  for (int it = 0; it < nit; ++it) {
+    const int q = q0 + it;
+    const unsigned round = round0 + it;
+    const int par = round & 1;
+    const unsigned tag = (p.epoch << 6) | (round + 1);
+    const bool last_of_l0 = (lvl == 0 && it + 1 == nit);
+    DBG_MARK(8 + q * 8 + 0);
+
+    // -------- phase 1: photometric correspondences of every model, then arrive at barrier A
+    for (int m = 0; m < NM; ++m) {
+      if (FS && m == 0)
+        phase1<true, true>(lvl, m);
+      else if (FS)
+        phase1<true, false>(lvl, m);
+      else
+        phase1<false, false>(lvl, m);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < NM) {  // integer sums commute exactly; the payload rides on the arrival itself
+      unsigned cc = 0, ss = 0;
+      for (int w = 0; w < kNW; ++w) {
+        cc += (unsigned)sm.cntw[threadIdx.x][w];
+        ss += (unsigned)sm.sigw[threadIdx.x][w];
+      }
+      red_add_u64(&p.acnt[round * kMaxM + threadIdx.x], 1ull | ((unsigned long long)cc << 8) | ((unsigned long long)ss << 32));
+    }
+    DBG_MARK(8 + q * 8 + 1);
+
+    // -------- phase 2: ICP rows (independent of the counts: hides barrier A)
+    for (int m = 0; m < NM; ++m) {
+      float* const err = last_of_l0 ? p.M[m].err : nullptr;
+      if (FS && m == 0)
+        phase2<true, true>(lvl, m, err);
+      else if (FS)
+        phase2<true, false>(lvl, m, err);
+      else
+        phase2<false, false>(lvl, m, err);
+    }
+    DBG_MARK(8 + q * 8 + 2);
+    if ((int)threadIdx.x < NM) {  // wait for barrier A: all G arrivals carry the global count / sigma
+      unsigned long long v;
+      do {
+        v = ld_u64_relaxed(&p.acnt[round * kMaxM + threadIdx.x]);
+      } while ((int)(v & 0xffull) != G);
+      sm.tot[threadIdx.x][0] = (int)((v >> 8) & 0xffffffull);
+      sm.tot[threadIdx.x][1] = (int)(unsigned)(v >> 32);
+    }
+    __syncthreads();
+    DBG_MARK(8 + q * 8 + 3);
+
+    // -------- phase 3: RGB rows weighted with the global count
+    for (int m = 0; m < NM; ++m) {
+      float tmpErr;
+      const float sigma = rgb_sigma_from_counts(sm.tot[m][0], sm.tot[m][1], &tmpErr);
+      if (threadIdx.x == 0) sm.tmpErr[m] = tmpErr;
+      if (FS && m == 0)
+        phase3<true, true>(lvl, m, sigma);
+      else if (FS)
+        phase3<true, false>(lvl, m, sigma);
+      else
+        phase3<false, false>(lvl, m, sigma);
+    }
+    __syncthreads();
+    DBG_MARK(8 + q * 8 + 4);
+
+    // -------- publish this CTA's packets, fold everybody's, solve
+    if ((int)threadIdx.x < NM * kChunks) publish_rows<kChunks>(threadIdx.x / kChunks, par, tag);
+    for (int m = 0; m < NM; ++m) fold_rows<kChunks, kGroups>(m, par, tag);
+    DBG_MARK(8 + q * 8 + 6);
+    const int is_last = (q + 1 == sm.nsched);
+    if ((int)warp < NM) {
+      const int m = (int)warp;
+      if (lane < 29) sm.S[m].icp_result[lane] = ((const float*)(dyn_smem_raw + p.o_out))[m * 64 + lane];
+      gn_solve_warp(m, is_last ? sm.sched[q] : sm.sched[q + 1], is_last, sm.tmpErr[m], sm.tot[m][0]);
+    }
+    __syncthreads();
+    DBG_MARK(8 + q * 8 + 7);
+  }
+}
+
+// SO(3) pre-alignment of every model on level 2 (RGBDOdometry.cpp:239-310); returns the rounds used
+__device__ __noinline__ unsigned run_so3() {
+  TSMEM();
+  const int NM = p.nmodels;
+  const FLevel& F = p.F[2];
+  const int x0 = (blockIdx.x % p.gx) * F.tw, y0 = (blockIdx.x / p.gx) * F.th;
+  const unsigned warp = threadIdx.x >> 5;
+  unsigned round = 0;
+  for (int it = 0; it < 10; ++it) {
+    bool all_done = true;  // identical in every CTA
+    for (int m = 0; m < NM; ++m) all_done = all_done && sm.S[m].so3_done;
+    if (all_done) break;
+    const int par = round & 1;
+    const unsigned tag = (p.epoch << 6) | (round + 1);
+    for (int m = 0; m < NM; ++m) {
+      if (sm.S[m].so3_done) continue;
+      const GNState& S = sm.S[m];
+      float acc[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+      bool work = false;
+      for (int i = threadIdx.x; i < F.tw * F.th; i += kT) {
+        const int ly = i / F.tw, lx = i - ly * F.tw, x = x0 + lx, y = y0 + ly;
+        if (x < F.w && y < F.h) {
+          so3_pixel(p.M[m].so3_last, p.M[m].so3_next, (size_t)F.w, F.w, F.h, S.so3_imageBasis, S.so3_kinv, S.so3_krlr, x, y, acc);
+          work = true;
+        }
+      }
+      store_warp_row(m, 0, work, acc);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < NM * kSo3Chunks && !sm.S[threadIdx.x / kSo3Chunks].so3_done)
+      publish_rows<kSo3Chunks>(threadIdx.x / kSo3Chunks, par, tag);
+    for (int m = 0; m < NM; ++m)
+      if (!sm.S[m].so3_done) fold_rows<kSo3Chunks, kSo3Groups>(m, par, tag);  // so3_done is uniform: no divergent barrier
+    if ((int)warp < NM && !sm.S[warp].so3_done) so3_update_warp((int)warp, it);
+    __syncthreads();
+    ++round;
+  }
+  return round;
+}
+
+__global__ void __launch_bounds__(kT, 1) gn_tiled_kernel(const TParams kp) {
+  extern __shared__ __align__(128) unsigned char dyn_smem_raw[];
+  TFixed& sm = *reinterpret_cast<TFixed*>(dyn_smem_raw);
+  {  // parameters -> shared memory (the phase functions are not inlined)
+    const int* src = reinterpret_cast<const int*>(&kp);
+    int* dst = reinterpret_cast<int*>(&sm.prm);
+    for (int i = threadIdx.x; i < (int)(sizeof(TParams) / 4); i += kT) dst[i] = src[i];
+  }
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int i = 2; i >= 0; --i)
+      for (int j = 0; j < kp.iters[i] && n < 19; ++j) sm.sched[n++] = i;
+    sm.nsched = n;
+    for (int l = 0; l < 3; ++l) mbar_init(&sm.bar_frame[l], 1);
+    mbar_init(&sm.bar_win, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (threadIdx.x >= 32 && threadIdx.x < 35) {
+    const int l = threadIdx.x - 32;
+    const LevelK k = kp.F[l].k;
+    gn::make_K(k.fx, k.fy, k.cx, k.cy, sm.K[l], sm.Kinv[l]);
+  }
+  __syncthreads();
+  const TParams& p = sm.prm;
+  const int NM = p.nmodels;
+  const unsigned warp = threadIdx.x >> 5;
+  DBG_MARK(0);
+  // every level's frame tiles are requested now; the finer levels land while the coarser ones iterate
+  if (threadIdx.x == 0)
+    for (int l = 2; l >= 0; --l)
+      if (p.F[l].staged == 1) issue_frame_tma(l);
+  if ((int)warp < NM) {
+    gn_init_warp((int)warp);
+    if (!p.use_so3) gn_begin_warp(&sm.S[warp], 0, sm.nsched ? sm.sched[0] : 0);
+  }
+  __syncthreads();
+  DBG_MARK(1);
+  unsigned round = 0;
+  if (p.use_so3) round = run_so3();
+  DBG_MARK(2);
+  // ---- Gauss-Newton iterations, coarse to fine (RGBDOdometry.cpp:331-461)
+  unsigned win_phase = 0;
+  int q0 = 0;
+  for (int lvl = 2; lvl >= 0; --lvl) {
+    int nit = p.iters[lvl];
+    if (q0 + nit > sm.nsched) nit = sm.nsched - q0;
+    if (nit <= 0) continue;
+    level_begin(lvl, win_phase);
+    run_level(lvl, q0, nit, round);
+    q0 += nit;
+    round += nit;
+  }
+  // ---- CTA 0 publishes pose + stats of every model
+  if (blockIdx.x == 0)
+    for (int m = 0; m < NM; ++m) {
+      const float* src = (const float*)&sm.S[m];
+      float* dst = (float*)p.M[m].g;
+      for (int i = threadIdx.x; i < (int)(sizeof(GNState) / 4); i += kT) dst[i] = src[i];
+    }
+  DBG_MARK(3);
+}
+
+// sobel + candidate gates for all three levels in one launch; also clears the barrier-A words of the
+// tracker launch that follows
+struct PrepLevel {
+  const unsigned char* img;
+  const float* nextDepth;
+  short *dx, *dy;
+  unsigned char* cand;
+  int w, h;
+  float minScale;
+};
+struct PrepParams {
+  PrepLevel L[3];
+  unsigned long long* acnt;  // kMaxRounds * kMaxM words, or null
+};
+__global__ void rgb_prepare_tiled_kernel(const PrepParams pp) {
+  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pp.acnt && q < kMaxRounds * kMaxM) pp.acnt[q] = 0ull;
+#pragma unroll
+  for (int l = 0; l < 3; ++l) {
+    const PrepLevel& L = pp.L[l];
+    const int n = L.w * L.h;
+    if (q < n) {
+      int y = q / L.w, x = q - y * L.w;
+      rgb_prepare_pixel(L.img, L.w, L.h, L.nextDepth, L.minScale, L.dx, L.dy, L.cand, x, y);
+      return;
+    }
+    q -= n;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+    cudaGetLastError();
+  }
+  return fn;
+}
+
+// planar image of `planes` planes of w x h elements -> tensor map with box (bw, bh[, planes]); false when the
+// image does not meet the TMA constraints (16-byte rows) or the driver refuses
+bool encode_map(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int esize, int w, int h, int planes, int bw, int bh) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  if (((size_t)w * esize) % 16 || ((size_t)bw * esize) % 16 || bw > 256 || bh > 256 || ((uintptr_t)base & 15)) return false;
+  cuuint64_t gdim[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)planes};
+  cuuint64_t gstr[2] = {(cuuint64_t)w * esize, (cuuint64_t)w * h * esize};
+  cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)planes};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const int rank = planes > 1 ? 3 : 2;
+  return fn(out, dt, rank, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int round_up(int a, int b) { return (a + b - 1) / b * b; }
+unsigned align128(unsigned a) { return (a + 127u) & ~127u; }
+
+}  // namespace
+
+#define RET_IF(e)                       \
+  do {                                  \
+    cudaError_t e__ = (e);              \
+    if (e__ != cudaSuccess) return e__; \
+  } while (0)
+
+// Tile plan + tensor maps of one odometry object (fixed buffers: built once, on first use).
+struct RGBDOdometry::TiledState {
+  int gx = 1, gy = 1;
+  FLevel F[3];          // plan part of the frame levels (pointers filled per launch)
+  unsigned smem_bytes = 0;
+  unsigned o_wrow = 0, o_part = 0, o_out = 0, o_corr = 0;
+  // device copies of the tensor maps: [level][which]; image / depth maps exist for both buffers they can name
+  enum { TM_V, TM_N, TM_DX, TM_DY, TM_IMG_A, TM_IMG_B, TM_D1_NEXT, TM_D1_LAST, TM_CAND, TM_PV, TM_PN, TM_LD, TM_LI, TM_COUNT };
+  CUtensorMap* d_maps = nullptr;  // [3][TM_COUNT]
+  const unsigned char* img_a[3] = {nullptr, nullptr, nullptr};  // the buffer TM_IMG_A describes
+  bool tma_ok[3] = {false, false, false};
+  unsigned epoch = 1;
+  bool attr_set = false;
+  int nmodels_planned = 0;
+};
+
+namespace {
+// choose the tile grid and the shared-memory layout for `nm` models on `sms` CTAs
+void plan_tiles(int W, int H, int sms, int nm, RGBDOdometry::TiledState& ts) {
+  const int maxG = sms < 255 ? sms : 255;  // barrier A counts arrivals in 8 bits
+  long best = -1;
+  for (int gx = 1; gx <= maxG; ++gx) {
+    const int gy = maxG / gx;
+    const int tw = (W + gx - 1) / gx, th = (H + gy - 1) / gy;
+    const int gxe = (W + tw - 1) / tw, gye = (H + th - 1) / th;  // tiles actually needed
+    const int rw = round_up(tw, 4);
+    const long frame = (long)rw * th;
+    const long win = (long)round_up(tw + 8, 16) * (th + 8);
+    const long cost = frame * 2 + win + (frame > kPP * kT ? 1000000L : 0) + (gxe * gye < maxG - 8 ? frame / 8 : 0);
+    if (best < 0 || cost < best) {
+      best = cost;
+      ts.gx = gxe;
+      ts.gy = gye;
+    }
+  }
+  unsigned off = align128((unsigned)sizeof(TFixed));
+  ts.o_wrow = off;
+  off = align128(off + (unsigned)nm * 2 * kNW * 32 * 4);
+  ts.o_part = off;
+  off = align128(off + kT * 16);
+  ts.o_out = off;
+  off = align128(off + (unsigned)nm * 64 * 4);
+  ts.o_corr = off;
+  off = align128(off + 2 * kPP * kT * 4);
+  const unsigned cap = 227u * 1024u;
+  auto window_bytes = [](const FLevel& F) {
+    const unsigned wn = (unsigned)F.ww * F.wh;
+    return align128(3 * wn * 4) * 2 + align128(wn * 4) + align128(wn);
+  };
+  unsigned wmax = 0;
+  for (int l = 2; l >= 0; --l) {  // coarse to fine: stage what fits (frame tiles of every staged level + one window)
+    FLevel& F = ts.F[l];
+    F.w = W >> l;
+    F.h = H >> l;
+    F.tw = (F.w + ts.gx - 1) / ts.gx;
+    F.th = (F.h + ts.gy - 1) / ts.gy;
+    F.rw = round_up(F.tw, 4);
+    F.npx = F.rw * F.th;
+    F.bws = round_up(F.tw, 8);
+    F.bwb = round_up(F.tw, 16);
+    F.ww = round_up(F.tw + 8, 16);
+    F.wh = F.th + 8;
+    F.staged = 0;
+    unsigned o = off;
+    F.o_v = o;
+    o = align128(o + 3u * F.npx * 4);
+    F.o_n = o;
+    o = align128(o + 3u * F.npx * 4);
+    F.o_dx = o;
+    o = align128(o + (unsigned)F.bws * F.th * 2);
+    F.o_dy = o;
+    o = align128(o + (unsigned)F.bws * F.th * 2);
+    F.o_img = o;
+    o = align128(o + (unsigned)F.bwb * F.th);
+    F.o_d1 = o;
+    o = align128(o + (unsigned)F.npx * 4);
+    F.o_cand = o;
+    o = align128(o + (unsigned)F.bwb * F.th);
+    F.frame_bytes = 7u * F.npx * 4 + 2u * F.bws * F.th * 2 + 2u * F.bwb * F.th;
+    const unsigned wb = window_bytes(F), wnew = wb > wmax ? wb : wmax;
+    if (F.npx <= kPP * kT && F.w < 2048 && F.h < 2048 && o + wnew <= cap) {
+      F.staged = 1;
+      off = o;
+      wmax = wnew;
+    }  // a global-memory level keeps the same pixel enumeration (row width rw): the pixel -> thread map, and
+       // with it the summation order, does not depend on where a level's data lives
+  }
+  for (int l = 0; l < 3; ++l) {  // the window region is shared by the staged levels, after all frame tiles
+    FLevel& F = ts.F[l];
+    if (!F.staged) continue;
+    const unsigned wn = (unsigned)F.ww * F.wh;
+    unsigned o = off;
+    F.o_pv = o;
+    o += align128(3 * wn * 4);
+    F.o_pn = o;
+    o += align128(3 * wn * 4);
+    F.o_ld = o;
+    o += align128(wn * 4);
+    F.o_li = o;
+    F.win_bytes = 7u * wn * 4 + wn;
+  }
+  ts.smem_bytes = off + wmax;
+  ts.nmodels_planned = nm;
+}
+}  // namespace
+
+void RGBDOdometry::destroyTiled() {
+  if (tiled_) {
+    cudaFree(tiled_->d_maps);
+    delete tiled_;
+    tiled_ = nullptr;
+  }
+}
+
+// (re)build plan + tensor maps of this object for launches with `nm` models
+cudaError_t RGBDOdometry::prepareTiled(int nm) {
+  if (tiled_ && tiled_->nmodels_planned == nm) return cudaSuccess;
+  const unsigned epoch = tiled_ ? tiled_->epoch : 1;
+  destroyTiled();
+  tiled_ = new TiledState();
+  TiledState& ts = *tiled_;
+  ts.epoch = epoch;
+  plan_tiles(width, height, num_sms(), nm, ts);
+  RET_IF(cudaMalloc((void**)&ts.d_maps, sizeof(CUtensorMap) * 3 * TiledState::TM_COUNT));
+  CUtensorMap h[3][TiledState::TM_COUNT];
+  memset(h, 0, sizeof(h));
+  for (int l = 0; l < 3; ++l) {
+    FLevel& F = ts.F[l];
+    if (!F.staged) continue;
+    const int w = F.w, hh = F.h;
+    bool ok = true;
+    const CUtensorMapDataType f32 = CU_TENSOR_MAP_DATA_TYPE_FLOAT32, u16 = CU_TENSOR_MAP_DATA_TYPE_UINT16, u8 = CU_TENSOR_MAP_DATA_TYPE_UINT8;
+    ok = ok && encode_map(&h[l][TiledState::TM_V], vmaps_curr_[l], f32, 4, w, hh, 3, F.rw, F.th);
+    ok = ok && encode_map(&h[l][TiledState::TM_N], nmaps_curr_[l], f32, 4, w, hh, 3, F.rw, F.th);
+    ok = ok && encode_map(&h[l][TiledState::TM_DX], nextdIdx[l], u16, 2, w, hh, 1, F.bws, F.th);
+    ok = ok && encode_map(&h[l][TiledState::TM_DY], nextdIdy[l], u16, 2, w, hh, 1, F.bws, F.th);
+    ok = ok && encode_map(&h[l][TiledState::TM_IMG_A], nextImage[l], u8, 1, w, hh, 1, F.bwb, F.th);
+    ok = ok && encode_map(&h[l][TiledState::TM_IMG_B], lastNextImage[l], u8, 1, w, hh, 1, F.bwb, F.th);
+    ok = ok && encode_map(&h[l][TiledState::TM_D1_NEXT], nextDepth[l], f32, 4, w, hh, 1, F.rw, F.th);
+    ok = ok && encode_map(&h[l][TiledState::TM_D1_LAST], lastDepth[l], f32, 4, w, hh, 1, F.rw, F.th);
+    ok = ok && encode_map(&h[l][TiledState::TM_CAND], rgbCand[l], u8, 1, w, hh, 1, F.bwb, F.th);
+    ok = ok && encode_map(&h[l][TiledState::TM_PV], vmaps_g_prev_[l], f32, 4, w, hh, 3, F.ww, F.wh);
+    ok = ok && encode_map(&h[l][TiledState::TM_PN], nmaps_g_prev_[l], f32, 4, w, hh, 3, F.ww, F.wh);
+    ok = ok && encode_map(&h[l][TiledState::TM_LD], lastDepth[l], f32, 4, w, hh, 1, F.ww, F.wh);
+    ok = ok && encode_map(&h[l][TiledState::TM_LI], lastImage[l], u8, 1, w, hh, 1, F.ww, F.wh);
+    ts.img_a[l] = nextImage[l];
+    ts.tma_ok[l] = ok;
+    F.staged = ok ? 1 : 2;
+  }
+  RET_IF(cudaMemcpy(ts.d_maps, h, sizeof(h), cudaMemcpyHostToDevice));
+  if (getenv("CFB_TILED_DEBUG")) {
+    fprintf(stderr, "[cfb tiled] %dx%d, %d models: grid %d x %d, %u bytes of shared memory\n", width, height, nm, ts.gx, ts.gy,
+            ts.smem_bytes);
+    for (int l = 0; l < 3; ++l)
+      fprintf(stderr, "[cfb tiled]   level %d: %dx%d tile %dx%d (row %d, %d px) staged %d window %dx%d frame %u B window %u B\n", l,
+              ts.F[l].w, ts.F[l].h, ts.F[l].tw, ts.F[l].th, ts.F[l].rw, ts.F[l].npx, ts.F[l].staged, ts.F[l].ww, ts.F[l].wh,
+              ts.F[l].staged ? ts.F[l].frame_bytes : 0u, ts.F[l].staged ? ts.F[l].win_bytes : 0u);
+  }
+  return cudaSuccess;
+}
+
+size_t RGBDOdometry::tiledScratchBytes() {
+  return sizeof(unsigned long long) * kMaxRounds * kMaxM + sizeof(float4) * 2 * 256 * kMaxM * kChunks;
+}
+
+bool RGBDOdometry::canBatch(int n) const { return n >= 1 && n <= kMaxM && mode_ == 0 && width < 2048 && height < 2048; }
+
+cudaError_t RGBDOdometry::enqueuePrepare(cudaStream_t s, void* acnt) {
+  PrepParams pp;
+  int total = 0;
+  for (int i = 0; i < NUM_PYRS; ++i) {
+    const int w = width >> i, h = height >> i;
+    pp.L[i] = PrepLevel{nextImage[i], (next_is_last_ ? lastDepth[i] : nextDepth[i]), nextdIdx[i], nextdIdy[i], rgbCand[i], w, h,
+                        (float)(pow(minimumGradientMagnitudes[i], 2.0) / pow(sobelScale, 2.0))};
+    total += w * h;
+  }
+  pp.acnt = (unsigned long long*)acnt;
+  rgb_prepare_tiled_kernel<<<(total + 255) / 256, 256, 0, s>>>(pp);
+  return cudaGetLastError();
+}
+
+// All odometry objects belong to one frame (same geometry, same frame-side inputs, initAll() done on
+// stream s); od[0] is the camera model whose tiles are staged.  trans / rot: n x 3 / n x 9 host arrays,
+// in/out.  scratch: tiledScratchBytes() of zero-initialised device memory owned by the caller.
+cudaError_t RGBDOdometry::trackTiled(RGBDOdometry* const* od, int n, float (*trans)[3], float (*rot)[9], float icpWeight,
+                                     bool pyramid, bool fastOdom, bool so3, float* const* err, size_t err_pitch,
+                                     void* scratch, cudaStream_t s) {
+  if (n < 1 || n > kMaxM || !scratch) return cudaErrorInvalidValue;
+  struct Out {
+    float trans[3];
+    float rot[9];
+    TrackStats st;
+  };
+  RGBDOdometry& f = *od[0];
+  RET_IF(f.prepareTiled(n));
+  TiledState& ts = *f.tiled_;
+  TParams p;
+  memset(&p, 0, sizeof(p));
+  p.acnt = (unsigned long long*)scratch;
+  p.rows = (float4*)((char*)scratch + sizeof(unsigned long long) * kMaxRounds * kMaxM);
+  for (int m = 0; m < n; ++m) {
+    RGBDOdometry& o = *od[m];
+    float* h_in = (float*)((char*)o.h_pinned + 1536);
+    memcpy(h_in, trans[m], 3 * sizeof(float));
+    memcpy(h_in + 3, rot[m], 9 * sizeof(float));
+    RET_IF(cudaMemcpyAsync(o.d_pose_in, h_in, 12 * sizeof(float), cudaMemcpyHostToDevice, s));
+    RET_IF(o.enqueuePrepare(s, m == 0 ? (void*)p.acnt : nullptr));  // Sobel images + candidate gates of this model
+    MParams& M = p.M[m];
+    for (int i = 0; i < NUM_PYRS; ++i) {
+      MLevel& L = M.L[i];
+      L.vmap_g_prev = o.vmaps_g_prev_[i];
+      L.nmap_g_prev = o.nmaps_g_prev_[i];
+      L.lastDepth = o.lastDepth[i];
+      L.nextDepth = o.next_is_last_ ? o.lastDepth[i] : o.nextDepth[i];
+      L.lastImage = o.lastImage[i];
+      L.cand = o.rgbCand[i];
+      if (m == 0) {
+        const CUtensorMap* tm = ts.d_maps + i * TiledState::TM_COUNT;
+        L.tm_d1 = tm + (o.next_is_last_ ? TiledState::TM_D1_LAST : TiledState::TM_D1_NEXT);
+        L.tm_cand = tm + TiledState::TM_CAND;
+        L.tm_pv = tm + TiledState::TM_PV;
+        L.tm_pn = tm + TiledState::TM_PN;
+        L.tm_ld = tm + TiledState::TM_LD;
+        L.tm_li = tm + TiledState::TM_LI;
+      }
+    }
+    M.so3_last = o.lastNextImage[2];
+    M.so3_next = o.nextImage[2];
+    M.g = o.gn;
+    M.pose_in = o.d_pose_in;
+    M.err = err ? err[m] : nullptr;
+  }
+  for (int i = 0; i < NUM_PYRS; ++i) {
+    FLevel& F = p.F[i];
+    F = ts.F[i];
+    const Intr k = f.intr.level(i);
+    F.vmap_curr = f.vmaps_curr_[i];
+    F.nmap_curr = f.nmaps_curr_[i];
+    F.nextImage = f.nextImage[i];
+    F.dIdx = f.nextdIdx[i];
+    F.dIdy = f.nextdIdy[i];
+    F.k = LevelK{k.fx, k.fy, k.cx, k.cy};
+    const CUtensorMap* tm = ts.d_maps + i * TiledState::TM_COUNT;
+    F.tm_v = tm + TiledState::TM_V;
+    F.tm_n = tm + TiledState::TM_N;
+    F.tm_dx = tm + TiledState::TM_DX;
+    F.tm_dy = tm + TiledState::TM_DY;
+    F.tm_img = tm + (f.nextImage[i] == ts.img_a[i] ? TiledState::TM_IMG_A : TiledState::TM_IMG_B);
+  }
+  p.nmodels = n;
+  p.gx = ts.gx;
+  p.gy = ts.gy;
+  p.epoch = (ts.epoch++) & 0x3ffffffu;
+  p.err_pitch = err_pitch;
+  p.distThres = f.distThres_;
+  p.angleThres = f.angleThres_;
+  p.maxDepthDelta = f.maxDepthDeltaRGB;
+  p.sobelScale = f.sobelScale;
+  p.icpWeight = icpWeight;
+  p.use_so3 = so3 ? 1 : 0;
+  p.iters[0] = fastOdom ? 3 : 10;
+  p.iters[1] = pyramid ? 5 : 0;
+  p.iters[2] = pyramid ? 4 : 0;
+  p.o_wrow = ts.o_wrow;
+  p.o_part = ts.o_part;
+  p.o_out = ts.o_out;
+  p.o_corr = ts.o_corr;
+  p.dbg = (unsigned long long*)f.dbg_trace_;
+  if (!ts.attr_set) {
+    RET_IF(cudaFuncSetAttribute(gn_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts.smem_bytes));
+    ts.attr_set = true;
+  }
+  void* args[] = {(void*)&p};
+  if (f.time_kernel_) RET_IF(cudaEventRecord(f.ev_k0_, s));
+  RET_IF(cudaLaunchCooperativeKernel((const void*)gn_tiled_kernel, dim3(ts.gx * ts.gy), dim3(kT), args, ts.smem_bytes, s));
+  if (f.time_kernel_) {
+    RET_IF(cudaEventRecord(f.ev_k1_, s));
+    f.ev_pending_ = true;
+  }
+  for (int m = 0; m < n; ++m) {
+    RGBDOdometry& o = *od[m];
+    Out* ho = (Out*)((char*)o.h_pinned + 2048);
+    RET_IF(cudaMemcpyAsync(ho->trans, o.gn->out_trans, 12 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    RET_IF(cudaMemcpyAsync(&ho->st, &o.gn->stats, sizeof(TrackStats), cudaMemcpyDeviceToHost, s));
+  }
+  RET_IF(cudaStreamSynchronize(s));
+  if (f.time_kernel_) f.kernelTiming(nullptr, nullptr, false);
+  for (int m = 0; m < n; ++m) {
+    RGBDOdometry& o = *od[m];
+    Out* ho = (Out*)((char*)o.h_pinned + 2048);
+    memcpy(trans[m], ho->trans, sizeof(float) * 3);
+    memcpy(rot[m], ho->rot, sizeof(float) * 9);
+    o.stats_ = ho->st;
+    if (so3) {
+      for (int i = 0; i < NUM_PYRS; i++) {
+        unsigned char* t = o.lastNextImage[i];
+        o.lastNextImage[i] = o.nextImage[i];
+        o.nextImage[i] = t;
+      }
+      o.parity_ ^= 1;
+    }
+  }
+  return cudaSuccess;
+}
+
+void RGBDOdometry::enableKernelTiming(bool on) {
+  if (on && !ev_k0_) {
+    cudaEventCreate(&ev_k0_);
+    cudaEventCreate(&ev_k1_);
+  }
+  time_kernel_ = on && ev_k0_ && ev_k1_;
+}
+
+void RGBDOdometry::kernelTiming(double* sum_ms, int* launches, bool reset) {
+  if (ev_pending_ && cudaEventSynchronize(ev_k1_) == cudaSuccess) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ev_k0_, ev_k1_) == cudaSuccess) {
+      kernel_ms_sum_ += ms;
+      kernel_launches_++;
+    }
+    ev_pending_ = false;
+  }
+  if (sum_ms) *sum_ms = kernel_ms_sum_;
+  if (launches) *launches = kernel_launches_;
+  if (reset) {
+    kernel_ms_sum_ = 0;
+    kernel_launches_ = 0;
+  }
+}
+
+}  // namespace cfb

@@ -71,6 +71,8 @@ RGBDOdometry::~RGBDOdometry() {
   for (auto& e : graphs_) cudaGraphExecDestroy(e.exec);
   cudaFree(d_pose_in);
   cudaFree(grid_sync_);
+  cudaFree(tiled_scratch_);
+  destroyTiled();
   if (ev_k0_) cudaEventDestroy(ev_k0_);
   if (ev_k1_) cudaEventDestroy(ev_k1_);
   cudaFree(vmaps_tmp);

@@ -9,7 +9,7 @@
 //                D2H per step, FP64 GN step on the host (gn_math.h).  Mirrors the reference loop 1:1.
 //   DeviceLoop - default flags (icp && rgb, no early exit): whole SO3 + 19-iteration GN sequence runs
 //                without host involvement; the FP64 GN step runs on the device.  Two realisations:
-//                mode 0 = ONE persistent cooperative kernel (gn_persistent.cu, default),
+//                mode 0 = ONE persistent cooperative kernel over shared-memory tiles (gn_tiled.cu, default),
 //                mode 1 = one fused kernel per step, captured in a CUDA graph (gn_device.cu).
 #pragma once
 #include <vector>
@@ -76,15 +76,17 @@ class RGBDOdometry {
                                            size_t error_pitch, bool force_host_loop, cudaStream_t s);
   const TrackStats& stats() const { return stats_; }
 
-  // ---- several models of one frame in ONE persistent launch (gn_batched.cu).  Every object had
-  // initAll() called for the same frame on stream s.  trans / rot: n x 3 / n x 9 host arrays (in/out),
-  // err: n device error maps (or null), scratch: batchScratchBytes() of zero-initialised device memory.
+  // ---- all models of one frame in ONE persistent launch (gn_tiled.cu).  Every object had initAll() called
+  // for the same frame on stream s; od[0] is the camera model (its tiles live in shared memory).
+  // trans / rot: n x 3 / n x 9 host arrays (in/out), err: n device error maps (or null),
+  // scratch: tiledScratchBytes() of zero-initialised device memory.
   static const int kMaxBatch = 5;
-  static size_t batchScratchBytes();
+  static size_t tiledScratchBytes();
   bool canBatch(int n) const;
-  static cudaError_t trackBatched(RGBDOdometry* const* od, int n, float (*trans)[3], float (*rot)[9], float icpWeight,
-                                  bool pyramid, bool fastOdom, bool so3, float* const* err, size_t err_pitch,
-                                  void* scratch, cudaStream_t s);
+  static cudaError_t trackTiled(RGBDOdometry* const* od, int n, float (*trans)[3], float (*rot)[9], float icpWeight,
+                                bool pyramid, bool fastOdom, bool so3, float* const* err, size_t err_pitch, void* scratch,
+                                cudaStream_t s);
+  struct TiledState;  // tile plan + tensor maps (gn_tiled.cu)
 
   // device views (tests / map_view): which as in oracle orc_odom_view
   const void* view(int which, int level, size_t* pitch) const;
@@ -98,9 +100,12 @@ class RGBDOdometry {
                          float* err, size_t err_pitch, cudaStream_t s);
   cudaError_t enqueueDeviceLoop(float icpWeight, bool pyramid, bool fastOdom, bool so3, float* err,
                                 size_t err_pitch, cudaStream_t s);
-  cudaError_t enqueuePersistent(float icpWeight, bool pyramid, bool fastOdom, bool so3, float* err,
-                                size_t err_pitch, cudaStream_t s);
-  cudaError_t enqueuePrepare(cudaStream_t s);  // Sobel images + photometric candidate gates, 3 levels, 1 launch
+  // Sobel images + photometric candidate gates, 3 levels, 1 launch (+ clears the barrier words `acnt`)
+  cudaError_t enqueuePrepare(cudaStream_t s, void* acnt = nullptr);
+  cudaError_t prepareTiled(int nmodels);
+  void destroyTiled();
+  TiledState* tiled_ = nullptr;
+  void* tiled_scratch_ = nullptr;  // single-model launches
 
   bool ok_ = false;
   int width, height;

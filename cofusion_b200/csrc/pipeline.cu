@@ -417,16 +417,15 @@ cudaError_t trackModels(Context* ctx, Model* const* models, int n, const TrackPa
   while (i < n) {
     int nb = n - i;
     if (nb > RGBDOdometry::kMaxBatch) nb = RGBDOdometry::kMaxBatch;
-    if (nb == RGBDOdometry::kMaxBatch + 0 && n - i - nb == 1) nb -= 1;  // never leave a single model for the last batch
-    const bool batch = nb >= 2 && icp && rgb && !tp.force_host_loop && models[i]->odom.canBatch(nb);
+    const bool batch = icp && rgb && !tp.force_host_loop && models[i]->odom.canBatch(nb);
     if (!batch) {
       RET_IF(models[i]->performTracking(tp));
       i += 1;
       continue;
     }
     if (!ctx->batchScratch) {
-      RET_IF(cudaMalloc(&ctx->batchScratch, RGBDOdometry::batchScratchBytes()));
-      RET_IF(cudaMemsetAsync(ctx->batchScratch, 0, RGBDOdometry::batchScratchBytes(), ctx->stream));
+      RET_IF(cudaMalloc(&ctx->batchScratch, RGBDOdometry::tiledScratchBytes()));
+      RET_IF(cudaMemsetAsync(ctx->batchScratch, 0, RGBDOdometry::tiledScratchBytes(), ctx->stream));
     }
     RGBDOdometry* od[RGBDOdometry::kMaxBatch];
     float trans[RGBDOdometry::kMaxBatch][3], rot[RGBDOdometry::kMaxBatch][9];
@@ -442,8 +441,8 @@ cudaError_t trackModels(Context* ctx, Model* const* models, int n, const TrackPa
       memcpy(trans[k], t, sizeof(t));
       memcpy(rot[k], r, sizeof(r));
     }
-    RET_IF(RGBDOdometry::trackBatched(od, nb, trans, rot, tp.icpWeight, tp.pyramid != 0, tp.fastOdom != 0, tp.so3 != 0, err,
-                                      (size_t)ctx->W * 4, ctx->batchScratch, ctx->stream));
+    RET_IF(RGBDOdometry::trackTiled(od, nb, trans, rot, tp.icpWeight, tp.pyramid != 0, tp.fastOdom != 0, tp.so3 != 0, err,
+                                    (size_t)ctx->W * 4, ctx->batchScratch, ctx->stream));
     for (int k = 0; k < nb; ++k) models[i + k]->finishTracking(trans[k], rot[k]);
     ctx->launches += nb + 1;  // one prepare per model + ONE persistent GN launch
     i += nb;

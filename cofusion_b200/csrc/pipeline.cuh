@@ -53,7 +53,7 @@ class Context {
   uint8_t* h_mask = nullptr;
   int launches = 0;                 // kernels launched since the last reset (bench accounting)
   bool keepMask = false;            // true: a frame without mask keeps the previous labels (segmentation on)
-  void* batchScratch = nullptr;     // RGBDOdometry::batchScratchBytes(), allocated on first multi-model frame
+  void* batchScratch = nullptr;     // RGBDOdometry::tiledScratchBytes(), allocated on first multi-model frame
 
  private:
   bool ok_ = false;
