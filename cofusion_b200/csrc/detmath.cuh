@@ -37,4 +37,62 @@ __host__ __device__ __forceinline__ float det_expf(float x) {
   return (x_in >= -87.0f) ? v : ((x_in != x_in) ? x_in : 0.0f);
 }
 
+// Deterministic double acos (Cephes asin / acos rational approximations, |err| <= 2 ulp): only IEEE
+// + - * / and sqrt in a fixed order, never contracted (explicit round-to-nearest intrinsics on the device,
+// no FMA instructions in the host build), so host, device and the CPU oracle agree bit for bit.
+// Model::computeFusionWeight (Model.cpp:391-406) takes the rotation angle through acos.
+#ifdef __CUDA_ARCH__
+#define CFB_DMUL(a, b) __dmul_rn((a), (b))
+#define CFB_DADD(a, b) __dadd_rn((a), (b))
+#else
+#define CFB_DMUL(a, b) ((a) * (b))
+#define CFB_DADD(a, b) ((a) + (b))
+#endif
+__host__ __device__ inline double det_polevl(double x, const double* c, int n) {
+  double a = c[0];
+  for (int i = 1; i <= n; ++i) a = CFB_DADD(CFB_DMUL(a, x), c[i]);
+  return a;
+}
+__host__ __device__ inline double det_p1evl(double x, const double* c, int n) {
+  double a = CFB_DADD(x, c[0]);
+  for (int i = 1; i < n; ++i) a = CFB_DADD(CFB_DMUL(a, x), c[i]);
+  return a;
+}
+__host__ __device__ inline double det_asin(double x) {
+  const double P[6] = {4.253011369004428248960E-3, -6.019598008014123785661E-1, 5.444622390564711410273E0,
+                       -1.626247967210700244449E1, 1.956261983317594739197E1, -8.198089802484824371615E0};
+  const double Q[5] = {-1.474091372988853791896E1, 7.049610280856842141659E1, -1.471791292232726029859E2,
+                       1.395105614657485689735E2, -4.918853881490881290097E1};
+  const double R[5] = {2.967721961301243206100E-3, -5.634242780008963776856E-1, 6.968710824104713396794E0,
+                       -2.556901049652824852289E1, 2.853665548261061424989E1};
+  const double S[4] = {-2.194779531642920639778E1, 1.470656354026814941758E2, -3.838770957603691357202E2,
+                       3.424398657913078477438E2};
+  const double PIO4 = 7.85398163397448309616E-1, MOREBITS = 6.123233995736765886130E-17;
+  const double a = x < 0 ? -x : x;
+  double z;
+  if (a > 0.625) {
+    double zz = CFB_DADD(1.0, -a);
+    const double p = CFB_DMUL(zz, det_polevl(zz, R, 4)) / det_p1evl(zz, S, 4);
+    zz = sqrt(CFB_DADD(zz, zz));
+    z = CFB_DADD(PIO4, -zz);
+    zz = CFB_DADD(CFB_DMUL(zz, p), -MOREBITS);
+    z = CFB_DADD(z, -zz);
+    z = CFB_DADD(z, PIO4);
+  } else {
+    if (a < 1.0e-8) return x;
+    const double zz = CFB_DMUL(a, a);
+    z = CFB_DMUL(zz, det_polevl(zz, P, 5)) / det_p1evl(zz, Q, 5);
+    z = CFB_DADD(CFB_DMUL(a, z), a);
+  }
+  return x < 0 ? -z : z;
+}
+__host__ __device__ inline double det_acos(double x) {  // x in [-1, 1]
+  const double PIO4 = 7.85398163397448309616E-1, MOREBITS = 6.123233995736765886130E-17;
+  if (x > 0.5) return CFB_DMUL(2.0, det_asin(sqrt(CFB_DADD(0.5, -CFB_DMUL(0.5, x)))));
+  double z = CFB_DADD(PIO4, -det_asin(x));
+  z = CFB_DADD(z, MOREBITS);
+  z = CFB_DADD(z, PIO4);
+  return z;
+}
+
 }  // namespace cfb

@@ -23,10 +23,11 @@
 // One Gauss-Newton iteration
 //     photometric correspondences -> red.add.u64 {arrived, count, sum floor(diff^2)} (barrier A, no fence:
 //     the payload IS the atomic) -> ICP rows (hides A) -> RGB rows weighted with the global count ->
-//     every CTA publishes its 58 partial sums as 20 x 16-byte packets {3 sums, tag} -> every CTA polls
-//     the packets of all CTAs (the tag makes the data its own flag: no barrier, no fence, one L2 round
-//     trip), folds them in a fixed order and runs the FP64 Gauss-Newton step on its own copy of the
-//     state, spread over the lanes of a warp (warp m solves model m).
+//     every CTA publishes its 58 partial sums as 20 x 16-byte packets {3 sums, tag} and bumps an arrival
+//     counter WITHOUT a fence -> one thread per CTA waits for the counter (a hint), then everybody reads
+//     the packets of all CTAs: the tag inside each packet says whether its data has landed (the rare
+//     packet that is late is simply read again) -> fixed-order fold -> FP64 Gauss-Newton step on the CTA's
+//     own copy of the state, spread over the lanes of a warp (warp m solves model m).
 // Sums are folded in a fixed order (thread -> warp -> CTA -> grid): bit-reproducible run to run.
 // Per-pixel arithmetic: SURVEY.md Appendix A1-A5 (tracker_device.cuh holds the stand-alone form).
 #include <cuda.h>  // CUtensorMap + enums only; the encoder is fetched through cudaGetDriverEntryPoint
@@ -52,6 +53,7 @@ constexpr int kSo3Chunks = 4;         // 11 sums
 constexpr int kSo3Groups = 36;
 constexpr unsigned kNoCorr = 0xffffffffu;
 constexpr int kMaxRounds = 32;        // 10 SO(3) + 19 GN reduction rounds
+constexpr int kMaxHalo = 4;           // model window = tile + halo pixels on every side (less when shared memory is short)
 
 struct MLevel {  // per model, per level
   const float *vmap_g_prev, *nmap_g_prev, *lastDepth, *nextDepth;
@@ -72,11 +74,13 @@ struct FLevel {  // frame side + tile plan of one level
   const CUtensorMap *tm_v, *tm_n, *tm_dx, *tm_dy, *tm_img;
   int w, h;
   LevelK k;
-  int tw, th;      // tile size in pixels
-  int rw, npx;     // row width of the pixel enumeration (tw rounded up to 4) and rw * th
-  int staged;      // 0: global memory, 1: shared-memory tiles filled by TMA, 2: filled by the threads
-  int bws, bwb;    // row pitch (elements) of the s16 / u8 frame tiles
-  int ww, wh;      // model window (pixels); ww is a multiple of 16
+  int tw, th, npx;  // tile size in pixels, tw * th
+  int staged;       // 0: global memory, 1: shared-memory tiles filled by TMA, 2: filled by the threads
+  // Shared-memory tiles.  A TMA box must start on a 16-byte boundary of the image row, so every element
+  // type has its own box: origin = tile origin rounded down to 16 bytes, pitch wide enough for any shift.
+  int pf, ps, pb;   // row pitch (elements) of the f32 / s16 / u8 frame tiles
+  int wwl, wh, halo;  // logical model window (pixels): tile + halo on every side
+  int wpf, wpb;     // row pitch of the f32 / u8 window planes
   unsigned o_v, o_n, o_dx, o_dy, o_img, o_d1, o_cand;  // byte offsets into dynamic shared memory
   unsigned o_pv, o_pn, o_ld, o_li;
   unsigned frame_bytes, win_bytes;  // TMA transaction sizes
@@ -87,6 +91,7 @@ struct TParams {
   int nmodels, gx, gy;
   float4* rows;              // [2][G][nmodels][kChunks] packets
   unsigned long long* acnt;  // [kMaxRounds][kMaxM] barrier-A words, zero before the launch
+  unsigned* bcnt;            // [kMaxRounds] arrivals of the packet exchange (a hint: the tags decide), zero before the launch
   unsigned epoch;            // launch counter: tags never repeat, the packet buffer is never cleared
   size_t err_pitch;
   float distThres, angleThres, maxDepthDelta, sobelScale, icpWeight;
@@ -95,23 +100,23 @@ struct TParams {
   unsigned o_wrow, o_part, o_out, o_corr;
   unsigned long long* dbg;
 };
+static_assert(sizeof(TParams) <= 4000, "kernel parameter block");
 
 // per level, per CTA: everything the pixel phases address, derived once per level (kept in shared memory:
-// the phase functions are separate register-allocation units and read it with uniform LDS)
+// the phase functions are separate register-allocation units and read it with uniform LDS).  Tiles are
+// named by byte offsets into the dynamic shared memory, never by generic pointers: the compiler then
+// emits LDS with immediate offsets.
 struct LvCtx {
-  int W, H, x0, y0, tw, th, rw, npx, bws, bwb;
+  int W, H, x0, y0, tw, th, npx;
+  int step_lx, step_ly;  // kT % tw, kT / tw: the pixel enumeration advances without a division
   float fx, fy, cx, cy;
-  const float *sV, *sN, *sD1;  // frame tiles (f32 planes of npx elements)
-  const short *sDX, *sDY;
-  const unsigned char *sIMG, *sCAND;
-  const float *sPV, *sPN, *sLD;  // model window of the camera model (planes of ww * wh elements)
-  const unsigned char* sLI;
-  int ww, wh, wn, wx0, wy0;
-  unsigned* corrZ;  // [kPP][kT] packed correspondence of the camera model
-  float* corrD;     // [kPP][kT] depth of the matched point
+  unsigned oV, oN, oD1, oDX, oDY, oIMG, oCAND;  // frame tiles
+  int pf, ps, pb, shf, shs, shb, fplane;       // pitches, x shifts (tile origin - box origin), f32 plane stride
+  unsigned oPV, oPN, oLD, oLI;                  // model window of the camera model
+  int wpf, wpb, wshf, wshb, wplane;
+  int wwl, wh, wx0, wy0;                        // logical window: columns [wx0, wx0 + wwl), rows [wy0, wy0 + wh)
+  unsigned oCorrZ, oCorrD;                      // [kPP][kT] packed correspondence / depth of the matched point
 };
-
-static_assert(sizeof(TParams) <= 4000, "kernel parameter block");
 
 struct TFixed {  // fixed head of the dynamic shared memory
   TParams prm;
@@ -133,6 +138,10 @@ struct TFixed {  // fixed head of the dynamic shared memory
   extern __shared__ __align__(128) unsigned char dyn_smem_raw[]; \
   TFixed& sm = *reinterpret_cast<TFixed*>(dyn_smem_raw);          \
   const TParams& p = sm.prm
+#define SM_F32(off) (reinterpret_cast<float*>(dyn_smem_raw + (off)))
+#define SM_S16(off) (reinterpret_cast<short*>(dyn_smem_raw + (off)))
+#define SM_U8(off) (dyn_smem_raw + (off))
+#define SM_U32(off) (reinterpret_cast<unsigned*>(dyn_smem_raw + (off)))
 
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
@@ -162,6 +171,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         : "memory");
   }
 }
+// A tensor map that lives in global memory (written by the host with cudaMemcpy) is read through the
+// tensormap proxy: the issuing thread acquires it first (CUDA programming guide, "tensor map in global memory").
+__device__ __forceinline__ void tmap_acquire(const CUtensorMap* tm) {
+  asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(tm) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, int c0, int c1, unsigned long long* bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
@@ -190,8 +204,20 @@ __device__ __forceinline__ unsigned long long ld_u64_relaxed(const unsigned long
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(q) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned ld_u32_relaxed(const unsigned* q) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(q) : "memory");
+  return v;
+}
 __device__ __forceinline__ void red_add_u64(unsigned long long* q, unsigned long long v) {
   asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(q), "l"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_u32(unsigned* q, unsigned v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(q), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ int floor_to(int x, int a) {  // largest multiple of a (power of two) <= x
+  return x & ~(a - 1);
 }
 
 // correspondence of one pixel packed into 32 bits: u0 (11) | v0 (11) | diff + 256 (10).  diff is the
@@ -209,44 +235,65 @@ __device__ __forceinline__ void make_lvctx(int lvl) {  // one thread
   c.H = F.h;
   c.tw = F.tw;
   c.th = F.th;
+  c.npx = F.npx;
   c.x0 = bx * F.tw;
   c.y0 = by * F.th;
-  c.rw = F.rw;
-  c.npx = F.npx;
-  c.bws = F.bws;
-  c.bwb = F.bwb;
+  c.step_lx = kT % F.tw;
+  c.step_ly = kT / F.tw;
   c.fx = F.k.fx;
   c.fy = F.k.fy;
   c.cx = F.k.cx;
   c.cy = F.k.cy;
-  unsigned char* base = dyn_smem_raw;
-  c.sV = (const float*)(base + F.o_v);
-  c.sN = (const float*)(base + F.o_n);
-  c.sD1 = (const float*)(base + F.o_d1);
-  c.sDX = (const short*)(base + F.o_dx);
-  c.sDY = (const short*)(base + F.o_dy);
-  c.sIMG = base + F.o_img;
-  c.sCAND = base + F.o_cand;
-  c.sPV = (const float*)(base + F.o_pv);
-  c.sPN = (const float*)(base + F.o_pn);
-  c.sLD = (const float*)(base + F.o_ld);
-  c.sLI = base + F.o_li;
-  c.ww = F.ww;
+  c.oV = F.o_v;
+  c.oN = F.o_n;
+  c.oD1 = F.o_d1;
+  c.oDX = F.o_dx;
+  c.oDY = F.o_dy;
+  c.oIMG = F.o_img;
+  c.oCAND = F.o_cand;
+  c.pf = F.pf;
+  c.ps = F.ps;
+  c.pb = F.pb;
+  c.shf = c.x0 - floor_to(c.x0, 4);
+  c.shs = c.x0 - floor_to(c.x0, 8);
+  c.shb = c.x0 - floor_to(c.x0, 16);
+  c.fplane = F.pf * F.th;
+  c.oPV = F.o_pv;
+  c.oPN = F.o_pn;
+  c.oLD = F.o_ld;
+  c.oLI = F.o_li;
+  c.wpf = F.wpf;
+  c.wpb = F.wpb;
+  c.wwl = F.wwl;
   c.wh = F.wh;
-  c.wn = F.ww * F.wh;
   c.wx0 = sm.win_x0;
   c.wy0 = sm.win_y0;
-  c.corrZ = (unsigned*)(base + p.o_corr);
-  c.corrD = (float*)(base + p.o_corr + kPP * kT * 4);
+  c.wshf = c.wx0 - floor_to(c.wx0, 4);
+  c.wshb = c.wx0 - floor_to(c.wx0, 16);
+  c.wplane = F.wpf * F.wh;
+  c.oCorrZ = p.o_corr;
+  c.oCorrD = p.o_corr + kPP * kT * 4;
 }
 
-// pixel i of the tile enumeration -> local / image coordinates; false for padding and image borders
-__device__ __forceinline__ bool tile_pixel(const LvCtx& c, int i, int& lx, int& ly, int& x, int& y) {
-  ly = i / c.rw;
-  lx = i - ly * c.rw;
-  x = c.x0 + lx;
-  y = c.y0 + ly;
-  return lx < c.tw && x < c.W && y < c.H;
+// the pixel enumeration of a thread: i = tid, tid + kT, ... < npx over the tw x th tile, row-major
+struct PixIt {
+  int i, lx, ly;
+};
+__device__ __forceinline__ PixIt pix_begin(const LvCtx& c) {
+  PixIt it;
+  it.i = threadIdx.x;
+  it.ly = (int)threadIdx.x / c.tw;
+  it.lx = (int)threadIdx.x - it.ly * c.tw;
+  return it;
+}
+__device__ __forceinline__ void pix_next(const LvCtx& c, PixIt& it) {
+  it.i += kT;
+  it.lx += c.step_lx;
+  it.ly += c.step_ly;
+  if (it.lx >= c.tw) {
+    it.lx -= c.tw;
+    it.ly += 1;
+  }
 }
 
 // ------------------------------------------------------------------------------------------ phase 1
@@ -254,13 +301,14 @@ __device__ __forceinline__ bool tile_pixel(const LvCtx& c, int i, int& lx, int& 
 // memory, MS: this model's window in shared memory.  Returns validity, fills u0 / v0 / diff / d0.
 template <bool FS, bool MS>
 __device__ __forceinline__ bool residual_pixel(const LvCtx& c, const MLevel& L, const RgbWarp& Wp, float maxDepthDelta,
-                                               int i, int lx, int ly, int x, int y, const unsigned char* nextImage,
-                                               int& u0, int& v0, float& diff, float& d0) {
+                                               int lx, int ly, int x, int y, const unsigned char* nextImage, int& u0,
+                                               int& v0, float& diff, float& d0) {
+  extern __shared__ __align__(128) unsigned char dyn_smem_raw[];
   bool cand;
   float d1;
   if (MS) {
-    cand = c.sCAND[ly * c.bwb + lx] != 0;
-    d1 = c.sD1[i];
+    cand = SM_U8(c.oCAND)[ly * c.pb + lx + c.shb] != 0;
+    d1 = SM_F32(c.oD1)[ly * c.pf + lx + c.shf];
   } else {
     cand = __ldg(L.cand + y * c.W + x) != 0;
     d1 = cand ? __ldg(L.nextDepth + y * c.W + x) : 0.f;
@@ -273,15 +321,15 @@ __device__ __forceinline__ bool residual_pixel(const LvCtx& c, const MLevel& L, 
   if (!(u0 >= 0 && v0 >= 0 && u0 < c.W && v0 < c.H)) return false;
   unsigned char li;
   const int wu = u0 - c.wx0, wv = v0 - c.wy0;
-  if (MS && (unsigned)wu < (unsigned)c.ww && (unsigned)wv < (unsigned)c.wh) {
-    d0 = c.sLD[wv * c.ww + wu];
-    li = c.sLI[wv * c.ww + wu];
+  if (MS && (unsigned)wu < (unsigned)c.wwl && (unsigned)wv < (unsigned)c.wh) {
+    d0 = SM_F32(c.oLD)[wv * c.wpf + wu + c.wshf];
+    li = SM_U8(c.oLI)[wv * c.wpb + wu + c.wshb];
   } else {
     d0 = __ldg(L.lastDepth + v0 * c.W + u0);
     li = __ldg(L.lastImage + v0 * c.W + u0);
   }
   if (!(d0 > 0 && fabsf(td1 - d0) <= maxDepthDelta && li != 0)) return false;
-  const unsigned char ni = FS ? c.sIMG[ly * c.bwb + lx] : __ldg(nextImage + y * c.W + x);
+  const unsigned char ni = FS ? SM_U8(c.oIMG)[ly * c.pb + lx + c.shb] : __ldg(nextImage + y * c.W + x);
   diff = (float)ni - (float)li;
   return true;
 }
@@ -295,20 +343,21 @@ __device__ __noinline__ void phase1(int lvl, int m) {
   const unsigned char* nextImage = p.F[lvl].nextImage;
   int cnt = 0, sig = 0;
   int k = 0;
-#pragma unroll 2
-  for (int i = threadIdx.x; i < c.npx; i += kT, ++k) {
-    int lx, ly, x, y, u0, v0;
+  for (PixIt it = pix_begin(c); it.i < c.npx; pix_next(c, it), ++k) {
+    const int x = c.x0 + it.lx, y = c.y0 + it.ly;
+    int u0, v0;
     float diff, d0;
     unsigned zero = kNoCorr;
-    if (tile_pixel(c, i, lx, ly, x, y) && residual_pixel<FS, MS>(c, L, Wp, p.maxDepthDelta, i, lx, ly, x, y, nextImage, u0, v0, diff, d0)) {
+    if (x < c.W && y < c.H &&
+        residual_pixel<FS, MS>(c, L, Wp, p.maxDepthDelta, it.lx, it.ly, x, y, nextImage, u0, v0, diff, d0)) {
       cnt += 1;
       sig += (int)(diff * diff);  // float -> int truncation, reduce.cu:851
       if (MS) {
         zero = pack_corr(u0, v0, diff);
-        c.corrD[k * kT + threadIdx.x] = d0;
+        SM_F32(c.oCorrD)[k * kT + threadIdx.x] = d0;
       }
     }
-    if (MS) c.corrZ[k * kT + threadIdx.x] = zero;
+    if (MS) SM_U32(c.oCorrZ)[k * kT + threadIdx.x] = zero;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -324,7 +373,7 @@ __device__ __noinline__ void phase1(int lvl, int m) {
 // ------------------------------------------------------------------------------------------ phase 2
 __device__ __forceinline__ void store_warp_row(int m, int set, bool any, float (&acc)[32]) {
   TSMEM();
-  float* wrow = (float*)(dyn_smem_raw + p.o_wrow) + ((size_t)(m * 2 + set) * kNW + (threadIdx.x >> 5)) * 32;
+  float* wrow = SM_F32(p.o_wrow) + ((size_t)(m * 2 + set) * kNW + (threadIdx.x >> 5)) * 32;
   // a warp without any contribution adds exact zeros: skip its 31-shuffle transpose
   wrow[threadIdx.x & 31] = __any_sync(0xffffffffu, any) ? warp_transpose_reduce32(acc) : 0.f;
 }
@@ -352,12 +401,13 @@ __device__ __noinline__ void phase2(int lvl, int m, float* error_map) {
   const float3 tprev = make_float3(P.tprev[0], P.tprev[1], P.tprev[2]);
   const int HW = c.W * c.H;
   bool any = false;
-#pragma unroll 2
-  for (int i = threadIdx.x; i < c.npx; i += kT) {
-    int lx, ly, x, y;
-    if (!tile_pixel(c, i, lx, ly, x, y)) continue;
+  for (PixIt it = pix_begin(c); it.i < c.npx; pix_next(c, it)) {
+    const int x = c.x0 + it.lx, y = c.y0 + it.ly;
+    if (x >= c.W || y >= c.H) continue;
+    const int fi = it.ly * c.pf + it.lx + c.shf;  // index into the f32 frame tiles
+    const int gi = y * c.W + x;
     float3 vcurr;
-    vcurr.x = FS ? c.sV[i] : __ldg(F.vmap_curr + y * c.W + x);
+    vcurr.x = FS ? SM_F32(c.oV)[fi] : __ldg(F.vmap_curr + gi);
     float* const err = error_map ? row_ptr(error_map, p.err_pitch, y) + x : nullptr;
     // an invalid vertex has NaN in x: every coordinate of vcurr_g is NaN, dist is NaN -> no
     // correspondence, error 0 (same outcome as running the arithmetic, without the gathers)
@@ -365,8 +415,8 @@ __device__ __noinline__ void phase2(int lvl, int m, float* error_map) {
       if (err) *err = 0.0f;
       continue;
     }
-    vcurr.y = FS ? c.sV[c.npx + i] : __ldg(F.vmap_curr + HW + y * c.W + x);
-    vcurr.z = FS ? c.sV[2 * c.npx + i] : __ldg(F.vmap_curr + 2 * HW + y * c.W + x);
+    vcurr.y = FS ? SM_F32(c.oV)[c.fplane + fi] : __ldg(F.vmap_curr + HW + gi);
+    vcurr.z = FS ? SM_F32(c.oV)[2 * c.fplane + fi] : __ldg(F.vmap_curr + 2 * HW + gi);
     const float3 vcurr_g = mul(P.Rcurr, vcurr) + tcurr;
     const float3 vcurr_cp = mul(P.Rprev_inv, vcurr_g - tprev);
     const int ux = __float2int_rn(vcurr_cp.x * c.fx / vcurr_cp.z + c.cx);
@@ -377,10 +427,10 @@ __device__ __noinline__ void phase2(int lvl, int m, float* error_map) {
     }
     float3 vp, np;
     const int wu = ux - c.wx0, wv = uy - c.wy0;
-    if (MS && (unsigned)wu < (unsigned)c.ww && (unsigned)wv < (unsigned)c.wh) {
-      const int j = wv * c.ww + wu;
-      vp = make_float3(c.sPV[j], c.sPV[c.wn + j], c.sPV[2 * c.wn + j]);
-      np = make_float3(c.sPN[j], c.sPN[c.wn + j], c.sPN[2 * c.wn + j]);
+    if (MS && (unsigned)wu < (unsigned)c.wwl && (unsigned)wv < (unsigned)c.wh) {
+      const int j = wv * c.wpf + wu + c.wshf;
+      vp = make_float3(SM_F32(c.oPV)[j], SM_F32(c.oPV)[c.wplane + j], SM_F32(c.oPV)[2 * c.wplane + j]);
+      np = make_float3(SM_F32(c.oPN)[j], SM_F32(c.oPN)[c.wplane + j], SM_F32(c.oPN)[2 * c.wplane + j]);
     } else {
       const int j = uy * c.W + ux;
       vp.x = __ldg(L.vmap_g_prev + j);
@@ -396,10 +446,9 @@ __device__ __noinline__ void phase2(int lvl, int m, float* error_map) {
     }
     float3 ncurr;
     if (FS)
-      ncurr = make_float3(c.sN[i], c.sN[c.npx + i], c.sN[2 * c.npx + i]);
+      ncurr = make_float3(SM_F32(c.oN)[fi], SM_F32(c.oN)[c.fplane + fi], SM_F32(c.oN)[2 * c.fplane + fi]);
     else
-      ncurr = make_float3(__ldg(F.nmap_curr + y * c.W + x), __ldg(F.nmap_curr + HW + y * c.W + x),
-                          __ldg(F.nmap_curr + 2 * HW + y * c.W + x));
+      ncurr = make_float3(__ldg(F.nmap_curr + gi), __ldg(F.nmap_curr + HW + gi), __ldg(F.nmap_curr + 2 * HW + gi));
     const float3 ncurr_g = mul(P.Rcurr, ncurr);
     const float dist = norm(vp - vcurr_g);
     const float sine = norm(cross(ncurr_g, np));
@@ -440,24 +489,25 @@ __device__ __noinline__ void phase3(int lvl, int m, float sigma) {
   for (int i = 0; i < 32; ++i) acc[i] = 0.f;
   bool any = false;
   int k = 0;
-#pragma unroll 2
-  for (int i = threadIdx.x; i < c.npx; i += kT, ++k) {
+  for (PixIt it = pix_begin(c); it.i < c.npx; pix_next(c, it), ++k) {
     if (MS) {  // the correspondences of phase 1 never left the SM
-      const unsigned zero = c.corrZ[k * kT + threadIdx.x];
+      const unsigned zero = SM_U32(c.oCorrZ)[k * kT + threadIdx.x];
       if (zero == kNoCorr) continue;
-      const int ly = i / c.rw, lx = i - ly * c.rw;
       any = true;
-      rgb_row(c, sigma, p.sobelScale, (int)(zero & 0x7ffu), (int)((zero >> 11) & 0x7ffu), c.corrD[k * kT + threadIdx.x],
-              (float)((int)(zero >> 22) - 256), c.sDX[ly * c.bws + lx], c.sDY[ly * c.bws + lx], acc);
+      const int si = it.ly * c.ps + it.lx + c.shs;
+      rgb_row(c, sigma, p.sobelScale, (int)(zero & 0x7ffu), (int)((zero >> 11) & 0x7ffu), SM_F32(c.oCorrD)[k * kT + threadIdx.x],
+              (float)((int)(zero >> 22) - 256), SM_S16(c.oDX)[si], SM_S16(c.oDY)[si], acc);
     } else {  // recomputed: the same decisions and values as phase 1
-      int lx, ly, x, y, u0, v0;
+      const int x = c.x0 + it.lx, y = c.y0 + it.ly;
+      int u0, v0;
       float diff, d0;
-      if (!tile_pixel(c, i, lx, ly, x, y)) continue;
-      if (!residual_pixel<FS, false>(c, p.M[m].L[lvl], sm.S[m].warp, p.maxDepthDelta, i, lx, ly, x, y, F.nextImage, u0, v0, diff, d0))
+      if (x >= c.W || y >= c.H) continue;
+      if (!residual_pixel<FS, false>(c, p.M[m].L[lvl], sm.S[m].warp, p.maxDepthDelta, it.lx, it.ly, x, y, F.nextImage, u0, v0, diff, d0))
         continue;
       any = true;
-      const short sdx = FS ? c.sDX[ly * c.bws + lx] : __ldg(F.dIdx + y * c.W + x);
-      const short sdy = FS ? c.sDY[ly * c.bws + lx] : __ldg(F.dIdy + y * c.W + x);
+      const int si = it.ly * c.ps + it.lx + c.shs;
+      const short sdx = FS ? SM_S16(c.oDX)[si] : __ldg(F.dIdx + y * c.W + x);
+      const short sdy = FS ? SM_S16(c.oDY)[si] : __ldg(F.dIdy + y * c.W + x);
       rgb_row(c, sigma, p.sobelScale, u0, v0, d0, diff, sdx, sdy, acc);
     }
   }
@@ -469,7 +519,7 @@ __device__ __noinline__ void phase3(int lvl, int m, float sigma) {
 template <int NCH>
 __device__ __forceinline__ void publish_rows(int m, int par, unsigned tag) {
   TSMEM();
-  const float* wrow = (const float*)(dyn_smem_raw + p.o_wrow) + (size_t)m * 2 * kNW * 32;
+  const float* wrow = SM_F32(p.o_wrow) + (size_t)m * 2 * kNW * 32;
   const int c = threadIdx.x - m * NCH;  // caller guarantees 0 <= c < NCH
   float v[3];
 #pragma unroll
@@ -488,13 +538,14 @@ __device__ __forceinline__ void publish_rows(int m, int par, unsigned tag) {
   st_packet(dst, make_float4(v[0], v[1], v[2], __uint_as_float(tag)));
 }
 
-// poll the packets of every CTA for model m, fold them in a fixed order into out[m][0..3*NCH)
+// read the packets of every CTA for model m (a packet whose tag is not `tag` yet has not landed: read it
+// again), fold them in a fixed order into out[m][0..3*NCH)
 template <int NCH, int NGRP>
 __device__ __forceinline__ void fold_rows(int m, int par, unsigned tag) {
   TSMEM();
   constexpr int JMAX = 6;
-  float4* part = (float4*)(dyn_smem_raw + p.o_part);
-  float* out = (float*)(dyn_smem_raw + p.o_out) + m * 64;
+  float4* part = reinterpret_cast<float4*>(dyn_smem_raw + p.o_part);
+  float* out = SM_F32(p.o_out) + m * 64;
   const int G = gridDim.x;
   const int t = threadIdx.x;
   if (t < NGRP * NCH) {
@@ -538,18 +589,68 @@ __device__ __forceinline__ void fold_rows(int m, int par, unsigned tag) {
   __syncthreads();
 }
 
+// every packet of this CTA is on its way: count the arrival (no fence -- the tags carry the ordering),
+// one thread waits until every CTA has counted, then the packets are (almost surely) there to be read once
+__device__ __forceinline__ void exchange_arrive_wait(unsigned round) {
+  TSMEM();
+  __syncthreads();  // the publishing threads have issued their stores
+  if (threadIdx.x == 0) {
+    red_add_u32(&p.bcnt[round], 1u);
+    while (ld_u32_relaxed(&p.bcnt[round]) < gridDim.x) {
+    }
+  }
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------------- FP64 Gauss-Newton step, one warp
+// exp of a rotation vector without sqrt / division / sin / cos: R = I + A [r]x + B [r]x^2 with
+// A = sin(t)/t, B = (1 - cos t)/t^2 as series in t^2 (|r| <= 0.5: truncation < 1e-17); the library
+// Rodrigues formula (gn_math.h) for anything larger
+__device__ __forceinline__ void exp_so3(const double r[3], double R[9]) {
+  const double x = r[0], y = r[1], z = r[2];
+  const double t2 = x * x + y * y + z * z;
+  if (t2 > 0.25) {
+    gn::rodrigues(r, R);
+    return;
+  }
+  double A = 1.0 - t2 * (1.0 / 210.0);
+  A = 1.0 - t2 * (1.0 / 156.0) * A;
+  A = 1.0 - t2 * (1.0 / 110.0) * A;
+  A = 1.0 - t2 * (1.0 / 72.0) * A;
+  A = 1.0 - t2 * (1.0 / 42.0) * A;
+  A = 1.0 - t2 * (1.0 / 20.0) * A;
+  A = 1.0 - t2 * (1.0 / 6.0) * A;
+  double B = 1.0 - t2 * (1.0 / 240.0);
+  B = 1.0 - t2 * (1.0 / 182.0) * B;
+  B = 1.0 - t2 * (1.0 / 132.0) * B;
+  B = 1.0 - t2 * (1.0 / 90.0) * B;
+  B = 1.0 - t2 * (1.0 / 56.0) * B;
+  B = 1.0 - t2 * (1.0 / 30.0) * B;
+  B = 1.0 - t2 * (1.0 / 12.0) * B;
+  B *= 0.5;
+  R[0] = 1.0 - B * (y * y + z * z);
+  R[1] = B * x * y - A * z;
+  R[2] = B * x * z + A * y;
+  R[3] = B * x * y + A * z;
+  R[4] = 1.0 - B * (x * x + z * z);
+  R[5] = B * y * z - A * x;
+  R[6] = B * x * z - A * y;
+  R[7] = B * y * z + A * x;
+  R[8] = 1.0 - B * (x * x + y * y);
+}
+
 // lower-triangular LDL^T of the 6x6 normal equations in registers (every lane runs it redundantly: no
 // exchange, and the pose update that follows is spread over the lanes)
 __device__ __forceinline__ void ldlt6_lower(double (&A)[21], double (&b)[6], double (&x)[6]) {
 #define LA(i, j) A[(i) * ((i) + 1) / 2 + (j)]
+  double inv[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
     const double d = LA(k, k);
-    const double inv = (d != 0.0) ? 1.0 / d : 0.0;
+    inv[k] = (d != 0.0) ? 1.0 / d : 0.0;
     double l[6];
 #pragma unroll
-    for (int i = k + 1; i < 6; ++i) l[i] = LA(i, k) * inv;
+    for (int i = k + 1; i < 6; ++i) l[i] = LA(i, k) * inv[k];
 #pragma unroll
     for (int i = k + 1; i < 6; ++i)
 #pragma unroll
@@ -562,7 +663,7 @@ __device__ __forceinline__ void ldlt6_lower(double (&A)[21], double (&b)[6], dou
 #pragma unroll
     for (int j = 0; j < i; ++j) b[i] -= LA(i, j) * b[j];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) b[i] = (LA(i, i) != 0.0) ? b[i] / LA(i, i) : 0.0;
+  for (int i = 0; i < 6; ++i) b[i] *= inv[i];  // a zero pivot (no inliers) yields a zero component
 #pragma unroll
   for (int i = 5; i >= 0; --i)
 #pragma unroll
@@ -576,7 +677,7 @@ __device__ __forceinline__ void ldlt6_lower(double (&A)[21], double (&b)[6], dou
 __device__ __noinline__ void gn_solve_warp(int m, int lvl_next, int is_last, float tmpError, int cnt) {
   TSMEM();
   GNState* g = &sm.S[m];
-  const float* out = (const float*)(dyn_smem_raw + p.o_out) + m * 64;  // [0..28] ICP sums, [29..57] RGB sums
+  const float* out = SM_F32(p.o_out) + m * 64;  // [0..28] ICP sums, [29..57] RGB sums
   double* sA = sm.solveA[m];
   const int lane = threadIdx.x & 31;
   const double w = p.icpWeight;
@@ -621,7 +722,7 @@ __device__ __noinline__ void gn_solve_warp(int m, int lvl_next, int is_last, flo
   double Rm[9];
   {
     const double rv[3] = {x[3], x[4], x[5]};
-    gn::rodrigues(rv, Rm);
+    exp_so3(rv, Rm);
   }
   double nrt = 0.0;
   if (lane < 12) {
@@ -746,11 +847,12 @@ __device__ __forceinline__ void gn_begin_warp(GNState* g, int use_so3, int lvl_f
 __device__ __noinline__ void so3_update_warp(int m, int it) {
   TSMEM();
   GNState* g = &sm.S[m];
-  const float* out = (const float*)(dyn_smem_raw + p.o_out) + m * 64;
+  const float* out = SM_F32(p.o_out) + m * 64;
   const int lane = threadIdx.x & 31;
   TrackStats& st = g->stats;
   const float err = sqrtf(out[9]) / out[10], count = out[10];
   const float lastError = g->so3_lastError, lastCount = g->so3_lastCount;
+  __syncwarp();
   int done = 0;
   if (err < lastError && fabsf(lastError - count) < 0.001f) {
     done = 1;
@@ -778,7 +880,7 @@ __device__ __noinline__ void so3_update_warp(int m, int it) {
     gn::ldlt_solve_unrolled<3>(Ad, bd, xd);
     const double delta[3] = {(double)(float)xd[0], (double)(float)xd[1], (double)(float)xd[2]};
     double rotUpdate[9];
-    gn::rodrigues(delta, rotUpdate);
+    exp_so3(delta, rotUpdate);
     float nr = 0.f;
     if (lane < 9) {
       const int r = lane / 3, c = lane - 3 * r;
@@ -815,7 +917,7 @@ __device__ __forceinline__ void gn_init_warp(int m) {
   const float* pose_in = p.M[m].pose_in;
   const int lane = threadIdx.x & 31;
   if (lane < 9) {
-    const float r = __ldg(pose_in + 3 + lane);
+    const float r = __ldcg(pose_in + 3 + lane);
     g->Rprev[lane] = r;
     g->pose.Rcurr.m[lane] = r;
     g->out_rot[lane] = r;
@@ -824,7 +926,7 @@ __device__ __forceinline__ void gn_init_warp(int m) {
     g->lastResultR[lane] = id;
     g->R_lr[lane] = (float)id;
   } else if (lane < 12) {
-    const float t = __ldg(pose_in + lane - 9);
+    const float t = __ldcg(pose_in + lane - 9);
     g->pose.tprev[lane - 9] = t;
     g->pose.tcurr[lane - 9] = t;
     g->out_trans[lane - 9] = t;
@@ -834,7 +936,7 @@ __device__ __forceinline__ void gn_init_warp(int m) {
     g->so3_done = 0;
     TrackStats z = {};
     g->stats = z;
-  } else if (lane >= 16) {  // resultRt row 3 = (0, 0, 0, 1); the top rows are set by gn_begin_warp
+  } else if (lane >= 16) {  // resultRt = identity; the top rows are set again by gn_begin_warp
     const int q = lane - 16;
     g->resultRt[q] = (q % 5 == 0) ? 1.0 : 0.0;
   }
@@ -858,16 +960,27 @@ __device__ __forceinline__ void issue_frame_tma(int lvl) {  // one thread
   const FLevel& F = p.F[lvl];
   const MLevel& L = p.M[0].L[lvl];
   const int x0 = (blockIdx.x % p.gx) * F.tw, y0 = (blockIdx.x / p.gx) * F.th;
-  unsigned char* base = dyn_smem_raw;
+  const int xf = floor_to(x0, 4), xs = floor_to(x0, 8), xb = floor_to(x0, 16);  // 16-byte aligned box origins
   unsigned long long* bar = &sm.bar_frame[lvl];
+  tmap_acquire(F.tm_v);
+  tmap_acquire(F.tm_n);
+  tmap_acquire(F.tm_dx);
+  tmap_acquire(F.tm_dy);
+  tmap_acquire(F.tm_img);
+  tmap_acquire(L.tm_d1);
+  tmap_acquire(L.tm_cand);
+  tmap_acquire(L.tm_pv);
+  tmap_acquire(L.tm_pn);
+  tmap_acquire(L.tm_ld);
+  tmap_acquire(L.tm_li);
   mbar_expect_tx(bar, F.frame_bytes);
-  tma_load_3d(base + F.o_v, F.tm_v, x0, y0, 0, bar);
-  tma_load_3d(base + F.o_n, F.tm_n, x0, y0, 0, bar);
-  tma_load_2d(base + F.o_dx, F.tm_dx, x0, y0, bar);
-  tma_load_2d(base + F.o_dy, F.tm_dy, x0, y0, bar);
-  tma_load_2d(base + F.o_img, F.tm_img, x0, y0, bar);
-  tma_load_2d(base + F.o_d1, L.tm_d1, x0, y0, bar);
-  tma_load_2d(base + F.o_cand, L.tm_cand, x0, y0, bar);
+  tma_load_3d(dyn_smem_raw + F.o_v, F.tm_v, xf, y0, 0, bar);
+  tma_load_3d(dyn_smem_raw + F.o_n, F.tm_n, xf, y0, 0, bar);
+  tma_load_2d(dyn_smem_raw + F.o_dx, F.tm_dx, xs, y0, bar);
+  tma_load_2d(dyn_smem_raw + F.o_dy, F.tm_dy, xs, y0, bar);
+  tma_load_2d(dyn_smem_raw + F.o_img, F.tm_img, xb, y0, bar);
+  tma_load_2d(dyn_smem_raw + F.o_d1, L.tm_d1, xf, y0, bar);
+  tma_load_2d(dyn_smem_raw + F.o_cand, L.tm_cand, xb, y0, bar);
 }
 
 __device__ __noinline__ void level_begin(int lvl, unsigned& win_phase) {
@@ -879,21 +992,22 @@ __device__ __noinline__ void level_begin(int lvl, unsigned& win_phase) {
     return;
   }
   const MLevel& L = p.M[0].L[lvl];
-  unsigned char* base = dyn_smem_raw;
   const int x0 = (blockIdx.x % p.gx) * F.tw, y0 = (blockIdx.x / p.gx) * F.th;
+  const int xf = floor_to(x0, 4), xs = floor_to(x0, 8), xb = floor_to(x0, 16);
   if (F.staged == 1) {
     mbar_wait(&sm.bar_frame[lvl], 0);
   } else {
     const size_t hw = (size_t)F.w * F.h;
+    const int fplane = F.pf * F.th;
     for (int k = 0; k < 3; ++k) {
-      fill_box((float*)(base + F.o_v) + k * F.npx, F.vmap_curr + k * hw, F.w, F.h, x0, y0, F.rw, F.th);
-      fill_box((float*)(base + F.o_n) + k * F.npx, F.nmap_curr + k * hw, F.w, F.h, x0, y0, F.rw, F.th);
+      fill_box(SM_F32(F.o_v) + k * fplane, F.vmap_curr + k * hw, F.w, F.h, xf, y0, F.pf, F.th);
+      fill_box(SM_F32(F.o_n) + k * fplane, F.nmap_curr + k * hw, F.w, F.h, xf, y0, F.pf, F.th);
     }
-    fill_box((short*)(base + F.o_dx), F.dIdx, F.w, F.h, x0, y0, F.bws, F.th);
-    fill_box((short*)(base + F.o_dy), F.dIdy, F.w, F.h, x0, y0, F.bws, F.th);
-    fill_box(base + F.o_img, F.nextImage, F.w, F.h, x0, y0, F.bwb, F.th);
-    fill_box((float*)(base + F.o_d1), L.nextDepth, F.w, F.h, x0, y0, F.rw, F.th);
-    fill_box(base + F.o_cand, L.cand, F.w, F.h, x0, y0, F.bwb, F.th);
+    fill_box(SM_S16(F.o_dx), F.dIdx, F.w, F.h, xs, y0, F.ps, F.th);
+    fill_box(SM_S16(F.o_dy), F.dIdy, F.w, F.h, xs, y0, F.ps, F.th);
+    fill_box(SM_U8(F.o_img), F.nextImage, F.w, F.h, xb, y0, F.pb, F.th);
+    fill_box(SM_F32(F.o_d1), L.nextDepth, F.w, F.h, xf, y0, F.pf, F.th);
+    fill_box(SM_U8(F.o_cand), L.cand, F.w, F.h, xb, y0, F.pb, F.th);
   }
   if (threadIdx.x < 3) sm.winacc[threadIdx.x] = 0;
   __syncthreads();
@@ -901,13 +1015,14 @@ __device__ __noinline__ void level_begin(int lvl, unsigned& win_phase) {
   {
     const RgbWarp& Wp = sm.S[0].warp;
     const float* kk = Wp.krkinv.m;
-    const float* sD1 = (const float*)(base + F.o_d1);
-    const unsigned char* sC = base + F.o_cand;
+    const float* sD1 = SM_F32(F.o_d1);
+    const unsigned char* sC = SM_U8(F.o_cand);
+    const int shf = x0 - xf, shb = x0 - xb;
     int sx = 0, sy = 0, n = 0;
     for (int i = threadIdx.x; i < F.npx; i += kT) {
-      const int ly = i / F.rw, lx = i - ly * F.rw, x = x0 + lx, y = y0 + ly;
-      if (lx < F.tw && x < F.w && y < F.h && sC[ly * F.bwb + lx]) {
-        const float d1 = sD1[i];
+      const int ly = i / F.tw, lx = i - ly * F.tw, x = x0 + lx, y = y0 + ly;
+      if (x < F.w && y < F.h && sC[ly * F.pb + lx + shb]) {
+        const float d1 = sD1[ly * F.pf + lx + shf];
         const float td1 = d1 * (kk[6] * x + kk[7] * y + kk[8]) + Wp.kt[2];
         const int u0 = __float2int_rn((d1 * (kk[0] * x + kk[1] * y + kk[2]) + Wp.kt[0]) / td1);
         const int v0 = __float2int_rn((d1 * (kk[3] * x + kk[4] * y + kk[5]) + Wp.kt[1]) / td1);
@@ -936,7 +1051,7 @@ __device__ __noinline__ void level_begin(int lvl, unsigned& win_phase) {
     const int n = sm.winacc[2];
     const int mx = n ? __float2int_rn((float)sm.winacc[0] / (float)n) : 0;
     const int my = n ? __float2int_rn((float)sm.winacc[1] / (float)n) : 0;
-    const int wx0 = x0 + mx - (F.ww - F.tw) / 2, wy0 = y0 + my - (F.wh - F.th) / 2;
+    const int wx0 = x0 + mx - F.halo, wy0 = y0 + my - F.halo;
     sm.win_x0 = wx0;
     sm.win_y0 = wy0;
     make_lvctx(lvl);
@@ -944,10 +1059,11 @@ __device__ __noinline__ void level_begin(int lvl, unsigned& win_phase) {
       // the window region was read by the previous level through the generic proxy
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(&sm.bar_win, F.win_bytes);
-      tma_load_3d(base + F.o_pv, L.tm_pv, wx0, wy0, 0, &sm.bar_win);
-      tma_load_3d(base + F.o_pn, L.tm_pn, wx0, wy0, 0, &sm.bar_win);
-      tma_load_2d(base + F.o_ld, L.tm_ld, wx0, wy0, &sm.bar_win);
-      tma_load_2d(base + F.o_li, L.tm_li, wx0, wy0, &sm.bar_win);
+      const int wxf = floor_to(wx0, 4), wxb = floor_to(wx0, 16);
+      tma_load_3d(dyn_smem_raw + F.o_pv, L.tm_pv, wxf, wy0, 0, &sm.bar_win);
+      tma_load_3d(dyn_smem_raw + F.o_pn, L.tm_pn, wxf, wy0, 0, &sm.bar_win);
+      tma_load_2d(dyn_smem_raw + F.o_ld, L.tm_ld, wxf, wy0, &sm.bar_win);
+      tma_load_2d(dyn_smem_raw + F.o_li, L.tm_li, wxb, wy0, &sm.bar_win);
     }
   }
   __syncthreads();
@@ -955,14 +1071,15 @@ __device__ __noinline__ void level_begin(int lvl, unsigned& win_phase) {
     mbar_wait(&sm.bar_win, win_phase);
     win_phase ^= 1u;
   } else {
-    const int wx0 = sm.win_x0, wy0 = sm.win_y0, wn = F.ww * F.wh;
+    const int wx0 = sm.win_x0, wy0 = sm.win_y0, wplane = F.wpf * F.wh;
+    const int wxf = floor_to(wx0, 4), wxb = floor_to(wx0, 16);
     const size_t hw = (size_t)F.w * F.h;
     for (int k = 0; k < 3; ++k) {
-      fill_box((float*)(base + F.o_pv) + k * wn, L.vmap_g_prev + k * hw, F.w, F.h, wx0, wy0, F.ww, F.wh);
-      fill_box((float*)(base + F.o_pn) + k * wn, L.nmap_g_prev + k * hw, F.w, F.h, wx0, wy0, F.ww, F.wh);
+      fill_box(SM_F32(F.o_pv) + k * wplane, L.vmap_g_prev + k * hw, F.w, F.h, wxf, wy0, F.wpf, F.wh);
+      fill_box(SM_F32(F.o_pn) + k * wplane, L.nmap_g_prev + k * hw, F.w, F.h, wxf, wy0, F.wpf, F.wh);
     }
-    fill_box((float*)(base + F.o_ld), L.lastDepth, F.w, F.h, wx0, wy0, F.ww, F.wh);
-    fill_box(base + F.o_li, L.lastImage, F.w, F.h, wx0, wy0, F.ww, F.wh);
+    fill_box(SM_F32(F.o_ld), L.lastDepth, F.w, F.h, wxf, wy0, F.wpf, F.wh);
+    fill_box(SM_U8(F.o_li), L.lastImage, F.w, F.h, wxb, wy0, F.wpb, F.wh);
     __syncthreads();
   }
 }
@@ -1040,12 +1157,14 @@ __device__ __noinline__ void run_level(int lvl, int q0, int nit, unsigned round0
 
     // -------- publish this CTA's packets, fold everybody's, solve
     if ((int)threadIdx.x < NM * kChunks) publish_rows<kChunks>(threadIdx.x / kChunks, par, tag);
+    exchange_arrive_wait(round);
+    DBG_MARK(8 + q * 8 + 5);
     for (int m = 0; m < NM; ++m) fold_rows<kChunks, kGroups>(m, par, tag);
     DBG_MARK(8 + q * 8 + 6);
     const int is_last = (q + 1 == sm.nsched);
     if ((int)warp < NM) {
       const int m = (int)warp;
-      if (lane < 29) sm.S[m].icp_result[lane] = ((const float*)(dyn_smem_raw + p.o_out))[m * 64 + lane];
+      if (lane < 29) sm.S[m].icp_result[lane] = SM_F32(p.o_out)[m * 64 + lane];
       gn_solve_warp(m, is_last ? sm.sched[q] : sm.sched[q + 1], is_last, sm.tmpErr[m], sm.tot[m][0]);
     }
     __syncthreads();
@@ -1074,7 +1193,7 @@ __device__ __noinline__ unsigned run_so3() {
 #pragma unroll
       for (int i = 0; i < 32; ++i) acc[i] = 0.f;
       bool work = false;
-      for (int i = threadIdx.x; i < F.tw * F.th; i += kT) {
+      for (int i = threadIdx.x; i < F.npx; i += kT) {
         const int ly = i / F.tw, lx = i - ly * F.tw, x = x0 + lx, y = y0 + ly;
         if (x < F.w && y < F.h) {
           so3_pixel(p.M[m].so3_last, p.M[m].so3_next, (size_t)F.w, F.w, F.h, S.so3_imageBasis, S.so3_kinv, S.so3_krlr, x, y, acc);
@@ -1086,6 +1205,7 @@ __device__ __noinline__ unsigned run_so3() {
     __syncthreads();
     if ((int)threadIdx.x < NM * kSo3Chunks && !sm.S[threadIdx.x / kSo3Chunks].so3_done)
       publish_rows<kSo3Chunks>(threadIdx.x / kSo3Chunks, par, tag);
+    exchange_arrive_wait(round);
     for (int m = 0; m < NM; ++m)
       if (!sm.S[m].so3_done) fold_rows<kSo3Chunks, kSo3Groups>(m, par, tag);  // so3_done is uniform: no divergent barrier
     if ((int)warp < NM && !sm.S[warp].so3_done) so3_update_warp((int)warp, it);
@@ -1158,7 +1278,7 @@ __global__ void __launch_bounds__(kT, 1) gn_tiled_kernel(const TParams kp) {
   DBG_MARK(3);
 }
 
-// sobel + candidate gates for all three levels in one launch; also clears the barrier-A words of the
+// sobel + candidate gates for all three levels in one launch; also clears the barrier words of the
 // tracker launch that follows
 struct PrepLevel {
   const unsigned char* img;
@@ -1170,11 +1290,12 @@ struct PrepLevel {
 };
 struct PrepParams {
   PrepLevel L[3];
-  unsigned long long* acnt;  // kMaxRounds * kMaxM words, or null
+  unsigned* sync_words;  // barrier A (u64 x kMaxRounds x kMaxM) then exchange counters (u32 x kMaxRounds), or null
 };
+constexpr int kSyncWords = kMaxRounds * kMaxM * 2 + kMaxRounds;
 __global__ void rgb_prepare_tiled_kernel(const PrepParams pp) {
   int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pp.acnt && q < kMaxRounds * kMaxM) pp.acnt[q] = 0ull;
+  if (pp.sync_words && q < kSyncWords) pp.sync_words[q] = 0u;
 #pragma unroll
   for (int l = 0; l < 3; ++l) {
     const PrepLevel& L = pp.L[l];
@@ -1224,6 +1345,8 @@ bool encode_map(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int 
 
 int round_up(int a, int b) { return (a + b - 1) / b * b; }
 unsigned align128(unsigned a) { return (a + 127u) & ~127u; }
+// row pitch of a box that covers `n` elements starting anywhere inside an `a`-element alignment unit
+int box_pitch(int n, int a, bool origin_aligned) { return origin_aligned ? round_up(n, a) : round_up(n + a - 1, a); }
 
 }  // namespace
 
@@ -1243,7 +1366,6 @@ struct RGBDOdometry::TiledState {
   enum { TM_V, TM_N, TM_DX, TM_DY, TM_IMG_A, TM_IMG_B, TM_D1_NEXT, TM_D1_LAST, TM_CAND, TM_PV, TM_PN, TM_LD, TM_LI, TM_COUNT };
   CUtensorMap* d_maps = nullptr;  // [3][TM_COUNT]
   const unsigned char* img_a[3] = {nullptr, nullptr, nullptr};  // the buffer TM_IMG_A describes
-  bool tma_ok[3] = {false, false, false};
   unsigned epoch = 1;
   bool attr_set = false;
   int nmodels_planned = 0;
@@ -1258,10 +1380,11 @@ void plan_tiles(int W, int H, int sms, int nm, RGBDOdometry::TiledState& ts) {
     const int gy = maxG / gx;
     const int tw = (W + gx - 1) / gx, th = (H + gy - 1) / gy;
     const int gxe = (W + tw - 1) / tw, gye = (H + th - 1) / th;  // tiles actually needed
-    const int rw = round_up(tw, 4);
-    const long frame = (long)rw * th;
-    const long win = (long)round_up(tw + 8, 16) * (th + 8);
-    const long cost = frame * 2 + win + (frame > kPP * kT ? 1000000L : 0) + (gxe * gye < maxG - 8 ? frame / 8 : 0);
+    const long frame = (long)tw * th;
+    const long win = (long)(tw + 2 * kMaxHalo + 3) * (th + 2 * kMaxHalo);
+    long cost = frame * 4 + win;                 // pixel work dominates, the window only costs shared memory
+    if (tw % 16) cost += frame / 4;              // unaligned f32 tiles at the coarser levels need wider boxes
+    if (frame > kPP * kT) cost += 1000000L;      // level 0 would not fit a shared-memory tile
     if (best < 0 || cost < best) {
       best = cost;
       ts.gx = gxe;
@@ -1271,68 +1394,75 @@ void plan_tiles(int W, int H, int sms, int nm, RGBDOdometry::TiledState& ts) {
   unsigned off = align128((unsigned)sizeof(TFixed));
   ts.o_wrow = off;
   off = align128(off + (unsigned)nm * 2 * kNW * 32 * 4);
-  ts.o_part = off;
-  off = align128(off + kT * 16);
   ts.o_out = off;
   off = align128(off + (unsigned)nm * 64 * 4);
-  ts.o_corr = off;
+  ts.o_corr = off;  // the fold's staging buffer shares this space: the correspondences are dead by then
+  ts.o_part = off;
   off = align128(off + 2 * kPP * kT * 4);
   const unsigned cap = 227u * 1024u;
   auto window_bytes = [](const FLevel& F) {
-    const unsigned wn = (unsigned)F.ww * F.wh;
-    return align128(3 * wn * 4) * 2 + align128(wn * 4) + align128(wn);
+    return align128(3u * F.wpf * F.wh * 4) * 2 + align128((unsigned)F.wpf * F.wh * 4) + align128((unsigned)F.wpb * F.wh);
   };
+  const unsigned off0 = off;
   unsigned wmax = 0;
-  for (int l = 2; l >= 0; --l) {  // coarse to fine: stage what fits (frame tiles of every staged level + one window)
-    FLevel& F = ts.F[l];
-    F.w = W >> l;
-    F.h = H >> l;
-    F.tw = (F.w + ts.gx - 1) / ts.gx;
-    F.th = (F.h + ts.gy - 1) / ts.gy;
-    F.rw = round_up(F.tw, 4);
-    F.npx = F.rw * F.th;
-    F.bws = round_up(F.tw, 8);
-    F.bwb = round_up(F.tw, 16);
-    F.ww = round_up(F.tw + 8, 16);
-    F.wh = F.th + 8;
-    F.staged = 0;
-    unsigned o = off;
-    F.o_v = o;
-    o = align128(o + 3u * F.npx * 4);
-    F.o_n = o;
-    o = align128(o + 3u * F.npx * 4);
-    F.o_dx = o;
-    o = align128(o + (unsigned)F.bws * F.th * 2);
-    F.o_dy = o;
-    o = align128(o + (unsigned)F.bws * F.th * 2);
-    F.o_img = o;
-    o = align128(o + (unsigned)F.bwb * F.th);
-    F.o_d1 = o;
-    o = align128(o + (unsigned)F.npx * 4);
-    F.o_cand = o;
-    o = align128(o + (unsigned)F.bwb * F.th);
-    F.frame_bytes = 7u * F.npx * 4 + 2u * F.bws * F.th * 2 + 2u * F.bwb * F.th;
-    const unsigned wb = window_bytes(F), wnew = wb > wmax ? wb : wmax;
-    if (F.npx <= kPP * kT && F.w < 2048 && F.h < 2048 && o + wnew <= cap) {
-      F.staged = 1;
-      off = o;
-      wmax = wnew;
-    }  // a global-memory level keeps the same pixel enumeration (row width rw): the pixel -> thread map, and
-       // with it the summation order, does not depend on where a level's data lives
+  for (int halo = kMaxHalo; halo >= 2; --halo) {  // shrink the window halo until the finest level fits too
+    off = off0;
+    wmax = 0;
+    for (int l = 2; l >= 0; --l) {  // coarse to fine: frame tiles of every staged level + one window
+      FLevel& F = ts.F[l];
+      F.w = W >> l;
+      F.h = H >> l;
+      F.tw = (F.w + ts.gx - 1) / ts.gx;
+      F.th = (F.h + ts.gy - 1) / ts.gy;
+      F.npx = F.tw * F.th;
+      F.pf = box_pitch(F.tw, 4, F.tw % 4 == 0);
+      F.ps = box_pitch(F.tw, 8, F.tw % 8 == 0);
+      F.pb = box_pitch(F.tw, 16, F.tw % 16 == 0);
+      F.halo = halo;
+      F.wwl = F.tw + 2 * halo;
+      F.wh = F.th + 2 * halo;
+      F.wpf = box_pitch(F.wwl, 4, false);
+      F.wpb = box_pitch(F.wwl, 16, false);
+      F.staged = 0;
+      unsigned o = off;
+      F.o_v = o;
+      o = align128(o + 3u * F.pf * F.th * 4);
+      F.o_n = o;
+      o = align128(o + 3u * F.pf * F.th * 4);
+      F.o_dx = o;
+      o = align128(o + (unsigned)F.ps * F.th * 2);
+      F.o_dy = o;
+      o = align128(o + (unsigned)F.ps * F.th * 2);
+      F.o_img = o;
+      o = align128(o + (unsigned)F.pb * F.th);
+      F.o_d1 = o;
+      o = align128(o + (unsigned)F.pf * F.th * 4);
+      F.o_cand = o;
+      o = align128(o + (unsigned)F.pb * F.th);
+      F.frame_bytes = 7u * F.pf * F.th * 4 + 2u * F.ps * F.th * 2 + 2u * F.pb * F.th;
+      const unsigned wb = window_bytes(F), wnew = wb > wmax ? wb : wmax;
+      if (!getenv("CFB_TILED_NOSTAGE") && F.npx <= kPP * kT && F.w < 2048 && F.h < 2048 && F.pf <= 256 && F.pb <= 256 &&
+          F.th <= 256 && F.wpb <= 256 && F.wh <= 256 && o + wnew <= cap) {
+        F.staged = 1;
+        off = o;
+        wmax = wnew;
+      }  // a global-memory level keeps the same pixel enumeration: the pixel -> thread map, and with it the
+         // summation order, does not depend on where a level's data lives
+    }
+    if (ts.F[0].staged || ts.F[0].npx > kPP * kT) break;  // level 0 staged, or it never can be
   }
   for (int l = 0; l < 3; ++l) {  // the window region is shared by the staged levels, after all frame tiles
     FLevel& F = ts.F[l];
     if (!F.staged) continue;
-    const unsigned wn = (unsigned)F.ww * F.wh;
     unsigned o = off;
     F.o_pv = o;
-    o += align128(3 * wn * 4);
+    o += align128(3u * F.wpf * F.wh * 4);
     F.o_pn = o;
-    o += align128(3 * wn * 4);
+    o += align128(3u * F.wpf * F.wh * 4);
     F.o_ld = o;
-    o += align128(wn * 4);
+    o += align128((unsigned)F.wpf * F.wh * 4);
     F.o_li = o;
-    F.win_bytes = 7u * wn * 4 + wn;
+    F.win_bytes = 7u * F.wpf * F.wh * 4 + (unsigned)F.wpb * F.wh;
   }
   ts.smem_bytes = off + wmax;
   ts.nmodels_planned = nm;
@@ -1365,21 +1495,21 @@ cudaError_t RGBDOdometry::prepareTiled(int nm) {
     const int w = F.w, hh = F.h;
     bool ok = true;
     const CUtensorMapDataType f32 = CU_TENSOR_MAP_DATA_TYPE_FLOAT32, u16 = CU_TENSOR_MAP_DATA_TYPE_UINT16, u8 = CU_TENSOR_MAP_DATA_TYPE_UINT8;
-    ok = ok && encode_map(&h[l][TiledState::TM_V], vmaps_curr_[l], f32, 4, w, hh, 3, F.rw, F.th);
-    ok = ok && encode_map(&h[l][TiledState::TM_N], nmaps_curr_[l], f32, 4, w, hh, 3, F.rw, F.th);
-    ok = ok && encode_map(&h[l][TiledState::TM_DX], nextdIdx[l], u16, 2, w, hh, 1, F.bws, F.th);
-    ok = ok && encode_map(&h[l][TiledState::TM_DY], nextdIdy[l], u16, 2, w, hh, 1, F.bws, F.th);
-    ok = ok && encode_map(&h[l][TiledState::TM_IMG_A], nextImage[l], u8, 1, w, hh, 1, F.bwb, F.th);
-    ok = ok && encode_map(&h[l][TiledState::TM_IMG_B], lastNextImage[l], u8, 1, w, hh, 1, F.bwb, F.th);
-    ok = ok && encode_map(&h[l][TiledState::TM_D1_NEXT], nextDepth[l], f32, 4, w, hh, 1, F.rw, F.th);
-    ok = ok && encode_map(&h[l][TiledState::TM_D1_LAST], lastDepth[l], f32, 4, w, hh, 1, F.rw, F.th);
-    ok = ok && encode_map(&h[l][TiledState::TM_CAND], rgbCand[l], u8, 1, w, hh, 1, F.bwb, F.th);
-    ok = ok && encode_map(&h[l][TiledState::TM_PV], vmaps_g_prev_[l], f32, 4, w, hh, 3, F.ww, F.wh);
-    ok = ok && encode_map(&h[l][TiledState::TM_PN], nmaps_g_prev_[l], f32, 4, w, hh, 3, F.ww, F.wh);
-    ok = ok && encode_map(&h[l][TiledState::TM_LD], lastDepth[l], f32, 4, w, hh, 1, F.ww, F.wh);
-    ok = ok && encode_map(&h[l][TiledState::TM_LI], lastImage[l], u8, 1, w, hh, 1, F.ww, F.wh);
+    ok = ok && encode_map(&h[l][TiledState::TM_V], vmaps_curr_[l], f32, 4, w, hh, 3, F.pf, F.th);
+    ok = ok && encode_map(&h[l][TiledState::TM_N], nmaps_curr_[l], f32, 4, w, hh, 3, F.pf, F.th);
+    ok = ok && encode_map(&h[l][TiledState::TM_DX], nextdIdx[l], u16, 2, w, hh, 1, F.ps, F.th);
+    ok = ok && encode_map(&h[l][TiledState::TM_DY], nextdIdy[l], u16, 2, w, hh, 1, F.ps, F.th);
+    ok = ok && encode_map(&h[l][TiledState::TM_IMG_A], nextImage[l], u8, 1, w, hh, 1, F.pb, F.th);
+    ok = ok && encode_map(&h[l][TiledState::TM_IMG_B], lastNextImage[l], u8, 1, w, hh, 1, F.pb, F.th);
+    ok = ok && encode_map(&h[l][TiledState::TM_D1_NEXT], nextDepth[l], f32, 4, w, hh, 1, F.pf, F.th);
+    ok = ok && encode_map(&h[l][TiledState::TM_D1_LAST], lastDepth[l], f32, 4, w, hh, 1, F.pf, F.th);
+    ok = ok && encode_map(&h[l][TiledState::TM_CAND], rgbCand[l], u8, 1, w, hh, 1, F.pb, F.th);
+    ok = ok && encode_map(&h[l][TiledState::TM_PV], vmaps_g_prev_[l], f32, 4, w, hh, 3, F.wpf, F.wh);
+    ok = ok && encode_map(&h[l][TiledState::TM_PN], nmaps_g_prev_[l], f32, 4, w, hh, 3, F.wpf, F.wh);
+    ok = ok && encode_map(&h[l][TiledState::TM_LD], lastDepth[l], f32, 4, w, hh, 1, F.wpf, F.wh);
+    ok = ok && encode_map(&h[l][TiledState::TM_LI], lastImage[l], u8, 1, w, hh, 1, F.wpb, F.wh);
+    if (getenv("CFB_TILED_NOTMA")) ok = false;  // debugging aid: fill the tiles with ordinary loads
     ts.img_a[l] = nextImage[l];
-    ts.tma_ok[l] = ok;
     F.staged = ok ? 1 : 2;
   }
   RET_IF(cudaMemcpy(ts.d_maps, h, sizeof(h), cudaMemcpyHostToDevice));
@@ -1387,20 +1517,18 @@ cudaError_t RGBDOdometry::prepareTiled(int nm) {
     fprintf(stderr, "[cfb tiled] %dx%d, %d models: grid %d x %d, %u bytes of shared memory\n", width, height, nm, ts.gx, ts.gy,
             ts.smem_bytes);
     for (int l = 0; l < 3; ++l)
-      fprintf(stderr, "[cfb tiled]   level %d: %dx%d tile %dx%d (row %d, %d px) staged %d window %dx%d frame %u B window %u B\n", l,
-              ts.F[l].w, ts.F[l].h, ts.F[l].tw, ts.F[l].th, ts.F[l].rw, ts.F[l].npx, ts.F[l].staged, ts.F[l].ww, ts.F[l].wh,
-              ts.F[l].staged ? ts.F[l].frame_bytes : 0u, ts.F[l].staged ? ts.F[l].win_bytes : 0u);
+      fprintf(stderr, "[cfb tiled]   level %d: %dx%d tile %dx%d (pitches %d/%d/%d) staged %d window %dx%d (pitches %d/%d) frame %u B window %u B\n",
+              l, ts.F[l].w, ts.F[l].h, ts.F[l].tw, ts.F[l].th, ts.F[l].pf, ts.F[l].ps, ts.F[l].pb, ts.F[l].staged, ts.F[l].wwl,
+              ts.F[l].wh, ts.F[l].wpf, ts.F[l].wpb, ts.F[l].staged ? ts.F[l].frame_bytes : 0u, ts.F[l].staged ? ts.F[l].win_bytes : 0u);
   }
   return cudaSuccess;
 }
 
-size_t RGBDOdometry::tiledScratchBytes() {
-  return sizeof(unsigned long long) * kMaxRounds * kMaxM + sizeof(float4) * 2 * 256 * kMaxM * kChunks;
-}
+size_t RGBDOdometry::tiledScratchBytes() { return sizeof(unsigned) * kSyncWords + 256 + sizeof(float4) * 2 * 256 * kMaxM * kChunks; }
 
 bool RGBDOdometry::canBatch(int n) const { return n >= 1 && n <= kMaxM && mode_ == 0 && width < 2048 && height < 2048; }
 
-cudaError_t RGBDOdometry::enqueuePrepare(cudaStream_t s, void* acnt) {
+cudaError_t RGBDOdometry::enqueuePrepare(cudaStream_t s, void* sync_words) {
   PrepParams pp;
   int total = 0;
   for (int i = 0; i < NUM_PYRS; ++i) {
@@ -1409,7 +1537,7 @@ cudaError_t RGBDOdometry::enqueuePrepare(cudaStream_t s, void* acnt) {
                         (float)(pow(minimumGradientMagnitudes[i], 2.0) / pow(sobelScale, 2.0))};
     total += w * h;
   }
-  pp.acnt = (unsigned long long*)acnt;
+  pp.sync_words = (unsigned*)sync_words;
   rgb_prepare_tiled_kernel<<<(total + 255) / 256, 256, 0, s>>>(pp);
   return cudaGetLastError();
 }
@@ -1432,14 +1560,15 @@ cudaError_t RGBDOdometry::trackTiled(RGBDOdometry* const* od, int n, float (*tra
   TParams p;
   memset(&p, 0, sizeof(p));
   p.acnt = (unsigned long long*)scratch;
-  p.rows = (float4*)((char*)scratch + sizeof(unsigned long long) * kMaxRounds * kMaxM);
+  p.bcnt = (unsigned*)scratch + kMaxRounds * kMaxM * 2;
+  p.rows = (float4*)((char*)scratch + ((sizeof(unsigned) * kSyncWords + 255) & ~(size_t)255));
   for (int m = 0; m < n; ++m) {
     RGBDOdometry& o = *od[m];
     float* h_in = (float*)((char*)o.h_pinned + 1536);
     memcpy(h_in, trans[m], 3 * sizeof(float));
     memcpy(h_in + 3, rot[m], 9 * sizeof(float));
     RET_IF(cudaMemcpyAsync(o.d_pose_in, h_in, 12 * sizeof(float), cudaMemcpyHostToDevice, s));
-    RET_IF(o.enqueuePrepare(s, m == 0 ? (void*)p.acnt : nullptr));  // Sobel images + candidate gates of this model
+    RET_IF(o.enqueuePrepare(s, m == 0 ? scratch : nullptr));  // Sobel images + candidate gates of this model
     MParams& M = p.M[m];
     for (int i = 0; i < NUM_PYRS; ++i) {
       MLevel& L = M.L[i];

@@ -81,6 +81,13 @@ __device__ __forceinline__ float3 get_normal_central(const float* depth, const S
                           ((yb.z + vpos.z) / 2) - ((yf.z + vpos.z) / 2));
   return normalize3(cross3(dx, dy));
 }
+__device__ __forceinline__ Pose34 resolve_pose(const PoseRef& r) {
+  if (!r.dev) return r.v;
+  Pose34 p;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) p.m[i] = __ldg(&r.dev->m[i]);
+  return p;
+}
 __device__ __forceinline__ float3 xform_point(const Pose34& T, float3 p) {
   return make_float3(T.m[0] * p.x + T.m[1] * p.y + T.m[2] * p.z + T.m[3],
                      T.m[4] * p.x + T.m[5] * p.y + T.m[6] * p.z + T.m[7],
@@ -249,10 +256,11 @@ __global__ void set_count_kernel(MapCounters* c, unsigned capacity) {
 
 // ------------------------------------------------------------------------------- a13 index map
 __global__ void index_project_kernel(SurfelGeom g, const Surfel* __restrict__ surfels, unsigned n_ub,
-                                     const MapCounters* __restrict__ ctr, Pose34 t_inv, int time, float maxDepth,
+                                     const MapCounters* __restrict__ ctr, PoseRef t_inv_ref, int time, float maxDepth,
                                      int timeDelta, unsigned long long* __restrict__ keys) {
   const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= n_ub || id >= ctr->count) return;
+  const Pose34 t_inv = resolve_pose(t_inv_ref);
   const float4 pos = __ldg(&surfels[id].pos);
   const float lastTime = __ldg(&surfels[id].col.w);
   float3 ph = xform_point(t_inv, make_float3(pos.x, pos.y, pos.z));
@@ -268,10 +276,11 @@ __global__ void index_project_kernel(SurfelGeom g, const Surfel* __restrict__ su
   unsigned long long key = ((unsigned long long)depth_key24(zn * 0.5f + 0.5f) << 32) | id;
   atomicMin(&keys[py * g.W + px], key);
 }
-__global__ void index_resolve_kernel(SurfelGeom g, const Surfel* __restrict__ surfels, Pose34 t_inv,
+__global__ void index_resolve_kernel(SurfelGeom g, const Surfel* __restrict__ surfels, PoseRef t_inv_ref,
                                      const unsigned long long* __restrict__ keys, IndexMaps out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.W * g.H) return;
+  const Pose34 t_inv = resolve_pose(t_inv_ref);
   const unsigned long long k = keys[i];
   if (k == ~0ull) {
     out.index[i] = 0;
@@ -294,15 +303,17 @@ __global__ void index_resolve_kernel(SurfelGeom g, const Surfel* __restrict__ su
 // ------------------------------------------------------------------------------- a16 fuse
 // data.vert for the eligible pixels only ((x%2,y%2) == (t%2,t%2), data.vert:116); e = column-major
 // ordinal among eligible pixels (monotonic in the reference's draw order).
-__global__ void fuse_associate_kernel(SurfelGeom g, Pose34 pose, int time, const uint8_t* __restrict__ rgb,
+__global__ void fuse_associate_kernel(SurfelGeom g, PoseRef pose_ref, int time, const uint8_t* __restrict__ rgb,
                                       const uint8_t* __restrict__ mask, const float* __restrict__ depthRaw,
-                                      const float* __restrict__ depthFiltered, float maxDepth, float weighting,
+                                      const float* __restrict__ depthFiltered, float maxDepth, WeightRef weight_ref,
                                       unsigned maskID, IndexMaps idx, uint32_t* __restrict__ winner,
                                       Surfel* __restrict__ cand, uint32_t* __restrict__ candBest,
                                       uint8_t* __restrict__ flags, int par, int W2, int H2) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;  // eligible column index (fast: coalesced image reads)
   const int b = blockIdx.y * blockDim.y + threadIdx.y;  // eligible row index
   if (a >= W2 || b >= H2) return;
+  const Pose34 pose = resolve_pose(pose_ref);
+  const float weighting = weight_ref.dev ? __ldg(weight_ref.dev) * weight_ref.mult : weight_ref.v;
   const int i = 2 * a + par, j = 2 * b + par;
   const unsigned e = (unsigned)a * H2 + b;
   const int W = g.W, H = g.H;
@@ -424,7 +435,7 @@ __global__ void fill_u32_kernel(uint32_t* p, unsigned n_ub, const unsigned* n_de
 // copy_unstable.vert for item i (old surfels first, then candidates); the modified record is written
 // back in place and its survival flag recorded for the stable compaction.
 __global__ void clean_evaluate_kernel(SurfelGeom g, Surfel* __restrict__ src, Surfel* __restrict__ unstable,
-                                      unsigned n_ub, const MapCounters* __restrict__ ctr, Pose34 t_inv, int time,
+                                      unsigned n_ub, const MapCounters* __restrict__ ctr, PoseRef t_inv_ref, int time,
                                       float confThreshold, int timeDelta, const float* __restrict__ depthFiltered,
                                       const uint8_t* __restrict__ mask, unsigned maskID, float outlierCoeff,
                                       IndexMaps idx, uint8_t* __restrict__ flags) {
@@ -435,6 +446,7 @@ __global__ void clean_evaluate_kernel(SurfelGeom g, Surfel* __restrict__ src, Su
     flags[i] = 0;  // the scan runs over the host-side upper bound
     return;
   }
+  const Pose34 t_inv = resolve_pose(t_inv_ref);
   Surfel* rec = (i < count) ? (src + i) : (unstable + (i - count));
   Surfel s = load_surfel(rec);
   const int W = g.W, H = g.H;
@@ -624,11 +636,12 @@ __device__ __forceinline__ bool splat_fragment(const SurfelGeom& g, const SplatV
   return true;
 }
 __global__ void splat_raster_kernel(SurfelGeom g, const Surfel* __restrict__ surfels, unsigned n_ub,
-                                    const MapCounters* __restrict__ ctr, Pose34 t_inv, float maxDepth,
+                                    const MapCounters* __restrict__ ctr, PoseRef t_inv_ref, float maxDepth,
                                     float confThreshold, int time, int maxTime, int timeDelta,
                                     unsigned long long* __restrict__ keys) {
   const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= n_ub || id >= ctr->count) return;
+  const Pose34 t_inv = resolve_pose(t_inv_ref);
   SplatVtx v;
   const Surfel s = load_surfel(surfels + id);
   if (!splat_vertex(g, t_inv, s, maxDepth, confThreshold, time, maxTime, timeDelta, v)) return;
@@ -649,11 +662,12 @@ __global__ void splat_raster_kernel(SurfelGeom g, const Surfel* __restrict__ sur
       atomicMin(&keys[py * g.W + px], key);
     }
 }
-__global__ void splat_resolve_kernel(SurfelGeom g, const Surfel* __restrict__ surfels, Pose34 t_inv, float maxDepth,
+__global__ void splat_resolve_kernel(SurfelGeom g, const Surfel* __restrict__ surfels, PoseRef t_inv_ref, float maxDepth,
                                      float confThreshold, int time, int maxTime, int timeDelta,
                                      const unsigned long long* __restrict__ keys, SplatMaps out) {
   const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
   if (px >= g.W || py >= g.H) return;
+  const Pose34 t_inv = resolve_pose(t_inv_ref);
   const int i = py * g.W + px;
   const unsigned long long k = keys[i];
   if (k == ~0ull) {
@@ -767,7 +781,7 @@ cudaError_t launch_surfel_initialise(const SurfelGeom& g, const uint8_t* rgb, co
 }
 
 cudaError_t launch_predict_indices(const SurfelGeom& g, const Surfel* surfels, unsigned count_ub,
-                                   const MapCounters* ctr, const Pose34& t_inv, int time, float maxDepth,
+                                   const MapCounters* ctr, const PoseRef& t_inv, int time, float maxDepth,
                                    int timeDelta, unsigned long long* keys, IndexMaps out, cudaStream_t s) {
   const unsigned n = (unsigned)g.W * g.H;
   RET_IF(cudaMemsetAsync(keys, 0xFF, (size_t)n * 8, s));
@@ -779,8 +793,8 @@ cudaError_t launch_predict_indices(const SurfelGeom& g, const Surfel* surfels, u
 }
 
 cudaError_t launch_fuse(const SurfelGeom& g, Surfel* surfels, unsigned count_ub, MapCounters* ctr,
-                        const Pose34& pose, int time, const uint8_t* rgb, const uint8_t* mask, const float* depthRaw,
-                        const float* depthFiltered, float maxDepth, float weighting, unsigned maskID, IndexMaps idx,
+                        const PoseRef& pose, int time, const uint8_t* rgb, const uint8_t* mask, const float* depthRaw,
+                        const float* depthFiltered, float maxDepth, const WeightRef& weighting, unsigned maskID, IndexMaps idx,
                         uint32_t* winner, Surfel* cand, uint32_t* candBest, Surfel* unstable, ScanScratch sc,
                         cudaStream_t s) {
   const int par = ((time % 2) + 2) % 2;
@@ -797,7 +811,7 @@ cudaError_t launch_fuse(const SurfelGeom& g, Surfel* surfels, unsigned count_ub,
 }
 
 cudaError_t launch_clean(const SurfelGeom& g, Surfel* src, Surfel* unstable, Surfel* dst, unsigned count_ub,
-                         unsigned cand_ub, unsigned capacity, MapCounters* ctr, const Pose34& t_inv, int time,
+                         unsigned cand_ub, unsigned capacity, MapCounters* ctr, const PoseRef& t_inv, int time,
                          float confThreshold, int timeDelta, const float* depthFiltered, const uint8_t* mask,
                          unsigned maskID, float outlierCoeff, IndexMaps idx, ScanScratch sc, cudaStream_t s) {
   const unsigned n_ub = count_ub + cand_ub;
@@ -815,7 +829,7 @@ cudaError_t launch_clean(const SurfelGeom& g, Surfel* src, Surfel* unstable, Sur
 }
 
 cudaError_t launch_combined_predict(const SurfelGeom& g, const Surfel* surfels, unsigned count_ub, MapCounters* ctr,
-                                    const Pose34& t_inv, float maxDepth, float confThreshold, int time, int maxTime,
+                                    const PoseRef& t_inv, float maxDepth, float confThreshold, int time, int maxTime,
                                     int timeDelta, unsigned long long* keys, SplatMaps out, cudaStream_t s) {
   const unsigned n = (unsigned)g.W * g.H;
   RET_IF(cudaMemsetAsync(keys, 0xFF, (size_t)n * 8, s));

@@ -23,6 +23,31 @@ struct Pose34 {  // first 3 rows of a row-major 4x4
   float m[12];
 };
 
+// Per-model pose block kept on the device: written by the tracker kernel's epilogue (or uploaded by the
+// host after a pose override), read by every surfel-stage kernel -- no host round trip inside a frame.
+struct PoseDev {
+  Pose34 pose;       // model pose (camera -> model frame)
+  Pose34 inv;        // its inverse
+  Pose34 last;       // the pose before the last tracking step
+  float tr[12];      // pose in the tracker's layout: t[3], R[9] row-major
+  float weightBase;  // Model::computeFusionWeight with multiplier 1 (pose vs last)
+  float pad[3];
+};
+// A pose argument: by value (host-driven seams, tests) or read from a PoseDev at kernel run time.
+struct PoseRef {
+  Pose34 v;
+  const Pose34* dev;
+  PoseRef(const Pose34& p) : v(p), dev(nullptr) {}
+  explicit PoseRef(const Pose34* d) : v(), dev(d) {}
+};
+struct WeightRef {  // fusion weight by value, or weightBase of a PoseDev times a multiplier
+  float v;
+  const float* dev;
+  float mult;
+  WeightRef(float w) : v(w), dev(nullptr), mult(1.f) {}
+  WeightRef(const float* d, float m) : v(0.f), dev(d), mult(m) {}
+};
+
 // Device-side counters of a map (kept on the device so no stage needs a host round trip).
 struct MapCounters {
   unsigned count;          // live surfels in the current source buffer
@@ -59,22 +84,22 @@ cudaError_t launch_surfel_initialise(const SurfelGeom& g, const uint8_t* rgb, co
                                      MapCounters* counters, cudaStream_t s);
 // a13: ModelProjection::predictIndices
 cudaError_t launch_predict_indices(const SurfelGeom& g, const Surfel* surfels, unsigned count_ub,
-                                   const MapCounters* counters, const Pose34& t_inv, int time, float maxDepth,
+                                   const MapCounters* counters, const PoseRef& t_inv, int time, float maxDepth,
                                    int timeDelta, unsigned long long* keys, IndexMaps out, cudaStream_t s);
 // a16: Model::fuse (data association + update), in place on `surfels`
 cudaError_t launch_fuse(const SurfelGeom& g, Surfel* surfels, unsigned count_ub, MapCounters* counters,
-                        const Pose34& pose, int time, const uint8_t* rgb, const uint8_t* mask, const float* depthRaw,
-                        const float* depthFiltered, float maxDepth, float weighting, unsigned maskID, IndexMaps idx,
+                        const PoseRef& pose, int time, const uint8_t* rgb, const uint8_t* mask, const float* depthRaw,
+                        const float* depthFiltered, float maxDepth, const WeightRef& weighting, unsigned maskID, IndexMaps idx,
                         uint32_t* winner, Surfel* candStaging, uint32_t* candBest, Surfel* unstable, ScanScratch sc,
                         cudaStream_t s);
 // a17: Model::clean (stable compaction of old surfels then candidates into dst)
 cudaError_t launch_clean(const SurfelGeom& g, Surfel* src, Surfel* unstable, Surfel* dst, unsigned count_ub,
-                         unsigned cand_ub, unsigned capacity, MapCounters* counters, const Pose34& t_inv, int time,
+                         unsigned cand_ub, unsigned capacity, MapCounters* counters, const PoseRef& t_inv, int time,
                          float confThreshold, int timeDelta, const float* depthFiltered, const uint8_t* mask,
                          unsigned maskID, float outlierCoeff, IndexMaps idx, ScanScratch sc, cudaStream_t s);
 // a14: ModelProjection::combinedPredict
 cudaError_t launch_combined_predict(const SurfelGeom& g, const Surfel* surfels, unsigned count_ub,
-                                    MapCounters* counters, const Pose34& t_inv, float maxDepth, float confThreshold,
+                                    MapCounters* counters, const PoseRef& t_inv, float maxDepth, float confThreshold,
                                     int time, int maxTime, int timeDelta, unsigned long long* keys, SplatMaps out,
                                     cudaStream_t s);
 // a15: Model::performFillIn + CoFusion::requiresFillIn

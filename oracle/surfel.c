@@ -359,7 +359,7 @@ float orc_fusion_weight(const float pose[16], const float lastPose[16], float we
   double s = sqrt((rx * rx + ry * ry + rz * rz) * 0.25);
   double c = ((double)d[0] + d[5] + d[10] - 1) * 0.5;
   c = c > 1. ? 1. : c < -1. ? -1. : c;
-  double theta = acos(c);
+  double theta = orc_acos(c); /* deterministic realisation shared with the GPU side (detmath.h) */
   if (s < 1e-5) {
     if (c > 0)
       rx = ry = rz = 0;

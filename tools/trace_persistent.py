@@ -19,6 +19,6 @@ print("barrier0 %.1f us, so3 %.1f us, gn %.1f us" % ((t[1]-t[0])/1e3, (t[2]-t[1]
 for q in range(19):
     b = 8 + q * 8
     nxt = t[b + 8] if q < 18 else t[3]
-    print("it %2d: residual+arriveA %.2f  icp %.2f  waitA %.2f  rgbrows %.2f  publish+fold %.2f  solve %.2f  | total %.2f" % (
-        q, (t[b+1]-t[b])/1e3, (t[b+2]-t[b+1])/1e3, (t[b+3]-t[b+2])/1e3, (t[b+4]-t[b+3])/1e3, (t[b+6]-t[b+4])/1e3,
-        (t[b+7]-t[b+6])/1e3, (nxt-t[b])/1e3))
+    print("it %2d: residual+arriveA %.2f  icp %.2f  waitA %.2f  rgbrows %.2f  publish+wait %.2f  fold %.2f  solve %.2f  | total %.2f" % (
+        q, (t[b+1]-t[b])/1e3, (t[b+2]-t[b+1])/1e3, (t[b+3]-t[b+2])/1e3, (t[b+4]-t[b+3])/1e3, (t[b+5]-t[b+4])/1e3,
+        (t[b+6]-t[b+5])/1e3, (t[b+7]-t[b+6])/1e3, (nxt-t[b])/1e3))
