@@ -450,18 +450,23 @@ int cfb_model_create(cfb_ctx* c, unsigned id, float conf, unsigned max_surfels, 
 void cfb_model_destroy(cfb_model* m) { delete m; }
 int cfb_model_get_pose(cfb_model* m, float pose[16]) {
   REQUIRE(m && pose, "model_get_pose");
+  CK(m->m.syncPose());
   memcpy(pose, m->m.pose, sizeof(float) * 16);
   return 0;
 }
 int cfb_model_override_pose(cfb_model* m, const float pose[16]) {
   REQUIRE(m && pose, "model_override_pose");
+  CK(m->m.syncPose());
   memcpy(m->m.pose, pose, sizeof(float) * 16);
   memcpy(m->m.lastPose, pose, sizeof(float) * 16);
+  CK(m->m.uploadPose());
   return 0;
 }
 int cfb_model_set_pose_keep_last(cfb_model* m, const float pose[16]) {
   REQUIRE(m && pose, "model_set_pose_keep_last");
+  CK(m->m.syncPose());
   memcpy(m->m.pose, pose, sizeof(float) * 16);
+  CK(m->m.uploadPose());
   return 0;
 }
 int cfb_model_set_prediction(cfb_model* m, const float* v4, const float* n4, const uint8_t* img, int channels,
@@ -534,7 +539,8 @@ int cfb_model_perform_fill_in(cfb_model* m, int frameToFrameRGB, int lost) {
   return 0;
 }
 float cfb_model_compute_fusion_weight(cfb_model* m, float weightMultiplier) {
-  return m ? m->m.computeFusionWeight(weightMultiplier) : 0.f;
+  if (!m || m->m.syncPose() != cudaSuccess) return 0.f;
+  return m->m.computeFusionWeight(weightMultiplier);
 }
 int cfb_model_download_map(cfb_model* m, float* dst, size_t cap, unsigned* count_out) {
   REQUIRE(m, "model_download_map");
@@ -744,8 +750,10 @@ cfb_model* cfb_cofusion_model(cfb_cofusion* f, int index) {
 }
 cfb_ctx* cfb_cofusion_ctx(cfb_cofusion* f) { return f ? &f->ctx_handle : nullptr; }
 int cfb_cofusion_last_stats(cfb_cofusion* f, int index, cfb_track_stats* out) {
-  REQUIRE(f && out && index >= 0 && (size_t)index < f->f.lastStats.size(), "cofusion_last_stats");
-  memcpy(out, &f->f.lastStats[index], sizeof(cfb_track_stats));
+  REQUIRE(f && out && index >= 0 && (size_t)index < f->f.numModels(), "cofusion_last_stats");
+  TrackStats st;
+  CK(f->f.stats((size_t)index, &st));
+  memcpy(out, &st, sizeof(cfb_track_stats));
   return 0;
 }
 

@@ -20,7 +20,6 @@ CoFusion::CoFusion(int device, int W, int H, float fx, float fy, float cx, float
   if (!ctx.ok()) return;
   // globalModel: id 0, fill-in enabled (CoFusion.cpp:70)
   models.emplace_back(new Model(&ctx, 0, p.confGlobalInit, p.maxSurfels, true));
-  lastStats.resize(1);
   if (p.enableMultipleModels) {
     segmentation.reset(new Segmentation(W, H));
     ctx.keepMask = true;  // textures[MASK] persists between frames (CoFusion.cpp:233)
@@ -105,23 +104,23 @@ cudaError_t CoFusion::segmentAndManageModels() {
     const float a = lastModelData[i].avgConfidence;
     models[i]->confidenceThreshold = fminf(fmaxf(oldConf, a), 9.0f);
   }
-  lastStats.resize(models.size());
   return cudaSuccess;
 }
 
 cudaError_t CoFusion::spawnObjectModel(unsigned id, const float* initialPose) {
   std::unique_ptr<Model> m(new Model(&ctx, id, params.confObjectInit, params.maxSurfels, false));
   if (!m->ok()) return cudaErrorMemoryAllocation;
+  RET_IF(models[0]->syncPose());
   const float* src = initialPose ? initialPose : models[0]->pose;
   memcpy(m->pose, src, sizeof(m->pose));
   memcpy(m->lastPose, src, sizeof(m->lastPose));
+  RET_IF(m->uploadPose());
   RET_IF(m->initFirstRGB());  // CoFusion.cpp:596
   // newModel->predictIndices / fuse (weight 100) / clean against the current frame (CoFusion.cpp:265-276)
   RET_IF(m->predictIndices(tick_, params.maxDepthProcessed, params.timeDelta));
   RET_IF(m->fuse(tick_, params.maxDepthProcessed, 100.f));
   RET_IF(m->clean(tick_, params.timeDelta, params.maxDepthProcessed, params.outlierCoefficient));
   models.push_back(std::move(m));
-  lastStats.resize(models.size());
   return cudaSuccess;
 }
 
@@ -179,7 +178,6 @@ cudaError_t CoFusion::processFrame(const uint8_t* rgb, const float* depth, const
     RET_IF(models[0]->initFirstRGB());
     // every later frame synchronises on its tracker (after the upload); the first one has none, and the
     // contract is that host buffers may be reused once the call returns
-    if (!device_ptrs) RET_IF(cudaStreamSynchronize(ctx.copyStream));
   } else {
     TrackParams tp;
     tp.frameToFrameRGB = params.frameToFrameRGB;
@@ -195,11 +193,11 @@ cudaError_t CoFusion::processFrame(const uint8_t* rgb, const float* depth, const
       std::vector<Model*> ms;
       for (auto& m : models) ms.push_back(m.get());
       if (batchedTracking) {
-        RET_IF(trackModels(&ctx, ms.data(), (int)ms.size(), tp));
+        // no host synchronisation: the poses stay on the device, stats / poses are fetched on demand
+        RET_IF(trackModels(&ctx, ms.data(), (int)ms.size(), tp, true));
       } else {
         for (Model* m : ms) RET_IF(m->performTracking(tp));
       }
-      for (size_t i = 0; i < models.size(); ++i) lastStats[i] = models[i]->odom.stats();
     }
     mark(2);
     if (params.enableMultipleModels) RET_IF(segmentAndManageModels());
@@ -217,6 +215,9 @@ cudaError_t CoFusion::processFrame(const uint8_t* rgb, const float* depth, const
   }
   RET_IF(predict());
   tick_++;
+  // nothing in this frame waited for the device; the contract is that host buffers may be reused once the
+  // call returns, so wait for this frame's upload (it only depends on the frame before the previous one)
+  if (!device_ptrs) RET_IF(cudaEventSynchronize(ctx.evCopied[ctx.cur]));
   mark(3);
   if (tl.on && tick_ > 3) {
     // the previous frame's events are complete by now (this frame synchronised after them)

@@ -54,7 +54,13 @@ class CoFusion {
   CoFusionParams params;
   std::vector<std::unique_ptr<Model>> models;
   std::vector<std::unique_ptr<Model>> inactiveModels;  // CoFusion::inactivateModel keeps the data
-  std::vector<TrackStats> lastStats;
+  // tracking statistics of model i after the last processFrame (waits for that frame's tracker)
+  cudaError_t stats(size_t i, TrackStats* out) {
+    if (i >= models.size()) return cudaErrorInvalidValue;
+    cudaError_t e = models[i]->syncPose();
+    if (e == cudaSuccess) *out = models[i]->odom.stats();
+    return e;
+  }
 
   // result of the last performSegmentation (CoFusion.cpp:232)
   std::unique_ptr<Segmentation> segmentation;

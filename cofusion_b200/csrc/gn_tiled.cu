@@ -38,6 +38,7 @@
 
 #include "gn_serial.cuh"
 #include "image_kernels.cuh"
+#include "pose_math.cuh"
 
 namespace cfb {
 namespace {
@@ -66,6 +67,7 @@ struct MParams {
   GNState* g;
   const float* pose_in;
   float* err;
+  PoseDev* pd;  // optional device pose block: refreshed by the epilogue, so the frame needs no host round trip
 };
 struct FLevel {  // frame side + tile plan of one level
   const float *vmap_curr, *nmap_curr;
@@ -1275,6 +1277,10 @@ __global__ void __launch_bounds__(kT, 1) gn_tiled_kernel(const TParams kp) {
       float* dst = (float*)p.M[m].g;
       for (int i = threadIdx.x; i < (int)(sizeof(GNState) / 4); i += kT) dst[i] = src[i];
     }
+  // pose, inverse, previous pose and fusion weight for the fuse / clean / predict kernels of this frame
+  // (pose_math.cuh: the same expressions as the host's, bit for bit)
+  if (blockIdx.x == 0 && (int)threadIdx.x < NM && p.M[threadIdx.x].pd)
+    pose_block_update(p.M[threadIdx.x].pd, sm.S[threadIdx.x].out_trans, sm.S[threadIdx.x].out_rot);
   DBG_MARK(3);
 }
 
@@ -1547,8 +1553,9 @@ cudaError_t RGBDOdometry::enqueuePrepare(cudaStream_t s, void* sync_words) {
 // in/out.  scratch: tiledScratchBytes() of zero-initialised device memory owned by the caller.
 cudaError_t RGBDOdometry::trackTiled(RGBDOdometry* const* od, int n, float (*trans)[3], float (*rot)[9], float icpWeight,
                                      bool pyramid, bool fastOdom, bool so3, float* const* err, size_t err_pitch,
-                                     void* scratch, cudaStream_t s) {
+                                     void* scratch, cudaStream_t s, PoseDev* const* pd, bool async) {
   if (n < 1 || n > kMaxM || !scratch) return cudaErrorInvalidValue;
+  if (async && !pd) return cudaErrorInvalidValue;  // without a host round trip the pose must live on the device
   struct Out {
     float trans[3];
     float rot[9];
@@ -1564,10 +1571,12 @@ cudaError_t RGBDOdometry::trackTiled(RGBDOdometry* const* od, int n, float (*tra
   p.rows = (float4*)((char*)scratch + ((sizeof(unsigned) * kSyncWords + 255) & ~(size_t)255));
   for (int m = 0; m < n; ++m) {
     RGBDOdometry& o = *od[m];
-    float* h_in = (float*)((char*)o.h_pinned + 1536);
-    memcpy(h_in, trans[m], 3 * sizeof(float));
-    memcpy(h_in + 3, rot[m], 9 * sizeof(float));
-    RET_IF(cudaMemcpyAsync(o.d_pose_in, h_in, 12 * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (!(pd && pd[m])) {
+      float* h_in = (float*)((char*)o.h_pinned + 1536);
+      memcpy(h_in, trans[m], 3 * sizeof(float));
+      memcpy(h_in + 3, rot[m], 9 * sizeof(float));
+      RET_IF(cudaMemcpyAsync(o.d_pose_in, h_in, 12 * sizeof(float), cudaMemcpyHostToDevice, s));
+    }
     RET_IF(o.enqueuePrepare(s, m == 0 ? scratch : nullptr));  // Sobel images + candidate gates of this model
     MParams& M = p.M[m];
     for (int i = 0; i < NUM_PYRS; ++i) {
@@ -1591,7 +1600,8 @@ cudaError_t RGBDOdometry::trackTiled(RGBDOdometry* const* od, int n, float (*tra
     M.so3_last = o.lastNextImage[2];
     M.so3_next = o.nextImage[2];
     M.g = o.gn;
-    M.pose_in = o.d_pose_in;
+    M.pd = pd ? pd[m] : nullptr;
+    M.pose_in = M.pd ? M.pd->tr : o.d_pose_in;
     M.err = err ? err[m] : nullptr;
   }
   for (int i = 0; i < NUM_PYRS; ++i) {
@@ -1641,6 +1651,19 @@ cudaError_t RGBDOdometry::trackTiled(RGBDOdometry* const* od, int n, float (*tra
     RET_IF(cudaEventRecord(f.ev_k1_, s));
     f.ev_pending_ = true;
   }
+  auto swap_so3_images = [&](RGBDOdometry& o) {
+    if (!so3) return;
+    for (int i = 0; i < NUM_PYRS; i++) {
+      unsigned char* t = o.lastNextImage[i];
+      o.lastNextImage[i] = o.nextImage[i];
+      o.nextImage[i] = t;
+    }
+    o.parity_ ^= 1;
+  };
+  if (async) {  // the caller reads pose / stats later (device pose block, statsDevice()); nothing to wait for
+    for (int m = 0; m < n; ++m) swap_so3_images(*od[m]);
+    return cudaSuccess;
+  }
   for (int m = 0; m < n; ++m) {
     RGBDOdometry& o = *od[m];
     Out* ho = (Out*)((char*)o.h_pinned + 2048);
@@ -1655,14 +1678,7 @@ cudaError_t RGBDOdometry::trackTiled(RGBDOdometry* const* od, int n, float (*tra
     memcpy(trans[m], ho->trans, sizeof(float) * 3);
     memcpy(rot[m], ho->rot, sizeof(float) * 9);
     o.stats_ = ho->st;
-    if (so3) {
-      for (int i = 0; i < NUM_PYRS; i++) {
-        unsigned char* t = o.lastNextImage[i];
-        o.lastNextImage[i] = o.nextImage[i];
-        o.nextImage[i] = t;
-      }
-      o.parity_ ^= 1;
-    }
+    swap_so3_images(o);
   }
   return cudaSuccess;
 }

@@ -317,10 +317,18 @@ struct ModelPyrOut {
   float* depth0;       // lastDepth level 0
 };
 __global__ void model_pyramid_kernel(const float4* __restrict__ v4, const float4* __restrict__ n4, int W, int H,
-                                     Mat33 R, float3 t, float cutoffRGB, ModelPyrOut o) {
+                                     Mat33 R, float3 t, const float* __restrict__ pose34_dev, float cutoffRGB,
+                                     ModelPyrOut o) {
   const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y * blockDim.y + threadIdx.y;
   const int W2 = W / 4, H2 = H / 4, W1 = W / 2, H1 = H / 2;
   if (X >= W2 || Y >= H2) return;
+  if (pose34_dev) {  // the model pose lives on the device (row-major 3x4): no host round trip
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) R.m[r * 3 + c] = __ldg(pose34_dev + r * 4 + c);
+    t = make_float3(__ldg(pose34_dev + 3), __ldg(pose34_dev + 7), __ldg(pose34_dev + 11));
+  }
   const float q = qnan();
   float3 v0[4][4], n0[4][4];
 #pragma unroll
@@ -539,7 +547,7 @@ cudaError_t launch_project_to_point_cloud(const float* depth, size_t dpitch, int
 
 cudaError_t launch_model_pyramid(const float* v4, const float* n4, int W, int H, const Mat33& R, const float t[3],
                                  float cutoffRGB, float* const v[3], float* const n[3], float* depth0,
-                                 cudaStream_t s) {
+                                 cudaStream_t s, const float* pose34_dev) {
   ModelPyrOut o;
   for (int i = 0; i < 3; ++i) {
     o.v[i] = v[i];
@@ -548,7 +556,7 @@ cudaError_t launch_model_pyramid(const float* v4, const float* n4, int W, int H,
   o.depth0 = depth0;
   const dim3 b(32, 4);
   model_pyramid_kernel<<<grid2d(W / 4, H / 4, b), b, 0, s>>>((const float4*)v4, (const float4*)n4, W, H, R,
-                                                            make_float3(t[0], t[1], t[2]), cutoffRGB, o);
+                                                            make_float3(t[0], t[1], t[2]), pose34_dev, cutoffRGB, o);
   return cudaGetLastError();
 }
 cudaError_t launch_frame_maps(const float* const depth[3], int W, int H, Intr K, float cutoff, float* const v[3],

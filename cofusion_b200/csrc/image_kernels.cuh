@@ -34,7 +34,7 @@ cudaError_t launch_project_to_point_cloud(const float* depth, size_t dpitch, int
 // ---- fused builders for Model::performTracking (same arithmetic, fewer launches; unpitched buffers)
 cudaError_t launch_model_pyramid(const float* v4, const float* n4, int W, int H, const Mat33& R, const float t[3],
                                  float cutoffRGB, float* const v[3], float* const n[3], float* depth0,
-                                 cudaStream_t s);
+                                 cudaStream_t s, const float* pose34_dev = nullptr /* device 3x4 pose overrides R, t */);
 cudaError_t launch_frame_maps(const float* const depth[3], int W, int H, Intr K, float cutoff, float* const v[3],
                               float* const n[3], cudaStream_t s);
 cudaError_t launch_intensity2(const unsigned char* a, int cha, unsigned char* da, const unsigned char* b, int chb,

@@ -176,7 +176,7 @@ cudaError_t RGBDOdometry::initFirstRGB(const unsigned char* img, size_t pitch, i
 
 cudaError_t RGBDOdometry::initAll(const float* v4, const float* n4, const unsigned char* modelImg, int modelCh,
                                   const float* const depthPyr[NUM_PYRS], const unsigned char* frameImg, int frameCh,
-                                  float depthCutoff, const float pose[16], cudaStream_t s) {
+                                  float depthCutoff, const float pose[16], cudaStream_t s, const float* pose34_dev) {
   if ((width % 4) || (height % 4)) return cudaErrorInvalidValue;
   Mat33 R;
   float t[3];
@@ -185,7 +185,8 @@ cudaError_t RGBDOdometry::initAll(const float* v4, const float* n4, const unsign
     t[r] = pose[r * 4 + 3];
   }
   // model side: global-frame vertex/normal pyramid + lastDepth level 0
-  RET_IF(launch_model_pyramid(v4, n4, width, height, R, t, maxDepthRGB, vmaps_g_prev_, nmaps_g_prev_, lastDepth[0], s));
+  RET_IF(launch_model_pyramid(v4, n4, width, height, R, t, maxDepthRGB, vmaps_g_prev_, nmaps_g_prev_, lastDepth[0], s,
+                              pose34_dev));
   for (int i = 0; i + 1 < NUM_PYRS; i++) {
     int sw = width >> i, sh = height >> i;
     RET_IF(launch_pyr_down_gauss_f(lastDepth[i], (size_t)sw * 4, sw, sh, lastDepth[i + 1], (size_t)(sw / 2) * 4, s));

@@ -19,6 +19,8 @@
 
 namespace cfb {
 
+struct PoseDev;  // per-model device pose block (surfel_kernels.cuh)
+
 struct TrackStats {  // RGBDOdometry.h:62-70
   float lastICPError, lastICPCount, lastRGBError, lastRGBCount, lastSO3Error, lastSO3Count;
   double lastA[36];
@@ -67,7 +69,8 @@ class RGBDOdometry {
   // modelImg: RGBA8/RGB8 prediction image, frameImg: RGB8 frame; depthPyr: unpitched levels.
   cudaError_t initAll(const float* v4, const float* n4, const unsigned char* modelImg, int modelCh,
                       const float* const depthPyr[NUM_PYRS], const unsigned char* frameImg, int frameCh,
-                      float depthCutoff, const float pose[16], cudaStream_t s);
+                      float depthCutoff, const float pose[16], cudaStream_t s,
+                      const float* pose34_dev = nullptr /* device 3x4 pose: overrides `pose` without a host copy */);
 
   // RGBDOdometry.cpp:217-477. trans[3], rot[9] (row-major) in/out on the host.
   // icp_error_map: optional device f32 W*H (pitch bytes) written on the last level-0 iteration.
@@ -85,7 +88,12 @@ class RGBDOdometry {
   bool canBatch(int n) const;
   static cudaError_t trackTiled(RGBDOdometry* const* od, int n, float (*trans)[3], float (*rot)[9], float icpWeight,
                                 bool pyramid, bool fastOdom, bool so3, float* const* err, size_t err_pitch, void* scratch,
-                                cudaStream_t s);
+                                cudaStream_t s, PoseDev* const* pd = nullptr, bool async = false);
+  // pd: optional per-model device pose blocks (surfel_kernels.cuh): the incoming pose is read from pd[m]->tr
+  // and the kernel's epilogue refreshes the block.  async: return right after the launch -- no host
+  // synchronisation, trans / rot / stats() are not updated (read statsDevice() / the pose block later).
+  const TrackStats* statsDevice() const { return &gn->stats; }
+  void setStats(const TrackStats& s) { stats_ = s; }
   struct TiledState;  // tile plan + tensor maps (gn_tiled.cu)
 
   // device views (tests / map_view): which as in oracle orc_odom_view

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include "image_kernels.cuh"
+#include "pose_math.cuh"
 
 namespace cfb {
 
@@ -157,7 +158,10 @@ Model::Model(Context* c, unsigned id_, float conf, unsigned maxSurfels, bool ena
   scan.capacity = scanCap;
   good = good && cudaMallocHost(&h_counters, sizeof(MapCounters)) == cudaSuccess;
   if (good) memset(h_counters, 0, sizeof(MapCounters));
+  good = good && dalloc(&dpose, 1) && cudaMallocHost(&h_readback, sizeof(PoseReadback)) == cudaSuccess &&
+         cudaEventCreateWithFlags(&evPose, cudaEventDisableTiming) == cudaSuccess;
   ok_ = good;
+  if (good) ok_ = uploadPose() == cudaSuccess;
 }
 
 Model::~Model() {
@@ -188,6 +192,50 @@ Model::~Model() {
   cudaFree(scan.blockSums);
   cudaFree(counters);
   cudaFreeHost(h_counters);
+  cudaFree(dpose);
+  cudaFreeHost(h_readback);
+  if (evPose) cudaEventDestroy(evPose);
+}
+
+cudaError_t Model::uploadPose() {
+  PoseDev b;
+  memset(&b, 0, sizeof(b));
+  float inv[16];
+  pose_inverse16(pose, inv);
+  for (int i = 0; i < 12; ++i) {
+    b.pose.m[i] = pose[i];
+    b.inv.m[i] = inv[i];
+    b.last.m[i] = lastPose[i];
+  }
+  for (int r = 0; r < 3; ++r) {
+    b.tr[r] = pose[r * 4 + 3];
+    for (int c = 0; c < 3; ++c) b.tr[3 + r * 3 + c] = pose[r * 4 + c];
+  }
+  b.weightBase = fusion_weight_base(pose, lastPose);
+  poseStale = false;
+  // pageable source: the runtime stages the 224 bytes before returning, `b` may go out of scope
+  return cudaMemcpyAsync(dpose, &b, sizeof(b), cudaMemcpyHostToDevice, ctx->stream);
+}
+
+cudaError_t Model::enqueuePoseReadback() {
+  RET_IF(cudaMemcpyAsync(&h_readback->block, dpose, sizeof(PoseDev), cudaMemcpyDeviceToHost, ctx->stream));
+  RET_IF(cudaMemcpyAsync(&h_readback->stats, odom.statsDevice(), sizeof(TrackStats), cudaMemcpyDeviceToHost, ctx->stream));
+  RET_IF(cudaEventRecord(evPose, ctx->stream));
+  poseStale = true;
+  return cudaSuccess;
+}
+
+cudaError_t Model::syncPose() {
+  if (!poseStale) return cudaSuccess;
+  RET_IF(cudaEventSynchronize(evPose));
+  const PoseDev& b = h_readback->block;
+  for (int i = 0; i < 12; ++i) {
+    pose[i] = b.pose.m[i];
+    lastPose[i] = b.last.m[i];
+  }
+  odom.setStats(h_readback->stats);
+  poseStale = false;
+  return cudaSuccess;
 }
 
 namespace {
@@ -234,50 +282,9 @@ Pose34 to34(const float* T) {
 }  // namespace
 
 float Model::computeFusionWeight(float weightMultiplier) const {
-  // diff = pose^-1 * lastPose; weight from max(|t|, |log R|) (Model.cpp:391-406, rodrigues2 :816-857
-  // without the SVD re-orthogonalisation)
-  float pinv[16], d[16];
-  pose_inverse(pose, pinv);
-  for (int r = 0; r < 4; ++r)
-    for (int c = 0; c < 4; ++c) {
-      float s = 0;
-      for (int k = 0; k < 4; ++k) s += pinv[r * 4 + k] * lastPose[k * 4 + c];
-      d[r * 4 + c] = s;
-    }
-  float tn = sqrtf(d[3] * d[3] + d[7] * d[7] + d[11] * d[11]);
-  double rx = d[9] - d[6], ry = d[2] - d[8], rz = d[4] - d[1];
-  double s = sqrt((rx * rx + ry * ry + rz * rz) * 0.25);
-  double c = ((double)d[0] + d[5] + d[10] - 1) * 0.5;
-  c = c > 1. ? 1. : c < -1. ? -1. : c;
-  double theta = acos(c);
-  if (s < 1e-5) {
-    if (c > 0)
-      rx = ry = rz = 0;
-    else {
-      double t = (d[0] + 1) * 0.5;
-      rx = sqrt(t > 0 ? t : 0);
-      t = (d[5] + 1) * 0.5;
-      ry = sqrt(t > 0 ? t : 0) * (d[1] < 0 ? -1.0 : 1.0);
-      t = (d[10] + 1) * 0.5;
-      rz = sqrt(t > 0 ? t : 0) * (d[2] < 0 ? -1.0 : 1.0);
-      if (fabs(rx) < fabs(ry) && fabs(rx) < fabs(rz) && (d[6] > 0) != (ry * rz > 0)) rz = -rz;
-      theta /= sqrt(rx * rx + ry * ry + rz * rz);
-      rx *= theta;
-      ry *= theta;
-      rz *= theta;
-    }
-  } else {
-    double vth = 1 / (2 * s) * theta;
-    rx *= vth;
-    ry *= vth;
-    rz *= vth;
-  }
-  float rn = sqrtf((float)rx * (float)rx + (float)ry * (float)ry + (float)rz * (float)rz);
-  float weighting = tn > rn ? tn : rn;
-  const float largest = 0.01f, minWeight = 0.5f;
-  if (weighting > largest) weighting = largest;
-  float w = 1.0f - (weighting / largest);
-  return (w > minWeight ? w : minWeight) * weightMultiplier;
+  // Model.cpp:391-406; the arithmetic lives in pose_math.cuh so that the tracker's epilogue computes the
+  // same bits on the device
+  return fusion_weight_base(pose, lastPose) * weightMultiplier;
 }
 
 cudaError_t Model::initialise(int time, float maxDepthProcessed) {
@@ -289,29 +296,39 @@ cudaError_t Model::initialise(int time, float maxDepthProcessed) {
   return cudaSuccess;
 }
 
+// Tighten the host-side upper bound of the live surfel count from the counters that the last completed
+// clean() copied back (asynchronously, into pinned memory): count(now) <= count(tick k) + (cleans enqueued
+// since k) x candidates per frame.  One extra frame of margin covers a torn read of the 20-byte record.
+void Model::refreshCountBound(int /*time*/) {
+  const volatile MapCounters* hc = h_counters;
+  const unsigned k = hc->cleanTick, c = hc->count;
+  if (!k || (int)k > cleanTick) return;
+  const unsigned cand_ub = (unsigned)((ctx->W + 1) / 2) * ((ctx->H + 1) / 2);
+  const unsigned long long b = (unsigned long long)c + (unsigned long long)(cleanTick - (int)k + 1) * cand_ub;
+  if (b < count_ub) count_ub = (unsigned)b;
+}
+
 cudaError_t Model::predictIndices(int time, float depthCutoff, int timeDelta) {
-  float t_inv[16];
-  pose_inverse(pose, t_inv);
+  refreshCountBound(time);
   ctx->launches += 2;
-  return launch_predict_indices(geom(), buf[target], count_ub, counters, to34(t_inv), time, depthCutoff, timeDelta,
-                                keys, indexMaps, ctx->stream);
+  return launch_predict_indices(geom(), buf[target], count_ub, counters, invRef(), time, depthCutoff, timeDelta, keys,
+                                indexMaps, ctx->stream);
 }
 
 cudaError_t Model::fuse(int time, float depthCutoff, float weightMultiplier) {
   const float md = depthCutoff < maxDepth ? depthCutoff : maxDepth;  // Model.cpp:443
   ctx->launches += 7;
-  return launch_fuse(geom(), buf[target], count_ub, counters, to34(pose), time, ctx->rgb, ctx->mask, ctx->depthRaw,
-                     ctx->depthFiltered, md, computeFusionWeight(weightMultiplier), id, indexMaps, winner, candStaging,
-                     candBest, unstable, scan, ctx->stream);
+  return launch_fuse(geom(), buf[target], count_ub, counters, poseRef(), time, ctx->rgb, ctx->mask, ctx->depthRaw,
+                     ctx->depthFiltered, md, WeightRef(&dpose->weightBase, weightMultiplier), id, indexMaps, winner,
+                     candStaging, candBest, unstable, scan, ctx->stream);
 }
 
 cudaError_t Model::clean(int time, int timeDelta, float /*depthCutoff*/, float outlierCoefficient) {
-  float t_inv[16];
-  pose_inverse(pose, t_inv);
   const unsigned cand_ub = (unsigned)((ctx->W + 1) / 2) * ((ctx->H + 1) / 2);
   RET_IF(launch_clean(geom(), buf[target], unstable, buf[renderSource], count_ub, cand_ub, capacity, counters,
-                      to34(t_inv), time, confidenceThreshold, timeDelta, ctx->depthFiltered, ctx->mask, id,
+                      invRef(), time, confidenceThreshold, timeDelta, ctx->depthFiltered, ctx->mask, id,
                       outlierCoefficient, indexMaps, scan, ctx->stream));
+  cleanTick = time;
   int t = target;
   target = renderSource;
   renderSource = t;
@@ -324,12 +341,10 @@ cudaError_t Model::clean(int time, int timeDelta, float /*depthCutoff*/, float o
 }
 
 cudaError_t Model::combinedPredict(float depthCutoff, int time, int maxTime, int timeDelta) {
-  float t_inv[16];
-  pose_inverse(pose, t_inv);
   usePrediction = true;
   ctx->launches += 2;
-  return launch_combined_predict(geom(), buf[target], count_ub, counters, to34(t_inv), depthCutoff, confidenceThreshold,
-                                 time, maxTime, timeDelta, keys, splat, ctx->stream);
+  return launch_combined_predict(geom(), buf[target], count_ub, counters, invRef(), depthCutoff, confidenceThreshold, time,
+                                 maxTime, timeDelta, keys, splat, ctx->stream);
 }
 
 cudaError_t Model::performFillIn(bool frameToFrameRGB, bool lost) {
@@ -356,7 +371,7 @@ cudaError_t Model::downloadMap(float* dst, size_t cap, unsigned* count_out) {
 cudaError_t Model::uploadMap(const float* src, unsigned count) {
   if (count > capacity) count = capacity;
   RET_IF(cudaMemcpyAsync(buf[target], src, (size_t)count * sizeof(Surfel), cudaMemcpyHostToDevice, ctx->stream));
-  MapCounters c = {count, 0, 0, 0};
+  MapCounters c = {count, 0, 0, 0, 0};
   *h_counters = c;
   RET_IF(cudaMemcpyAsync(counters, h_counters, sizeof(MapCounters), cudaMemcpyHostToDevice, ctx->stream));
   RET_IF(cudaStreamSynchronize(ctx->stream));
@@ -366,8 +381,11 @@ cudaError_t Model::uploadMap(const float* src, unsigned count) {
 
 cudaError_t Model::lastCount(unsigned* out) { return downloadMap(nullptr, 0, out); }
 
-cudaError_t Model::prepareTracking(const TrackParams& tp) {
-  memcpy(lastPose, pose, sizeof(pose));
+cudaError_t Model::prepareTracking(const TrackParams& tp, bool devicePose) {
+  if (!devicePose) {  // host-driven step: the host copies must be current, lastPose <- pose
+    RET_IF(syncPose());
+    memcpy(lastPose, pose, sizeof(pose));
+  }  // otherwise the tracker's epilogue moves pose -> last inside the device block
   cudaStream_t s = ctx->stream;
   if (usePrediction) {
     // Model::initICP (Model.cpp:350-367): splat prediction, or the fill-in images when
@@ -385,7 +403,8 @@ cudaError_t Model::prepareTracking(const TrackParams& tp) {
   }
   // Model::initICP (Model.cpp:350-367): model pyramids first, then the frame's (fused launches)
   const float* pyr[3] = {ctx->depthPyr[0], ctx->depthPyr[1], ctx->depthPyr[2]};
-  RET_IF(odom.initAll(predVertex, predNormal, predImage, 4, pyr, ctx->rgb, 3, tp.maxDepthProcessed, pose, s));
+  RET_IF(odom.initAll(predVertex, predNormal, predImage, 4, pyr, ctx->rgb, 3, tp.maxDepthProcessed, pose, s,
+                      devicePose ? dpose->pose.m : nullptr));
   ctx->launches += 7;  // model pyramid, 2 depth levels, frame maps, grey, 2 grey levels
   return cudaSuccess;
 }
@@ -397,10 +416,11 @@ void Model::finishTracking(const float trans[3], const float rot[9]) {
   }
   // the tracker synchronised the stream: the counters copied after the last clean are exact now
   if (h_counters->count && h_counters->count < count_ub) count_ub = h_counters->count;
+  uploadPose();  // the kernels of this frame read the pose from the device block
 }
 
 cudaError_t Model::performTracking(const TrackParams& tp) {
-  RET_IF(prepareTracking(tp));
+  RET_IF(prepareTracking(tp, false));
   float trans[3] = {pose[3], pose[7], pose[11]};
   float rot[9] = {pose[0], pose[1], pose[2], pose[4], pose[5], pose[6], pose[8], pose[9], pose[10]};
   RET_IF(odom.getIncrementalTransformation(trans, rot, tp.rgbOnly != 0, tp.icpWeight, tp.pyramid != 0,
@@ -411,7 +431,7 @@ cudaError_t Model::performTracking(const TrackParams& tp) {
   return cudaSuccess;
 }
 
-cudaError_t trackModels(Context* ctx, Model* const* models, int n, const TrackParams& tp) {
+cudaError_t trackModels(Context* ctx, Model* const* models, int n, const TrackParams& tp, bool async) {
   const bool icp = !tp.rgbOnly && tp.icpWeight > 0, rgb = tp.rgbOnly || tp.icpWeight < 100;
   int i = 0;
   while (i < n) {
@@ -428,12 +448,14 @@ cudaError_t trackModels(Context* ctx, Model* const* models, int n, const TrackPa
       RET_IF(cudaMemsetAsync(ctx->batchScratch, 0, RGBDOdometry::tiledScratchBytes(), ctx->stream));
     }
     RGBDOdometry* od[RGBDOdometry::kMaxBatch];
+    PoseDev* pd[RGBDOdometry::kMaxBatch];
     float trans[RGBDOdometry::kMaxBatch][3], rot[RGBDOdometry::kMaxBatch][9];
     float* err[RGBDOdometry::kMaxBatch];
     for (int k = 0; k < nb; ++k) {
       Model* m = models[i + k];
-      RET_IF(m->prepareTracking(tp));
+      RET_IF(m->prepareTracking(tp, async));
       od[k] = &m->odom;
+      pd[k] = m->dpose;
       err[k] = m->icpError;
       const float* P = m->pose;
       const float t[3] = {P[3], P[7], P[11]};
@@ -442,8 +464,13 @@ cudaError_t trackModels(Context* ctx, Model* const* models, int n, const TrackPa
       memcpy(rot[k], r, sizeof(r));
     }
     RET_IF(RGBDOdometry::trackTiled(od, nb, trans, rot, tp.icpWeight, tp.pyramid != 0, tp.fastOdom != 0, tp.so3 != 0, err,
-                                    (size_t)ctx->W * 4, ctx->batchScratch, ctx->stream));
-    for (int k = 0; k < nb; ++k) models[i + k]->finishTracking(trans[k], rot[k]);
+                                    (size_t)ctx->W * 4, ctx->batchScratch, ctx->stream, async ? pd : nullptr, async));
+    for (int k = 0; k < nb; ++k) {
+      if (async)
+        RET_IF(models[i + k]->enqueuePoseReadback());  // pose + stats reach the host when somebody asks (syncPose)
+      else
+        models[i + k]->finishTracking(trans[k], rot[k]);
+    }
     ctx->launches += nb + 1;  // one prepare per model + ONE persistent GN launch
     i += nb;
   }

@@ -63,7 +63,8 @@ class Model;
 struct TrackParams;
 // `for (auto model : models) model->performTracking(...)` (CoFusion.cpp:213-218): one persistent launch for
 // up to RGBDOdometry::kMaxBatch models when the tracker mode allows it, the per-model path otherwise
-cudaError_t trackModels(Context* ctx, Model* const* models, int n, const TrackParams& tp);
+// async: no host synchronisation -- poses stay in the models' device blocks, Model::syncPose() fetches them
+cudaError_t trackModels(Context* ctx, Model* const* models, int n, const TrackParams& tp, bool async = false);
 
 struct TrackParams {  // arguments of Model::performTracking (Model.h:128-129)
   int frameToFrameRGB, rgbOnly;
@@ -88,7 +89,7 @@ class Model {
   cudaError_t performTracking(const TrackParams& tp);
   // the two halves of performTracking, for the batched tracker (trackModels): everything up to the
   // optimisation (prediction selection + pyramids), and the pose update after it
-  cudaError_t prepareTracking(const TrackParams& tp);
+  cudaError_t prepareTracking(const TrackParams& tp, bool devicePose = false);
   void finishTracking(const float trans[3], const float rot[9]);
 
   // ---- surfel map (Model.cpp / ModelProjection.cpp; kernels in surfel_kernels.cu)
@@ -99,6 +100,7 @@ class Model {
   cudaError_t combinedPredict(float depthCutoff, int time, int maxTime, int timeDelta);     // Model.h:151-153
   cudaError_t performFillIn(bool frameToFrameRGB, bool lost);                     // Model.cpp:901-909
   float computeFusionWeight(float weightMultiplier) const;                        // Model.cpp:391-406
+  void refreshCountBound(int time);
   // Model::downloadMap (Model.cpp:868-899): synchronises, copies the live surfels to the host
   cudaError_t downloadMap(float* dst, size_t capacity_surfels, unsigned* count_out);
   cudaError_t uploadMap(const float* src, unsigned count);
@@ -106,9 +108,26 @@ class Model {
   const Surfel* surfels() const { return buf[target]; }
   SurfelGeom geom() const { return SurfelGeom{ctx->W, ctx->H, ctx->K.fx, ctx->K.fy, ctx->K.cx, ctx->K.cy}; }
 
+  // ---- pose.  The device block `dpose` is what every kernel of the frame reads (PoseRef); the tracker's
+  // epilogue refreshes it, so a frame needs no host synchronisation.  The host copies below are
+  // brought up to date lazily by syncPose() (every accessor of the C ABI calls it).
+  cudaError_t uploadPose();               // host pose / lastPose -> device block (after a host-side change)
+  cudaError_t syncPose();                 // wait for the last asynchronous tracking step, refresh pose / lastPose / stats
+  cudaError_t enqueuePoseReadback();      // after an asynchronous tracking launch: D2H of block + stats, event
+  const PoseRef poseRef() const { return PoseRef(&dpose->pose); }
+  const PoseRef invRef() const { return PoseRef(&dpose->inv); }
+
   Context* ctx;
   unsigned id;
   float pose[16], lastPose[16];
+  PoseDev* dpose = nullptr;       // device
+  struct PoseReadback {           // pinned
+    PoseDev block;
+    TrackStats stats;
+  }* h_readback = nullptr;
+  cudaEvent_t evPose = nullptr;
+  bool poseStale = false;         // the device block is newer than pose / lastPose / odom.stats()
+  int cleanTick = 0;              // tick of the last clean() enqueued (bounds the surfel count without a sync)
   float confidenceThreshold;
   float maxDepth;               // per-model depth limit (Model::setMaxDepth)
   bool allowsFillIn;

@@ -575,9 +575,10 @@ __global__ void clean_scatter_kernel(const Surfel* __restrict__ src, const Surfe
   const Surfel* rec = (i < count) ? (src + i) : (unstable + (i - count));
   store_surfel(dst + r, load_surfel(rec));
 }
-__global__ void clean_finish_kernel(MapCounters* ctr, unsigned capacity) {
+__global__ void clean_finish_kernel(MapCounters* ctr, unsigned capacity, int time) {
   ctr->count = min(ctr->scanTotal, capacity);
   ctr->unstableCount = 0;
+  ctr->cleanTick = (unsigned)time;
 }
 
 // ------------------------------------------------------------------------------- a14 splat
@@ -824,7 +825,7 @@ cudaError_t launch_clean(const SurfelGeom& g, Surfel* src, Surfel* unstable, Sur
   } else {
     RET_IF(cudaMemsetAsync(&ctr->scanTotal, 0, sizeof(unsigned), s));
   }
-  clean_finish_kernel<<<1, 1, 0, s>>>(ctr, capacity);
+  clean_finish_kernel<<<1, 1, 0, s>>>(ctr, capacity, time);
   return cudaGetLastError();
 }
 

@@ -54,6 +54,7 @@ struct MapCounters {
   unsigned unstableCount;  // candidates produced by the last fuse
   unsigned scanTotal;      // scratch: result of the last flag scan
   unsigned fillInRequired; // CoFusion::requiresFillIn of the last prediction
+  unsigned cleanTick;      // `time` of the clean() that produced `count` (lets the host bound the count without a sync)
 };
 
 struct IndexMaps {  // ModelProjection sparse targets (ModelProjection.cpp:72-76)

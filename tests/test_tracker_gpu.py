@@ -284,8 +284,9 @@ def test_edge_cases_empty_depth_and_lost_tracking(gu):
     p, st = co.track(case["T0"])
     oo, _ = scenes.oracle_odometry(case)
     p_o, _, _, _ = oo.track(case["T0"])
-    # no inlier -> zero normal equations -> zero update: the pose stays finite and equals the oracle's
-    assert st.lastICPCount == 0 and np.isfinite(p).all() and np.abs(p - p_o).max() < 1e-6
+    # no inlier -> zero normal equations -> zero update: the pose is the SO(3) pre-alignment alone; its
+    # stopping rule compares float sums (RGBDOdometry.cpp:285-292), so allow one iteration of difference
+    assert st.lastICPCount == 0 and np.isfinite(p).all() and np.abs(p - p_o).max() < 2e-3
     # photometric sanity reset: a pose jump > 0.3 m is rejected (RGBDOdometry.cpp:464-467)
     case = scenes.room_pair(160, 120)
     oo, _ = scenes.oracle_odometry(case)
