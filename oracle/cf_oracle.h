@@ -186,6 +186,15 @@ typedef struct { /* SegmentationResult::ModelData (Segmentation.h:41-67) */
   unsigned short top, right, bottom, left;
 } OrcModelData;
 void orc_seg_default_params(OrcSegParams* p);
+/* second witness (lattice.c): 1 = evaluate the CRF kernel products on a permutohedral lattice like densecrf,
+ * 0 (default) = exactly.  Affects the following orc_segment_crf calls. */
+void orc_segment_set_kernel_mode(int mode);
+typedef struct OrcLattice OrcLattice;
+OrcLattice* orc_lattice_create(const float* feat, int d, int N);
+void orc_lattice_destroy(OrcLattice* L);
+void orc_lattice_compute(const OrcLattice* L, const float* in, int vs, float* out);
+void orc_lattice_norm(const OrcLattice* L, float* norm);
+void orc_lattice_apply(const OrcLattice* L, const float* norm, const float* Q, int Lbl, float* out);
 /* gSLICr restatement: labels[H*W] in [0, ceil(W/s)*ceil(H/s)) */
 void orc_slic(const uint8_t* rgb, int W, int H, int spixel_size, int no_iters, float coh_weight, int* labels);
 /* performSegmentationCRF.  icpError[m]: HxW f32 (Model::icpError), vertConf4[m]: HxW float4 splat

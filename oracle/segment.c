@@ -291,6 +291,11 @@ ORC_FMA_CLONES static void build_kernel(const float* feat, int D, int N, float* 
   }
 }
 
+/* kernel realisation of the next orc_segment_crf calls: 0 = exact products (the oracle of record),
+ * 1 = permutohedral lattice (lattice.c, the densecrf realisation -- second witness only) */
+static int g_crf_kernel_mode = 0;
+void orc_segment_set_kernel_mode(int mode) { g_crf_kernel_mode = mode; }
+
 /* ---------------------------------------------------------------- Segmentation::performSegmentationCRF */
 void orc_seg_default_params(OrcSegParams* p) {
   /* GUI defaults (GUI/Tools/GUI.h:212-227) which override the class defaults each frame
@@ -429,12 +434,21 @@ int orc_segment_crf(const uint8_t* rgb, const float* depth, int W, int H, int nu
       float fd = lowDepth[index] * prm->scaleFeaturesDepth;
       f6[index * 6 + 5] = fd < 100.0f ? fd : 100.0f;
     }
-  float* K2 = (float*)malloc(sizeof(float) * (size_t)N * N);
-  float* K6 = (float*)malloc(sizeof(float) * (size_t)N * N);
+  const int lattice = g_crf_kernel_mode == 1;
+  float* K2 = (float*)malloc(sizeof(float) * (lattice ? 1 : (size_t)N * N));
+  float* K6 = (float*)malloc(sizeof(float) * (lattice ? 1 : (size_t)N * N));
   float* n2 = (float*)malloc(sizeof(float) * N);
   float* n6 = (float*)malloc(sizeof(float) * N);
-  build_kernel(f2, 2, N, K2, n2);
-  build_kernel(f6, 6, N, K6, n6);
+  OrcLattice *L2 = NULL, *L6 = NULL;
+  if (lattice) {
+    L2 = orc_lattice_create(f2, 2, N);
+    L6 = orc_lattice_create(f6, 6, N);
+    orc_lattice_norm(L2, n2);
+    orc_lattice_norm(L6, n6);
+  } else {
+    build_kernel(f2, 2, N, K2, n2);
+    build_kernel(f6, 6, N, K6, n6);
+  }
 
   /* mean field (:455-471) */
   const int L = numLabels;
@@ -445,9 +459,15 @@ int orc_segment_crf(const uint8_t* rgb, const float* depth, int W, int H, int nu
   exp_and_normalize(Q, t1, L, N);
   for (int it = 0; it < prm->crfIterations; it++) {
     for (int i = 0; i < N * L; ++i) t1[i] = -unary[i];
-    kernel_apply(K2, n2, Q, N, L, t2); /* Potts: tmp2 = -w * filtered ; tmp1 -= tmp2 */
+    if (lattice)
+      orc_lattice_apply(L2, n2, Q, L, t2);
+    else
+      kernel_apply(K2, n2, Q, N, L, t2); /* Potts: tmp2 = -w * filtered ; tmp1 -= tmp2 */
     for (int i = 0; i < N * L; ++i) t1[i] -= -prm->weightSmoothness * t2[i];
-    kernel_apply(K6, n6, Q, N, L, t2);
+    if (lattice)
+      orc_lattice_apply(L6, n6, Q, L, t2);
+    else
+      kernel_apply(K6, n6, Q, N, L, t2);
     for (int i = 0; i < N * L; ++i) t1[i] -= -prm->weightAppearance * t2[i];
     exp_and_normalize(Q, t1, L, N);
   }
@@ -591,6 +611,8 @@ int orc_segment_crf(const uint8_t* rgb, const float* depth, int W, int H, int nu
   free(unary);
   free(f2);
   free(f6);
+  orc_lattice_destroy(L2);
+  orc_lattice_destroy(L6);
   free(K2);
   free(K6);
   free(n2);

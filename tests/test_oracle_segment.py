@@ -99,3 +99,38 @@ def test_depth_hole_quirk_path_is_finite():
     c = seg_cases.noise_case()
     seg, mds, has_new, lab, unary, low = orc.segment_crf(c["rgb"], c["depth"], [0], c["icp"], c["vc"], 1, True)
     assert np.isfinite(unary).all() and set(np.unique(seg)) <= {0, 1, 255}
+
+
+def test_lattice_witness_agrees_with_exact_kernels():
+    """Second witness for the dense CRF (row a19): the library the reference links (densecrf) evaluates the
+    kernel products on a permutohedral lattice, the oracle of record and the CUDA kernels evaluate them
+    exactly.  oracle/lattice.c restates the lattice; the two realisations must take the same decisions and
+    agree on (nearly) every label -- the measured figures are in profiles/crf_witness_r02.txt."""
+    import ctypes as C
+    o = orc.orc()
+    # the lattice reproduces the Gaussian it approximates up to a constant scale (removed by the symmetric normalisation)
+    o.orc_lattice_create.restype = C.c_void_p
+    o.orc_lattice_create.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    o.orc_lattice_destroy.argtypes = [C.c_void_p]
+    o.orc_lattice_compute.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    W, H = 20, 15
+    f = np.array([[i / 2.0, j / 2.0] for j in range(H) for i in range(W)], np.float32)
+    L = o.orc_lattice_create(f.ctypes.data, 2, W * H)
+    q = np.random.default_rng(0).random((W * H, 2)).astype(np.float32)
+    out = np.zeros_like(q)
+    o.orc_lattice_compute(L, q.ctypes.data, 2, out.ctypes.data)
+    o.orc_lattice_destroy(L)
+    K = np.exp(-0.5 * ((f[:, None, :] - f[None, :, :]) ** 2).sum(-1))
+    ex = K @ q
+    scale = (out * ex).sum() / (ex * ex).sum()
+    assert 0.7 < scale < 1.1 and np.linalg.norm(out - scale * ex) / np.linalg.norm(scale * ex) < 0.08
+    for case, allow_new in ((seg_cases.room_case(320, 240), True), (seg_cases.noise_case(320, 240), True)):
+        res = {}
+        for mode in (0, 1):
+            o.orc_segment_set_kernel_mode(mode)
+            res[mode] = orc.segment_crf(case["rgb"], case["depth"], case["model_ids"], case["icp"], case["vc"],
+                                        case["next_id"], allow_new)
+        o.orc_segment_set_kernel_mode(0)
+        (seg_e, md_e, new_e, _, _, low_e), (seg_l, md_l, new_l, _, _, low_l) = res[0], res[1]
+        assert new_e == new_l and len(md_e) == len(md_l)
+        assert (low_e == low_l).mean() >= 0.98 and (seg_e == seg_l).mean() >= 0.98
