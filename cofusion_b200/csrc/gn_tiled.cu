@@ -23,12 +23,13 @@
 // One Gauss-Newton iteration
 //     photometric correspondences -> red.add.u64 {arrived, count, sum floor(diff^2)} (barrier A, no fence:
 //     the payload IS the atomic) -> ICP rows (hides A) -> RGB rows weighted with the global count ->
-//     every CTA publishes its 58 partial sums as 20 x 16-byte packets {3 sums, tag} and bumps an arrival
-//     counter WITHOUT a fence -> one thread per CTA waits for the counter (a hint), then everybody reads
-//     the packets of all CTAs: the tag inside each packet says whether its data has landed (the rare
-//     packet that is late is simply read again) -> fixed-order fold -> FP64 Gauss-Newton step on the CTA's
-//     own copy of the state, spread over the lanes of a warp (warp m solves model m).
-// Sums are folded in a fixed order (thread -> warp -> CTA -> grid): bit-reproducible run to run.
+//     every CTA adds its 58 partial sums to 58 global accumulators with integer atomics: each f32 partial is
+//     split exactly into two fixed-point words (value = hi * 2^8 + lo * 2^-39) whose low byte counts the
+//     contributions, so the sum is order independent (integers commute: bit-reproducible run to run), needs
+//     no fence (a word that does not show all G contributions yet is simply read again) and no per-CTA rows
+//     have to be re-read by everybody -> every CTA reads the 116 words once -> FP64 Gauss-Newton step on the
+//     CTA's own copy of the state, spread over the lanes of a warp (warp m solves model m).
+// Within a CTA sums are folded in a fixed order (thread -> warp -> CTA); across CTAs they are exact.
 // Per-pixel arithmetic: SURVEY.md Appendix A1-A5 (tracker_device.cuh holds the stand-alone form).
 #include <cuda.h>  // CUtensorMap + enums only; the encoder is fetched through cudaGetDriverEntryPoint
 
@@ -48,10 +49,10 @@ constexpr int kT = 576;               // threads per CTA, one CTA per SM
 constexpr int kNW = kT / 32;          // 18 warps
 constexpr int kPP = 4;                // pixels per thread of a shared-memory tile
 constexpr int kMaxM = RGBDOdometry::kMaxBatch;
-constexpr int kChunks = 20;           // 16-byte packets per (CTA, model, GN iteration): 58 sums
-constexpr int kGroups = kT / kChunks; // 28 thread groups share the rows of the fold
-constexpr int kSo3Chunks = 4;         // 11 sums
-constexpr int kSo3Groups = 36;
+constexpr int kSums = 58;             // 29 ICP + 29 RGB sums of a Gauss-Newton iteration (11 for an SO(3) iteration)
+constexpr int kXWords = 2 * kSums;    // two fixed-point words per sum
+constexpr int kXStride = 32;          // u64 per accumulator slot: every word sits in its own 256-byte block, so the
+                                      // 16,000 atomics of a round spread over the L2 slices instead of queueing on 8 lines
 constexpr unsigned kNoCorr = 0xffffffffu;
 constexpr int kMaxRounds = 32;        // 10 SO(3) + 19 GN reduction rounds
 constexpr int kMaxHalo = 4;           // model window = tile + halo pixels on every side (less when shared memory is short)
@@ -91,15 +92,13 @@ struct TParams {
   MParams M[kMaxM];
   FLevel F[3];
   int nmodels, gx, gy;
-  float4* rows;              // [2][G][nmodels][kChunks] packets
   unsigned long long* acnt;  // [kMaxRounds][kMaxM] barrier-A words, zero before the launch
-  unsigned* bcnt;            // [kMaxRounds] arrivals of the packet exchange (a hint: the tags decide), zero before the launch
-  unsigned epoch;            // launch counter: tags never repeat, the packet buffer is never cleared
+  unsigned long long* xacc;  // [kMaxRounds][nmodels][kXWords] fixed-point accumulators, zero before the launch
   size_t err_pitch;
   float distThres, angleThres, maxDepthDelta, sobelScale, icpWeight;
   int use_so3;
   int iters[3];
-  unsigned o_wrow, o_part, o_out, o_corr;
+  unsigned o_wrow, o_out, o_corr;
   unsigned long long* dbg;
 };
 static_assert(sizeof(TParams) <= 4000, "kernel parameter block");
@@ -193,31 +192,14 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
       "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
       : "memory");
 }
-__device__ __forceinline__ float4 ld_packet(const float4* q) {  // one 16-byte access, never cached in L1
-  float4 v;
-  asm volatile("ld.relaxed.gpu.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(q) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_packet(float4* q, float4 v) {
-  asm volatile("st.relaxed.gpu.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
 __device__ __forceinline__ unsigned long long ld_u64_relaxed(const unsigned long long* q) {
   unsigned long long v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(q) : "memory");
   return v;
 }
-__device__ __forceinline__ unsigned ld_u32_relaxed(const unsigned* q) {
-  unsigned v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(q) : "memory");
-  return v;
-}
 __device__ __forceinline__ void red_add_u64(unsigned long long* q, unsigned long long v) {
   asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(q), "l"(v) : "memory");
 }
-__device__ __forceinline__ void red_add_u32(unsigned* q, unsigned v) {
-  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(q), "r"(v) : "memory");
-}
-
 __device__ __forceinline__ int floor_to(int x, int a) {  // largest multiple of a (power of two) <= x
   return x & ~(a - 1);
 }
@@ -298,6 +280,35 @@ __device__ __forceinline__ void pix_next(const LvCtx& c, PixIt& it) {
   }
 }
 
+// ------------------------------------------------------------------------------------------ arithmetic
+// Every operation that feeds a decision or a sum is written with an explicit rounding (no implicit FMA
+// contraction): the three instantiations of each phase (shared-memory tiles / global memory, camera model /
+// object model) then perform the same operation sequence, so a model tracked alone and the same model
+// tracked inside a batch produce the same bits.
+__device__ __forceinline__ float3 xsub(float3 a, float3 b) { return make_float3(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z)); }
+__device__ __forceinline__ float3 xadd(float3 a, float3 b) { return make_float3(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z)); }
+__device__ __forceinline__ float xdot(float3 a, float3 b) { return __fmaf_rn(a.z, b.z, __fmaf_rn(a.y, b.y, __fmul_rn(a.x, b.x))); }
+__device__ __forceinline__ float xnorm(float3 a) { return __fsqrt_rn(xdot(a, a)); }
+__device__ __forceinline__ float3 xcross(float3 a, float3 b) {
+  return make_float3(__fmaf_rn(a.y, b.z, -__fmul_rn(a.z, b.y)), __fmaf_rn(a.z, b.x, -__fmul_rn(a.x, b.z)),
+                     __fmaf_rn(a.x, b.y, -__fmul_rn(a.y, b.x)));
+}
+__device__ __forceinline__ float3 xmul(const Mat33& m, float3 a) {
+  return make_float3(__fmaf_rn(m.m[2], a.z, __fmaf_rn(m.m[1], a.y, __fmul_rn(m.m[0], a.x))),
+                     __fmaf_rn(m.m[5], a.z, __fmaf_rn(m.m[4], a.y, __fmul_rn(m.m[3], a.x))),
+                     __fmaf_rn(m.m[8], a.z, __fmaf_rn(m.m[7], a.y, __fmul_rn(m.m[6], a.x))));
+}
+// 27 upper-triangular products + row6^2 + inlier (JtJJtrSE3 order, types.cuh:101-112)
+__device__ __forceinline__ void xaccumulate_se3(float (&acc)[32], const float (&row)[7]) {
+  int k = 0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = i; j < 7; ++j, ++k) acc[k] = __fmaf_rn(row[i], row[j], acc[k]);
+  acc[27] = __fmaf_rn(row[6], row[6], acc[27]);
+  acc[28] = __fadd_rn(acc[28], 1.f);
+}
+
 // ------------------------------------------------------------------------------------------ phase 1
 // RGBResidual::getProducts for a candidate pixel (reduce.cu:827-853).  FS: frame tiles in shared
 // memory, MS: this model's window in shared memory.  Returns validity, fills u0 / v0 / diff / d0.
@@ -317,9 +328,10 @@ __device__ __forceinline__ bool residual_pixel(const LvCtx& c, const MLevel& L, 
   }
   if (!cand) return false;
   const float* kk = Wp.krkinv.m;
-  const float td1 = d1 * (kk[6] * x + kk[7] * y + kk[8]) + Wp.kt[2];
-  u0 = __float2int_rn((d1 * (kk[0] * x + kk[1] * y + kk[2]) + Wp.kt[0]) / td1);
-  v0 = __float2int_rn((d1 * (kk[3] * x + kk[4] * y + kk[5]) + Wp.kt[1]) / td1);
+  const float fx_ = (float)x, fy_ = (float)y;
+  const float td1 = __fmaf_rn(d1, __fadd_rn(__fmaf_rn(kk[7], fy_, __fmul_rn(kk[6], fx_)), kk[8]), Wp.kt[2]);
+  u0 = __float2int_rn(__fdiv_rn(__fmaf_rn(d1, __fadd_rn(__fmaf_rn(kk[1], fy_, __fmul_rn(kk[0], fx_)), kk[2]), Wp.kt[0]), td1));
+  v0 = __float2int_rn(__fdiv_rn(__fmaf_rn(d1, __fadd_rn(__fmaf_rn(kk[4], fy_, __fmul_rn(kk[3], fx_)), kk[5]), Wp.kt[1]), td1));
   if (!(u0 >= 0 && v0 >= 0 && u0 < c.W && v0 < c.H)) return false;
   unsigned char li;
   const int wu = u0 - c.wx0, wv = v0 - c.wy0;
@@ -330,9 +342,9 @@ __device__ __forceinline__ bool residual_pixel(const LvCtx& c, const MLevel& L, 
     d0 = __ldg(L.lastDepth + v0 * c.W + u0);
     li = __ldg(L.lastImage + v0 * c.W + u0);
   }
-  if (!(d0 > 0 && fabsf(td1 - d0) <= maxDepthDelta && li != 0)) return false;
+  if (!(d0 > 0 && fabsf(__fsub_rn(td1, d0)) <= maxDepthDelta && li != 0)) return false;
   const unsigned char ni = FS ? SM_U8(c.oIMG)[ly * c.pb + lx + c.shb] : __ldg(nextImage + y * c.W + x);
-  diff = (float)ni - (float)li;
+  diff = __fsub_rn((float)ni, (float)li);
   return true;
 }
 
@@ -353,7 +365,7 @@ __device__ __noinline__ void phase1(int lvl, int m) {
     if (x < c.W && y < c.H &&
         residual_pixel<FS, MS>(c, L, Wp, p.maxDepthDelta, it.lx, it.ly, x, y, nextImage, u0, v0, diff, d0)) {
       cnt += 1;
-      sig += (int)(diff * diff);  // float -> int truncation, reduce.cu:851
+      sig += (int)__fmul_rn(diff, diff);  // float -> int truncation, reduce.cu:851
       if (MS) {
         zero = pack_corr(u0, v0, diff);
         SM_F32(c.oCorrD)[k * kT + threadIdx.x] = d0;
@@ -382,11 +394,11 @@ __device__ __forceinline__ void store_warp_row(int m, int set, bool any, float (
 
 __device__ __forceinline__ void icp_found_row(const IcpPose& P, float3 tprev, float3 vcurr_cp, float3 vp, float3 np,
                                               float (&acc)[32]) {
-  const float3 d_cp = mul(P.Rprev_inv, vp - tprev);
-  const float3 n_cp = mul(P.Rprev_inv, np);
-  const float3 cr = cross(vcurr_cp, n_cp);
-  const float row[7] = {n_cp.x, n_cp.y, n_cp.z, cr.x, cr.y, cr.z, dot(n_cp, vcurr_cp - d_cp)};
-  accumulate_se3(acc, row, true);
+  const float3 d_cp = xmul(P.Rprev_inv, xsub(vp, tprev));
+  const float3 n_cp = xmul(P.Rprev_inv, np);
+  const float3 cr = xcross(vcurr_cp, n_cp);
+  const float row[7] = {n_cp.x, n_cp.y, n_cp.z, cr.x, cr.y, cr.z, xdot(n_cp, xsub(vcurr_cp, d_cp))};
+  xaccumulate_se3(acc, row);
 }
 
 template <bool FS, bool MS>
@@ -419,10 +431,10 @@ __device__ __noinline__ void phase2(int lvl, int m, float* error_map) {
     }
     vcurr.y = FS ? SM_F32(c.oV)[c.fplane + fi] : __ldg(F.vmap_curr + HW + gi);
     vcurr.z = FS ? SM_F32(c.oV)[2 * c.fplane + fi] : __ldg(F.vmap_curr + 2 * HW + gi);
-    const float3 vcurr_g = mul(P.Rcurr, vcurr) + tcurr;
-    const float3 vcurr_cp = mul(P.Rprev_inv, vcurr_g - tprev);
-    const int ux = __float2int_rn(vcurr_cp.x * c.fx / vcurr_cp.z + c.cx);
-    const int uy = __float2int_rn(vcurr_cp.y * c.fy / vcurr_cp.z + c.cy);
+    const float3 vcurr_g = xadd(xmul(P.Rcurr, vcurr), tcurr);
+    const float3 vcurr_cp = xmul(P.Rprev_inv, xsub(vcurr_g, tprev));
+    const int ux = __float2int_rn(__fadd_rn(__fdiv_rn(__fmul_rn(vcurr_cp.x, c.fx), vcurr_cp.z), c.cx));
+    const int uy = __float2int_rn(__fadd_rn(__fdiv_rn(__fmul_rn(vcurr_cp.y, c.fy), vcurr_cp.z), c.cy));
     if (ux < 0 || uy < 0 || ux >= c.W || uy >= c.H || vcurr_cp.z < 0) {
       if (err) *err = 0.0f;
       continue;
@@ -451,9 +463,9 @@ __device__ __noinline__ void phase2(int lvl, int m, float* error_map) {
       ncurr = make_float3(SM_F32(c.oN)[fi], SM_F32(c.oN)[c.fplane + fi], SM_F32(c.oN)[2 * c.fplane + fi]);
     else
       ncurr = make_float3(__ldg(F.nmap_curr + gi), __ldg(F.nmap_curr + HW + gi), __ldg(F.nmap_curr + 2 * HW + gi));
-    const float3 ncurr_g = mul(P.Rcurr, ncurr);
-    const float dist = norm(vp - vcurr_g);
-    const float sine = norm(cross(ncurr_g, np));
+    const float3 ncurr_g = xmul(P.Rcurr, ncurr);
+    const float dist = xnorm(xsub(vp, vcurr_g));
+    const float sine = xnorm(xcross(ncurr_g, np));
     if (err) *err = isfinite(dist) ? dist : 0.0f;
     if (sine < p.angleThres && dist <= p.distThres && !isnan(ncurr.x) && !isnan(np.x)) {
       any = true;
@@ -466,19 +478,26 @@ __device__ __noinline__ void phase2(int lvl, int m, float* error_map) {
 // ------------------------------------------------------------------------------------------ phase 3
 __device__ __forceinline__ void rgb_row(const LvCtx& c, float sigma, float sobelScale, int zx, int zy, float z, float diff,
                                         short sdx, short sdy, float (&acc)[32]) {
-  float w = sigma + fabsf(diff);
-  w = w > 1.19209290E-07F ? 1.0f / w : 1.0f;
+  float w = __fadd_rn(sigma, fabsf(diff));
+  w = w > 1.19209290E-07F ? __fdiv_rn(1.0f, w) : 1.0f;
   if (sigma == -1.f) w = 1.f;
-  const float invFx = 1.0f / c.fx, invFy = 1.0f / c.fy;
-  const float3 Pt = make_float3(((float)zx - c.cx) * z * invFx, ((float)zy - c.cy) * z * invFy, z);
+  const float invFx = __fdiv_rn(1.0f, c.fx), invFy = __fdiv_rn(1.0f, c.fy);
+  const float3 Pt = make_float3(__fmul_rn(__fmul_rn(__fsub_rn((float)zx, c.cx), z), invFx),
+                                __fmul_rn(__fmul_rn(__fsub_rn((float)zy, c.cy), z), invFy), z);
   const float invz = (float)(1.0 / (double)Pt.z);
-  const float dI_dx_val = w * sobelScale * (float)sdx;
-  const float dI_dy_val = w * sobelScale * (float)sdy;
-  const float v0 = dI_dx_val * c.fx * invz;
-  const float v1 = dI_dy_val * c.fy * invz;
-  const float v2 = -(v0 * Pt.x + v1 * Pt.y) * invz;
-  const float row[7] = {v0, v1, v2, -Pt.z * v1 + Pt.y * v2, Pt.z * v0 - Pt.x * v2, -Pt.y * v0 + Pt.x * v1, -w * diff};
-  accumulate_se3(acc, row, true);
+  const float dI_dx_val = __fmul_rn(__fmul_rn(w, sobelScale), (float)sdx);
+  const float dI_dy_val = __fmul_rn(__fmul_rn(w, sobelScale), (float)sdy);
+  const float v0 = __fmul_rn(__fmul_rn(dI_dx_val, c.fx), invz);
+  const float v1 = __fmul_rn(__fmul_rn(dI_dy_val, c.fy), invz);
+  const float v2 = __fmul_rn(-__fmaf_rn(v1, Pt.y, __fmul_rn(v0, Pt.x)), invz);
+  const float row[7] = {v0,
+                        v1,
+                        v2,
+                        __fmaf_rn(Pt.y, v2, -__fmul_rn(Pt.z, v1)),
+                        __fmaf_rn(Pt.z, v0, -__fmul_rn(Pt.x, v2)),
+                        __fmaf_rn(Pt.x, v1, -__fmul_rn(Pt.y, v0)),
+                        -__fmul_rn(w, diff)};
+  xaccumulate_se3(acc, row);
 }
 
 template <bool FS, bool MS>
@@ -516,90 +535,53 @@ __device__ __noinline__ void phase3(int lvl, int m, float sigma) {
   store_warp_row(m, 1, any, acc);
 }
 
-// ------------------------------------------------------------------------- publish / fold / barrier A
-// warp rows -> this CTA's packets of model m: packet c holds sums 3c..3c+2 of [set 0 (29), set 1 (29)]
-template <int NCH>
-__device__ __forceinline__ void publish_rows(int m, int par, unsigned tag) {
+// ------------------------------------------------------------------------- exact grid-wide sums
+// Thread t < nm * NS adds sum (m = t / NS, j = t % NS) of this CTA -- its 18 warp rows folded in warp order --
+// to the global accumulators of the round.  The f32 partial is split exactly: d = hi * 2^8 + rem, |rem| < 2^8,
+// lo = rint(rem * 2^39) (|error| <= 2^-40); both integers go up by 8 bits and carry a 1 in the low byte, so a
+// word also counts its contributions.  Integer addition commutes: the grid total does not depend on the
+// order in which the CTAs arrive.
+template <int NS>
+__device__ __forceinline__ void publish_sums(unsigned round) {
   TSMEM();
-  const float* wrow = SM_F32(p.o_wrow) + (size_t)m * 2 * kNW * 32;
-  const int c = threadIdx.x - m * NCH;  // caller guarantees 0 <= c < NCH
-  float v[3];
+  const int t = threadIdx.x, m = t / NS, j = t - m * NS;
+  const int set = j >= 29 ? 1 : 0, idx = j - 29 * set;
+  const float* r = SM_F32(p.o_wrow) + ((size_t)(m * 2 + set) * kNW) * 32 + idx;
+  float s = 0.f;
 #pragma unroll
-  for (int e = 0; e < 3; ++e) {
-    const int j = 3 * c + e;
-    float s = 0.f;
-    if (NCH == kSo3Chunks ? (j < 11) : (j < 58)) {
-      const int set = (NCH == kSo3Chunks) ? 0 : (j >= 29 ? 1 : 0), idx = j - 29 * set;
-      const float* r = wrow + set * kNW * 32 + idx;
-#pragma unroll
-      for (int w = 0; w < kNW; ++w) s += r[w * 32];  // warp order
-    }
-    v[e] = s;
-  }
-  float4* dst = p.rows + ((size_t)(par * gridDim.x + blockIdx.x) * p.nmodels + m) * kChunks + c;
-  st_packet(dst, make_float4(v[0], v[1], v[2], __uint_as_float(tag)));
+  for (int w = 0; w < kNW; ++w) s += r[w * 32];  // warp order
+  double d = (double)s;
+  if (!(fabs(d) < 9.0e15)) d = 0.0;  // non-finite (or absurd) partial: contributes nothing but still counts
+  const long long hi = (long long)(d * (1.0 / 256.0));
+  const long long lo = __double2ll_rn((d - (double)hi * 256.0) * 549755813888.0 /* 2^39 */);
+  unsigned long long* x = p.xacc + (((size_t)round * p.nmodels + m) * kXWords + 2 * j) * kXStride;
+  red_add_u64(x, ((unsigned long long)hi << 8) + 1ull);
+  red_add_u64(x + kXStride, ((unsigned long long)lo << 8) + 1ull);
 }
 
-// read the packets of every CTA for model m (a packet whose tag is not `tag` yet has not landed: read it
-// again), fold them in a fixed order into out[m][0..3*NCH)
-template <int NCH, int NGRP>
-__device__ __forceinline__ void fold_rows(int m, int par, unsigned tag) {
+// one thread waits until word 0 of model 0 shows every CTA (a hint, no fence anywhere); then thread t < nm * NS
+// reads its two words -- again if one of them does not count G contributions yet -- into outd[m][j] (double)
+template <int NS>
+__device__ __forceinline__ void collect_sums(unsigned round, int nactive_threads) {
   TSMEM();
-  constexpr int JMAX = 6;
-  float4* part = reinterpret_cast<float4*>(dyn_smem_raw + p.o_part);
-  float* out = SM_F32(p.o_out) + m * 64;
-  const int G = gridDim.x;
-  const int t = threadIdx.x;
-  if (t < NGRP * NCH) {
-    const int c = t % NCH, b0 = t / NCH;
-    const float4* base = p.rows + ((size_t)par * G * p.nmodels + m) * kChunks + c;
-    const size_t stride = (size_t)p.nmodels * kChunks;
-    float3 s = make_float3(0.f, 0.f, 0.f);
-    for (int bb = b0; bb < G; bb += NGRP * JMAX) {
-      float4 v[JMAX];
-      unsigned pend = 0;
-#pragma unroll
-      for (int j = 0; j < JMAX; ++j)
-        if (bb + j * NGRP < G) pend |= 1u << j;
-      while (pend) {
-#pragma unroll
-        for (int j = 0; j < JMAX; ++j)
-          if (pend & (1u << j)) v[j] = ld_packet(base + (size_t)(bb + j * NGRP) * stride);
-#pragma unroll
-        for (int j = 0; j < JMAX; ++j)
-          if ((pend & (1u << j)) && __float_as_uint(v[j].w) == tag) pend &= ~(1u << j);
-      }
-#pragma unroll
-      for (int j = 0; j < JMAX; ++j)
-        if (bb + j * NGRP < G) {
-          s.x += v[j].x;
-          s.y += v[j].y;
-          s.z += v[j].z;
-        }
-    }
-    part[b0 * NCH + c] = make_float4(s.x, s.y, s.z, 0.f);
-  }
-  __syncthreads();
-  if (t < NCH * 3) {
-    const int c = t / 3, e = t - 3 * c;
-    const float* q = (const float*)(part + c) + e;
-    float tot = 0.f;
-#pragma unroll 4
-    for (int g = 0; g < NGRP; ++g) tot += q[g * NCH * 4];
-    out[t] = tot;
-  }
-  __syncthreads();
-}
-
-// every packet of this CTA is on its way: count the arrival (no fence -- the tags carry the ordering),
-// one thread waits until every CTA has counted, then the packets are (almost surely) there to be read once
-__device__ __forceinline__ void exchange_arrive_wait(unsigned round) {
-  TSMEM();
-  __syncthreads();  // the publishing threads have issued their stores
+  const unsigned G = gridDim.x;
   if (threadIdx.x == 0) {
-    red_add_u32(&p.bcnt[round], 1u);
-    while (ld_u32_relaxed(&p.bcnt[round]) < gridDim.x) {
+    const unsigned long long* w0 = p.xacc + (size_t)round * p.nmodels * kXWords * kXStride;
+    while ((unsigned)(ld_u64_relaxed(w0) & 0xffull) != G) {
     }
+  }
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t < nactive_threads) {
+    const int m = t / NS, j = t - m * NS;
+    const unsigned long long* x = p.xacc + (((size_t)round * p.nmodels + m) * kXWords + 2 * j) * kXStride;
+    unsigned long long a, b;
+    do {
+      a = ld_u64_relaxed(x);
+      b = ld_u64_relaxed(x + kXStride);
+    } while ((unsigned)(a & 0xffull) != G || (unsigned)(b & 0xffull) != G);
+    double* outd = reinterpret_cast<double*>(dyn_smem_raw + p.o_out) + m * 64;
+    outd[j] = (double)((long long)a >> 8) * 256.0 + (double)((long long)b >> 8) * (1.0 / 549755813888.0);
   }
   __syncthreads();
 }
@@ -679,7 +661,7 @@ __device__ __forceinline__ void ldlt6_lower(double (&A)[21], double (&b)[6], dou
 __device__ __noinline__ void gn_solve_warp(int m, int lvl_next, int is_last, float tmpError, int cnt) {
   TSMEM();
   GNState* g = &sm.S[m];
-  const float* out = SM_F32(p.o_out) + m * 64;  // [0..28] ICP sums, [29..57] RGB sums
+  const double* out = reinterpret_cast<const double*>(dyn_smem_raw + p.o_out) + m * 64;  // [0..28] ICP sums, [29..57] RGB sums
   double* sA = sm.solveA[m];
   const int lane = threadIdx.x & 31;
   const double w = p.icpWeight;
@@ -691,7 +673,7 @@ __device__ __noinline__ void gn_solve_warp(int m, int lvl_next, int is_last, flo
       ++i;
     }
     const int j = i + rem;
-    const double icp = (double)out[lane], rgb = (double)out[29 + lane];
+    const double icp = out[lane], rgb = out[29 + lane];
     if (j == 6) {
       sA[36 + i] = rgb + w * icp;
     } else {
@@ -704,8 +686,8 @@ __device__ __noinline__ void gn_solve_warp(int m, int lvl_next, int is_last, flo
     TrackStats& st = g->stats;
     st.lastRGBError = tmpError;
     st.lastRGBCount = (float)cnt;
-    st.lastICPError = sqrtf(out[27]) / out[28];
-    st.lastICPCount = out[28];
+    st.lastICPError = sqrtf((float)out[27]) / (float)out[28];
+    st.lastICPCount = (float)out[28];
   }
   __syncwarp();
   if (is_last) {  // lastA / lastb are reported for the final iteration (RGBDOdometry.h:62-70)
@@ -849,7 +831,10 @@ __device__ __forceinline__ void gn_begin_warp(GNState* g, int use_so3, int lvl_f
 __device__ __noinline__ void so3_update_warp(int m, int it) {
   TSMEM();
   GNState* g = &sm.S[m];
-  const float* out = SM_F32(p.o_out) + m * 64;
+  const double* outd = reinterpret_cast<const double*>(dyn_smem_raw + p.o_out) + m * 64;
+  float out[11];
+#pragma unroll
+  for (int q = 0; q < 11; ++q) out[q] = (float)outd[q];
   const int lane = threadIdx.x & 31;
   TrackStats& st = g->stats;
   const float err = sqrtf(out[9]) / out[10], count = out[10];
@@ -1095,8 +1080,6 @@ __device__ __noinline__ void run_level(int lvl, int q0, int nit, unsigned round0
   for (int it = 0; it < nit; ++it) {
     const int q = q0 + it;
     const unsigned round = round0 + it;
-    const int par = round & 1;
-    const unsigned tag = (p.epoch << 6) | (round + 1);
     const bool last_of_l0 = (lvl == 0 && it + 1 == nit);
     DBG_MARK(8 + q * 8 + 0);
 
@@ -1157,16 +1140,15 @@ __device__ __noinline__ void run_level(int lvl, int q0, int nit, unsigned round0
     __syncthreads();
     DBG_MARK(8 + q * 8 + 4);
 
-    // -------- publish this CTA's packets, fold everybody's, solve
-    if ((int)threadIdx.x < NM * kChunks) publish_rows<kChunks>(threadIdx.x / kChunks, par, tag);
-    exchange_arrive_wait(round);
+    // -------- add this CTA's sums to the grid accumulators, read the totals, solve
+    if ((int)threadIdx.x < NM * kSums) publish_sums<kSums>(round);
     DBG_MARK(8 + q * 8 + 5);
-    for (int m = 0; m < NM; ++m) fold_rows<kChunks, kGroups>(m, par, tag);
+    collect_sums<kSums>(round, NM * kSums);
     DBG_MARK(8 + q * 8 + 6);
     const int is_last = (q + 1 == sm.nsched);
     if ((int)warp < NM) {
       const int m = (int)warp;
-      if (lane < 29) sm.S[m].icp_result[lane] = SM_F32(p.o_out)[m * 64 + lane];
+      if (lane < 29) sm.S[m].icp_result[lane] = (float)reinterpret_cast<const double*>(dyn_smem_raw + p.o_out)[m * 64 + lane];
       gn_solve_warp(m, is_last ? sm.sched[q] : sm.sched[q + 1], is_last, sm.tmpErr[m], sm.tot[m][0]);
     }
     __syncthreads();
@@ -1186,30 +1168,26 @@ __device__ __noinline__ unsigned run_so3() {
     bool all_done = true;  // identical in every CTA
     for (int m = 0; m < NM; ++m) all_done = all_done && sm.S[m].so3_done;
     if (all_done) break;
-    const int par = round & 1;
-    const unsigned tag = (p.epoch << 6) | (round + 1);
     for (int m = 0; m < NM; ++m) {
-      if (sm.S[m].so3_done) continue;
-      const GNState& S = sm.S[m];
       float acc[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) acc[i] = 0.f;
       bool work = false;
-      for (int i = threadIdx.x; i < F.npx; i += kT) {
-        const int ly = i / F.tw, lx = i - ly * F.tw, x = x0 + lx, y = y0 + ly;
-        if (x < F.w && y < F.h) {
-          so3_pixel(p.M[m].so3_last, p.M[m].so3_next, (size_t)F.w, F.w, F.h, S.so3_imageBasis, S.so3_kinv, S.so3_krlr, x, y, acc);
-          work = true;
+      if (!sm.S[m].so3_done) {  // a finished model contributes zeros (its words still count every CTA)
+        const GNState& S = sm.S[m];
+        for (int i = threadIdx.x; i < F.npx; i += kT) {
+          const int ly = i / F.tw, lx = i - ly * F.tw, x = x0 + lx, y = y0 + ly;
+          if (x < F.w && y < F.h) {
+            so3_pixel(p.M[m].so3_last, p.M[m].so3_next, (size_t)F.w, F.w, F.h, S.so3_imageBasis, S.so3_kinv, S.so3_krlr, x, y, acc);
+            work = true;
+          }
         }
       }
       store_warp_row(m, 0, work, acc);
     }
     __syncthreads();
-    if ((int)threadIdx.x < NM * kSo3Chunks && !sm.S[threadIdx.x / kSo3Chunks].so3_done)
-      publish_rows<kSo3Chunks>(threadIdx.x / kSo3Chunks, par, tag);
-    exchange_arrive_wait(round);
-    for (int m = 0; m < NM; ++m)
-      if (!sm.S[m].so3_done) fold_rows<kSo3Chunks, kSo3Groups>(m, par, tag);  // so3_done is uniform: no divergent barrier
+    if ((int)threadIdx.x < NM * 11) publish_sums<11>(round);
+    collect_sums<11>(round, NM * 11);
     if ((int)warp < NM && !sm.S[warp].so3_done) so3_update_warp((int)warp, it);
     __syncthreads();
     ++round;
@@ -1296,12 +1274,16 @@ struct PrepLevel {
 };
 struct PrepParams {
   PrepLevel L[3];
-  unsigned* sync_words;  // barrier A (u64 x kMaxRounds x kMaxM) then exchange counters (u32 x kMaxRounds), or null
+  unsigned long long* sync_words;  // barrier A words (kMaxRounds x kMaxM) then the accumulator slots, or null
+  int nacc;                        // accumulator words in use: kMaxRounds x nmodels x kXWords
 };
-constexpr int kSyncWords = kMaxRounds * kMaxM * 2 + kMaxRounds;
+constexpr size_t kSyncBytes = 8ull * (kMaxRounds * kMaxM + (size_t)kMaxRounds * kMaxM * kXWords * kXStride);  // barrier A + accumulator slots
 __global__ void rgb_prepare_tiled_kernel(const PrepParams pp) {
   int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pp.sync_words && q < kSyncWords) pp.sync_words[q] = 0u;
+  if (pp.sync_words) {
+    if (q < kMaxRounds * kMaxM) pp.sync_words[q] = 0ull;
+    if (q < pp.nacc) pp.sync_words[kMaxRounds * kMaxM + (size_t)q * kXStride] = 0ull;
+  }
 #pragma unroll
   for (int l = 0; l < 3; ++l) {
     const PrepLevel& L = pp.L[l];
@@ -1367,12 +1349,11 @@ struct RGBDOdometry::TiledState {
   int gx = 1, gy = 1;
   FLevel F[3];          // plan part of the frame levels (pointers filled per launch)
   unsigned smem_bytes = 0;
-  unsigned o_wrow = 0, o_part = 0, o_out = 0, o_corr = 0;
+  unsigned o_wrow = 0, o_out = 0, o_corr = 0;
   // device copies of the tensor maps: [level][which]; image / depth maps exist for both buffers they can name
   enum { TM_V, TM_N, TM_DX, TM_DY, TM_IMG_A, TM_IMG_B, TM_D1_NEXT, TM_D1_LAST, TM_CAND, TM_PV, TM_PN, TM_LD, TM_LI, TM_COUNT };
   CUtensorMap* d_maps = nullptr;  // [3][TM_COUNT]
   const unsigned char* img_a[3] = {nullptr, nullptr, nullptr};  // the buffer TM_IMG_A describes
-  unsigned epoch = 1;
   bool attr_set = false;
   int nmodels_planned = 0;
 };
@@ -1401,9 +1382,8 @@ void plan_tiles(int W, int H, int sms, int nm, RGBDOdometry::TiledState& ts) {
   ts.o_wrow = off;
   off = align128(off + (unsigned)nm * 2 * kNW * 32 * 4);
   ts.o_out = off;
-  off = align128(off + (unsigned)nm * 64 * 4);
-  ts.o_corr = off;  // the fold's staging buffer shares this space: the correspondences are dead by then
-  ts.o_part = off;
+  off = align128(off + (unsigned)nm * 64 * 8);
+  ts.o_corr = off;
   off = align128(off + 2 * kPP * kT * 4);
   const unsigned cap = 227u * 1024u;
   auto window_bytes = [](const FLevel& F) {
@@ -1486,11 +1466,9 @@ void RGBDOdometry::destroyTiled() {
 // (re)build plan + tensor maps of this object for launches with `nm` models
 cudaError_t RGBDOdometry::prepareTiled(int nm) {
   if (tiled_ && tiled_->nmodels_planned == nm) return cudaSuccess;
-  const unsigned epoch = tiled_ ? tiled_->epoch : 1;
   destroyTiled();
   tiled_ = new TiledState();
   TiledState& ts = *tiled_;
-  ts.epoch = epoch;
   plan_tiles(width, height, num_sms(), nm, ts);
   RET_IF(cudaMalloc((void**)&ts.d_maps, sizeof(CUtensorMap) * 3 * TiledState::TM_COUNT));
   CUtensorMap h[3][TiledState::TM_COUNT];
@@ -1530,11 +1508,11 @@ cudaError_t RGBDOdometry::prepareTiled(int nm) {
   return cudaSuccess;
 }
 
-size_t RGBDOdometry::tiledScratchBytes() { return sizeof(unsigned) * kSyncWords + 256 + sizeof(float4) * 2 * 256 * kMaxM * kChunks; }
+size_t RGBDOdometry::tiledScratchBytes() { return kSyncBytes + 256; }
 
 bool RGBDOdometry::canBatch(int n) const { return n >= 1 && n <= kMaxM && mode_ == 0 && width < 2048 && height < 2048; }
 
-cudaError_t RGBDOdometry::enqueuePrepare(cudaStream_t s, void* sync_words) {
+cudaError_t RGBDOdometry::enqueuePrepare(cudaStream_t s, void* sync_words, int nmodels) {
   PrepParams pp;
   int total = 0;
   for (int i = 0; i < NUM_PYRS; ++i) {
@@ -1543,7 +1521,8 @@ cudaError_t RGBDOdometry::enqueuePrepare(cudaStream_t s, void* sync_words) {
                         (float)(pow(minimumGradientMagnitudes[i], 2.0) / pow(sobelScale, 2.0))};
     total += w * h;
   }
-  pp.sync_words = (unsigned*)sync_words;
+  pp.sync_words = (unsigned long long*)sync_words;
+  pp.nacc = kMaxRounds * nmodels * kXWords;
   rgb_prepare_tiled_kernel<<<(total + 255) / 256, 256, 0, s>>>(pp);
   return cudaGetLastError();
 }
@@ -1567,8 +1546,7 @@ cudaError_t RGBDOdometry::trackTiled(RGBDOdometry* const* od, int n, float (*tra
   TParams p;
   memset(&p, 0, sizeof(p));
   p.acnt = (unsigned long long*)scratch;
-  p.bcnt = (unsigned*)scratch + kMaxRounds * kMaxM * 2;
-  p.rows = (float4*)((char*)scratch + ((sizeof(unsigned) * kSyncWords + 255) & ~(size_t)255));
+  p.xacc = p.acnt + kMaxRounds * kMaxM;
   for (int m = 0; m < n; ++m) {
     RGBDOdometry& o = *od[m];
     if (!(pd && pd[m])) {
@@ -1577,7 +1555,7 @@ cudaError_t RGBDOdometry::trackTiled(RGBDOdometry* const* od, int n, float (*tra
       memcpy(h_in + 3, rot[m], 9 * sizeof(float));
       RET_IF(cudaMemcpyAsync(o.d_pose_in, h_in, 12 * sizeof(float), cudaMemcpyHostToDevice, s));
     }
-    RET_IF(o.enqueuePrepare(s, m == 0 ? scratch : nullptr));  // Sobel images + candidate gates of this model
+    RET_IF(o.enqueuePrepare(s, m == 0 ? scratch : nullptr, n));  // Sobel images + candidate gates of this model
     MParams& M = p.M[m];
     for (int i = 0; i < NUM_PYRS; ++i) {
       MLevel& L = M.L[i];
@@ -1624,7 +1602,6 @@ cudaError_t RGBDOdometry::trackTiled(RGBDOdometry* const* od, int n, float (*tra
   p.nmodels = n;
   p.gx = ts.gx;
   p.gy = ts.gy;
-  p.epoch = (ts.epoch++) & 0x3ffffffu;
   p.err_pitch = err_pitch;
   p.distThres = f.distThres_;
   p.angleThres = f.angleThres_;
@@ -1636,7 +1613,6 @@ cudaError_t RGBDOdometry::trackTiled(RGBDOdometry* const* od, int n, float (*tra
   p.iters[1] = pyramid ? 5 : 0;
   p.iters[2] = pyramid ? 4 : 0;
   p.o_wrow = ts.o_wrow;
-  p.o_part = ts.o_part;
   p.o_out = ts.o_out;
   p.o_corr = ts.o_corr;
   p.dbg = (unsigned long long*)f.dbg_trace_;

@@ -109,7 +109,7 @@ class RGBDOdometry {
   cudaError_t enqueueDeviceLoop(float icpWeight, bool pyramid, bool fastOdom, bool so3, float* err,
                                 size_t err_pitch, cudaStream_t s);
   // Sobel images + photometric candidate gates, 3 levels, 1 launch (+ clears the barrier words `acnt`)
-  cudaError_t enqueuePrepare(cudaStream_t s, void* acnt = nullptr);
+  cudaError_t enqueuePrepare(cudaStream_t s, void* sync_words = nullptr, int nmodels = 1);
   cudaError_t prepareTiled(int nmodels);
   void destroyTiled();
   TiledState* tiled_ = nullptr;

@@ -132,7 +132,7 @@ def test_multi_model_segmentation_sequence():
 
 
 def test_batched_tracking_is_bit_identical_to_per_model_launches():
-    """gn_batched.cu: five models (background + 4 boxes, labels from the renderer) tracked by ONE
+    """gn_tiled.cu: five models (background + 4 boxes, labels from the renderer) tracked by ONE
     persistent launch per frame must reproduce the per-model launches bit for bit -- poses, tracker
     statistics, ICP error maps and therefore every surfel."""
     import cofusion_b200 as cfb
@@ -163,6 +163,9 @@ def test_batched_tracking_is_bit_identical_to_per_model_launches():
         for i, (x, y) in enumerate(zip(a[t], b[t])):
             assert np.array_equal(x[0], y[0]), (t, i, x[0], y[0])
             assert x[1] == y[1] and x[3] == y[3] and x[4] == y[4], (t, i, x[1], y[1], x[3], y[3])
-            assert np.array_equal(x[2], y[2]), (t, i)
+            if not np.array_equal(x[2], y[2]):
+                bad = np.argwhere(x[2] != y[2])
+                raise AssertionError("ICP error maps differ: frame %d model %d, %d pixels, first %s: %r vs %r" % (
+                    t, i, len(bad), bad[:4].tolist(), x[2][tuple(bad[0])], y[2][tuple(bad[0])]))
     # the objects are actually tracked (non-trivial systems) in the batched run
     assert all(s[3] > 100 for s in a[-1]), [s[3] for s in a[-1]]
