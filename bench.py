@@ -40,6 +40,17 @@ def gn_algorithmic_bytes(w, h):
     return total
 
 
+WORKLOAD = ("configs[1]: single model, 640x480 synthetic room sequence, full processFrame (bilateral, pyramids, SO3 + "
+            "10/5/4-iteration ICP+RGB tracking, index map, fuse, index map, clean, predict + fill-in; predictBeforeFuse=0: the "
+            "prediction of CoFusion.cpp:347 that only the out-of-scope loop closure reads is not rendered)")
+
+
+def base_config(world=1):
+    """the `config` object both arms print (the driver compares them)"""
+    return {"workload": WORKLOAD, "width": W, "height": H, "models_per_rank": 1, "scene_models": max(1, world),
+            "predictBeforeFuse": 0, "sequence": "synth.room_sequence(seed=1234, noise=True), ping-pong over the rendered frames"}
+
+
 def make_frames(n):
     from cofusion_b200 import synth
     return [(rgb, d) for _, rgb, d, _, _ in synth.room_sequence(n, W, H, synth.K_DEFAULT, noise=True, seed=1234)]
@@ -94,7 +105,7 @@ def cpu_port_fps(frames, n_frames, warm=2):
     """The CPU restatement of the same per-frame path (oracle/, single thread) on a bounded sample."""
     from orc_pipeline import OraclePipeline
     from cofusion_b200 import synth
-    op = OraclePipeline(W, H, synth.K_DEFAULT, 1 << 21)
+    op = OraclePipeline(W, H, synth.K_DEFAULT, 1 << 21, predict_before_fuse=False)
     for t in range(warm):
         op.process_frame(*frames[frame_index(t, len(frames))])
     t0 = time.perf_counter()
@@ -157,7 +168,7 @@ def run_reference(args, budget_s=120.0):
     frames = make_frames(24)
     from orc_pipeline import OraclePipeline
     from cofusion_b200 import synth
-    op = OraclePipeline(W, H, synth.K_DEFAULT, 1 << 21)
+    op = OraclePipeline(W, H, synth.K_DEFAULT, 1 << 21, predict_before_fuse=False)
     warm = max(2, min(args.warmup, 3))  # frame 1 only initialises the map: at least one tracked frame of warm-up
     t0 = time.perf_counter()
     for t in range(warm):
@@ -172,15 +183,50 @@ def run_reference(args, budget_s=120.0):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / n,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: single model, 640x480 synthetic room sequence (CPU port of the "
-                                   "reference path: bilateral, pyramids, SO3+ICP+RGB tracking, predict, fuse, clean)",
-                       "parallelism": "1 host thread", "steps_timed": n, "warmup_run": warm},
+            "config": base_config(1), "reference_run": {"parallelism": "1 host thread", "steps_timed": n, "warmup_run": warm},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "port",
                              "sample": "%d of the %d requested steps timed (bounded to %.0f s of CPU work) after %d "
                                        "warm-up frames, oracle/ C restatement" % (n, args.steps, budget_s, warm)},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def objects4_bench(steps, warmup, local):
+    """BASELINE.json configs[2] on this GPU: background + 4 moving boxes at 640x480 with the motion segmentation IN
+    the loop (enableMultipleModels: tracking of every model -> SLIC + CRF -> spawn / lose models -> fuse / clean with
+    the CRF's labels -> predict).  The number of live models is whatever the closed loop produces; it is reported."""
+    import torch
+    import cofusion_b200 as cfb
+    from cofusion_b200 import synth
+    n_render = 32
+    seq = list(synth.room_sequence(n_render, W, H, synth.K_DEFAULT, noise=True, n_boxes=4, box_speed=1.0, seed=1234))
+    dev = [(torch.from_numpy(np.ascontiguousarray(r)).cuda(), torch.from_numpy(np.ascontiguousarray(d)).cuda()) for _, r, d, _, _ in seq]
+    p = cfb.CoFusionParams.default(1 << 21)
+    p.enableMultipleModels = 1
+    cf = cfb.CoFusion(W, H, synth.K_DEFAULT, p, device=local)
+    ext = torch.cuda.ExternalStream(cf.ctx.stream)
+    nm = []
+    for t in range(warmup):
+        cf.process_frame(*dev[frame_index(t, n_render)])
+    cf.ctx.sync()
+    cf.ctx.take_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for t in range(warmup, warmup + steps):
+        cf.process_frame(*dev[frame_index(t, n_render)])
+        nm.append(cf.num_models)
+    e1.record(ext)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = cf.ctx.take_launch_count()
+    out = {"workload": "configs[2]: 640x480 synthetic room + 4 moving boxes, motion-CRF segmentation in the loop, 1 GPU",
+           "value": steps / (ms / 1e3), "unit": "frames/s", "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+           "models_mean": float(np.mean(nm)), "models_min": int(min(nm)), "models_max": int(max(nm)),
+           "gpu_launches_per_step": launches / steps}
+    del e0, e1, ext, dev
+    cf.ctx.sync()
+    return out, cf
 
 
 def main():
@@ -190,6 +236,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=30)
     ap.add_argument("--impl", default="cofusion_b200")
     ap.add_argument("--cpu-frames", type=int, default=8, help="frames of the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--objects-steps", type=int, default=300, help="steps of the configs[2] leg at N = 1 (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         # the reference's path on the host cores: a bounded sample of the K requested steps (run_reference)
@@ -198,7 +245,7 @@ def main():
     import torch
     import torch.distributed as dist
     import cofusion_b200 as cfb
-    from cofusion_b200 import synth
+    from cofusion_b200 import sharding, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -209,86 +256,54 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     K = synth.K_DEFAULT
     n_render = 32
-    frames = make_frames(n_render)
+    n_models = sharding.scene_models(world)  # N ranks track ONE scene with N models: background + N - 1 moving boxes
     P = W * H
-    # packed frame = [rgb u8 3P | depth f32 4P]: the unit the multi-GPU path broadcasts (7P bytes)
-    packed_host = []
-    for rgb, d in frames:
-        buf = torch.empty(7 * P, dtype=torch.uint8).pin_memory()
-        buf[:3 * P] = torch.from_numpy(np.ascontiguousarray(rgb).reshape(-1))
-        buf[3 * P:] = torch.from_numpy(np.ascontiguousarray(d).reshape(-1).view(np.uint8))
-        packed_host.append(buf)
-    packed_dev = [b.cuda() for b in packed_host] if rank == 0 else None
-    # N > 1: the frame travels on a torch-owned stream (H2D / D2D into a double-buffered receive buffer, then
-    # ONE NCCL broadcast); the pipeline's own stream only waits on an event.  NCCL and torch's allocator
-    # never see the library's stream.
-    recv = [torch.empty(7 * P, dtype=torch.uint8, device="cuda") for _ in range(2)] if world > 1 else None
-    comm = torch.cuda.Stream() if world > 1 else None
-    ev_ready = [torch.cuda.Event() for _ in range(2)]
-    ev_consumed = [torch.cuda.Event() for _ in range(2)]
+    # only the root renders / holds the frames: the other ranks receive them by the library's NCCL broadcast
+    host, devf = [], []
+    if rank == 0:
+        for _, rgb, d, _, ids in synth.room_sequence(n_render, W, H, K, noise=True, seed=1234, n_boxes=n_models - 1, box_speed=0.5):
+            trip = (torch.from_numpy(np.ascontiguousarray(rgb)).pin_memory(), torch.from_numpy(np.ascontiguousarray(d)).pin_memory(),
+                    torch.from_numpy(np.ascontiguousarray(ids.astype(np.uint8))).pin_memory() if world > 1 else None)
+            host.append(trip)
+            devf.append(tuple(None if x is None else x.cuda() for x in trip))
+    uid = [cfb.nccl_unique_id() if (world > 1 and rank == 0) else None]
+    if world > 1:
+        dist.broadcast_object_list(uid, src=0)
 
     def build():
         params = cfb.CoFusionParams.default(1 << 21)
         cf = cfb.CoFusion(W, H, K, params, device=local)
+        if world > 1:
+            cf.shard_init(rank, world, uid[0])  # collective: the library's own NCCL communicator
         cfb.lib().cfb_model_odometry.restype = cfb.C.c_void_p
-        odom = cfb.C.c_void_p(cfb.lib().cfb_model_odometry(cf.model(0)._h))
-        cfb.check(cfb.lib().cfb_odom_enable_kernel_timing(odom, 1))
-        return cf, odom
+        return cf
 
-    def step_broadcast(cf, ext, t, source):
-        """root copies frame t into the receive buffer, all ranks broadcast, the pipeline consumes it"""
-        i, k = frame_index(t, n_render), t & 1
-        with torch.cuda.stream(comm):
-            comm.wait_event(ev_consumed[k])  # the frame that used this buffer two steps ago is done with it
-            if rank == 0:
-                recv[k].copy_(source[i], non_blocking=True)
-            dist.broadcast(recv[k], src=0)  # one NCCL broadcast of the packed frame per time step
-            ev_ready[k].record(comm)
-        ext.wait_event(ev_ready[k])
-        cf.process_frame(recv[k][:3 * P], recv[k][3 * P:].view(torch.float32))
-        ev_consumed[k].record(ext)
+    def step(cf, t, frames):
+        if rank == 0:
+            rgb, d, m = frames[frame_index(t, n_render)]
+            cf.process_frame(rgb, d, m)
+        else:
+            cf.process_frame(None, None, None)
+        if world > 1 and t == 1:
+            # frame 1: every rank spawns the object model it owns from the renderer's labels (FrameData::mask path)
+            for mdl in sharding.models_of_rank(n_models, rank, world):
+                if mdl > 0:
+                    cf.spawn_object_model(mdl)
 
-    def step_resident(cf, ext, t):
-        if world > 1:
-            return step_broadcast(cf, ext, t, packed_dev)
-        src = packed_dev[frame_index(t, n_render)]
-        cf.process_frame(src[:3 * P], src[3 * P:].view(torch.float32))
+    keep = []
 
-    def step_e2e(cf, ext, t):
-        if world > 1:
-            return step_broadcast(cf, ext, t, packed_host)  # H2D on the root, then NVLink broadcast
-        b = packed_host[frame_index(t, n_render)]
-        cf.process_frame(b[:3 * P], b[3 * P:].view(torch.float32))
-
-    keep = []  # the pipelines (and their streams) outlive every torch tensor that was used on them
-
-    def shutdown():
-        # torch's caching allocators record events on the streams a block was used on when it is freed:
-        # free the frame buffers while the library streams are still alive, then the pipelines, then NCCL
-        nonlocal packed_dev, recv
-        torch.cuda.synchronize()
-        ev_ready.clear()
-        ev_consumed.clear()
-        packed_host.clear()
-        packed_dev = None
-        recv = None
-        import gc
-        gc.collect()
-        torch.cuda.synchronize()
-        keep.clear()
-        gc.collect()
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-
-    def timed(step_fn, sampler=None):
-        cf, odom = build()
+    def timed(frames, sampler=None):
+        cf = build()
         keep.append(cf)
         ext = torch.cuda.ExternalStream(cf.ctx.stream)  # only used to record / wait on events
         for t in range(args.warmup):
-            step_fn(cf, ext, t)
+            step(cf, t, frames)
         cf.ctx.sync()
         cf.ctx.take_launch_count()
+        mine = [m for m in sharding.models_of_rank(n_models, rank, world)]
+        tracked = cf.model(0 if rank == 0 else cf.num_models - 1)
+        odom = cfb.C.c_void_p(cfb.lib().cfb_model_odometry(tracked._h))
+        cfb.check(cfb.lib().cfb_odom_enable_kernel_timing(odom, 1))
         sm, n = cfb.C.c_double(0), cfb.C.c_int(0)
         cfb.check(cfb.lib().cfb_odom_kernel_timing(odom, cfb.C.byref(sm), cfb.C.byref(n), 1))
         torch.cuda.synchronize()
@@ -300,7 +315,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(ext)
         for t in range(args.warmup, args.warmup + args.steps):
-            step_fn(cf, ext, t)
+            step(cf, t, frames)
         e1.record(ext)
         torch.cuda.synchronize()
         if world > 1:
@@ -309,23 +324,33 @@ def main():
         if sampler:
             sampler.stop_flag = True
         launches = cf.ctx.take_launch_count()
-        cfb.check(cfb.lib().cfb_odom_kernel_timing(odom, cfb.C.byref(sm), cfb.C.byref(n), 0))
+        # the tracker kernel is timed with CUDA events on its own stream: every launch of a short extra run (the
+        # event pair is read back per launch, which would serialise the timed region above)
+        ksum, kn = 0.0, 0
+        for t in range(args.warmup + args.steps, args.warmup + args.steps + 50):
+            step(cf, t, frames)
+            cf.ctx.sync()
+            cfb.check(cfb.lib().cfb_odom_kernel_timing(odom, cfb.C.byref(sm), cfb.C.byref(n), 1))
+            ksum, kn = ksum + sm.value, kn + n.value
         t_ms = torch.tensor([ms], device="cuda")
         if world > 1:
             dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)  # max over ranks
-        nsurf = cf.model(0).last_count()
+        nsurf = tracked.last_count()
         del e0, e1, ext
-        return float(t_ms.item()), launches, (sm.value, n.value), nsurf
+        return float(t_ms.item()), launches, (ksum, kn), nsurf, mine
 
     sampler = ClockSampler(local) if rank == 0 else None
-    ms, launches, (kms, kn), nsurf = timed(step_resident, sampler)
-    ms_e2e, _, _, _ = timed(step_e2e)
+    ms, launches, (kms, kn), nsurf, mine = timed(devf, sampler)
+    ms_e2e, _, _, _, _ = timed(host)
     if rank != 0:
-        shutdown()
+        torch.cuda.synchronize()
+        keep.clear()
+        dist.barrier()
+        dist.destroy_process_group()
         return
 
-    value = world * args.steps / (ms / 1e3)
-    e2e = world * args.steps / (ms_e2e / 1e3)
+    value = sharding.aggregate_value(n_models, args.steps, ms)
+    e2e = sharding.aggregate_value(n_models, args.steps, ms_e2e)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -338,30 +363,47 @@ def main():
     achieved = alg / (k_avg_ms * 1e-3) / 1e9 if kn else None
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["gn_persistent_kernel"]["dram_bytes_per_launch"]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["gn_tiled_kernel"]["dram_bytes_per_launch"]
     except Exception:
         pass
     cpu = None
-    if args.cpu_frames > 0:
-        fps_cpu, dt = cpu_port_fps(frames, args.cpu_frames)
+    frames_np = None
+    if args.cpu_frames > 0 and world == 1:
+        frames_np = make_frames(24)
+        fps_cpu, dt = cpu_port_fps(frames_np, args.cpu_frames)
         cpu = {"value": fps_cpu, "unit": "frames/s", "cores": 1, "kind": "port",
                "sample": "%d frames of the same 640x480 room sequence through the oracle/ C restatement "
                          "(single thread, like the reference's CPU loops), %.1f s" % (args.cpu_frames, dt),
-               "segmentation_ms_per_frame": cpu_segmentation_ms(frames),
-               "segmentation_ms_per_frame_5_models": cpu_segmentation_ms(frames, reps=2, n_models=5)}
+               "segmentation_ms_per_frame": cpu_segmentation_ms(frames_np),
+               "segmentation_ms_per_frame_5_models": cpu_segmentation_ms(frames_np, reps=2, n_models=5)}
+    cfg = base_config(world)
+    cfg.update({"surfels": nsurf,
+                "parallelism": ("object sharding: rank r owns model r of ONE %d-model scene (background + %d moving boxes, labels "
+                                "from the renderer), one ncclBroadcast of the packed frame per step inside the library" %
+                                (n_models, n_models - 1)) if world > 1 else "1 GPU",
+                "l2": "inputs cycle over %d distinct frames (%.0f MB) + a %.0f MB surfel map; per-step working set is L2 resident "
+                      "by nature of the workload, no flush" % (n_render, n_render * 7 * P / 1e6, nsurf * 96 / 1e6)})
+    objects4 = None
+    if world == 1 and args.objects_steps > 0:
+        keep.clear()
+        torch.cuda.synchronize()
+        try:
+            objects4, cf4 = objects4_bench(args.objects_steps, 60, local)
+            keep.append(cf4)
+        except Exception as e:  # the second workload must never take the headline line down
+            objects4 = {"unavailable": repr(e)[:300]}
+    cfg["objects4"] = objects4
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: single model, 640x480 synthetic room sequence, full processFrame "
-                               "(bilateral, pyramids, SO3 + 10/5/4-iteration ICP+RGB tracking, predict, fuse, clean)",
-                   "surfels": nsurf, "parallelism": "one model per GPU, frame broadcast over NCCL" if world > 1 else "1 GPU",
-                   "l2": "inputs cycle over %d distinct frames (%.0f MB) + a %.0f MB surfel map; per-step working set "
-                         "is L2 resident by nature of the workload, no flush" % (n_render, n_render * 7 * P / 1e6, nsurf * 96 / 1e6)},
-        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": 7 * P, "d2h_bytes_per_step": 48 + 376,
-                "ms_per_step": ms_e2e / args.steps},
+        "config": cfg,
+        "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": (8 if world > 1 else 7) * P, "d2h_bytes_per_step": 224 + 376,
+                "ms_per_step": ms_e2e / args.steps,
+                "note": "host RGB-D frame in pinned memory -> C-ABI processFrame -> pose block + tracker statistics copied back "
+                        "every step (read by the host without stalling the pipeline)"},
         "gpu_launches": launches,
-        "roofline": {"kernel": "gn_persistent_kernel (SO3 + 19 GN iterations of ICP/RGB reductions, 1 launch/frame)",
+        "roofline": {"kernel": "gn_tiled_kernel (SO3 + 19 GN iterations of ICP/RGB reductions over shared-memory tiles, 1 launch/frame)",
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                      "algorithmic_bytes_per_launch": alg, "avg_launch_ms": k_avg_ms, "launches_timed": kn,
@@ -372,7 +414,11 @@ def main():
         "clocks": sampler.summary() if sampler else None,
     }
     print(json.dumps(line), flush=True)
-    shutdown()
+    torch.cuda.synchronize()
+    keep.clear()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

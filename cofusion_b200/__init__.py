@@ -435,6 +435,23 @@ class CoFusionParams(C.Structure):
         return p
 
 
+def nccl_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it, the application distributes it)"""
+    buf = (C.c_ubyte * 128)()
+    check(lib().cfb_nccl_unique_id(buf))
+    return bytes(buf)
+
+
+def shard_owner(index, world):
+    """rank that owns the model at list position `index` of a scene sharded over `world` ranks (shard.cuh)"""
+    return index % world if world > 0 else 0
+
+
+class Frame(C.Structure):  # cfb_frame
+    _fields_ = [("rgb", C.c_void_p), ("depth", C.c_void_p), ("depth_u16", C.c_void_p), ("depth_scale", C.c_float),
+                ("flip_colors", C.c_int), ("mask", C.c_void_p), ("device_ptrs", C.c_int), ("timestamp", C.c_int64)]
+
+
 class _Borrowed:
     pass
 
@@ -466,18 +483,82 @@ class CoFusion:
             _lib.cfb_cofusion_destroy(self._h)
             self._h = C.c_void_p()
 
-    def process_frame(self, rgb, depth, mask=None, weight_multiplier=1.0):
-        """rgb/depth/mask: host numpy arrays, pinned torch tensors, or CUDA torch tensors"""
-        dev = hasattr(rgb, "is_cuda") and rgb.is_cuda
+    def _checked(self, a, dtype, shape, what):
+        """dtype / shape / contiguity of an image crossing the ABI (raw pointers carry none of it)"""
+        if a is None:
+            return None
+        if hasattr(a, "data_ptr"):  # torch tensor (CUDA, or pinned / pageable host)
+            import torch
+            want = {np.uint8: torch.uint8, np.float32: torch.float32, np.uint16: getattr(torch, "uint16", None)}[dtype]
+            ok_dtype = a.dtype == want or (dtype is np.uint16 and a.dtype == torch.int16)
+            if not ok_dtype or a.numel() != int(np.prod(shape)) or not a.is_contiguous():
+                raise CfbError("%s: expected contiguous %s%s, got %s %s" % (what, np.dtype(dtype).name, shape, a.dtype, tuple(a.shape)))
+            return a
+        a = np.asarray(a)
+        if a.dtype != dtype or a.size != int(np.prod(shape)):
+            raise CfbError("%s: expected %s%s, got %s %s" % (what, np.dtype(dtype).name, shape, a.dtype, a.shape))
+        return np.ascontiguousarray(a)
 
-        def ptr(a):
-            if a is None:
-                return C.c_void_p(0)
-            if hasattr(a, "data_ptr"):
-                return C.c_void_p(a.data_ptr())
-            return a.ctypes.data_as(C.c_void_p)
-        check(lib().cfb_cofusion_process_frame(self._h, ptr(rgb), ptr(depth), ptr(mask), int(dev),
+    @staticmethod
+    def _ptr(a):
+        if a is None:
+            return C.c_void_p(0)
+        if hasattr(a, "data_ptr"):
+            return C.c_void_p(a.data_ptr())
+        return a.ctypes.data_as(C.c_void_p)
+
+    def shard_init(self, rank, world, unique_id):
+        """collective: join the object-sharded job (one process per GPU); unique_id = nccl_unique_id() of rank 0"""
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
+        check(lib().cfb_cofusion_shard_init(self._h, int(rank), int(world), buf))
+        self.rank, self.world = rank, world
+
+    def process_frame(self, rgb, depth, mask=None, weight_multiplier=1.0):
+        """rgb/depth/mask: host numpy arrays, pinned torch tensors, or CUDA torch tensors (None on the ranks of a
+        sharded job that are not the root: the frame arrives by broadcast)"""
+        dev = hasattr(rgb, "is_cuda") and rgb.is_cuda
+        rgb = self._checked(rgb, np.uint8, (self.H, self.W, 3), "rgb")
+        depth = self._checked(depth, np.float32, (self.H, self.W), "depth")
+        mask = self._checked(mask, np.uint8, (self.H, self.W), "mask")
+        check(lib().cfb_cofusion_process_frame(self._h, self._ptr(rgb), self._ptr(depth), self._ptr(mask), int(dev),
                                                C.c_float(weight_multiplier)))
+
+    def process_frame_ex(self, rgb, depth=None, depth_u16=None, depth_scale=0.001, flip_colors=False, mask=None,
+                         in_pose=None, bootstrap=False, timestamp=0, weight_multiplier=1.0):
+        """cfb_cofusion_process_frame_ex: CoFusion::processFrame(frame, inPose, weightMultiplier, bootstrap) with the
+        log readers' conversions (u16 depth x scale, BGR flip) done on the device"""
+        dev = hasattr(rgb, "is_cuda") and rgb.is_cuda
+        fr = Frame()
+        rgb = self._checked(rgb, np.uint8, (self.H, self.W, 3), "rgb")
+        depth = self._checked(depth, np.float32, (self.H, self.W), "depth")
+        depth_u16 = self._checked(depth_u16, np.uint16, (self.H, self.W), "depth_u16")
+        mask = self._checked(mask, np.uint8, (self.H, self.W), "mask")
+        fr.rgb, fr.depth, fr.depth_u16, fr.mask = (self._ptr(x).value for x in (rgb, depth, depth_u16, mask))
+        fr.depth_scale, fr.flip_colors, fr.device_ptrs, fr.timestamp = depth_scale, int(flip_colors), int(dev), int(timestamp)
+        pp = None
+        if in_pose is not None:
+            pa = np.ascontiguousarray(in_pose, np.float32).reshape(16)
+            pp = pa.ctypes.data_as(c_float_p)
+        check(lib().cfb_cofusion_process_frame_ex(self._h, C.byref(fr), pp, C.c_float(weight_multiplier), int(bool(bootstrap))))
+
+    def enable_pose_logging(self, on=True):
+        check(lib().cfb_cofusion_enable_pose_logging(self._h, int(bool(on))))
+
+    def pose_log(self, index):
+        n = C.c_int(0)
+        check(lib().cfb_cofusion_pose_log(self._h, int(index), None, None, 0, C.byref(n)))
+        ts = np.zeros(n.value, np.int64)
+        p7 = np.zeros((n.value, 7), np.float32)
+        if n.value:
+            check(lib().cfb_cofusion_pose_log(self._h, int(index), ts.ctypes.data_as(C.c_void_p), p7.ctypes.data_as(C.c_void_p),
+                                              n.value, C.byref(n)))
+        return ts, p7
+
+    def export_poses(self, directory):
+        check(lib().cfb_cofusion_export_poses(self._h, str(directory).encode()))
+
+    def save_ply(self, directory):
+        check(lib().cfb_cofusion_save_ply(self._h, str(directory).encode()))
 
     def spawn_object_model(self, model_id, pose=None):
         pp = None

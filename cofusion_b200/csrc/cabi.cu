@@ -710,9 +710,64 @@ int cfb_cofusion_create(int device, int W, int H, float fx, float fy, float cx, 
 void cfb_cofusion_destroy(cfb_cofusion* f) { delete f; }
 int cfb_cofusion_process_frame(cfb_cofusion* f, const uint8_t* rgb, const float* depth, const uint8_t* mask,
                                int device_ptrs, float weightMultiplier) {
-  REQUIRE(f && rgb && depth, "cofusion_process_frame");
+  REQUIRE(f && ((rgb && depth) || (f->f.shard.active() && f->f.shard.rank() != 0)), "cofusion_process_frame");
   CK(f->f.processFrame(rgb, depth, mask, device_ptrs != 0, weightMultiplier));
   if (f->f.params.enableMultipleModels) f->sync_handles();
+  return 0;
+}
+int cfb_cofusion_process_frame_ex(cfb_cofusion* f, const cfb_frame* fr, const float* inPose16, float weightMultiplier,
+                                  int bootstrap) {
+  REQUIRE(f && fr && (!bootstrap || inPose16), "cofusion_process_frame_ex");
+  REQUIRE((f->f.shard.active() && f->f.shard.rank() != 0) || (fr->rgb && (fr->depth || fr->depth_u16)), "cofusion_process_frame_ex: frame");
+  FrameInput in;
+  in.rgb = fr->rgb;
+  in.depth = fr->depth;
+  in.depth16 = fr->depth ? nullptr : fr->depth_u16;
+  in.depthScale = fr->depth_scale;
+  in.flipColors = fr->flip_colors != 0;
+  in.mask = fr->mask;
+  in.device_ptrs = fr->device_ptrs != 0;
+  in.timestamp = fr->timestamp;
+  CK(f->f.processFrameEx(in, inPose16, bootstrap != 0, weightMultiplier));
+  if (f->f.params.enableMultipleModels) f->sync_handles();
+  return 0;
+}
+int cfb_nccl_unique_id(unsigned char id[128]) {
+  REQUIRE(id, "nccl_unique_id");
+  const char* err = "";
+  if (FrameShard::uniqueId(id, &err) != 0) return set_error_msg(5, err);
+  return 0;
+}
+int cfb_cofusion_shard_init(cfb_cofusion* f, int rank, int world, const unsigned char id[128]) {
+  REQUIRE(f && id, "cofusion_shard_init");
+  const char* err = "";
+  if (f->f.shardInit(rank, world, id, &err) != cudaSuccess) return set_error_msg(5, err);
+  return 0;
+}
+int cfb_cofusion_enable_pose_logging(cfb_cofusion* f, int on) {
+  REQUIRE(f, "cofusion_enable_pose_logging");
+  f->f.enablePoseLogging(on != 0);
+  return 0;
+}
+int cfb_cofusion_pose_log(cfb_cofusion* f, int index, int64_t* ts, float* pose7, int capacity, int* n) {
+  REQUIRE(f && n && index >= 0 && (size_t)index < f->f.numModels(), "cofusion_pose_log");
+  std::vector<int64_t> t;
+  std::vector<float> p;
+  CK(f->f.poseLog((size_t)index, &t, &p));
+  *n = (int)t.size();
+  const int m = *n < capacity ? *n : capacity;
+  if (ts && m > 0) memcpy(ts, t.data(), sizeof(int64_t) * m);
+  if (pose7 && m > 0) memcpy(pose7, p.data(), sizeof(float) * 7 * m);
+  return 0;
+}
+int cfb_cofusion_export_poses(cfb_cofusion* f, const char* dir) {
+  REQUIRE(f && dir, "cofusion_export_poses");
+  CK(f->f.exportPoses(dir));
+  return 0;
+}
+int cfb_cofusion_save_ply(cfb_cofusion* f, const char* dir) {
+  REQUIRE(f && dir, "cofusion_save_ply");
+  CK(f->f.savePly(dir));
   return 0;
 }
 int cfb_cofusion_last_segmentation(cfb_cofusion* f, cfb_model_data* md_out, int* md_count, int* hasNewLabel,

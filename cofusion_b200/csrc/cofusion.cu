@@ -7,6 +7,8 @@
 #include <string.h>
 #include <time.h>
 
+#include <string>
+
 namespace cfb {
 
 #define RET_IF(e)                       \
@@ -124,8 +126,15 @@ cudaError_t CoFusion::spawnObjectModel(unsigned id, const float* initialPose) {
   return cudaSuccess;
 }
 
+std::vector<Model*> CoFusion::processed() {
+  std::vector<Model*> v;
+  for (size_t i = 0; i < models.size(); ++i)
+    if (i > 0 || processGlobalModel) v.push_back(models[i].get());
+  return v;
+}
+
 cudaError_t CoFusion::predict() {
-  for (auto& m : models) {
+  for (Model* m : processed()) {
     // lastFrameRecovery is never set without loop closure -> maxTime = tick (CoFusion.cpp:538)
     RET_IF(m->combinedPredict(params.maxDepthProcessed, tick_, tick_, params.timeDelta));
     RET_IF(m->performFillIn(params.frameToFrameRGB != 0, false));
@@ -153,6 +162,59 @@ Timeline g_tl;
 
 cudaError_t CoFusion::processFrame(const uint8_t* rgb, const float* depth, const uint8_t* mask, bool device_ptrs,
                                    float weightMultiplier) {
+  FrameInput in;
+  in.rgb = rgb;
+  in.depth = depth;
+  in.mask = mask;
+  in.device_ptrs = device_ptrs;
+  in.timestamp = (int64_t)(tick_ - 1) * 33;
+  return processFrameEx(in, nullptr, false, weightMultiplier);
+}
+
+cudaError_t CoFusion::shardInit(int rank, int world, const unsigned char id[128], const char** err) {
+  if (params.enableMultipleModels) {
+    *err = "shard_init: the sharded path takes external label masks (enableMultipleModels = 0)";
+    return cudaErrorInvalidValue;
+  }
+  RET_IF(cudaSetDevice(ctx.device));
+  if (shard.init(rank, world, id, (size_t)ctx.W * ctx.H * 8, err) != 0) return cudaErrorUnknown;
+  processGlobalModel = rank == 0;
+  return cudaSuccess;
+}
+
+cudaError_t CoFusion::processFrameEx(const FrameInput& in_, const float* inPose, bool bootstrap, float weightMultiplier) {
+  FrameInput in = in_;
+  if (shard.active()) {
+    // pack [rgb 3P | depth f32 4P | mask P] on the root, one broadcast, then every rank sees a device-resident frame
+    const size_t P = (size_t)ctx.W * ctx.H;
+    uint8_t* buf = nullptr;
+    cudaEvent_t freeEvt = nullptr;
+    RET_IF(shard.acquire(ctx.stream, &buf, &freeEvt));
+    cudaEvent_t ready = nullptr;
+    if (shard.rank() == 0) {
+      if (!in.rgb || !in.depth || in.depth16 || in.flipColors) return cudaErrorInvalidValue;  // f32 RGB frames on the sharded path
+      const cudaMemcpyKind k = in.device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+      RET_IF(cudaStreamWaitEvent(ctx.copyStream, freeEvt, 0));
+      RET_IF(cudaMemcpyAsync(buf, in.rgb, P * 3, k, ctx.copyStream));
+      RET_IF(cudaMemcpyAsync(buf + 3 * P, in.depth, P * 4, k, ctx.copyStream));
+      if (in.mask)
+        RET_IF(cudaMemcpyAsync(buf + 7 * P, in.mask, P, k, ctx.copyStream));
+      else
+        RET_IF(cudaMemsetAsync(buf + 7 * P, 0, P, ctx.copyStream));
+      RET_IF(cudaEventRecord(ctx.evCopied[0], ctx.copyStream));
+      ready = ctx.evCopied[0];
+    }
+    RET_IF(shard.broadcast(ready, ctx.stream, &lastShardError));
+    in.rgb = buf;
+    in.depth = (const float*)(buf + 3 * P);
+    in.depth16 = nullptr;
+    in.flipColors = false;
+    in.mask = buf + 7 * P;
+    in.device_ptrs = true;
+    if (shard.rank() == 0 && !in_.device_ptrs) RET_IF(cudaEventSynchronize(ctx.evCopied[0]));  // host buffers are free again
+  }
+  if (!in.rgb || (!in.depth && !in.depth16) || (bootstrap && !inPose)) return cudaErrorInvalidValue;
+  const bool device_ptrs = in.device_ptrs;
   Timeline& tl = g_tl;
   if (!tl.init) {
     tl.init = true;
@@ -168,16 +230,31 @@ cudaError_t CoFusion::processFrame(const uint8_t* rgb, const float* depth, const
     cudaEventRecord(tl.ev[tl.cur][k], ctx.stream);
   };
   mark(0);
-  if (device_ptrs)
-    RET_IF(ctx.setFrameDevice(rgb, depth, mask));
-  else
-    RET_IF(ctx.uploadFrame(rgb, depth, mask));
+  RET_IF(ctx.uploadFrameRaw(in.rgb, in.flipColors, in.depth, in.depth16, in.depthScale, in.mask, device_ptrs));
   RET_IF(ctx.preprocess(params.depthCutoff));
   if (tick_ == 1) {
-    RET_IF(models[0]->initialise(tick_, params.maxDepthProcessed));
-    RET_IF(models[0]->initFirstRGB());
+    if (processGlobalModel) {
+      RET_IF(models[0]->initialise(tick_, params.maxDepthProcessed));
+      RET_IF(models[0]->initFirstRGB());
+    }
     // every later frame synchronises on its tracker (after the upload); the first one has none, and the
     // contract is that host buffers may be reused once the call returns
+  } else if (inPose && !bootstrap) {
+    // pose provided by the caller: Model::overridePose on the camera model, no tracking, no segmentation
+    // (CoFusion.cpp:343-345); the fuse block below still runs (trackingOk stays true, :463)
+    Model* g = models[0].get();
+    RET_IF(g->syncPose());
+    memcpy(g->pose, inPose, sizeof(g->pose));
+    memcpy(g->lastPose, inPose, sizeof(g->lastPose));
+    RET_IF(g->uploadPose());
+    if (params.predictBeforeFuse) RET_IF(predict());
+    if (!params.rgbOnly) {
+      const std::vector<Model*> act = processed();
+      for (Model* m : act) RET_IF(m->predictIndices(tick_, params.maxDepthProcessed, params.timeDelta));
+      for (Model* m : act) RET_IF(m->fuse(tick_, params.maxDepthProcessed, weightMultiplier));
+      for (Model* m : act) RET_IF(m->predictIndices(tick_, params.maxDepthProcessed, params.timeDelta));
+      for (Model* m : act) RET_IF(m->clean(tick_, params.timeDelta, params.maxDepthProcessed, params.outlierCoefficient));
+    }
   } else {
     TrackParams tp;
     tp.frameToFrameRGB = params.frameToFrameRGB;
@@ -190,9 +267,9 @@ cudaError_t CoFusion::processFrame(const uint8_t* rgb, const float* depth, const
     tp.force_host_loop = 0;
     mark(1);
     {
-      std::vector<Model*> ms;
-      for (auto& m : models) ms.push_back(m.get());
-      if (batchedTracking) {
+      std::vector<Model*> ms = processed();
+      if (ms.empty()) {
+      } else if (batchedTracking) {
         // no host synchronisation: the poses stay on the device, stats / poses are fetched on demand
         RET_IF(trackModels(&ctx, ms.data(), (int)ms.size(), tp, true));
       } else {
@@ -200,21 +277,36 @@ cudaError_t CoFusion::processFrame(const uint8_t* rgb, const float* depth, const
       }
     }
     mark(2);
+    if (bootstrap) {  // globalModel->overridePose(globalModel->getPose() * inPose) (CoFusion.cpp:219-222)
+      Model* g = models[0].get();
+      RET_IF(g->syncPose());
+      float r[16];
+      for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+          float acc = 0.f;
+          for (int k = 0; k < 4; ++k) acc += g->pose[i * 4 + k] * inPose[k * 4 + j];
+          r[i * 4 + j] = acc;
+        }
+      memcpy(g->pose, r, sizeof(r));
+      memcpy(g->lastPose, r, sizeof(r));
+      RET_IF(g->uploadPose());
+    }
     if (params.enableMultipleModels) RET_IF(segmentAndManageModels());
     // CoFusion.cpp:347: this prediction only feeds performSegmentation / the (dead) loop-closure
     // block; the fuse stage below uses the index maps and the frame, and the final predict()
     // overwrites every target -> skipped unless asked for.
     if (params.predictBeforeFuse) RET_IF(predict());
     if (!params.rgbOnly) {
-      for (auto& m : models) RET_IF(m->predictIndices(tick_, params.maxDepthProcessed, params.timeDelta));
-      for (auto& m : models) RET_IF(m->fuse(tick_, params.maxDepthProcessed, weightMultiplier));
-      for (auto& m : models) RET_IF(m->predictIndices(tick_, params.maxDepthProcessed, params.timeDelta));
-      for (auto& m : models)
-        RET_IF(m->clean(tick_, params.timeDelta, params.maxDepthProcessed, params.outlierCoefficient));
+      const std::vector<Model*> act = processed();
+      for (Model* m : act) RET_IF(m->predictIndices(tick_, params.maxDepthProcessed, params.timeDelta));
+      for (Model* m : act) RET_IF(m->fuse(tick_, params.maxDepthProcessed, weightMultiplier));
+      for (Model* m : act) RET_IF(m->predictIndices(tick_, params.maxDepthProcessed, params.timeDelta));
+      for (Model* m : act) RET_IF(m->clean(tick_, params.timeDelta, params.maxDepthProcessed, params.outlierCoefficient));
     }
   }
   RET_IF(predict());
   tick_++;
+  if (poseLogging_) RET_IF(logPoses(in.timestamp));
   // nothing in this frame waited for the device; the contract is that host buffers may be reused once the
   // call returns, so wait for this frame's upload (it only depends on the frame before the previous one)
   if (!device_ptrs) RET_IF(cudaEventSynchronize(ctx.evCopied[ctx.cur]));
@@ -243,6 +335,154 @@ cudaError_t CoFusion::processFrame(const uint8_t* rgb, const float* depth, const
     }
   }
   if (tl.on) tl.cur ^= 1;
+  return cudaSuccess;
+}
+
+// ------------------------------------------------------------------------------------------------ export
+cudaError_t CoFusion::logPoses(int64_t timestamp) {
+  // CoFusion.cpp:503-518: one entry per active model and frame.  The 3x4 pose is copied device to device from the
+  // model's pose block (the frame is not waited for); quaternions are formed when the log is read.
+  for (auto& m : models) RET_IF(m->appendPoseLog(timestamp, logFrames_));
+  logFrames_++;
+  return cudaSuccess;
+}
+
+namespace {
+void rigid_inverse(const float* T, float* Ti) {  // 3x4 row-major
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) Ti[r * 4 + c] = T[c * 4 + r];
+  for (int r = 0; r < 3; ++r) Ti[r * 4 + 3] = -(Ti[r * 4] * T[3] + Ti[r * 4 + 1] * T[7] + Ti[r * 4 + 2] * T[11]);
+}
+void rigid_mul(const float* A, const float* B, float* C) {  // 3x4 * 3x4 (implicit last row 0 0 0 1)
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 4; ++c)
+      C[r * 4 + c] = A[r * 4] * B[c] + A[r * 4 + 1] * B[4 + c] + A[r * 4 + 2] * B[8 + c] + (c == 3 ? A[r * 4 + 3] : 0.f);
+  }
+}
+void quaternion_of(const float* T, float* q) {  // Eigen::Quaternionf(Matrix3f): x y z w
+  const float m00 = T[0], m01 = T[1], m02 = T[2], m10 = T[4], m11 = T[5], m12 = T[6], m20 = T[8], m21 = T[9], m22 = T[10];
+  float t = m00 + m11 + m22;
+  if (t > 0.f) {
+    t = sqrtf(t + 1.0f);
+    q[3] = 0.5f * t;
+    t = 0.5f / t;
+    q[0] = (m21 - m12) * t;
+    q[1] = (m02 - m20) * t;
+    q[2] = (m10 - m01) * t;
+  } else {
+    const float M[3][3] = {{m00, m01, m02}, {m10, m11, m12}, {m20, m21, m22}};
+    int i = 0;
+    if (m11 > m00) i = 1;
+    if (m22 > M[i][i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = sqrtf(M[i][i] - M[j][j] - M[k][k] + 1.0f);
+    q[i] = 0.5f * t;
+    t = 0.5f / t;
+    q[3] = (M[k][j] - M[j][k]) * t;
+    q[j] = (M[j][i] + M[i][j]) * t;
+    q[k] = (M[k][i] + M[i][k]) * t;
+  }
+}
+}  // namespace
+
+cudaError_t CoFusion::modelPoseLog(Model* m, std::vector<int64_t>* ts, std::vector<float>* p7) {
+  Model* g = models[0].get();
+  RET_IF(g->fetchPoseLog());
+  RET_IF(m->fetchPoseLog());
+  const size_t n = m->poseLogTs.size();
+  if (ts) *ts = m->poseLogTs;
+  if (p7) {
+    p7->resize(n * 7);
+    for (size_t k = 0; k < n; ++k) {
+      const float* P = m->poseLogHost.data() + k * 12;
+      float T[12];
+      if (m == g) {
+        memcpy(T, P, sizeof(T));
+      } else {  // object -> world = cameraPose * modelPose^-1 of the same frame
+        const int f = m->poseLogFrame[k];
+        float inv[12];
+        rigid_inverse(P, inv);
+        rigid_mul(g->poseLogHost.data() + (size_t)f * 12, inv, T);
+      }
+      float* o = p7->data() + k * 7;
+      o[0] = T[3];
+      o[1] = T[7];
+      o[2] = T[11];
+      quaternion_of(T, o + 3);
+    }
+  }
+  return cudaSuccess;
+}
+
+cudaError_t CoFusion::poseLog(size_t i, std::vector<int64_t>* ts, std::vector<float>* p7) {
+  if (i >= models.size()) return cudaErrorInvalidValue;
+  return modelPoseLog(models[i].get(), ts, p7);
+}
+
+cudaError_t CoFusion::exportPoses(const char* dir) {  // CoFusion.cpp:758-783
+  auto one = [&](Model* m) -> cudaError_t {
+    std::vector<int64_t> ts;
+    std::vector<float> p;
+    RET_IF(modelPoseLog(m, &ts, &p));
+    if (ts.empty()) return cudaSuccess;  // Model::isLoggingPoses
+    const std::string fn = std::string(dir) + "/poses-" + std::to_string(m->id) + ".txt";
+    FILE* f = fopen(fn.c_str(), "w");
+    if (!f) return cudaErrorInvalidValue;
+    for (size_t k = 0; k < ts.size(); ++k) {
+      fprintf(f, "%lld", (long long)ts[k]);
+      for (int q = 0; q < 7; ++q) fprintf(f, " %.9g", p[k * 7 + q]);
+      fprintf(f, "\n");
+    }
+    fclose(f);
+    return cudaSuccess;
+  };
+  for (auto& m : models) RET_IF(one(m.get()));
+  for (auto& m : inactiveModels) RET_IF(one(m.get()));
+  return cudaSuccess;
+}
+
+cudaError_t CoFusion::savePly(const char* dir) {  // CoFusion.cpp:646-756
+  Model* g = models[0].get();
+  RET_IF(g->syncPose());
+  for (auto& mp : models) {
+    Model* m = mp.get();
+    RET_IF(m->syncPose());
+    unsigned n = 0;
+    RET_IF(m->lastCount(&n));
+    std::vector<float> map((size_t)n * 12);
+    if (n) RET_IF(m->downloadMap(map.data(), n, &n));
+    // Tp = globalPose * modelPose^-1 for the points; its inverse transpose (= its rotation) for the normals --
+    // the reference initialises Tn from itself (CoFusion.cpp:703), the intended matrix is used here
+    float inv[12], Tp[12];
+    rigid_inverse(m->pose, inv);
+    rigid_mul(g->pose, inv, Tp);
+    size_t valid = 0;
+    for (unsigned i = 0; i < n; ++i) valid += map[(size_t)i * 12 + 3] > m->confidenceThreshold;
+    const std::string fn = std::string(dir) + "/cloud-" + std::to_string(m->id) + ".ply";
+    FILE* f = fopen(fn.c_str(), "wb");
+    if (!f) return cudaErrorInvalidValue;
+    fprintf(f,
+            "ply\nformat binary_little_endian 1.0\nelement vertex %zu\nproperty float x\nproperty float y\nproperty float z"
+            "\nproperty uchar red\nproperty uchar green\nproperty uchar blue\nproperty float nx\nproperty float ny"
+            "\nproperty float nz\nproperty float radius\nend_header\n",
+            valid);
+    for (unsigned i = 0; i < n; ++i) {
+      const float* s = map.data() + (size_t)i * 12;
+      if (!(s[3] > m->confidenceThreshold)) continue;
+      float rec[3], nor[3];
+      for (int r = 0; r < 3; ++r) {
+        rec[r] = Tp[r * 4] * s[0] + Tp[r * 4 + 1] * s[1] + Tp[r * 4 + 2] * s[2] + Tp[r * 4 + 3];
+        nor[r] = -(Tp[r * 4] * s[8] + Tp[r * 4 + 1] * s[9] + Tp[r * 4 + 2] * s[10]);
+      }
+      const int col = (int)s[4];
+      const unsigned char rgb[3] = {(unsigned char)(col >> 16 & 0xFF), (unsigned char)(col >> 8 & 0xFF), (unsigned char)(col & 0xFF)};
+      fwrite(rec, sizeof(float), 3, f);
+      fwrite(rgb, 1, 3, f);
+      fwrite(nor, sizeof(float), 3, f);
+      fwrite(&s[11], sizeof(float), 1, f);
+    }
+    fclose(f);
+  }
   return cudaSuccess;
 }
 

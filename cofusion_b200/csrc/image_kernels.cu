@@ -472,6 +472,26 @@ __global__ void pyr_down_uchar2_kernel(const unsigned char* __restrict__ sa, uns
 
 }  // namespace
 
+// ---- f1: frame ingest on the device (GUI/Tools/KlgLogReader.cpp:53-84: raw u16 depth x 0.001 as cv::Mat::convertTo
+// does it in f32; Core/FrameData.h:38-41: flipColors swaps the first and third channel)
+__global__ void ingest_kernel(const uint8_t* __restrict__ img, const uint16_t* __restrict__ d16, float scale, int flip,
+                              uint8_t* __restrict__ rgb, float* __restrict__ depth, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (d16) depth[i] = __fmul_rn((float)__ldg(d16 + i), scale);
+  if (img) {
+    const uint8_t a = __ldg(img + 3 * i), b = __ldg(img + 3 * i + 1), c = __ldg(img + 3 * i + 2);
+    rgb[3 * i] = flip ? c : a;
+    rgb[3 * i + 1] = b;
+    rgb[3 * i + 2] = flip ? a : c;
+  }
+}
+cudaError_t launch_ingest(const uint8_t* img, const uint16_t* d16, float scale, int flip, uint8_t* rgb, float* depth, int n,
+                          cudaStream_t s) {
+  ingest_kernel<<<(n + 255) / 256, 256, 0, s>>>(img, d16, scale, flip, rgb, depth, n);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_bilateral(const float* depth, size_t dpitch, int W, int H, float maxD, float* out,
                              size_t opitch, cudaStream_t s) {
   bilateral_kernel<<<dim3((W + 31) / 32, (H + 8 * BROWS - 1) / (8 * BROWS)), kBlock, 0, s>>>(depth, dpitch, W, H, maxD, out, opitch);

@@ -5,6 +5,10 @@
 
 namespace cfb {
 
+// frame ingest: raw u16 depth -> metric f32 (x scale), optional first/third channel swap of the 8-bit image
+// (either input may be null: that output is left untouched)
+cudaError_t launch_ingest(const uint8_t* img, const uint16_t* depth_u16, float scale, int flip, uint8_t* rgb, float* depth,
+                          int n, cudaStream_t s);
 cudaError_t launch_bilateral(const float* depth, size_t dpitch, int W, int H, float maxD, float* out,
                              size_t opitch, cudaStream_t s);
 cudaError_t launch_pyr_down_gauss_f(const float* src, size_t spitch, int sw, int sh, float* dst,

@@ -48,6 +48,9 @@ Context::~Context() {
   if (stream) cudaStreamSynchronize(stream);
   if (copyStream) cudaStreamSynchronize(copyStream);
   for (int k = 0; k < 2; ++k) {
+    cudaFree(d16Buf[k]);
+    cudaFreeHost(h_d16Buf[k]);
+    cudaFree(rawImgBuf[k]);
     cudaFree(rgbBuf[k]);
     cudaFree(depthBuf[k]);
     cudaFreeHost(h_rgbBuf[k]);
@@ -110,6 +113,78 @@ cudaError_t Context::uploadFrame(const uint8_t* rgb_h, const float* depth_h, con
     RET_IF(cudaMemcpyAsync(mask, m, n, cudaMemcpyHostToDevice, stream));
   } else if (!keepMask) {
     // static scene: everything is background (CoFusion.cpp:190-197)
+    RET_IF(cudaMemsetAsync(mask, 0, n, stream));
+  }
+  return cudaSuccess;
+}
+
+cudaError_t Context::uploadFrameRaw(const uint8_t* img, bool flip, const float* depth, const uint16_t* depth16, float scale,
+                                    const uint8_t* mask_p, bool device_ptrs) {
+  if (!depth16 && !flip) return device_ptrs ? setFrameDevice(img, depth, mask_p) : uploadFrame(img, depth, mask_p);
+  const size_t n = (size_t)W * H;
+  for (int k = 0; k < 2; ++k) {  // raw buffers of the ingest path, on first use
+    if (depth16 && !d16Buf[k]) {
+      RET_IF(cudaMalloc((void**)&d16Buf[k], n * 2));
+      RET_IF(cudaMallocHost((void**)&h_d16Buf[k], n * 2));
+    }
+    if (flip && !rawImgBuf[k]) RET_IF(cudaMalloc((void**)&rawImgBuf[k], n * 3));
+  }
+  RET_IF(cudaEventRecord(evBufferFree[cur], stream));
+  cur ^= 1;
+  rgb = rgbBuf[cur];
+  depthRaw = depthBuf[cur];
+  cudaStream_t cs = device_ptrs ? stream : copyStream;
+  const cudaMemcpyKind kind = device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  if (!device_ptrs) RET_IF(cudaStreamWaitEvent(copyStream, evBufferFree[cur], 0));
+  cudaPointerAttributes a;
+  auto pinned = [&](const void* q) { return cudaPointerGetAttributes(&a, q) == cudaSuccess && a.type == cudaMemoryTypeHost; };
+  const void *src_img = img, *src_d = depth16 ? (const void*)depth16 : (const void*)depth;
+  if (!device_ptrs) {
+    const bool pi = pinned(img), pd = pinned(src_d);
+    if (!pi || !pd) {
+      cudaGetLastError();
+      RET_IF(cudaEventSynchronize(evCopied[cur]));  // the staging buffers' previous transfer is done
+    }
+    if (!pi) {
+      memcpy(h_rgbBuf[cur], img, n * 3);
+      src_img = h_rgbBuf[cur];
+    }
+    if (!pd) {
+      if (depth16) {
+        memcpy(h_d16Buf[cur], depth16, n * 2);
+        src_d = h_d16Buf[cur];
+      } else {
+        memcpy(h_depthBuf[cur], depth, n * 4);
+        src_d = h_depthBuf[cur];
+      }
+    }
+  }
+  RET_IF(cudaMemcpyAsync(flip ? rawImgBuf[cur] : rgb, src_img, n * 3, kind, cs));
+  if (depth16)
+    RET_IF(cudaMemcpyAsync(d16Buf[cur], src_d, n * 2, kind, cs));
+  else
+    RET_IF(cudaMemcpyAsync(depthRaw, src_d, n * 4, kind, cs));
+  if (!device_ptrs) {
+    RET_IF(cudaEventRecord(evCopied[cur], copyStream));
+    RET_IF(cudaStreamWaitEvent(stream, evCopied[cur], 0));
+  }
+  RET_IF(launch_ingest(flip ? rawImgBuf[cur] : nullptr, depth16 ? d16Buf[cur] : nullptr, scale, flip ? 1 : 0, rgb, depthRaw,
+                       (int)n, stream));
+  launches += 1;
+  if (mask_p) {
+    if (device_ptrs) {
+      RET_IF(cudaMemcpyAsync(mask, mask_p, n, cudaMemcpyDeviceToDevice, stream));
+    } else {
+      const uint8_t* m = mask_p;
+      if (!pinned(mask_p)) {
+        cudaGetLastError();
+        RET_IF(cudaStreamSynchronize(stream));
+        memcpy(h_mask, mask_p, n);
+        m = h_mask;
+      }
+      RET_IF(cudaMemcpyAsync(mask, m, n, cudaMemcpyHostToDevice, stream));
+    }
+  } else if (!keepMask) {
     RET_IF(cudaMemsetAsync(mask, 0, n, stream));
   }
   return cudaSuccess;
@@ -193,8 +268,34 @@ Model::~Model() {
   cudaFree(counters);
   cudaFreeHost(h_counters);
   cudaFree(dpose);
+  cudaFree(poseLogDev);
   cudaFreeHost(h_readback);
   if (evPose) cudaEventDestroy(evPose);
+}
+
+cudaError_t Model::appendPoseLog(int64_t ts, int frame) {
+  const int n = (int)poseLogTs.size(), fetched = (int)(poseLogHost.size() / 12);
+  if (n - fetched >= poseLogCap) {
+    if (poseLogCap) RET_IF(fetchPoseLog());  // device chunk full: move it to the host, reuse it
+    if (!poseLogDev) {
+      poseLogCap = 4096;
+      RET_IF(cudaMalloc((void**)&poseLogDev, (size_t)poseLogCap * 12 * sizeof(float)));
+    }
+  }
+  const int slot = (int)poseLogTs.size() - (int)(poseLogHost.size() / 12);
+  RET_IF(cudaMemcpyAsync(poseLogDev + (size_t)slot * 12, dpose->pose.m, 12 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  poseLogTs.push_back(ts);
+  poseLogFrame.push_back(frame);
+  return cudaSuccess;
+}
+
+cudaError_t Model::fetchPoseLog() {
+  const int fetched = (int)(poseLogHost.size() / 12), pending = (int)poseLogTs.size() - fetched;
+  if (pending <= 0) return cudaSuccess;
+  poseLogHost.resize((size_t)(fetched + pending) * 12);
+  RET_IF(cudaMemcpyAsync(poseLogHost.data() + (size_t)fetched * 12, poseLogDev, (size_t)pending * 12 * sizeof(float),
+                         cudaMemcpyDeviceToHost, ctx->stream));
+  return cudaStreamSynchronize(ctx->stream);
 }
 
 cudaError_t Model::uploadPose() {

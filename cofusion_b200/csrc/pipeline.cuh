@@ -10,6 +10,8 @@
 #pragma once
 #include <stdint.h>
 
+#include <vector>
+
 #include "cfb_common.cuh"
 #include "odometry.cuh"
 #include "surfel_kernels.cuh"
@@ -26,6 +28,11 @@ class Context {
   cudaError_t uploadFrame(const uint8_t* rgb_hwc, const float* depth, const uint8_t* mask);
   // same, inputs already resident in device memory
   cudaError_t setFrameDevice(const uint8_t* rgb_hwc, const float* depth, const uint8_t* mask);
+  // Frame ingest on the device (KlgLogReader.cpp:53-84, FrameData.h:38-41): raw u16 depth (x depthScale) and / or an
+  // image whose first and third channels are swapped travel as they are (1.54 MB instead of 2.15 MB per VGA frame) and
+  // are converted by one kernel.  depth16 == nullptr: `depth` is metric f32 as in uploadFrame.
+  cudaError_t uploadFrameRaw(const uint8_t* img_hwc, bool flipColors, const float* depth, const uint16_t* depth16,
+                             float depthScale, const uint8_t* mask, bool device_ptrs);
   // filterDepth (CoFusion.cpp:567-574) + Model::generateCUDATextures (Model.cpp:319-348)
   cudaError_t preprocess(float depthCutoff);
   cudaError_t sync() { return cudaStreamSynchronize(stream); }
@@ -48,6 +55,9 @@ class Context {
   float* depthFiltered = nullptr;   // level 0 of the pyramid
   float* depthPyr[3] = {nullptr, nullptr, nullptr};
   uint8_t* mask = nullptr;          // label image (model ids)
+  uint16_t* d16Buf[2] = {nullptr, nullptr};    // raw depth of the ingest path (allocated on first use)
+  uint16_t* h_d16Buf[2] = {nullptr, nullptr};
+  uint8_t* rawImgBuf[2] = {nullptr, nullptr};  // image before the channel swap
   uint8_t* h_rgb = nullptr;         // pinned staging for pageable callers
   float* h_depth = nullptr;
   uint8_t* h_mask = nullptr;
@@ -128,6 +138,14 @@ class Model {
   cudaEvent_t evPose = nullptr;
   bool poseStale = false;         // the device block is newer than pose / lastPose / odom.stats()
   int cleanTick = 0;              // tick of the last clean() enqueued (bounds the surfel count without a sync)
+  // optional pose log (Model::poseLog, Model.h:230-242): one 3x4 pose per logged frame, kept on the device
+  float* poseLogDev = nullptr;
+  int poseLogCap = 0;
+  std::vector<int64_t> poseLogTs;     // timestamp of entry k
+  std::vector<int> poseLogFrame;      // index of the frame (camera-model entry) entry k belongs to
+  std::vector<float> poseLogHost;     // entries already fetched (12 floats each)
+  cudaError_t appendPoseLog(int64_t ts, int frame);
+  cudaError_t fetchPoseLog();         // device entries -> poseLogHost (synchronises)
   float confidenceThreshold;
   float maxDepth;               // per-model depth limit (Model::setMaxDepth)
   bool allowsFillIn;

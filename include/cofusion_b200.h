@@ -313,6 +313,41 @@ void cfb_cofusion_destroy(cfb_cofusion* f);
  * f32 metres, mask: HxW u8 labels or NULL (static scene).  Host buffers unless device_ptrs != 0. */
 int cfb_cofusion_process_frame(cfb_cofusion* f, const uint8_t* rgb, const float* depth, const uint8_t* mask,
                                int device_ptrs, float weightMultiplier);
+/* FrameData (Core/FrameData.h:25-50) as the log readers hand it to processFrame, plus the two conversions
+ * they perform on the CPU (GUI/Tools/KlgLogReader.cpp:53-84: raw u16 depth x 0.001 -> f32 metres;
+ * FrameData::flipColors :38-41: BGR -> RGB), which this module runs on the device instead. */
+typedef struct cfb_frame {
+  const uint8_t* rgb;         /* H x W x 3, 8 bit */
+  const float* depth;         /* metric f32, or NULL when depth_u16 is given */
+  const uint16_t* depth_u16;  /* raw sensor units, or NULL */
+  float depth_scale;          /* metres per raw unit (0.001) */
+  int flip_colors;            /* != 0: the image is BGR */
+  const uint8_t* mask;        /* external label image or NULL */
+  int device_ptrs;            /* != 0: the pointers above are device pointers */
+  int64_t timestamp;          /* FrameData::timestamp, logged with the poses (CoFusion.cpp:516) */
+} cfb_frame;
+/* bool CoFusion::processFrame(const FrameData& frame, const Eigen::Matrix4f* inPose, const float
+ * weightMultiplier, const bool bootstrap) (Core/CoFusion.h:67-68, Core/CoFusion.cpp:170).  inPose16 (row-major
+ * 4x4) NULL: regular tracking.  inPose16 && !bootstrap: the camera pose is overridden, nothing is tracked or
+ * segmented (CoFusion.cpp:343-345).  bootstrap (needs inPose16): track, then pose <- pose * inPose (:219-222). */
+int cfb_cofusion_process_frame_ex(cfb_cofusion* f, const cfb_frame* frame, const float* inPose16, float weightMultiplier,
+                                  int bootstrap);
+/* Model pose logging (Model.h:230-242, enablePoseLogging) and the exports of CoFusion.cpp:646-783.
+ * pose_log: entries of model `index` -- ts[k], pose7[7k..7k+6] = t.xyz, q.xyzw: camera -> world for model 0,
+ * object -> world = cameraPose * modelPose^-1 otherwise (CoFusion.cpp:503-518).  *n = entries available. */
+int cfb_cofusion_enable_pose_logging(cfb_cofusion* f, int on);
+int cfb_cofusion_pose_log(cfb_cofusion* f, int index, int64_t* ts, float* pose7, int capacity, int* n);
+int cfb_cofusion_export_poses(cfb_cofusion* f, const char* directory); /* poses-<id>.txt (exportPoses) */
+int cfb_cofusion_save_ply(cfb_cofusion* f, const char* directory);     /* cloud-<id>.ply (savePly) */
+/* Object sharding over the GPUs of one node (one process per GPU): rank r owns the models spawned in ITS cfb_cofusion
+ * (convention: model k of the scene on rank k % world).  cfb_nccl_unique_id on rank 0, distributed by the application;
+ * cfb_cofusion_shard_init is collective.  Afterwards EVERY rank calls cfb_cofusion_process_frame(_ex) for every frame:
+ * only rank 0's rgb / f32 depth / mask pointers are read (the others may pass NULL), the packed frame reaches the other
+ * ranks by one ncclBroadcast, every rank filters the depth and builds the pyramids locally.  External label masks only
+ * (enableMultipleModels = 0).  Replaces the implicit `for (auto model : models)` loops of Core/CoFusion.cpp:214-217,
+ * :465-488, :536-542 by one loop per rank. */
+int cfb_nccl_unique_id(unsigned char id[128]);
+int cfb_cofusion_shard_init(cfb_cofusion* f, int rank, int world, const unsigned char id[128]);
 /* CoFusion::spawnObjectModel + the first fuse of the new model (CoFusion.cpp:252-276) */
 int cfb_cofusion_spawn_object_model(cfb_cofusion* f, unsigned id, const float* initialPose16);
 int cfb_cofusion_num_models(cfb_cofusion* f);

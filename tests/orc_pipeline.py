@@ -7,8 +7,11 @@ import orc
 
 class OraclePipeline:
     def __init__(self, W, H, K, max_surfels=1 << 20, conf_global=10.0, depth_cutoff=5.0, max_depth=20.0,
-                 icp_weight=10.0, time_delta=200, outlier_coeff=3.0):
+                 icp_weight=10.0, time_delta=200, outlier_coeff=3.0, predict_before_fuse=True):
         self.W, self.H, self.K = W, H, K
+        # CoFusion.cpp:347 renders a prediction between tracking and fusing that only the loop closure reads
+        # (out of scope); the product skips it (predictBeforeFuse = 0).  Results do not depend on it.
+        self.predict_before_fuse = predict_before_fuse
         self.map = orc.OrcMap(W, H, K, max_surfels)
         self.odom = orc.OrcOdometry(W, H, K)
         self.pose = np.eye(4, dtype=np.float32)
@@ -39,7 +42,8 @@ class OraclePipeline:
             self.odom.init_model(v4, n4, img, self.pose)
             self.odom.init_frame(df, rgb, self.max_depth)
             self.pose, self.stats, _, _ = self.odom.track(self.pose, icp_weight=self.icp_weight)
-            self.predict(rgb, df)
+            if self.predict_before_fuse:
+                self.predict(rgb, df)
             w = orc.OrcMap.fusion_weight(self.pose, self.last_pose, 1.0)
             m.predict_indices(self.pose, self.tick, self.max_depth, self.time_delta)
             m.fuse(self.pose, self.tick, rgb, mask, depth, df, self.max_depth, w, 0)

@@ -77,3 +77,41 @@ int main(void) {
             C.sizeof(cfb.CoFusionParams), cfb.CoFusionParams.seg.offset, cfb.CoFusionParams.modelSpawnOffset.offset,
             cfb.ModelData.left.offset, cfb.TrackStats.so3_iterations.offset]
     assert got == want, (got, want)
+
+
+def _build_binding(tmp_path):
+    import subprocess
+    exe = tmp_path / "binding_test"
+    libdir = os.path.join(ROOT, "cofusion_b200")
+    subprocess.run(["g++", "-std=c++14", "-Wall", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "binding", "cofusion_binding.cpp"), "-L", libdir, "-lcofusion_b200",
+                    "-Wl,-rpath," + libdir, "-o", str(exe)], check=True)
+    return exe
+
+
+def test_reference_side_binding_compiles_and_fails_loudly_without_a_device(tmp_path):
+    """INTEGRATION.md section 1 as a compiled C++ translation unit (tests/binding/cofusion_binding.cpp): the
+    header is valid C++ and C, the binding links against the shared library alone, and without a CUDA device the
+    reference-side constructor throws the library's error instead of computing on the CPU."""
+    import subprocess
+    cfb_build.build()
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), "-x", "c",
+                    "-include", "cofusion_b200.h", "/dev/null"], check=True)
+    exe = _build_binding(tmp_path)
+    if cofusion_b200.lib().cfb_device_count() > 0:
+        return  # the GPU suite runs it for real (tests/test_boundary_gpu.py)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "no CUDA device" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+def test_frame_struct_matches_the_header(tmp_path):
+    import ctypes as C
+    import subprocess
+    import cofusion_b200 as cfb
+    src = tmp_path / "frame.c"
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "cofusion_b200.h"\nint main(void){printf("%zu %zu %zu\\n", '
+                   'sizeof(cfb_frame), offsetof(cfb_frame, timestamp), offsetof(cfb_frame, mask));return 0;}\n')
+    exe = tmp_path / "frame"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert got == [C.sizeof(cfb.Frame), cfb.Frame.timestamp.offset, cfb.Frame.mask.offset], got

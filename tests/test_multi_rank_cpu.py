@@ -25,32 +25,30 @@ def _worker(rank, world, port, W, H, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import bench
-    P = W * H
+    from cofusion_b200 import sharding
     rng = np.random.default_rng(7)
     rgb = rng.integers(1, 255, (H, W, 3), dtype=np.uint8)
     depth = rng.uniform(0.5, 4.0, (H, W)).astype(np.float32)
-    recv = torch.zeros(7 * P, dtype=torch.uint8)
-    sums = []
+    mask = rng.integers(0, 3, (H, W), dtype=np.uint8)
+    recv = torch.zeros(sharding.packed_bytes(W, H), dtype=torch.uint8)
     for step in range(3):
-        if rank == 0:  # the root packs [rgb u8 3P | depth f32 4P]
-            recv[:3 * P] = torch.from_numpy(rgb.reshape(-1)) + step
-            recv[3 * P:] = torch.from_numpy((depth + step).reshape(-1).view(np.uint8))
-        dist.broadcast(recv, src=0)  # the single collective of the data path
-        r = recv[:3 * P].numpy().reshape(H, W, 3)
-        d = recv[3 * P:].view(torch.float32).numpy().reshape(H, W)
-        assert np.array_equal(r, rgb + step) and np.array_equal(d, depth + step)
-        sums.append(float(d.sum()))
+        if rank == 0:  # the root packs [rgb u8 3P | depth f32 4P | mask u8 P]: the layout the library broadcasts
+            recv.copy_(torch.from_numpy(sharding.pack_frame(rgb + step, depth + step, mask)))
+        dist.broadcast(recv, src=0)  # the single collective of the data path (ncclBroadcast in csrc/shard.cu)
+        r, d, m = sharding.unpack_frame(recv.numpy(), W, H)
+        assert np.array_equal(r, rgb + step) and np.array_equal(d, depth + step) and np.array_equal(m, mask)
         assert bench.frame_index(step, 4) in range(4)
-    # rank r owns model r: ids are disjoint and cover the model list
-    models = list(range(5))
-    mine = [m for m in models if m % world == rank]
+    # rank r owns model r: the per-rank model lists are disjoint and cover the scene
+    n_models = 5
+    mine = sharding.models_of_rank(n_models, rank, world)
     gathered = [None] * world
     dist.all_gather_object(gathered, mine)
-    if rank == 0:
-        assert sorted(sum(gathered, [])) == models
+    assert sorted(sum(gathered, [])) == list(range(n_models))
+    assert sharding.scene_models(1) == 1 and sharding.scene_models(8) == 8 and sharding.owner(0, world) == 0
     t = torch.tensor([float(rank + 1)])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max-over-ranks timing reduction used by bench.py
     assert t.item() == world
+    assert abs(sharding.aggregate_value(world, 100, 50.0) - world * 2000.0) < 1e-6
     dist.destroy_process_group()
 
 
