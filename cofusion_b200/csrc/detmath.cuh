@@ -37,6 +37,36 @@ __host__ __device__ __forceinline__ float det_expf(float x) {
   return (x_in >= -87.0f) ? v : ((x_in != x_in) ? x_in : 0.0f);
 }
 
+#ifdef __CUDACC__
+// Two det_expf at once on Blackwell's packed f32x2 pipe (fma.rn.f32x2 / mul / add: IEEE per lane, so each lane is
+// bit-identical to det_expf): the polynomial, which is most of the work, costs half the issue slots.  For
+// arguments <= 0 only (the bilateral weights): the upper clamp of det_expf can never bind there.
+__device__ __forceinline__ float2 det_expf2_nonpos(float2 x) {
+  const float2 x_in = x;
+  x.x = fmaxf(x.x, -87.0f);
+  x.y = fmaxf(x.y, -87.0f);
+  float2 n = __fmul2_rn(x, make_float2(1.44269504088896341f, 1.44269504088896341f));
+  n.x = rintf(n.x);
+  n.y = rintf(n.y);
+  float2 r = __ffma2_rn(n, make_float2(-0.693359375f, -0.693359375f), x);
+  r = __ffma2_rn(n, make_float2(2.12194440e-4f, 2.12194440e-4f), r);
+  float2 p = make_float2(1.9875691500E-4f, 1.9875691500E-4f);
+  p = __ffma2_rn(p, r, make_float2(1.3981999507E-3f, 1.3981999507E-3f));
+  p = __ffma2_rn(p, r, make_float2(8.3334519073E-3f, 8.3334519073E-3f));
+  p = __ffma2_rn(p, r, make_float2(4.1665795894E-2f, 4.1665795894E-2f));
+  p = __ffma2_rn(p, r, make_float2(1.6666665459E-1f, 1.6666665459E-1f));
+  p = __ffma2_rn(p, r, make_float2(5.0000001201E-1f, 5.0000001201E-1f));
+  const float2 y = __fadd2_rn(__ffma2_rn(p, __fmul2_rn(r, r), r), make_float2(1.0f, 1.0f));
+  float2 sc;
+  sc.x = __int_as_float(((int)n.x + 127) << 23);
+  sc.y = __int_as_float(((int)n.y + 127) << 23);
+  float2 v = __fmul2_rn(y, sc);
+  v.x = (x_in.x >= -87.0f) ? v.x : ((x_in.x != x_in.x) ? x_in.x : 0.0f);
+  v.y = (x_in.y >= -87.0f) ? v.y : ((x_in.y != x_in.y) ? x_in.y : 0.0f);
+  return v;
+}
+#endif
+
 // Deterministic double acos (Cephes asin / acos rational approximations, |err| <= 2 ulp): only IEEE
 // + - * / and sqrt in a fixed order, never contracted (explicit round-to-nearest intrinsics on the device,
 // no FMA instructions in the host build), so host, device and the CPU oracle agree bit for bit.

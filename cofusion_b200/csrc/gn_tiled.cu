@@ -98,7 +98,7 @@ struct TParams {
   float distThres, angleThres, maxDepthDelta, sobelScale, icpWeight;
   int use_so3;
   int iters[3];
-  unsigned o_wrow, o_out, o_corr;
+  unsigned o_wrow, o_blk, o_out, o_corr;
   unsigned long long* dbg;
 };
 static_assert(sizeof(TParams) <= 4000, "kernel parameter block");
@@ -385,11 +385,25 @@ __device__ __noinline__ void phase1(int lvl, int m) {
 }
 
 // ------------------------------------------------------------------------------------------ phase 2
-__device__ __forceinline__ void store_warp_row(int m, int set, bool any, float (&acc)[32]) {
+// Per-CTA reduction of a phase: every warp leaves its 32 sums (warp transpose) in one of two alternating
+// row buffers; after the block barrier that follows the phase, fold_warp_rows() adds the 18 rows in warp order
+// into blk[m][set * 29 + j].  The buffers alternate from phase to phase, so the fold of one phase overlaps the
+// next phase and one barrier per phase suffices (the buffer written two phases ago has been folded by then).
+__device__ __forceinline__ void store_warp_row(int buf, bool any, float (&acc)[32]) {
   TSMEM();
-  float* wrow = SM_F32(p.o_wrow) + ((size_t)(m * 2 + set) * kNW + (threadIdx.x >> 5)) * 32;
+  float* wrow = SM_F32(p.o_wrow) + ((size_t)buf * kNW + (threadIdx.x >> 5)) * 32;
   // a warp without any contribution adds exact zeros: skip its 31-shuffle transpose
   wrow[threadIdx.x & 31] = __any_sync(0xffffffffu, any) ? warp_transpose_reduce32(acc) : 0.f;
+}
+__device__ __forceinline__ void fold_warp_rows(int buf, int m, int set, int nsums) {
+  TSMEM();
+  if ((int)threadIdx.x < nsums) {
+    const float* r = SM_F32(p.o_wrow) + (size_t)buf * kNW * 32 + threadIdx.x;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kNW; ++w) s += r[w * 32];  // warp order
+    SM_F32(p.o_blk)[m * 64 + set * 29 + threadIdx.x] = s;
+  }
 }
 
 __device__ __forceinline__ void icp_found_row(const IcpPose& P, float3 tprev, float3 vcurr_cp, float3 vp, float3 np,
@@ -401,8 +415,92 @@ __device__ __forceinline__ void icp_found_row(const IcpPose& P, float3 tprev, fl
   xaccumulate_se3(acc, row);
 }
 
+// One pixel of the ICP pass, written without early exits (everything is computed, invalid stages are masked):
+// two pixels evaluated back to back form one straight-line block, which lets the scheduler interleave their
+// dependency chains -- the pass is bound by instruction latency, not by memory (the gathers are shared-memory
+// reads).  Returns the Jacobian row (zeros unless a correspondence was found).
+struct IcpEval {
+  float row[7];
+  bool found;
+};
 template <bool FS, bool MS>
-__device__ __noinline__ void phase2(int lvl, int m, float* error_map) {
+__device__ __forceinline__ IcpEval icp_eval(const LvCtx& c, const MLevel& L, const FLevel& F, const IcpPose& P, float3 tcurr,
+                                             float3 tprev, float distThres, float angleThres, bool live, int lx, int ly,
+                                             float* error_map, size_t err_pitch) {
+  extern __shared__ __align__(128) unsigned char dyn_smem_raw[];
+  const int x = c.x0 + lx, y = c.y0 + ly;
+  const bool valid = live && x < c.W && y < c.H;
+  const int HW = c.W * c.H;
+  const int fi = valid ? ly * c.pf + lx + c.shf : 0;  // index into the f32 frame tiles (0: always readable)
+  const int gi = valid ? y * c.W + x : 0;
+  float3 vcurr, ncurr;
+  if (FS) {
+    vcurr = make_float3(SM_F32(c.oV)[fi], SM_F32(c.oV)[c.fplane + fi], SM_F32(c.oV)[2 * c.fplane + fi]);
+    ncurr = make_float3(SM_F32(c.oN)[fi], SM_F32(c.oN)[c.fplane + fi], SM_F32(c.oN)[2 * c.fplane + fi]);
+  } else {
+    vcurr = make_float3(__ldg(F.vmap_curr + gi), __ldg(F.vmap_curr + HW + gi), __ldg(F.vmap_curr + 2 * HW + gi));
+    ncurr = make_float3(__ldg(F.nmap_curr + gi), __ldg(F.nmap_curr + HW + gi), __ldg(F.nmap_curr + 2 * HW + gi));
+  }
+  // an invalid vertex has NaN in x: every coordinate of vcurr_g is NaN, dist is NaN -> no correspondence, error 0
+  const bool has_v = valid && !isnan(vcurr.x);
+  const float3 vcurr_g = xadd(xmul(P.Rcurr, vcurr), tcurr);
+  const float3 vcurr_cp = xmul(P.Rprev_inv, xsub(vcurr_g, tprev));
+  const int ux = __float2int_rn(__fadd_rn(__fdiv_rn(__fmul_rn(vcurr_cp.x, c.fx), vcurr_cp.z), c.cx));
+  const int uy = __float2int_rn(__fadd_rn(__fdiv_rn(__fmul_rn(vcurr_cp.y, c.fy), vcurr_cp.z), c.cy));
+  const bool inb = has_v && !(ux < 0 || uy < 0 || ux >= c.W || uy >= c.H || vcurr_cp.z < 0);
+  const int wu = ux - c.wx0, wv = uy - c.wy0;
+  const bool inwin = MS && inb && (unsigned)wu < (unsigned)c.wwl && (unsigned)wv < (unsigned)c.wh;
+  float3 vp = make_float3(0.f, 0.f, 0.f), np = vp;
+  if (MS) {
+    const int j = inwin ? wv * c.wpf + wu + c.wshf : 0;
+    vp = make_float3(SM_F32(c.oPV)[j], SM_F32(c.oPV)[c.wplane + j], SM_F32(c.oPV)[2 * c.wplane + j]);
+    np = make_float3(SM_F32(c.oPN)[j], SM_F32(c.oPN)[c.wplane + j], SM_F32(c.oPN)[2 * c.wplane + j]);
+  }
+  bool have = inwin;
+  if (inb && !inwin) {  // outside the staged window (always, for object models): the same values from global memory
+    const int j = uy * c.W + ux;
+    vp.x = __ldg(L.vmap_g_prev + j);
+    // An object model predicts a few percent of the image; everywhere else its vertex map is NaN.  A NaN in the
+    // x plane makes dist NaN whatever the other five planes hold: they are only fetched where the object is.
+    if (!isnan(vp.x)) {
+      vp.y = __ldg(L.vmap_g_prev + HW + j);
+      vp.z = __ldg(L.vmap_g_prev + 2 * HW + j);
+      np = make_float3(__ldg(L.nmap_g_prev + j), __ldg(L.nmap_g_prev + HW + j), __ldg(L.nmap_g_prev + 2 * HW + j));
+      have = true;
+    }
+  }
+  const float3 ncurr_g = xmul(P.Rcurr, ncurr);
+  const float dist = xnorm(xsub(vp, vcurr_g));
+  const float sine = xnorm(xcross(ncurr_g, np));
+  if (error_map && valid) row_ptr(error_map, err_pitch, y)[x] = (have && isfinite(dist)) ? dist : 0.0f;
+  IcpEval e;
+  e.found = have && sine < angleThres && dist <= distThres && !isnan(ncurr.x) && !isnan(np.x);
+  const float3 d_cp = xmul(P.Rprev_inv, xsub(vp, tprev));
+  const float3 n_cp = xmul(P.Rprev_inv, np);
+  const float3 cr = xcross(vcurr_cp, n_cp);
+  const float r6 = xdot(n_cp, xsub(vcurr_cp, d_cp));
+  e.row[0] = e.found ? n_cp.x : 0.f;
+  e.row[1] = e.found ? n_cp.y : 0.f;
+  e.row[2] = e.found ? n_cp.z : 0.f;
+  e.row[3] = e.found ? cr.x : 0.f;
+  e.row[4] = e.found ? cr.y : 0.f;
+  e.row[5] = e.found ? cr.z : 0.f;
+  e.row[6] = e.found ? r6 : 0.f;
+  return e;
+}
+// products of a row that is all zeros are exact zeros: masked pixels leave the sums untouched
+__device__ __forceinline__ void xaccumulate_masked(float (&acc)[32], const IcpEval& e) {
+  int k = 0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = i; j < 7; ++j, ++k) acc[k] = __fmaf_rn(e.row[i], e.row[j], acc[k]);
+  acc[27] = __fmaf_rn(e.row[6], e.row[6], acc[27]);
+  acc[28] = __fadd_rn(acc[28], e.found ? 1.f : 0.f);
+}
+
+template <bool FS, bool MS>
+__device__ __noinline__ void phase2(int lvl, int m, float* error_map, int buf) {
   TSMEM();
   const LvCtx& c = sm.lv;
   const MLevel& L = p.M[m].L[lvl];
@@ -413,66 +511,22 @@ __device__ __noinline__ void phase2(int lvl, int m, float* error_map) {
   for (int i = 0; i < 32; ++i) acc[i] = 0.f;
   const float3 tcurr = make_float3(P.tcurr[0], P.tcurr[1], P.tcurr[2]);
   const float3 tprev = make_float3(P.tprev[0], P.tprev[1], P.tprev[2]);
-  const int HW = c.W * c.H;
   bool any = false;
-  for (PixIt it = pix_begin(c); it.i < c.npx; pix_next(c, it)) {
-    const int x = c.x0 + it.lx, y = c.y0 + it.ly;
-    if (x >= c.W || y >= c.H) continue;
-    const int fi = it.ly * c.pf + it.lx + c.shf;  // index into the f32 frame tiles
-    const int gi = y * c.W + x;
-    float3 vcurr;
-    vcurr.x = FS ? SM_F32(c.oV)[fi] : __ldg(F.vmap_curr + gi);
-    float* const err = error_map ? row_ptr(error_map, p.err_pitch, y) + x : nullptr;
-    // an invalid vertex has NaN in x: every coordinate of vcurr_g is NaN, dist is NaN -> no
-    // correspondence, error 0 (same outcome as running the arithmetic, without the gathers)
-    if (isnan(vcurr.x)) {
-      if (err) *err = 0.0f;
-      continue;
-    }
-    vcurr.y = FS ? SM_F32(c.oV)[c.fplane + fi] : __ldg(F.vmap_curr + HW + gi);
-    vcurr.z = FS ? SM_F32(c.oV)[2 * c.fplane + fi] : __ldg(F.vmap_curr + 2 * HW + gi);
-    const float3 vcurr_g = xadd(xmul(P.Rcurr, vcurr), tcurr);
-    const float3 vcurr_cp = xmul(P.Rprev_inv, xsub(vcurr_g, tprev));
-    const int ux = __float2int_rn(__fadd_rn(__fdiv_rn(__fmul_rn(vcurr_cp.x, c.fx), vcurr_cp.z), c.cx));
-    const int uy = __float2int_rn(__fadd_rn(__fdiv_rn(__fmul_rn(vcurr_cp.y, c.fy), vcurr_cp.z), c.cy));
-    if (ux < 0 || uy < 0 || ux >= c.W || uy >= c.H || vcurr_cp.z < 0) {
-      if (err) *err = 0.0f;
-      continue;
-    }
-    float3 vp, np;
-    const int wu = ux - c.wx0, wv = uy - c.wy0;
-    if (MS && (unsigned)wu < (unsigned)c.wwl && (unsigned)wv < (unsigned)c.wh) {
-      const int j = wv * c.wpf + wu + c.wshf;
-      vp = make_float3(SM_F32(c.oPV)[j], SM_F32(c.oPV)[c.wplane + j], SM_F32(c.oPV)[2 * c.wplane + j]);
-      np = make_float3(SM_F32(c.oPN)[j], SM_F32(c.oPN)[c.wplane + j], SM_F32(c.oPN)[2 * c.wplane + j]);
-    } else {
-      const int j = uy * c.W + ux;
-      vp.x = __ldg(L.vmap_g_prev + j);
-      // An object model predicts a few percent of the image; everywhere else its vertex map is NaN.
-      // A NaN in the x plane makes dist NaN whatever the other five planes hold.
-      if (isnan(vp.x)) {
-        if (err) *err = 0.0f;
-        continue;
-      }
-      vp.y = __ldg(L.vmap_g_prev + HW + j);
-      vp.z = __ldg(L.vmap_g_prev + 2 * HW + j);
-      np = make_float3(__ldg(L.nmap_g_prev + j), __ldg(L.nmap_g_prev + HW + j), __ldg(L.nmap_g_prev + 2 * HW + j));
-    }
-    float3 ncurr;
-    if (FS)
-      ncurr = make_float3(SM_F32(c.oN)[fi], SM_F32(c.oN)[c.fplane + fi], SM_F32(c.oN)[2 * c.fplane + fi]);
-    else
-      ncurr = make_float3(__ldg(F.nmap_curr + gi), __ldg(F.nmap_curr + HW + gi), __ldg(F.nmap_curr + 2 * HW + gi));
-    const float3 ncurr_g = xmul(P.Rcurr, ncurr);
-    const float dist = xnorm(xsub(vp, vcurr_g));
-    const float sine = xnorm(xcross(ncurr_g, np));
-    if (err) *err = isfinite(dist) ? dist : 0.0f;
-    if (sine < p.angleThres && dist <= p.distThres && !isnan(ncurr.x) && !isnan(np.x)) {
-      any = true;
-      icp_found_row(P, tprev, vcurr_cp, vp, np, acc);
-    }
+  PixIt it = pix_begin(c);
+  while (it.i < c.npx) {  // two pixels per trip (the second may lie past the tile: masked)
+    const int lxa = it.lx, lya = it.ly;
+    pix_next(c, it);
+    const bool liveb = it.i < c.npx;
+    const int lxb = it.lx, lyb = it.ly;
+    pix_next(c, it);
+    const IcpEval a = icp_eval<FS, MS>(c, L, F, P, tcurr, tprev, p.distThres, p.angleThres, true, lxa, lya, error_map, p.err_pitch);
+    const IcpEval b = icp_eval<FS, MS>(c, L, F, P, tcurr, tprev, p.distThres, p.angleThres, liveb, lxb, lyb, error_map, p.err_pitch);
+    any = any || a.found || b.found;
+    // the order of the two accumulations is the pixel order: the sums are the same as one pixel per trip
+    xaccumulate_masked(acc, a);
+    xaccumulate_masked(acc, b);
   }
-  store_warp_row(m, 0, any, acc);
+  store_warp_row(buf, any, acc);
 }
 
 // ------------------------------------------------------------------------------------------ phase 3
@@ -501,7 +555,7 @@ __device__ __forceinline__ void rgb_row(const LvCtx& c, float sigma, float sobel
 }
 
 template <bool FS, bool MS>
-__device__ __noinline__ void phase3(int lvl, int m, float sigma) {
+__device__ __noinline__ void phase3(int lvl, int m, float sigma, int buf) {
   TSMEM();
   const LvCtx& c = sm.lv;
   const FLevel& F = p.F[lvl];
@@ -532,12 +586,12 @@ __device__ __noinline__ void phase3(int lvl, int m, float sigma) {
       rgb_row(c, sigma, p.sobelScale, u0, v0, d0, diff, sdx, sdy, acc);
     }
   }
-  store_warp_row(m, 1, any, acc);
+  store_warp_row(buf, any, acc);
 }
 
 // ------------------------------------------------------------------------- exact grid-wide sums
-// Thread t < nm * NS adds sum (m = t / NS, j = t % NS) of this CTA -- its 18 warp rows folded in warp order --
-// to the global accumulators of the round.  The f32 partial is split exactly: d = hi * 2^8 + rem, |rem| < 2^8,
+// Thread t < nm * NS adds sum (m = t / NS, j = t % NS) of this CTA (blk[m][j], see fold_warp_rows) to the global
+// accumulators of the round.  The f32 partial is split exactly: d = hi * 2^8 + rem, |rem| < 2^8,
 // lo = rint(rem * 2^39) (|error| <= 2^-40); both integers go up by 8 bits and carry a 1 in the low byte, so a
 // word also counts its contributions.  Integer addition commutes: the grid total does not depend on the
 // order in which the CTAs arrive.
@@ -545,12 +599,7 @@ template <int NS>
 __device__ __forceinline__ void publish_sums(unsigned round) {
   TSMEM();
   const int t = threadIdx.x, m = t / NS, j = t - m * NS;
-  const int set = j >= 29 ? 1 : 0, idx = j - 29 * set;
-  const float* r = SM_F32(p.o_wrow) + ((size_t)(m * 2 + set) * kNW) * 32 + idx;
-  float s = 0.f;
-#pragma unroll
-  for (int w = 0; w < kNW; ++w) s += r[w * 32];  // warp order
-  double d = (double)s;
+  double d = (double)SM_F32(p.o_blk)[m * 64 + j];
   if (!(fabs(d) < 9.0e15)) d = 0.0;  // non-finite (or absurd) partial: contributes nothing but still counts
   const long long hi = (long long)(d * (1.0 / 256.0));
   const long long lo = __double2ll_rn((d - (double)hi * 256.0) * 549755813888.0 /* 2^39 */);
@@ -1077,6 +1126,7 @@ __device__ __noinline__ void run_level(int lvl, int q0, int nit, unsigned round0
   const int NM = p.nmodels, G = gridDim.x;
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool FS = p.F[lvl].staged != 0;
+  int wbuf = 0;
   for (int it = 0; it < nit; ++it) {
     const int q = q0 + it;
     const unsigned round = round0 + it;
@@ -1104,14 +1154,16 @@ __device__ __noinline__ void run_level(int lvl, int q0, int nit, unsigned round0
     DBG_MARK(8 + q * 8 + 1);
 
     // -------- phase 2: ICP rows (independent of the counts: hides barrier A)
-    for (int m = 0; m < NM; ++m) {
+    for (int m = 0; m < NM; ++m, wbuf ^= 1) {
       float* const err = last_of_l0 ? p.M[m].err : nullptr;
       if (FS && m == 0)
-        phase2<true, true>(lvl, m, err);
+        phase2<true, true>(lvl, m, err, wbuf);
       else if (FS)
-        phase2<true, false>(lvl, m, err);
+        phase2<true, false>(lvl, m, err, wbuf);
       else
-        phase2<false, false>(lvl, m, err);
+        phase2<false, false>(lvl, m, err, wbuf);
+      __syncthreads();
+      fold_warp_rows(wbuf, m, 0, 29);
     }
     DBG_MARK(8 + q * 8 + 2);
     if ((int)threadIdx.x < NM) {  // wait for barrier A: all G arrivals carry the global count / sigma
@@ -1131,11 +1183,14 @@ __device__ __noinline__ void run_level(int lvl, int q0, int nit, unsigned round0
       const float sigma = rgb_sigma_from_counts(sm.tot[m][0], sm.tot[m][1], &tmpErr);
       if (threadIdx.x == 0) sm.tmpErr[m] = tmpErr;
       if (FS && m == 0)
-        phase3<true, true>(lvl, m, sigma);
+        phase3<true, true>(lvl, m, sigma, wbuf);
       else if (FS)
-        phase3<true, false>(lvl, m, sigma);
+        phase3<true, false>(lvl, m, sigma, wbuf);
       else
-        phase3<false, false>(lvl, m, sigma);
+        phase3<false, false>(lvl, m, sigma, wbuf);
+      __syncthreads();
+      fold_warp_rows(wbuf, m, 1, 29);
+      wbuf ^= 1;
     }
     __syncthreads();
     DBG_MARK(8 + q * 8 + 4);
@@ -1164,6 +1219,7 @@ __device__ __noinline__ unsigned run_so3() {
   const int x0 = (blockIdx.x % p.gx) * F.tw, y0 = (blockIdx.x / p.gx) * F.th;
   const unsigned warp = threadIdx.x >> 5;
   unsigned round = 0;
+  int wbuf = 0;
   for (int it = 0; it < 10; ++it) {
     bool all_done = true;  // identical in every CTA
     for (int m = 0; m < NM; ++m) all_done = all_done && sm.S[m].so3_done;
@@ -1183,7 +1239,10 @@ __device__ __noinline__ unsigned run_so3() {
           }
         }
       }
-      store_warp_row(m, 0, work, acc);
+      store_warp_row(wbuf, work, acc);
+      __syncthreads();
+      fold_warp_rows(wbuf, m, 0, 11);
+      wbuf ^= 1;
     }
     __syncthreads();
     if ((int)threadIdx.x < NM * 11) publish_sums<11>(round);
@@ -1349,7 +1408,7 @@ struct RGBDOdometry::TiledState {
   int gx = 1, gy = 1;
   FLevel F[3];          // plan part of the frame levels (pointers filled per launch)
   unsigned smem_bytes = 0;
-  unsigned o_wrow = 0, o_out = 0, o_corr = 0;
+  unsigned o_wrow = 0, o_blk = 0, o_out = 0, o_corr = 0;
   // device copies of the tensor maps: [level][which]; image / depth maps exist for both buffers they can name
   enum { TM_V, TM_N, TM_DX, TM_DY, TM_IMG_A, TM_IMG_B, TM_D1_NEXT, TM_D1_LAST, TM_CAND, TM_PV, TM_PN, TM_LD, TM_LI, TM_COUNT };
   CUtensorMap* d_maps = nullptr;  // [3][TM_COUNT]
@@ -1380,7 +1439,9 @@ void plan_tiles(int W, int H, int sms, int nm, RGBDOdometry::TiledState& ts) {
   }
   unsigned off = align128((unsigned)sizeof(TFixed));
   ts.o_wrow = off;
-  off = align128(off + (unsigned)nm * 2 * kNW * 32 * 4);
+  off = align128(off + 2u * kNW * 32 * 4);
+  ts.o_blk = off;
+  off = align128(off + (unsigned)nm * 64 * 4);
   ts.o_out = off;
   off = align128(off + (unsigned)nm * 64 * 8);
   ts.o_corr = off;
@@ -1613,6 +1674,7 @@ cudaError_t RGBDOdometry::trackTiled(RGBDOdometry* const* od, int n, float (*tra
   p.iters[1] = pyramid ? 5 : 0;
   p.iters[2] = pyramid ? 4 : 0;
   p.o_wrow = ts.o_wrow;
+  p.o_blk = ts.o_blk;
   p.o_out = ts.o_out;
   p.o_corr = ts.o_corr;
   p.dbg = (unsigned long long*)f.dbg_trace_;

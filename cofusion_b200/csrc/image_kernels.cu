@@ -10,6 +10,8 @@
 // plane only, :131).
 #include "image_kernels.cuh"
 
+#include <string.h>
+
 #include "detmath.cuh"
 
 namespace cfb {
@@ -63,10 +65,29 @@ __global__ void __launch_bounds__(256) bilateral_kernel(const float* __restrict_
         // interior (97 % of a VGA frame): the window is the full 13x13, so the loops unroll completely
         // and the spatial term (float)x - (float)cx = -ox (exact) folds into one constant per tap; same
         // taps, same order, same roundings as the clamped loop below
+        // two taps per step on the packed f32x2 pipe (det_expf2_nonpos: bit-identical lanes); the running sums
+        // stay scalar and in tap order
+        const float2 vv = make_float2(value, value);
+        const float2 ncol = make_float2(-sigma_color2_inv_half, -sigma_color2_inv_half);
 #pragma unroll
-        for (int oy = -BR; oy <= BR; ++oy)
+        for (int oy = -BR; oy <= BR; ++oy) {
 #pragma unroll
-          for (int ox = -BR; ox <= BR; ++ox) {
+          for (int ox = -BR; ox + 1 <= BR; ox += 2) {
+            const float2 tmp = make_float2(tile[ly + BR + oy][threadIdx.x + BR + ox], tile[ly + BR + oy][threadIdx.x + BR + ox + 1]);
+            const float dy = (float)(-oy), dx0 = (float)(-ox), dx1 = (float)(-ox - 1);
+            // -(space2 * ss + color2 * sc) = (-(space2 * ss)) + color2 * (-sc): negation is exact
+            const float2 nsp = make_float2(-((dx0 * dx0 + dy * dy) * sigma_space2_inv_half), -((dx1 * dx1 + dy * dy) * sigma_space2_inv_half));
+            const float2 d = __fadd2_rn(vv, make_float2(-tmp.x, -tmp.y));
+            const float2 color2 = __fmul2_rn(d, d);
+            const float2 weight = det_expf2_nonpos(__fadd2_rn(nsp, __fmul2_rn(color2, ncol)));
+            const float2 tw = __fmul2_rn(tmp, weight);
+            sum1 += tw.x;
+            sum2 += weight.x;
+            sum1 += tw.y;
+            sum2 += weight.y;
+          }
+          {  // the 13th tap of the row
+            const int ox = BR;
             const float tmp = tile[ly + BR + oy][threadIdx.x + BR + ox];
             const float dx = (float)(-ox), dy = (float)(-oy);
             const float space2 = dx * dx + dy * dy;
@@ -75,6 +96,7 @@ __global__ void __launch_bounds__(256) bilateral_kernel(const float* __restrict_
             sum1 += tmp * weight;
             sum2 += weight;
           }
+        }
       } else {
         int tx = min(x - D / 2 + D, W), ty = min(y - D / 2 + D, H);
         for (int cy = max(y - D / 2, 0); cy < ty; ++cy)
@@ -470,6 +492,104 @@ __global__ void pyr_down_uchar2_kernel(const unsigned char* __restrict__ sa, uns
   dst[y * dw + x] = (unsigned char)min(max(v, 0), 255);
 }
 
+
+// ---- a2/a5 fused: BOTH pyramid levels of up to four images in ONE launch.  The reference builds every level
+// with its own launch (cudafuncs.cu:510-532, :566-588; 6 launches per frame here before), each a few microseconds of
+// latency for a tiny output.  A CTA owns a 16x8 tile of level 2: it stages the 76x44 level-0 pixels that tile
+// depends on in shared memory, produces the 36x20 level-1 pixels under it (writing the 32x16 it owns) and from
+// those its level-2 pixels.  Per output pixel the taps, their order and every rounding are those of
+// pyr_down_gauss_f_kernel / pyr_down_uchar_kernel above (the clamped window that drops the last row / column and
+// indexes the weights from the window's end, the float -> int weight count): results are bit-identical.
+struct PyrJob {
+  const void* src;  // level 0, unpitched sw x sh
+  void *l1, *l2;    // level 1 (sw/2 x sh/2), level 2 (sw/4 x sh/4)
+  int is_u8;        // 0: f32, NaN = invalid; 1: u8, 0 = invalid
+};
+struct PyrJobs {
+  PyrJob j[4];
+  int sw, sh;
+};
+constexpr int P2W = 16, P2H = 8;                  // level-2 tile
+constexpr int P1W = 2 * P2W + 4, P1H = 2 * P2H + 4;  // level-1 pixels under it: 36 x 20
+constexpr int P0W = 2 * P1W + 4, P0H = 2 * P1H + 4;  // level-0 pixels under those: 76 x 44
+
+// one output pixel (x, y) of a (sw x sh) -> (sw/2 x sh/2) reduction; the source is read through `at(cx, cy)`,
+// invalid samples are NaN
+template <class At>
+__device__ __forceinline__ float gauss_down_pixel(int x, int y, int sw, int sh, At at) {
+  const int D = 5;
+  const int tx = min(2 * x - D / 2 + D, sw - 1), ty = min(2 * y - D / 2 + D, sh - 1);
+  float sum = 0.f;
+  int count = 0;
+  for (int cy = max(0, 2 * y - D / 2); cy < ty; ++cy)
+    for (int cx = max(0, 2 * x - D / 2); cx < tx; ++cx) {
+      const float s = at(cx, cy);
+      if (!isnan(s)) {
+        const float w = c_gauss25[(ty - cy - 1) * 5 + (tx - cx - 1)];
+        sum += s * w;
+        count = (int)((float)count + w);
+      }
+    }
+  return sum / (float)count;
+}
+__device__ __forceinline__ float u8_quantise(float q) {  // pyr_down_uchar_kernel's store, kept as a float (0 = invalid)
+  const int v = isnan(q) ? 0 : (int)q;
+  return (float)min(max(v, 0), 255);
+}
+
+__global__ void __launch_bounds__(256) pyramid2_kernel(const PyrJobs jobs) {
+  __shared__ float t0[P0H][P0W + 1];
+  __shared__ float t1[P1H][P1W + 1];
+  const PyrJob job = jobs.j[blockIdx.z];
+  const int sw = jobs.sw, sh = jobs.sh, w1 = sw / 2, h1 = sh / 2, w2 = sw / 4, h2 = sh / 4;
+  const int X2 = blockIdx.x * P2W, Y2 = blockIdx.y * P2H;  // level-2 tile origin
+  const int X1 = 2 * X2 - 2, Y1 = 2 * Y2 - 2;              // level-1 region origin
+  const int X0 = 2 * X1 - 2, Y0 = 2 * Y1 - 2;              // level-0 region origin
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const float q = qnan();
+  for (int i = tid; i < P0W * P0H; i += 256) {
+    const int ly = i / P0W, lx = i - ly * P0W, gx = X0 + lx, gy = Y0 + ly;
+    float v = q;
+    if (gx >= 0 && gy >= 0 && gx < sw && gy < sh) {
+      if (job.is_u8) {
+        const unsigned char s = __ldg((const unsigned char*)job.src + (size_t)gy * sw + gx);
+        v = s > 0 ? (float)s : q;
+      } else {
+        v = __ldg((const float*)job.src + (size_t)gy * sw + gx);
+      }
+    }
+    t0[ly][lx] = v;
+  }
+  __syncthreads();
+  for (int i = tid; i < P1W * P1H; i += 256) {
+    const int ly = i / P1W, lx = i - ly * P1W, gx = X1 + lx, gy = Y1 + ly;
+    float v = q;
+    if (gx >= 0 && gy >= 0 && gx < w1 && gy < h1) {
+      v = gauss_down_pixel(gx, gy, sw, sh, [&](int cx, int cy) { return t0[cy - Y0][cx - X0]; });
+      const bool own = lx >= 2 && lx < P1W - 2 && ly >= 2 && ly < P1H - 2;
+      if (job.is_u8) {
+        v = u8_quantise(v);
+        if (own) ((unsigned char*)job.l1)[(size_t)gy * w1 + gx] = (unsigned char)v;
+        v = v > 0.f ? v : q;
+      } else if (own) {
+        ((float*)job.l1)[(size_t)gy * w1 + gx] = v;
+      }
+    }
+    t1[ly][lx] = v;
+  }
+  __syncthreads();
+  if (tid < P2W * P2H) {
+    const int ly = tid / P2W, lx = tid - ly * P2W, gx = X2 + lx, gy = Y2 + ly;
+    if (gx < w2 && gy < h2) {
+      const float v = gauss_down_pixel(gx, gy, w1, h1, [&](int cx, int cy) { return t1[cy - Y1][cx - X1]; });
+      if (job.is_u8)
+        ((unsigned char*)job.l2)[(size_t)gy * w2 + gx] = (unsigned char)u8_quantise(v);
+      else
+        ((float*)job.l2)[(size_t)gy * w2 + gx] = v;
+    }
+  }
+}
+
 }  // namespace
 
 // ---- f1: frame ingest on the device (GUI/Tools/KlgLogReader.cpp:53-84: raw u16 depth x 0.001 as cv::Mat::convertTo
@@ -489,6 +609,19 @@ __global__ void ingest_kernel(const uint8_t* __restrict__ img, const uint16_t* _
 cudaError_t launch_ingest(const uint8_t* img, const uint16_t* d16, float scale, int flip, uint8_t* rgb, float* depth, int n,
                           cudaStream_t s) {
   ingest_kernel<<<(n + 255) / 256, 256, 0, s>>>(img, d16, scale, flip, rgb, depth, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pyramid2(int njobs, const void* const* src, void* const* l1, void* const* l2, const int* is_u8, int sw, int sh,
+                            cudaStream_t s) {
+  if (njobs < 1 || njobs > 4 || (sw % 4) || (sh % 4)) return cudaErrorInvalidValue;
+  PyrJobs jobs;
+  memset(&jobs, 0, sizeof(jobs));
+  for (int k = 0; k < njobs; ++k) jobs.j[k] = PyrJob{src[k], l1[k], l2[k], is_u8[k]};
+  jobs.sw = sw;
+  jobs.sh = sh;
+  const dim3 g((sw / 4 + P2W - 1) / P2W, (sh / 4 + P2H - 1) / P2H, njobs);
+  pyramid2_kernel<<<g, dim3(32, 8), 0, s>>>(jobs);
   return cudaGetLastError();
 }
 

@@ -9,6 +9,10 @@ namespace cfb {
 // (either input may be null: that output is left untouched)
 cudaError_t launch_ingest(const uint8_t* img, const uint16_t* depth_u16, float scale, int flip, uint8_t* rgb, float* depth,
                           int n, cudaStream_t s);
+// both pyramid levels (sw/2 x sh/2, sw/4 x sh/4) of up to four unpitched images in ONE launch; is_u8[k]: 0 = f32 with NaN
+// as invalid (pyrDownGaussF), 1 = u8 with 0 as invalid (pyrDownUcharGauss).  Bit-identical to two launch_pyr_down_* calls.
+cudaError_t launch_pyramid2(int njobs, const void* const* src, void* const* l1, void* const* l2, const int* is_u8, int sw, int sh,
+                            cudaStream_t s);
 cudaError_t launch_bilateral(const float* depth, size_t dpitch, int W, int H, float maxD, float* out,
                              size_t opitch, cudaStream_t s);
 cudaError_t launch_pyr_down_gauss_f(const float* src, size_t spitch, int sw, int sh, float* dst,

@@ -187,19 +187,19 @@ cudaError_t RGBDOdometry::initAll(const float* v4, const float* n4, const unsign
   // model side: global-frame vertex/normal pyramid + lastDepth level 0
   RET_IF(launch_model_pyramid(v4, n4, width, height, R, t, maxDepthRGB, vmaps_g_prev_, nmaps_g_prev_, lastDepth[0], s,
                               pose34_dev));
-  for (int i = 0; i + 1 < NUM_PYRS; i++) {
-    int sw = width >> i, sh = height >> i;
-    RET_IF(launch_pyr_down_gauss_f(lastDepth[i], (size_t)sw * 4, sw, sh, lastDepth[i + 1], (size_t)(sw / 2) * 4, s));
-  }
   // quirk kept: initRGB derives nextDepth from the same model prediction (vmaps_tmp) -> it IS
   // lastDepth; the device loop reads lastDepth for both instead of building a second copy
   next_is_last_ = true;
   // frame side
   RET_IF(launch_frame_maps(depthPyr, width, height, intr, depthCutoff, vmaps_curr_, nmaps_curr_, s));
   RET_IF(launch_intensity2(modelImg, modelCh, lastImage[0], frameImg, frameCh, nextImage[0], width * height, s));
-  for (int i = 0; i + 1 < NUM_PYRS; i++)
-    RET_IF(launch_pyr_down_uchar2(lastImage[i], lastImage[i + 1], nextImage[i], nextImage[i + 1], width >> i,
-                                  height >> i, s));
+  {  // lastDepth + both grey images, both levels each, in ONE launch
+    const void* src[3] = {lastDepth[0], lastImage[0], nextImage[0]};
+    void* l1[3] = {lastDepth[1], lastImage[1], nextImage[1]};
+    void* l2[3] = {lastDepth[2], lastImage[2], nextImage[2]};
+    const int u8[3] = {0, 1, 1};
+    RET_IF(launch_pyramid2(3, src, l1, l2, u8, width, height, s));
+  }
   return cudaSuccess;
 }
 

@@ -203,10 +203,14 @@ cudaError_t Context::setFrameDevice(const uint8_t* rgb_d, const float* depth_d, 
 
 cudaError_t Context::preprocess(float depthCutoff) {
   RET_IF(launch_bilateral(depthRaw, (size_t)W * 4, W, H, depthCutoff, depthFiltered, (size_t)W * 4, stream));
-  RET_IF(launch_pyr_down_gauss_f(depthPyr[0], (size_t)W * 4, W, H, depthPyr[1], (size_t)(W / 2) * 4, stream));
-  RET_IF(launch_pyr_down_gauss_f(depthPyr[1], (size_t)(W / 2) * 4, W / 2, H / 2, depthPyr[2], (size_t)(W / 4) * 4,
-                                 stream));
-  launches += 3;
+  {
+    const void* src[1] = {depthPyr[0]};
+    void* l1[1] = {depthPyr[1]};
+    void* l2[1] = {depthPyr[2]};
+    const int u8[1] = {0};
+    RET_IF(launch_pyramid2(1, src, l1, l2, u8, W, H, stream));
+  }
+  launches += 2;
   return cudaSuccess;
 }
 
@@ -229,8 +233,9 @@ Model::Model(Context* c, unsigned id_, float conf, unsigned maxSurfels, bool ena
          dalloc(&indexMaps.normRad, n) && dalloc(&splat.image, n) && dalloc(&splat.vertexConf, n) &&
          dalloc(&splat.normalRad, n) && dalloc(&splat.time, n) && dalloc(&fill.image, n) && dalloc(&fill.vertex, n) &&
          dalloc(&fill.normal, n) && dalloc(&scan.flags, scanCap) && dalloc(&scan.ranks, scanCap) &&
-         dalloc(&scan.blockSums, scanCap / 1024 + 2) && dalloc(&counters, 1);
+         dalloc(&scan.blockSums, 2 * (scanCap / 2048 + 4)) && dalloc(&counters, 1);
   scan.capacity = scanCap;
+  scan.host = new ScanHostState();
   good = good && cudaMallocHost(&h_counters, sizeof(MapCounters)) == cudaSuccess;
   if (good) memset(h_counters, 0, sizeof(MapCounters));
   good = good && dalloc(&dpose, 1) && cudaMallocHost(&h_readback, sizeof(PoseReadback)) == cudaSuccess &&
@@ -265,6 +270,7 @@ Model::~Model() {
   cudaFree(scan.flags);
   cudaFree(scan.ranks);
   cudaFree(scan.blockSums);
+  delete scan.host;
   cudaFree(counters);
   cudaFreeHost(h_counters);
   cudaFree(dpose);
@@ -393,7 +399,7 @@ cudaError_t Model::initialise(int time, float maxDepthProcessed) {
                                   buf[target], capacity, candStaging, unstable, scan, counters, ctx->stream));
   const unsigned n = (unsigned)ctx->W * ctx->H;
   count_ub = n < capacity ? n : capacity;
-  ctx->launches += 12;
+  ctx->launches += 8;
   return cudaSuccess;
 }
 
@@ -418,7 +424,7 @@ cudaError_t Model::predictIndices(int time, float depthCutoff, int timeDelta) {
 
 cudaError_t Model::fuse(int time, float depthCutoff, float weightMultiplier) {
   const float md = depthCutoff < maxDepth ? depthCutoff : maxDepth;  // Model.cpp:443
-  ctx->launches += 7;
+  ctx->launches += 5;
   return launch_fuse(geom(), buf[target], count_ub, counters, poseRef(), time, ctx->rgb, ctx->mask, ctx->depthRaw,
                      ctx->depthFiltered, md, WeightRef(&dpose->weightBase, weightMultiplier), id, indexMaps, winner,
                      candStaging, candBest, unstable, scan, ctx->stream);
@@ -435,7 +441,7 @@ cudaError_t Model::clean(int time, int timeDelta, float /*depthCutoff*/, float o
   renderSource = t;
   unsigned ub = count_ub + cand_ub;
   count_ub = ub < capacity ? ub : capacity;
-  ctx->launches += 6;
+  ctx->launches += 4;
   // refresh the host-side bound with the exact count whenever the stream is next synchronised
   RET_IF(cudaMemcpyAsync(h_counters, counters, sizeof(MapCounters), cudaMemcpyDeviceToHost, ctx->stream));
   return cudaSuccess;
@@ -506,7 +512,7 @@ cudaError_t Model::prepareTracking(const TrackParams& tp, bool devicePose) {
   const float* pyr[3] = {ctx->depthPyr[0], ctx->depthPyr[1], ctx->depthPyr[2]};
   RET_IF(odom.initAll(predVertex, predNormal, predImage, 4, pyr, ctx->rgb, 3, tp.maxDepthProcessed, pose, s,
                       devicePose ? dpose->pose.m : nullptr));
-  ctx->launches += 7;  // model pyramid, 2 depth levels, frame maps, grey, 2 grey levels
+  ctx->launches += 4;  // model pyramid, frame maps, grey, all pyramids (lastDepth + both grey images, both levels)
   return cudaSuccess;
 }
 

@@ -21,7 +21,6 @@ namespace cfb {
 namespace {
 
 #define COS_HALF 0.87758256189037276f
-constexpr int kTile = 1024;  // items per scan tile (256 threads x 4)
 
 // ------------------------------------------------------------------------------- GLSL helpers
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -120,76 +119,98 @@ __device__ __forceinline__ void store_surfel(Surfel* d, const Surfel& s) {
 
 // ------------------------------------------------------------------------------- flag scan
 // ranks[i] = number of set flags before i (tile-local prefix + scanned tile sums), total -> *total.
-__global__ void scan_tile_sums_kernel(const uint8_t* __restrict__ flags, unsigned n_ub, const unsigned* n_dev,
-                                      unsigned n_extra, uint32_t* __restrict__ blockSums) {
-  const unsigned n = min(n_ub, (n_dev ? *n_dev : n_ub) + n_extra);
-  const unsigned base = blockIdx.x * kTile + threadIdx.x * 4;
-  unsigned c = 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if (base + k < n) c += flags[base + k] ? 1u : 0u;
-  __shared__ unsigned ws[8];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned t = 0;
-    for (int w = 0; w < 8; ++w) t += ws[w];
-    blockSums[blockIdx.x] = t;
-  }
+// Exclusive prefix sum of the survival flags in ONE launch (decoupled look-back): a CTA takes the next tile by a
+// ticket, publishes its tile total, adds up the totals of the tiles before it (stopping at the first one that has
+// already published an inclusive prefix) and writes the ranks.  Status word: epoch (30) | state (2) | value (32); the
+// epoch and the ticket base come from the host, so nothing has to be cleared between scans.
+constexpr unsigned kScanTile = 2048;  // 256 threads x 8 items
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* q) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(q) : "memory");
+  return v;
 }
-__global__ void scan_block_sums_kernel(uint32_t* blockSums, unsigned nblocks, unsigned* total) {
-  __shared__ unsigned buf[1024];
-  __shared__ unsigned carry;
-  if (threadIdx.x == 0) carry = 0;
+__device__ __forceinline__ void st_status(unsigned long long* q, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(q), "l"(v) : "memory");
+}
+__global__ void __launch_bounds__(256) scan_lookback_kernel(const uint8_t* __restrict__ flags, unsigned n_ub, const unsigned* n_dev,
+                                                           unsigned n_extra, unsigned long long* status, unsigned* ticket,
+                                                           unsigned ticket_base, unsigned epoch, uint32_t* __restrict__ ranks,
+                                                           unsigned* total, unsigned ntiles) {
+  __shared__ unsigned s_tile, s_prefix, ws[8];
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
   __syncthreads();
-  for (unsigned base = 0; base < nblocks; base += 1024) {
-    unsigned i = base + threadIdx.x;
-    unsigned v = (i < nblocks) ? blockSums[i] : 0;
-    buf[threadIdx.x] = v;
-    __syncthreads();
-    for (unsigned o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive
-      unsigned t = (threadIdx.x >= o) ? buf[threadIdx.x - o] : 0;
-      __syncthreads();
-      buf[threadIdx.x] += t;
-      __syncthreads();
+  const unsigned tile = s_tile;
+  const unsigned n = min(n_ub, (n_dev ? *n_dev : n_ub) + n_extra);
+  const unsigned base = tile * kScanTile + threadIdx.x * 8;
+  unsigned f[8], c = 0;
+  if (base + 8 <= n) {
+    const uint2 v = *reinterpret_cast<const uint2*>(flags + base);  // 8 flag bytes, 8-byte aligned
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      f[k] = (((k < 4 ? v.x : v.y) >> (8 * (k & 3))) & 0xffu) ? 1u : 0u;
+      c += f[k];
     }
-    unsigned incl = buf[threadIdx.x];
-    if (i < nblocks) blockSums[i] = carry + incl - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += incl;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *total = carry;
-}
-__global__ void scan_ranks_kernel(const uint8_t* __restrict__ flags, unsigned n_ub, const unsigned* n_dev,
-                                  unsigned n_extra, const uint32_t* __restrict__ blockSums,
-                                  uint32_t* __restrict__ ranks) {
-  const unsigned n = min(n_ub, (n_dev ? *n_dev : n_ub) + n_extra);
-  const unsigned base = blockIdx.x * kTile + threadIdx.x * 4;
-  unsigned f[4], c = 0;
+  } else {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    f[k] = (base + k < n && flags[base + k]) ? 1u : 0u;
-    c += f[k];
+    for (int k = 0; k < 8; ++k) {
+      f[k] = (base + k < n && flags[base + k]) ? 1u : 0u;
+      c += f[k];
+    }
   }
-  // exclusive prefix of c over the 256 threads
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned incl = c;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+    const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= (unsigned)o) incl += t;
   }
-  __shared__ unsigned ws[8];
   if (lane == 31) ws[warp] = incl;
   __syncthreads();
-  unsigned woff = 0;
-  for (unsigned w = 0; w < warp; ++w) woff += ws[w];
-  unsigned r = blockSums[blockIdx.x] + woff + incl - c;
+  unsigned woff = 0, agg = 0;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (unsigned w = 0; w < 8; ++w) {
+    if (w < warp) woff += ws[w];
+    agg += ws[w];
+  }
+  const unsigned long long tagE = (unsigned long long)(epoch & 0x3fffffffu) << 34;
+  if (warp == 0) {
+    unsigned prefix = 0;
+    if (tile == 0) {
+      if (lane == 0) st_status(status + 0, tagE | (2ull << 32) | agg);
+    } else {
+      if (lane == 0) st_status(status + tile, tagE | (1ull << 32) | agg);
+      int look = (int)tile - 1;
+      while (true) {
+        const int idx = look - (int)lane;
+        unsigned state = 2, val = 0;  // tiles before the first: inclusive prefix 0
+        if (idx >= 0) {
+          unsigned long long w;
+          do {
+            w = ld_status(status + idx);
+          } while ((w >> 34) != (tagE >> 34) || ((w >> 32) & 3ull) == 0ull);
+          state = (unsigned)((w >> 32) & 3ull);
+          val = (unsigned)(w & 0xffffffffull);
+        }
+        const unsigned incl_mask = __ballot_sync(0xffffffffu, state == 2);
+        const int first = incl_mask ? (__ffs(incl_mask) - 1) : 32;
+        unsigned contrib = ((int)lane <= first) ? val : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        prefix += contrib;
+        if (incl_mask) break;
+        look -= 32;
+      }
+      if (lane == 0) st_status(status + tile, tagE | (2ull << 32) | (prefix + agg));
+    }
+    if (lane == 0) {
+      s_prefix = prefix;
+      if (tile == ntiles - 1) *total = prefix + agg;
+    }
+  }
+  __syncthreads();
+  unsigned r = s_prefix + woff + incl - c;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
     if (base + k < n) ranks[base + k] = r;
     r += f[k];
   }
@@ -198,10 +219,13 @@ __global__ void scan_ranks_kernel(const uint8_t* __restrict__ flags, unsigned n_
 cudaError_t scan_flags(ScanScratch sc, unsigned n_ub, const unsigned* n_dev, unsigned n_extra, unsigned* total,
                        cudaStream_t s) {
   if (n_ub == 0) return cudaMemsetAsync(total, 0, sizeof(unsigned), s);
-  const unsigned nb = (n_ub + kTile - 1) / kTile;
-  scan_tile_sums_kernel<<<nb, 256, 0, s>>>(sc.flags, n_ub, n_dev, n_extra, sc.blockSums);
-  scan_block_sums_kernel<<<1, 1024, 0, s>>>(sc.blockSums, nb, total);
-  scan_ranks_kernel<<<nb, 256, 0, s>>>(sc.flags, n_ub, n_dev, n_extra, sc.blockSums, sc.ranks);
+  const unsigned nb = (n_ub + kScanTile - 1) / kScanTile;
+  unsigned long long* status = reinterpret_cast<unsigned long long*>(sc.blockSums) + 1;
+  unsigned* ticket = reinterpret_cast<unsigned*>(sc.blockSums);
+  ScanHostState& h = *sc.host;
+  h.epoch += 1;
+  scan_lookback_kernel<<<nb, 256, 0, s>>>(sc.flags, n_ub, n_dev, n_extra, status, ticket, h.ticketBase, h.epoch, sc.ranks, total, nb);
+  h.ticketBase += nb;
   return cudaGetLastError();
 }
 

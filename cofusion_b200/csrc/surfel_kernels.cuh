@@ -71,11 +71,16 @@ struct FillMaps {  // FillIn targets (FillIn.cpp:21-23)
   float4 *vertex, *normal;
 };
 
+struct ScanHostState {  // host-side bookkeeping of the single-pass scan (no reset launch between scans)
+  unsigned epoch = 0;       // bumped per scan: tile status words of earlier scans never match
+  unsigned ticketBase = 0;  // tickets handed out by all earlier scans
+};
 struct ScanScratch {
   uint8_t* flags;       // one byte per item
   uint32_t* ranks;      // exclusive prefix of flags
-  uint32_t* blockSums;  // per 1024-item tile
+  uint32_t* blockSums;  // tile status words of the single-pass scan (u64 per 2048-item tile) + the ticket counter
   size_t capacity;      // items
+  ScanHostState* host;  // owned by the Model
 };
 
 // a18: Model::initialise (Model.cpp:227-272) from the first frame
