@@ -400,7 +400,7 @@ int cfb_ctx_upload_frame(cfb_ctx* c, const uint8_t* rgb, const float* depth, con
 }
 int cfb_ctx_set_frame_device(cfb_ctx* c, const uint8_t* rgb, const float* depth, const uint8_t* mask) {
   REQUIRE(c && rgb && depth, "ctx_set_frame_device");
-  CK(c->c.setFrameDevice(rgb, depth, mask));
+  CK(c->c.setFrameDevice(rgb, depth, mask, true));
   return 0;
 }
 int cfb_ctx_preprocess(cfb_ctx* c, float depthCutoff) {

@@ -133,6 +133,15 @@ std::vector<Model*> CoFusion::processed() {
   return v;
 }
 
+// The fuse / clean / predict stages of a frame are independent per model (CoFusion.cpp:465-488, :536-542): with
+// more than one model each runs on its own stream from here to the end of the frame (joined after predict()).
+cudaError_t CoFusion::forkModels(const std::vector<Model*>& act) {
+  if (act.size() < 2 || !batchedTracking) return cudaSuccess;
+  RET_IF(cudaEventRecord(ctx.evFork, ctx.stream));
+  for (Model* m : act) RET_IF(m->fork(ctx.evFork));
+  return cudaSuccess;
+}
+
 cudaError_t CoFusion::predict() {
   for (Model* m : processed()) {
     // lastFrameRecovery is never set without loop closure -> maxTime = tick (CoFusion.cpp:538)
@@ -230,7 +239,10 @@ cudaError_t CoFusion::processFrameEx(const FrameInput& in_, const float* inPose,
     cudaEventRecord(tl.ev[tl.cur][k], ctx.stream);
   };
   mark(0);
-  RET_IF(ctx.uploadFrameRaw(in.rgb, in.flipColors, in.depth, in.depth16, in.depthScale, in.mask, device_ptrs));
+  // device inputs produced on the pipeline stream itself (the broadcast of the sharded path, a caller's own stream)
+  // are ordered after it; otherwise the frame side starts right away, next to the previous frame's tail
+  RET_IF(ctx.uploadFrameRaw(in.rgb, in.flipColors, in.depth, in.depth16, in.depthScale, in.mask, device_ptrs,
+                            shard.active() || !ctx.owns_stream));
   RET_IF(ctx.preprocess(params.depthCutoff));
   if (tick_ == 1) {
     if (processGlobalModel) {
@@ -250,6 +262,7 @@ cudaError_t CoFusion::processFrameEx(const FrameInput& in_, const float* inPose,
     if (params.predictBeforeFuse) RET_IF(predict());
     if (!params.rgbOnly) {
       const std::vector<Model*> act = processed();
+      RET_IF(forkModels(act));
       for (Model* m : act) RET_IF(m->predictIndices(tick_, params.maxDepthProcessed, params.timeDelta));
       for (Model* m : act) RET_IF(m->fuse(tick_, params.maxDepthProcessed, weightMultiplier));
       for (Model* m : act) RET_IF(m->predictIndices(tick_, params.maxDepthProcessed, params.timeDelta));
@@ -298,6 +311,7 @@ cudaError_t CoFusion::processFrameEx(const FrameInput& in_, const float* inPose,
     if (params.predictBeforeFuse) RET_IF(predict());
     if (!params.rgbOnly) {
       const std::vector<Model*> act = processed();
+      RET_IF(forkModels(act));
       for (Model* m : act) RET_IF(m->predictIndices(tick_, params.maxDepthProcessed, params.timeDelta));
       for (Model* m : act) RET_IF(m->fuse(tick_, params.maxDepthProcessed, weightMultiplier));
       for (Model* m : act) RET_IF(m->predictIndices(tick_, params.maxDepthProcessed, params.timeDelta));
@@ -305,6 +319,7 @@ cudaError_t CoFusion::processFrameEx(const FrameInput& in_, const float* inPose,
     }
   }
   RET_IF(predict());
+  for (auto& m : models) RET_IF(m->join());
   tick_++;
   if (poseLogging_) RET_IF(logPoses(in.timestamp));
   // nothing in this frame waited for the device; the contract is that host buffers may be reused once the

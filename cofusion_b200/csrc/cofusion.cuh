@@ -79,7 +79,8 @@ class CoFusion {
   Model* model(size_t i) { return i < models.size() ? models[i].get() : nullptr; }
   size_t numModels() const { return models.size(); }
   int tick() const { return tick_; }
-  cudaError_t predict();  // CoFusion::predict (CoFusion.cpp:533-545)
+  cudaError_t predict();
+  cudaError_t forkModels(const std::vector<Model*>& act);  // CoFusion::predict (CoFusion.cpp:533-545)
 
   bool batchedTracking = true;  // track all models of a frame in one persistent launch (gn_tiled.cu)
   Context ctx;

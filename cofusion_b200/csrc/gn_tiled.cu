@@ -415,90 +415,6 @@ __device__ __forceinline__ void icp_found_row(const IcpPose& P, float3 tprev, fl
   xaccumulate_se3(acc, row);
 }
 
-// One pixel of the ICP pass, written without early exits (everything is computed, invalid stages are masked):
-// two pixels evaluated back to back form one straight-line block, which lets the scheduler interleave their
-// dependency chains -- the pass is bound by instruction latency, not by memory (the gathers are shared-memory
-// reads).  Returns the Jacobian row (zeros unless a correspondence was found).
-struct IcpEval {
-  float row[7];
-  bool found;
-};
-template <bool FS, bool MS>
-__device__ __forceinline__ IcpEval icp_eval(const LvCtx& c, const MLevel& L, const FLevel& F, const IcpPose& P, float3 tcurr,
-                                             float3 tprev, float distThres, float angleThres, bool live, int lx, int ly,
-                                             float* error_map, size_t err_pitch) {
-  extern __shared__ __align__(128) unsigned char dyn_smem_raw[];
-  const int x = c.x0 + lx, y = c.y0 + ly;
-  const bool valid = live && x < c.W && y < c.H;
-  const int HW = c.W * c.H;
-  const int fi = valid ? ly * c.pf + lx + c.shf : 0;  // index into the f32 frame tiles (0: always readable)
-  const int gi = valid ? y * c.W + x : 0;
-  float3 vcurr, ncurr;
-  if (FS) {
-    vcurr = make_float3(SM_F32(c.oV)[fi], SM_F32(c.oV)[c.fplane + fi], SM_F32(c.oV)[2 * c.fplane + fi]);
-    ncurr = make_float3(SM_F32(c.oN)[fi], SM_F32(c.oN)[c.fplane + fi], SM_F32(c.oN)[2 * c.fplane + fi]);
-  } else {
-    vcurr = make_float3(__ldg(F.vmap_curr + gi), __ldg(F.vmap_curr + HW + gi), __ldg(F.vmap_curr + 2 * HW + gi));
-    ncurr = make_float3(__ldg(F.nmap_curr + gi), __ldg(F.nmap_curr + HW + gi), __ldg(F.nmap_curr + 2 * HW + gi));
-  }
-  // an invalid vertex has NaN in x: every coordinate of vcurr_g is NaN, dist is NaN -> no correspondence, error 0
-  const bool has_v = valid && !isnan(vcurr.x);
-  const float3 vcurr_g = xadd(xmul(P.Rcurr, vcurr), tcurr);
-  const float3 vcurr_cp = xmul(P.Rprev_inv, xsub(vcurr_g, tprev));
-  const int ux = __float2int_rn(__fadd_rn(__fdiv_rn(__fmul_rn(vcurr_cp.x, c.fx), vcurr_cp.z), c.cx));
-  const int uy = __float2int_rn(__fadd_rn(__fdiv_rn(__fmul_rn(vcurr_cp.y, c.fy), vcurr_cp.z), c.cy));
-  const bool inb = has_v && !(ux < 0 || uy < 0 || ux >= c.W || uy >= c.H || vcurr_cp.z < 0);
-  const int wu = ux - c.wx0, wv = uy - c.wy0;
-  const bool inwin = MS && inb && (unsigned)wu < (unsigned)c.wwl && (unsigned)wv < (unsigned)c.wh;
-  float3 vp = make_float3(0.f, 0.f, 0.f), np = vp;
-  if (MS) {
-    const int j = inwin ? wv * c.wpf + wu + c.wshf : 0;
-    vp = make_float3(SM_F32(c.oPV)[j], SM_F32(c.oPV)[c.wplane + j], SM_F32(c.oPV)[2 * c.wplane + j]);
-    np = make_float3(SM_F32(c.oPN)[j], SM_F32(c.oPN)[c.wplane + j], SM_F32(c.oPN)[2 * c.wplane + j]);
-  }
-  bool have = inwin;
-  if (inb && !inwin) {  // outside the staged window (always, for object models): the same values from global memory
-    const int j = uy * c.W + ux;
-    vp.x = __ldg(L.vmap_g_prev + j);
-    // An object model predicts a few percent of the image; everywhere else its vertex map is NaN.  A NaN in the
-    // x plane makes dist NaN whatever the other five planes hold: they are only fetched where the object is.
-    if (!isnan(vp.x)) {
-      vp.y = __ldg(L.vmap_g_prev + HW + j);
-      vp.z = __ldg(L.vmap_g_prev + 2 * HW + j);
-      np = make_float3(__ldg(L.nmap_g_prev + j), __ldg(L.nmap_g_prev + HW + j), __ldg(L.nmap_g_prev + 2 * HW + j));
-      have = true;
-    }
-  }
-  const float3 ncurr_g = xmul(P.Rcurr, ncurr);
-  const float dist = xnorm(xsub(vp, vcurr_g));
-  const float sine = xnorm(xcross(ncurr_g, np));
-  if (error_map && valid) row_ptr(error_map, err_pitch, y)[x] = (have && isfinite(dist)) ? dist : 0.0f;
-  IcpEval e;
-  e.found = have && sine < angleThres && dist <= distThres && !isnan(ncurr.x) && !isnan(np.x);
-  const float3 d_cp = xmul(P.Rprev_inv, xsub(vp, tprev));
-  const float3 n_cp = xmul(P.Rprev_inv, np);
-  const float3 cr = xcross(vcurr_cp, n_cp);
-  const float r6 = xdot(n_cp, xsub(vcurr_cp, d_cp));
-  e.row[0] = e.found ? n_cp.x : 0.f;
-  e.row[1] = e.found ? n_cp.y : 0.f;
-  e.row[2] = e.found ? n_cp.z : 0.f;
-  e.row[3] = e.found ? cr.x : 0.f;
-  e.row[4] = e.found ? cr.y : 0.f;
-  e.row[5] = e.found ? cr.z : 0.f;
-  e.row[6] = e.found ? r6 : 0.f;
-  return e;
-}
-// products of a row that is all zeros are exact zeros: masked pixels leave the sums untouched
-__device__ __forceinline__ void xaccumulate_masked(float (&acc)[32], const IcpEval& e) {
-  int k = 0;
-#pragma unroll
-  for (int i = 0; i < 6; ++i)
-#pragma unroll
-    for (int j = i; j < 7; ++j, ++k) acc[k] = __fmaf_rn(e.row[i], e.row[j], acc[k]);
-  acc[27] = __fmaf_rn(e.row[6], e.row[6], acc[27]);
-  acc[28] = __fadd_rn(acc[28], e.found ? 1.f : 0.f);
-}
-
 template <bool FS, bool MS>
 __device__ __noinline__ void phase2(int lvl, int m, float* error_map, int buf) {
   TSMEM();
@@ -511,20 +427,64 @@ __device__ __noinline__ void phase2(int lvl, int m, float* error_map, int buf) {
   for (int i = 0; i < 32; ++i) acc[i] = 0.f;
   const float3 tcurr = make_float3(P.tcurr[0], P.tcurr[1], P.tcurr[2]);
   const float3 tprev = make_float3(P.tprev[0], P.tprev[1], P.tprev[2]);
+  const int HW = c.W * c.H;
   bool any = false;
-  PixIt it = pix_begin(c);
-  while (it.i < c.npx) {  // two pixels per trip (the second may lie past the tile: masked)
-    const int lxa = it.lx, lya = it.ly;
-    pix_next(c, it);
-    const bool liveb = it.i < c.npx;
-    const int lxb = it.lx, lyb = it.ly;
-    pix_next(c, it);
-    const IcpEval a = icp_eval<FS, MS>(c, L, F, P, tcurr, tprev, p.distThres, p.angleThres, true, lxa, lya, error_map, p.err_pitch);
-    const IcpEval b = icp_eval<FS, MS>(c, L, F, P, tcurr, tprev, p.distThres, p.angleThres, liveb, lxb, lyb, error_map, p.err_pitch);
-    any = any || a.found || b.found;
-    // the order of the two accumulations is the pixel order: the sums are the same as one pixel per trip
-    xaccumulate_masked(acc, a);
-    xaccumulate_masked(acc, b);
+  for (PixIt it = pix_begin(c); it.i < c.npx; pix_next(c, it)) {
+    const int x = c.x0 + it.lx, y = c.y0 + it.ly;
+    if (x >= c.W || y >= c.H) continue;
+    const int fi = it.ly * c.pf + it.lx + c.shf;  // index into the f32 frame tiles
+    const int gi = y * c.W + x;
+    float3 vcurr;
+    vcurr.x = FS ? SM_F32(c.oV)[fi] : __ldg(F.vmap_curr + gi);
+    float* const err = error_map ? row_ptr(error_map, p.err_pitch, y) + x : nullptr;
+    // an invalid vertex has NaN in x: every coordinate of vcurr_g is NaN, dist is NaN -> no
+    // correspondence, error 0 (same outcome as running the arithmetic, without the gathers)
+    if (isnan(vcurr.x)) {
+      if (err) *err = 0.0f;
+      continue;
+    }
+    vcurr.y = FS ? SM_F32(c.oV)[c.fplane + fi] : __ldg(F.vmap_curr + HW + gi);
+    vcurr.z = FS ? SM_F32(c.oV)[2 * c.fplane + fi] : __ldg(F.vmap_curr + 2 * HW + gi);
+    const float3 vcurr_g = xadd(xmul(P.Rcurr, vcurr), tcurr);
+    const float3 vcurr_cp = xmul(P.Rprev_inv, xsub(vcurr_g, tprev));
+    const int ux = __float2int_rn(__fadd_rn(__fdiv_rn(__fmul_rn(vcurr_cp.x, c.fx), vcurr_cp.z), c.cx));
+    const int uy = __float2int_rn(__fadd_rn(__fdiv_rn(__fmul_rn(vcurr_cp.y, c.fy), vcurr_cp.z), c.cy));
+    if (ux < 0 || uy < 0 || ux >= c.W || uy >= c.H || vcurr_cp.z < 0) {
+      if (err) *err = 0.0f;
+      continue;
+    }
+    float3 vp, np;
+    const int wu = ux - c.wx0, wv = uy - c.wy0;
+    if (MS && (unsigned)wu < (unsigned)c.wwl && (unsigned)wv < (unsigned)c.wh) {
+      const int j = wv * c.wpf + wu + c.wshf;
+      vp = make_float3(SM_F32(c.oPV)[j], SM_F32(c.oPV)[c.wplane + j], SM_F32(c.oPV)[2 * c.wplane + j]);
+      np = make_float3(SM_F32(c.oPN)[j], SM_F32(c.oPN)[c.wplane + j], SM_F32(c.oPN)[2 * c.wplane + j]);
+    } else {
+      const int j = uy * c.W + ux;
+      vp.x = __ldg(L.vmap_g_prev + j);
+      // An object model predicts a few percent of the image; everywhere else its vertex map is NaN.
+      // A NaN in the x plane makes dist NaN whatever the other five planes hold.
+      if (isnan(vp.x)) {
+        if (err) *err = 0.0f;
+        continue;
+      }
+      vp.y = __ldg(L.vmap_g_prev + HW + j);
+      vp.z = __ldg(L.vmap_g_prev + 2 * HW + j);
+      np = make_float3(__ldg(L.nmap_g_prev + j), __ldg(L.nmap_g_prev + HW + j), __ldg(L.nmap_g_prev + 2 * HW + j));
+    }
+    float3 ncurr;
+    if (FS)
+      ncurr = make_float3(SM_F32(c.oN)[fi], SM_F32(c.oN)[c.fplane + fi], SM_F32(c.oN)[2 * c.fplane + fi]);
+    else
+      ncurr = make_float3(__ldg(F.nmap_curr + gi), __ldg(F.nmap_curr + HW + gi), __ldg(F.nmap_curr + 2 * HW + gi));
+    const float3 ncurr_g = xmul(P.Rcurr, ncurr);
+    const float dist = xnorm(xsub(vp, vcurr_g));
+    const float sine = xnorm(xcross(ncurr_g, np));
+    if (err) *err = isfinite(dist) ? dist : 0.0f;
+    if (sine < p.angleThres && dist <= p.distThres && !isnan(ncurr.x) && !isnan(np.x)) {
+      any = true;
+      icp_found_row(P, tprev, vcurr_cp, vp, np, acc);
+    }
   }
   store_warp_row(buf, any, acc);
 }
@@ -1593,7 +1553,7 @@ cudaError_t RGBDOdometry::enqueuePrepare(cudaStream_t s, void* sync_words, int n
 // in/out.  scratch: tiledScratchBytes() of zero-initialised device memory owned by the caller.
 cudaError_t RGBDOdometry::trackTiled(RGBDOdometry* const* od, int n, float (*trans)[3], float (*rot)[9], float icpWeight,
                                      bool pyramid, bool fastOdom, bool so3, float* const* err, size_t err_pitch,
-                                     void* scratch, cudaStream_t s, PoseDev* const* pd, bool async) {
+                                     void* scratch, cudaStream_t s, PoseDev* const* pd, bool async, bool prepared) {
   if (n < 1 || n > kMaxM || !scratch) return cudaErrorInvalidValue;
   if (async && !pd) return cudaErrorInvalidValue;  // without a host round trip the pose must live on the device
   struct Out {
@@ -1616,7 +1576,8 @@ cudaError_t RGBDOdometry::trackTiled(RGBDOdometry* const* od, int n, float (*tra
       memcpy(h_in + 3, rot[m], 9 * sizeof(float));
       RET_IF(cudaMemcpyAsync(o.d_pose_in, h_in, 12 * sizeof(float), cudaMemcpyHostToDevice, s));
     }
-    RET_IF(o.enqueuePrepare(s, m == 0 ? scratch : nullptr, n));  // Sobel images + candidate gates of this model
+    // Sobel images + candidate gates of this model (a caller that spreads the models over streams has done it)
+    if (!prepared) RET_IF(o.enqueuePrepare(s, m == 0 ? scratch : nullptr, n));
     MParams& M = p.M[m];
     for (int i = 0; i < NUM_PYRS; ++i) {
       MLevel& L = M.L[i];

@@ -79,7 +79,10 @@ __global__ void __launch_bounds__(256) bilateral_kernel(const float* __restrict_
             const float2 nsp = make_float2(-((dx0 * dx0 + dy * dy) * sigma_space2_inv_half), -((dx1 * dx1 + dy * dy) * sigma_space2_inv_half));
             const float2 d = __fadd2_rn(vv, make_float2(-tmp.x, -tmp.y));
             const float2 color2 = __fmul2_rn(d, d);
-            const float2 weight = det_expf2_nonpos(__fadd2_rn(nsp, __fmul2_rn(color2, ncol)));
+            // this product and sum stay scalar: ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (seen in the
+            // SASS, also with inline PTX and -fmad=false), which would change the rounding of the exponent
+            const float2 arg = make_float2(__fadd_rn(nsp.x, __fmul_rn(color2.x, ncol.x)), __fadd_rn(nsp.y, __fmul_rn(color2.y, ncol.y)));
+            const float2 weight = det_expf2_nonpos(arg);
             const float2 tw = __fmul2_rn(tmp, weight);
             sum1 += tw.x;
             sum2 += weight.x;

@@ -88,7 +88,7 @@ class RGBDOdometry {
   bool canBatch(int n) const;
   static cudaError_t trackTiled(RGBDOdometry* const* od, int n, float (*trans)[3], float (*rot)[9], float icpWeight,
                                 bool pyramid, bool fastOdom, bool so3, float* const* err, size_t err_pitch, void* scratch,
-                                cudaStream_t s, PoseDev* const* pd = nullptr, bool async = false);
+                                cudaStream_t s, PoseDev* const* pd = nullptr, bool async = false, bool prepared = false);
   // pd: optional per-model device pose blocks (surfel_kernels.cuh): the incoming pose is read from pd[m]->tr
   // and the kernel's epilogue refreshes the block.  async: return right after the launch -- no host
   // synchronisation, trans / rot / stats() are not updated (read statsDevice() / the pose block later).
@@ -99,6 +99,9 @@ class RGBDOdometry {
   // device views (tests / map_view): which as in oracle orc_odom_view
   const void* view(int which, int level, size_t* pitch) const;
 
+ // Sobel images + photometric candidate gates, 3 levels, 1 launch (+ clears the barrier words `acnt`)
+  cudaError_t enqueuePrepare(cudaStream_t s, void* sync_words = nullptr, int nmodels = 1);
+
  private:
   cudaError_t populateRGBDData(const unsigned char* img, size_t pitch, int channels, float* const* destDepths,
                                unsigned char* const* destImages, cudaStream_t s);
@@ -108,8 +111,6 @@ class RGBDOdometry {
                          float* err, size_t err_pitch, cudaStream_t s);
   cudaError_t enqueueDeviceLoop(float icpWeight, bool pyramid, bool fastOdom, bool so3, float* err,
                                 size_t err_pitch, cudaStream_t s);
-  // Sobel images + photometric candidate gates, 3 levels, 1 launch (+ clears the barrier words `acnt`)
-  cudaError_t enqueuePrepare(cudaStream_t s, void* sync_words = nullptr, int nmodels = 1);
   cudaError_t prepareTiled(int nmodels);
   void destroyTiled();
   TiledState* tiled_ = nullptr;

@@ -29,14 +29,24 @@ Context::Context(int dev, int w, int h, float fx, float fy, float cx, float cy)
   if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess) return;
   const size_t n = (size_t)W * H;
   bool good = dalloc(&rgbBuf[0], n * 3) && dalloc(&rgbBuf[1], n * 3) && dalloc(&depthBuf[0], n) && dalloc(&depthBuf[1], n) &&
-              dalloc(&depthFiltered, n) && dalloc(&mask, n) && dalloc(&depthPyr[1], n / 4) && dalloc(&depthPyr[2], n / 16);
+              dalloc(&mask, n);
+  for (int k = 0; k < 2; ++k) {
+    good = good && dalloc(&depthFilteredBuf[k], n) && dalloc(&depthPyrBuf[k][1], n / 4) && dalloc(&depthPyrBuf[k][2], n / 16);
+    depthPyrBuf[k][0] = depthFilteredBuf[k];
+    good = good && cudaEventCreateWithFlags(&evInputs[k], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&evPre[k], cudaEventDisableTiming) == cudaSuccess;
+  }
+  good = good && cudaEventCreateWithFlags(&evOrder, cudaEventDisableTiming) == cudaSuccess &&
+         cudaStreamCreateWithFlags(&preStream, cudaStreamNonBlocking) == cudaSuccess;
   rgb = rgbBuf[0];
   depthRaw = depthBuf[0];
-  depthPyr[0] = depthFiltered;
+  depthFiltered = depthFilteredBuf[0];
+  for (int i = 0; i < 3; ++i) depthPyr[i] = depthPyrBuf[0][i];
   for (int k = 0; k < 2; ++k)
     good = good && cudaMallocHost(&h_rgbBuf[k], n * 3) == cudaSuccess && cudaMallocHost(&h_depthBuf[k], n * 4) == cudaSuccess &&
            cudaEventCreateWithFlags(&evCopied[k], cudaEventDisableTiming) == cudaSuccess &&
            cudaEventCreateWithFlags(&evBufferFree[k], cudaEventDisableTiming) == cudaSuccess;
+  good = good && cudaEventCreateWithFlags(&evFork, cudaEventDisableTiming) == cudaSuccess;
   h_rgb = h_rgbBuf[0];
   h_depth = h_depthBuf[0];
   good = good && cudaMallocHost(&h_mask, n) == cudaSuccess &&
@@ -47,7 +57,13 @@ Context::Context(int dev, int w, int h, float fx, float fy, float cx, float cy)
 Context::~Context() {
   if (stream) cudaStreamSynchronize(stream);
   if (copyStream) cudaStreamSynchronize(copyStream);
+  if (preStream) cudaStreamSynchronize(preStream);
   for (int k = 0; k < 2; ++k) {
+    cudaFree(depthFilteredBuf[k]);
+    cudaFree(depthPyrBuf[k][1]);
+    cudaFree(depthPyrBuf[k][2]);
+    if (evInputs[k]) cudaEventDestroy(evInputs[k]);
+    if (evPre[k]) cudaEventDestroy(evPre[k]);
     cudaFree(d16Buf[k]);
     cudaFreeHost(h_d16Buf[k]);
     cudaFree(rawImgBuf[k]);
@@ -58,25 +74,38 @@ Context::~Context() {
     if (evCopied[k]) cudaEventDestroy(evCopied[k]);
     if (evBufferFree[k]) cudaEventDestroy(evBufferFree[k]);
   }
-  cudaFree(depthFiltered);
+  if (evFork) cudaEventDestroy(evFork);
+  if (evOrder) cudaEventDestroy(evOrder);
+  if (preStream) cudaStreamDestroy(preStream);
   cudaFree(mask);
-  cudaFree(depthPyr[1]);
-  cudaFree(depthPyr[2]);
   cudaFreeHost(h_mask);
   cudaFree(batchScratch);
   if (copyStream) cudaStreamDestroy(copyStream);
   if (stream && owns_stream) cudaStreamDestroy(stream);
 }
 
-cudaError_t Context::uploadFrame(const uint8_t* rgb_h, const float* depth_h, const uint8_t* mask_h) {
-  const size_t n = (size_t)W * H;
-  // everything enqueued so far on the pipeline stream (the whole previous frame) is what still reads the
-  // current buffers: they may be overwritten once that point is reached
+// Start a frame: flip the double buffers.  Everything enqueued so far on the pipeline stream (the whole previous
+// frame) is what still reads the buffers being left; the ones being entered were last read by the frame before
+// that, whose end evBufferFree[] of the new index marks.
+cudaError_t Context::beginFrame(bool inputs_follow_stream) {
   RET_IF(cudaEventRecord(evBufferFree[cur], stream));
   cur ^= 1;
   rgb = rgbBuf[cur];
   depthRaw = depthBuf[cur];
-  RET_IF(cudaStreamWaitEvent(copyStream, evBufferFree[cur], 0));  // the frame before the previous one
+  depthFiltered = depthFilteredBuf[cur];
+  for (int i = 0; i < 3; ++i) depthPyr[i] = depthPyrBuf[cur][i];
+  RET_IF(cudaStreamWaitEvent(copyStream, evBufferFree[cur], 0));
+  RET_IF(cudaStreamWaitEvent(preStream, evBufferFree[cur], 0));
+  if (inputs_follow_stream) {
+    RET_IF(cudaEventRecord(evOrder, stream));
+    RET_IF(cudaStreamWaitEvent(preStream, evOrder, 0));
+  }
+  return cudaSuccess;
+}
+
+cudaError_t Context::uploadFrame(const uint8_t* rgb_h, const float* depth_h, const uint8_t* mask_h) {
+  const size_t n = (size_t)W * H;
+  RET_IF(beginFrame(false));
   // Pinned callers are copied straight from their buffers; pageable ones are staged through the
   // context's pinned buffers so that the copy is truly asynchronous either way.
   cudaPointerAttributes a;
@@ -101,6 +130,7 @@ cudaError_t Context::uploadFrame(const uint8_t* rgb_h, const float* depth_h, con
   RET_IF(cudaMemcpyAsync(rgb, r, n * 3, cudaMemcpyHostToDevice, copyStream));
   RET_IF(cudaMemcpyAsync(depthRaw, d, n * 4, cudaMemcpyHostToDevice, copyStream));
   RET_IF(cudaEventRecord(evCopied[cur], copyStream));
+  RET_IF(cudaStreamWaitEvent(preStream, evCopied[cur], 0));
   RET_IF(cudaStreamWaitEvent(stream, evCopied[cur], 0));
   if (mask_h) {
     const uint8_t* m = mask_h;
@@ -119,8 +149,9 @@ cudaError_t Context::uploadFrame(const uint8_t* rgb_h, const float* depth_h, con
 }
 
 cudaError_t Context::uploadFrameRaw(const uint8_t* img, bool flip, const float* depth, const uint16_t* depth16, float scale,
-                                    const uint8_t* mask_p, bool device_ptrs) {
-  if (!depth16 && !flip) return device_ptrs ? setFrameDevice(img, depth, mask_p) : uploadFrame(img, depth, mask_p);
+                                    const uint8_t* mask_p, bool device_ptrs, bool inputs_follow_stream) {
+  if (!depth16 && !flip)
+    return device_ptrs ? setFrameDevice(img, depth, mask_p, inputs_follow_stream) : uploadFrame(img, depth, mask_p);
   const size_t n = (size_t)W * H;
   for (int k = 0; k < 2; ++k) {  // raw buffers of the ingest path, on first use
     if (depth16 && !d16Buf[k]) {
@@ -129,13 +160,9 @@ cudaError_t Context::uploadFrameRaw(const uint8_t* img, bool flip, const float* 
     }
     if (flip && !rawImgBuf[k]) RET_IF(cudaMalloc((void**)&rawImgBuf[k], n * 3));
   }
-  RET_IF(cudaEventRecord(evBufferFree[cur], stream));
-  cur ^= 1;
-  rgb = rgbBuf[cur];
-  depthRaw = depthBuf[cur];
-  cudaStream_t cs = device_ptrs ? stream : copyStream;
+  RET_IF(beginFrame(device_ptrs && inputs_follow_stream));
+  cudaStream_t cs = device_ptrs ? preStream : copyStream;
   const cudaMemcpyKind kind = device_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  if (!device_ptrs) RET_IF(cudaStreamWaitEvent(copyStream, evBufferFree[cur], 0));
   cudaPointerAttributes a;
   auto pinned = [&](const void* q) { return cudaPointerGetAttributes(&a, q) == cudaSuccess && a.type == cudaMemoryTypeHost; };
   const void *src_img = img, *src_d = depth16 ? (const void*)depth16 : (const void*)depth;
@@ -166,11 +193,13 @@ cudaError_t Context::uploadFrameRaw(const uint8_t* img, bool flip, const float* 
     RET_IF(cudaMemcpyAsync(depthRaw, src_d, n * 4, kind, cs));
   if (!device_ptrs) {
     RET_IF(cudaEventRecord(evCopied[cur], copyStream));
-    RET_IF(cudaStreamWaitEvent(stream, evCopied[cur], 0));
+    RET_IF(cudaStreamWaitEvent(preStream, evCopied[cur], 0));
   }
   RET_IF(launch_ingest(flip ? rawImgBuf[cur] : nullptr, depth16 ? d16Buf[cur] : nullptr, scale, flip ? 1 : 0, rgb, depthRaw,
-                       (int)n, stream));
+                       (int)n, preStream));
   launches += 1;
+  RET_IF(cudaEventRecord(evInputs[cur], preStream));
+  RET_IF(cudaStreamWaitEvent(stream, evInputs[cur], 0));
   if (mask_p) {
     if (device_ptrs) {
       RET_IF(cudaMemcpyAsync(mask, mask_p, n, cudaMemcpyDeviceToDevice, stream));
@@ -190,10 +219,13 @@ cudaError_t Context::uploadFrameRaw(const uint8_t* img, bool flip, const float* 
   return cudaSuccess;
 }
 
-cudaError_t Context::setFrameDevice(const uint8_t* rgb_d, const float* depth_d, const uint8_t* mask_d) {
+cudaError_t Context::setFrameDevice(const uint8_t* rgb_d, const float* depth_d, const uint8_t* mask_d, bool inputs_follow_stream) {
   const size_t n = (size_t)W * H;
-  RET_IF(cudaMemcpyAsync(rgb, rgb_d, n * 3, cudaMemcpyDeviceToDevice, stream));
-  RET_IF(cudaMemcpyAsync(depthRaw, depth_d, n * 4, cudaMemcpyDeviceToDevice, stream));
+  RET_IF(beginFrame(inputs_follow_stream));
+  RET_IF(cudaMemcpyAsync(rgb, rgb_d, n * 3, cudaMemcpyDeviceToDevice, preStream));
+  RET_IF(cudaMemcpyAsync(depthRaw, depth_d, n * 4, cudaMemcpyDeviceToDevice, preStream));
+  RET_IF(cudaEventRecord(evInputs[cur], preStream));
+  RET_IF(cudaStreamWaitEvent(stream, evInputs[cur], 0));
   if (mask_d)
     RET_IF(cudaMemcpyAsync(mask, mask_d, n, cudaMemcpyDeviceToDevice, stream));
   else if (!keepMask)
@@ -202,14 +234,16 @@ cudaError_t Context::setFrameDevice(const uint8_t* rgb_d, const float* depth_d, 
 }
 
 cudaError_t Context::preprocess(float depthCutoff) {
-  RET_IF(launch_bilateral(depthRaw, (size_t)W * 4, W, H, depthCutoff, depthFiltered, (size_t)W * 4, stream));
+  RET_IF(launch_bilateral(depthRaw, (size_t)W * 4, W, H, depthCutoff, depthFiltered, (size_t)W * 4, preStream));
   {
     const void* src[1] = {depthPyr[0]};
     void* l1[1] = {depthPyr[1]};
     void* l2[1] = {depthPyr[2]};
     const int u8[1] = {0};
-    RET_IF(launch_pyramid2(1, src, l1, l2, u8, W, H, stream));
+    RET_IF(launch_pyramid2(1, src, l1, l2, u8, W, H, preStream));
   }
+  RET_IF(cudaEventRecord(evPre[cur], preStream));
+  RET_IF(cudaStreamWaitEvent(stream, evPre[cur], 0));
   launches += 2;
   return cudaSuccess;
 }
@@ -222,6 +256,7 @@ Model::Model(Context* c, unsigned id_, float conf, unsigned maxSurfels, bool ena
       allowsFillIn(enableFillIn),
       odom(c->W, c->H, c->K.cx, c->K.cy, c->K.fx, c->K.fy),
       capacity(maxSurfels) {
+  work = c->stream;
   for (int i = 0; i < 16; ++i) pose[i] = lastPose[i] = (i % 5 == 0) ? 1.f : 0.f;
   const size_t n = (size_t)c->W * c->H;
   bool good = dalloc(&predVertex, n * 4) && dalloc(&predNormal, n * 4) && dalloc(&predImage, n * 4) &&
@@ -273,10 +308,32 @@ Model::~Model() {
   delete scan.host;
   cudaFree(counters);
   cudaFreeHost(h_counters);
+  if (mstream) cudaStreamDestroy(mstream);
+  if (evJoin) cudaEventDestroy(evJoin);
   cudaFree(dpose);
   cudaFree(poseLogDev);
   cudaFreeHost(h_readback);
   if (evPose) cudaEventDestroy(evPose);
+}
+
+// Run this model's next calls on its own stream, ordered after `after` (an event on the context's stream); join()
+// makes the context's stream wait for them.  The per-model stages of a frame are independent
+// (`for (auto model : models)`, CoFusion.cpp:465-488, :536-542): with several models their small kernels overlap.
+cudaError_t Model::fork(cudaEvent_t after) {
+  if (!mstream) {
+    RET_IF(cudaStreamCreateWithFlags(&mstream, cudaStreamNonBlocking));
+    RET_IF(cudaEventCreateWithFlags(&evJoin, cudaEventDisableTiming));
+  }
+  RET_IF(cudaStreamWaitEvent(mstream, after, 0));
+  work = mstream;
+  return cudaSuccess;
+}
+cudaError_t Model::join() {
+  if (work == ctx->stream) return cudaSuccess;
+  RET_IF(cudaEventRecord(evJoin, mstream));
+  RET_IF(cudaStreamWaitEvent(ctx->stream, evJoin, 0));
+  work = ctx->stream;
+  return cudaSuccess;
 }
 
 cudaError_t Model::appendPoseLog(int64_t ts, int frame) {
@@ -289,7 +346,7 @@ cudaError_t Model::appendPoseLog(int64_t ts, int frame) {
     }
   }
   const int slot = (int)poseLogTs.size() - (int)(poseLogHost.size() / 12);
-  RET_IF(cudaMemcpyAsync(poseLogDev + (size_t)slot * 12, dpose->pose.m, 12 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  RET_IF(cudaMemcpyAsync(poseLogDev + (size_t)slot * 12, dpose->pose.m, 12 * sizeof(float), cudaMemcpyDeviceToDevice, work));
   poseLogTs.push_back(ts);
   poseLogFrame.push_back(frame);
   return cudaSuccess;
@@ -300,8 +357,8 @@ cudaError_t Model::fetchPoseLog() {
   if (pending <= 0) return cudaSuccess;
   poseLogHost.resize((size_t)(fetched + pending) * 12);
   RET_IF(cudaMemcpyAsync(poseLogHost.data() + (size_t)fetched * 12, poseLogDev, (size_t)pending * 12 * sizeof(float),
-                         cudaMemcpyDeviceToHost, ctx->stream));
-  return cudaStreamSynchronize(ctx->stream);
+                         cudaMemcpyDeviceToHost, work));
+  return cudaStreamSynchronize(work);
 }
 
 cudaError_t Model::uploadPose() {
@@ -321,13 +378,13 @@ cudaError_t Model::uploadPose() {
   b.weightBase = fusion_weight_base(pose, lastPose);
   poseStale = false;
   // pageable source: the runtime stages the 224 bytes before returning, `b` may go out of scope
-  return cudaMemcpyAsync(dpose, &b, sizeof(b), cudaMemcpyHostToDevice, ctx->stream);
+  return cudaMemcpyAsync(dpose, &b, sizeof(b), cudaMemcpyHostToDevice, work);
 }
 
 cudaError_t Model::enqueuePoseReadback() {
-  RET_IF(cudaMemcpyAsync(&h_readback->block, dpose, sizeof(PoseDev), cudaMemcpyDeviceToHost, ctx->stream));
-  RET_IF(cudaMemcpyAsync(&h_readback->stats, odom.statsDevice(), sizeof(TrackStats), cudaMemcpyDeviceToHost, ctx->stream));
-  RET_IF(cudaEventRecord(evPose, ctx->stream));
+  RET_IF(cudaMemcpyAsync(&h_readback->block, dpose, sizeof(PoseDev), cudaMemcpyDeviceToHost, work));
+  RET_IF(cudaMemcpyAsync(&h_readback->stats, odom.statsDevice(), sizeof(TrackStats), cudaMemcpyDeviceToHost, work));
+  RET_IF(cudaEventRecord(evPose, work));
   poseStale = true;
   return cudaSuccess;
 }
@@ -355,14 +412,14 @@ __global__ void rgb_to_rgba_kernel(const uint8_t* __restrict__ src, uchar4* __re
 cudaError_t Model::setPrediction(const float* v4, const float* n4, const uint8_t* img, int channels, bool dev) {
   const size_t n = (size_t)ctx->W * ctx->H;
   cudaMemcpyKind k = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  RET_IF(cudaMemcpyAsync(predVertex, v4, n * 16, k, ctx->stream));
-  RET_IF(cudaMemcpyAsync(predNormal, n4, n * 16, k, ctx->stream));
+  RET_IF(cudaMemcpyAsync(predVertex, v4, n * 16, k, work));
+  RET_IF(cudaMemcpyAsync(predNormal, n4, n * 16, k, work));
   if (channels == 4) {
-    RET_IF(cudaMemcpyAsync(predImage, img, n * 4, k, ctx->stream));
+    RET_IF(cudaMemcpyAsync(predImage, img, n * 4, k, work));
   } else {
     // RGB8 -> RGBA8: staged through the ICP error buffer (4n bytes, rewritten by the next track)
-    RET_IF(cudaMemcpyAsync(icpError, img, n * 3, k, ctx->stream));
-    rgb_to_rgba_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const uint8_t*)icpError,
+    RET_IF(cudaMemcpyAsync(icpError, img, n * 3, k, work));
+    rgb_to_rgba_kernel<<<(unsigned)((n + 255) / 256), 256, 0, work>>>((const uint8_t*)icpError,
                                                                             (uchar4*)predImage, (int)n);
     RET_IF(cudaGetLastError());
   }
@@ -370,7 +427,7 @@ cudaError_t Model::setPrediction(const float* v4, const float* n4, const uint8_t
 }
 
 cudaError_t Model::initFirstRGB() {
-  return odom.initFirstRGB(ctx->rgb, (size_t)ctx->W * 3, 3, ctx->stream);
+  return odom.initFirstRGB(ctx->rgb, (size_t)ctx->W * 3, 3, work);
 }
 
 namespace {
@@ -396,7 +453,7 @@ float Model::computeFusionWeight(float weightMultiplier) const {
 
 cudaError_t Model::initialise(int time, float maxDepthProcessed) {
   RET_IF(launch_surfel_initialise(geom(), ctx->rgb, ctx->depthRaw, ctx->depthFiltered, time, maxDepthProcessed,
-                                  buf[target], capacity, candStaging, unstable, scan, counters, ctx->stream));
+                                  buf[target], capacity, candStaging, unstable, scan, counters, work));
   const unsigned n = (unsigned)ctx->W * ctx->H;
   count_ub = n < capacity ? n : capacity;
   ctx->launches += 8;
@@ -419,7 +476,7 @@ cudaError_t Model::predictIndices(int time, float depthCutoff, int timeDelta) {
   refreshCountBound(time);
   ctx->launches += 2;
   return launch_predict_indices(geom(), buf[target], count_ub, counters, invRef(), time, depthCutoff, timeDelta, keys,
-                                indexMaps, ctx->stream);
+                                indexMaps, work);
 }
 
 cudaError_t Model::fuse(int time, float depthCutoff, float weightMultiplier) {
@@ -427,14 +484,14 @@ cudaError_t Model::fuse(int time, float depthCutoff, float weightMultiplier) {
   ctx->launches += 5;
   return launch_fuse(geom(), buf[target], count_ub, counters, poseRef(), time, ctx->rgb, ctx->mask, ctx->depthRaw,
                      ctx->depthFiltered, md, WeightRef(&dpose->weightBase, weightMultiplier), id, indexMaps, winner,
-                     candStaging, candBest, unstable, scan, ctx->stream);
+                     candStaging, candBest, unstable, scan, work);
 }
 
 cudaError_t Model::clean(int time, int timeDelta, float /*depthCutoff*/, float outlierCoefficient) {
   const unsigned cand_ub = (unsigned)((ctx->W + 1) / 2) * ((ctx->H + 1) / 2);
   RET_IF(launch_clean(geom(), buf[target], unstable, buf[renderSource], count_ub, cand_ub, capacity, counters,
                       invRef(), time, confidenceThreshold, timeDelta, ctx->depthFiltered, ctx->mask, id,
-                      outlierCoefficient, indexMaps, scan, ctx->stream));
+                      outlierCoefficient, indexMaps, scan, work));
   cleanTick = time;
   int t = target;
   target = renderSource;
@@ -443,7 +500,7 @@ cudaError_t Model::clean(int time, int timeDelta, float /*depthCutoff*/, float o
   count_ub = ub < capacity ? ub : capacity;
   ctx->launches += 4;
   // refresh the host-side bound with the exact count whenever the stream is next synchronised
-  RET_IF(cudaMemcpyAsync(h_counters, counters, sizeof(MapCounters), cudaMemcpyDeviceToHost, ctx->stream));
+  RET_IF(cudaMemcpyAsync(h_counters, counters, sizeof(MapCounters), cudaMemcpyDeviceToHost, work));
   return cudaSuccess;
 }
 
@@ -451,37 +508,37 @@ cudaError_t Model::combinedPredict(float depthCutoff, int time, int maxTime, int
   usePrediction = true;
   ctx->launches += 2;
   return launch_combined_predict(geom(), buf[target], count_ub, counters, invRef(), depthCutoff, confidenceThreshold, time,
-                                 maxTime, timeDelta, keys, splat, ctx->stream);
+                                 maxTime, timeDelta, keys, splat, work);
 }
 
 cudaError_t Model::performFillIn(bool frameToFrameRGB, bool lost) {
   if (!allowsFillIn) return cudaSuccess;
   ctx->launches += 2;
   return launch_fill_in(geom(), splat, ctx->rgb, ctx->depthFiltered, lost ? 1 : 0, (lost || frameToFrameRGB) ? 1 : 0,
-                        fill, counters, 0.75f, ctx->stream);
+                        fill, counters, 0.75f, work);
 }
 
 cudaError_t Model::downloadMap(float* dst, size_t cap, unsigned* count_out) {
-  RET_IF(cudaMemcpyAsync(h_counters, counters, sizeof(MapCounters), cudaMemcpyDeviceToHost, ctx->stream));
-  RET_IF(cudaStreamSynchronize(ctx->stream));
+  RET_IF(cudaMemcpyAsync(h_counters, counters, sizeof(MapCounters), cudaMemcpyDeviceToHost, work));
+  RET_IF(cudaStreamSynchronize(work));
   unsigned n = h_counters->count;
   count_ub = n;
   if (count_out) *count_out = n;
   if (dst && n) {
     if (n > cap) n = (unsigned)cap;
-    RET_IF(cudaMemcpyAsync(dst, buf[target], (size_t)n * sizeof(Surfel), cudaMemcpyDeviceToHost, ctx->stream));
-    RET_IF(cudaStreamSynchronize(ctx->stream));
+    RET_IF(cudaMemcpyAsync(dst, buf[target], (size_t)n * sizeof(Surfel), cudaMemcpyDeviceToHost, work));
+    RET_IF(cudaStreamSynchronize(work));
   }
   return cudaSuccess;
 }
 
 cudaError_t Model::uploadMap(const float* src, unsigned count) {
   if (count > capacity) count = capacity;
-  RET_IF(cudaMemcpyAsync(buf[target], src, (size_t)count * sizeof(Surfel), cudaMemcpyHostToDevice, ctx->stream));
+  RET_IF(cudaMemcpyAsync(buf[target], src, (size_t)count * sizeof(Surfel), cudaMemcpyHostToDevice, work));
   MapCounters c = {count, 0, 0, 0, 0};
   *h_counters = c;
-  RET_IF(cudaMemcpyAsync(counters, h_counters, sizeof(MapCounters), cudaMemcpyHostToDevice, ctx->stream));
-  RET_IF(cudaStreamSynchronize(ctx->stream));
+  RET_IF(cudaMemcpyAsync(counters, h_counters, sizeof(MapCounters), cudaMemcpyHostToDevice, work));
+  RET_IF(cudaStreamSynchronize(work));
   count_ub = count;
   return cudaSuccess;
 }
@@ -493,7 +550,7 @@ cudaError_t Model::prepareTracking(const TrackParams& tp, bool devicePose) {
     RET_IF(syncPose());
     memcpy(lastPose, pose, sizeof(pose));
   }  // otherwise the tracker's epilogue moves pose -> last inside the device block
-  cudaStream_t s = ctx->stream;
+  cudaStream_t s = work;
   if (usePrediction) {
     // Model::initICP (Model.cpp:350-367): splat prediction, or the fill-in images when
     // CoFusion::requiresFillIn says so -- selected on the device (no host wait)
@@ -532,7 +589,7 @@ cudaError_t Model::performTracking(const TrackParams& tp) {
   float rot[9] = {pose[0], pose[1], pose[2], pose[4], pose[5], pose[6], pose[8], pose[9], pose[10]};
   RET_IF(odom.getIncrementalTransformation(trans, rot, tp.rgbOnly != 0, tp.icpWeight, tp.pyramid != 0,
                                            tp.fastOdom != 0, tp.so3 != 0, icpError, (size_t)ctx->W * 4,
-                                           tp.force_host_loop != 0, ctx->stream));
+                                           tp.force_host_loop != 0, work));
   finishTracking(trans, rot);
   ctx->launches += 2;  // prepare, persistent GN
   return cudaSuccess;
@@ -558,9 +615,16 @@ cudaError_t trackModels(Context* ctx, Model* const* models, int n, const TrackPa
     PoseDev* pd[RGBDOdometry::kMaxBatch];
     float trans[RGBDOdometry::kMaxBatch][3], rot[RGBDOdometry::kMaxBatch][9];
     float* err[RGBDOdometry::kMaxBatch];
+    // several models: each one's model pyramids and Sobel / candidate pass run on its own stream
+    const bool spread = async && nb > 1;
+    if (spread) {
+      RET_IF(cudaEventRecord(ctx->evFork, ctx->stream));
+      for (int k = 0; k < nb; ++k) RET_IF(models[i + k]->fork(ctx->evFork));
+    }
     for (int k = 0; k < nb; ++k) {
       Model* m = models[i + k];
       RET_IF(m->prepareTracking(tp, async));
+      if (spread) RET_IF(m->odom.enqueuePrepare(m->work, k == 0 ? ctx->batchScratch : nullptr, nb));
       od[k] = &m->odom;
       pd[k] = m->dpose;
       err[k] = m->icpError;
@@ -570,8 +634,10 @@ cudaError_t trackModels(Context* ctx, Model* const* models, int n, const TrackPa
       memcpy(trans[k], t, sizeof(t));
       memcpy(rot[k], r, sizeof(r));
     }
+    if (spread)
+      for (int k = 0; k < nb; ++k) RET_IF(models[i + k]->join());
     RET_IF(RGBDOdometry::trackTiled(od, nb, trans, rot, tp.icpWeight, tp.pyramid != 0, tp.fastOdom != 0, tp.so3 != 0, err,
-                                    (size_t)ctx->W * 4, ctx->batchScratch, ctx->stream, async ? pd : nullptr, async));
+                                    (size_t)ctx->W * 4, ctx->batchScratch, ctx->stream, async ? pd : nullptr, async, spread));
     for (int k = 0; k < nb; ++k) {
       if (async)
         RET_IF(models[i + k]->enqueuePoseReadback());  // pose + stats reach the host when somebody asks (syncPose)

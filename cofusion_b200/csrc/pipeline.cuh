@@ -27,12 +27,14 @@ class Context {
   // CoFusion::processFrame :179-184: upload + bilateral filter.  Host buffers (pinned or pageable).
   cudaError_t uploadFrame(const uint8_t* rgb_hwc, const float* depth, const uint8_t* mask);
   // same, inputs already resident in device memory
-  cudaError_t setFrameDevice(const uint8_t* rgb_hwc, const float* depth, const uint8_t* mask);
+  // inputs_follow_stream: the device inputs were produced by work enqueued on `stream` (otherwise they are taken
+  // to be complete when the call is made)
+  cudaError_t setFrameDevice(const uint8_t* rgb_hwc, const float* depth, const uint8_t* mask, bool inputs_follow_stream = false);
   // Frame ingest on the device (KlgLogReader.cpp:53-84, FrameData.h:38-41): raw u16 depth (x depthScale) and / or an
   // image whose first and third channels are swapped travel as they are (1.54 MB instead of 2.15 MB per VGA frame) and
   // are converted by one kernel.  depth16 == nullptr: `depth` is metric f32 as in uploadFrame.
   cudaError_t uploadFrameRaw(const uint8_t* img_hwc, bool flipColors, const float* depth, const uint16_t* depth16,
-                             float depthScale, const uint8_t* mask, bool device_ptrs);
+                             float depthScale, const uint8_t* mask, bool device_ptrs, bool inputs_follow_stream = false);
   // filterDepth (CoFusion.cpp:567-574) + Model::generateCUDATextures (Model.cpp:319-348)
   cudaError_t preprocess(float depthCutoff);
   cudaError_t sync() { return cudaStreamSynchronize(stream); }
@@ -52,7 +54,14 @@ class Context {
   int cur = 0;
   cudaStream_t copyStream = nullptr;
   cudaEvent_t evCopied[2] = {nullptr, nullptr}, evBufferFree[2] = {nullptr, nullptr};
-  float* depthFiltered = nullptr;   // level 0 of the pyramid
+  // The frame side of a frame (device copies / ingest, bilateral filter, depth pyramid) depends on nothing the
+  // models produce: it runs on preStream into double buffers, so that frame t+1's 80 us of filtering overlap the
+  // many small surfel kernels of frame t, which leave most SMs idle.  `stream` joins at evPre.
+  cudaStream_t preStream = nullptr;
+  cudaEvent_t evInputs[2] = {nullptr, nullptr}, evPre[2] = {nullptr, nullptr}, evOrder = nullptr;
+  float* depthFilteredBuf[2] = {nullptr, nullptr};
+  float* depthPyrBuf[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+  float* depthFiltered = nullptr;   // level 0 of the pyramid of the CURRENT frame
   float* depthPyr[3] = {nullptr, nullptr, nullptr};
   uint8_t* mask = nullptr;          // label image (model ids)
   uint16_t* d16Buf[2] = {nullptr, nullptr};    // raw depth of the ingest path (allocated on first use)
@@ -63,9 +72,11 @@ class Context {
   uint8_t* h_mask = nullptr;
   int launches = 0;                 // kernels launched since the last reset (bench accounting)
   bool keepMask = false;            // true: a frame without mask keeps the previous labels (segmentation on)
+  cudaEvent_t evFork = nullptr;     // fork point of the per-model streams
   void* batchScratch = nullptr;     // RGBDOdometry::tiledScratchBytes(), allocated on first multi-model frame
 
  private:
+  cudaError_t beginFrame(bool inputs_follow_stream);
   bool ok_ = false;
 };
 
@@ -126,6 +137,12 @@ class Model {
   cudaError_t enqueuePoseReadback();      // after an asynchronous tracking launch: D2H of block + stats, event
   const PoseRef poseRef() const { return PoseRef(&dpose->pose); }
   const PoseRef invRef() const { return PoseRef(&dpose->inv); }
+
+  cudaError_t fork(cudaEvent_t after);  // per-model stream (see pipeline.cu)
+  cudaError_t join();
+  cudaStream_t work = nullptr;      // the stream this model's calls are enqueued on (the context's unless forked)
+  cudaStream_t mstream = nullptr;
+  cudaEvent_t evJoin = nullptr;
 
   Context* ctx;
   unsigned id;
