@@ -25,7 +25,21 @@ CoFusion::CoFusion(int device, int W, int H, float fx, float fy, float cx, float
   if (p.enableMultipleModels) {
     segmentation.reset(new Segmentation(W, H));
     ctx.keepMask = true;  // textures[MASK] persists between frames (CoFusion.cpp:233)
+    // one object model made ahead: the first spawn of a sequence costs no allocation inside a frame
+    std::unique_ptr<Model> spare(new Model(&ctx, 255, p.confObjectInit, p.maxSurfels, false));
+    if (spare->ok()) spareModels.push_back(std::move(spare));
   }
+}
+
+// CoFusion::spawnObjectModel's `std::make_shared<Model>(...)` (CoFusion.cpp:590): from the pool when it has one
+cudaError_t CoFusion::acquireModel(unsigned id, float conf, std::unique_ptr<Model>* out) {
+  if (!spareModels.empty() && !getenv("CFB_NO_MODEL_POOL")) {  // (the switch is for the equivalence test)
+    *out = std::move(spareModels.back());
+    spareModels.pop_back();
+    return (*out)->recycle(id, conf);
+  }
+  out->reset(new Model(&ctx, id, conf, params.maxSurfels, false));
+  return (*out)->ok() ? cudaSuccess : cudaErrorMemoryAllocation;
 }
 
 unsigned char CoFusion::takeNextModelID() {  // CoFusion.cpp:628-645
@@ -64,6 +78,7 @@ cudaError_t CoFusion::segmentAndManageModels() {
   lastModelData.assign(n + 1, SegModelData{});
   int cnt = 0;
   bool hasNew = false;
+  if (segmentation->slicAheadOf == ctx.rgb) RET_IF(cudaStreamWaitEvent(ctx.stream, ctx.evOrder2, 0));
   RET_IF(segmentation->performSegmentationCRF(ctx.rgb, ctx.depthRaw, n, ids, icp, conf, nextID_, allowNew, params.seg,
                                               ctx.mask, lastModelData.data(), &cnt, &hasNew, ctx.stream));
   ctx.launches += segmentation->launches;
@@ -74,8 +89,7 @@ cudaError_t CoFusion::segmentAndManageModels() {
   std::unique_ptr<Model> newModel;
   if (hasNew) {  // CoFusion.cpp:243-259, spawnObjectModel :588-597
     const unsigned char id = takeNextModelID();
-    newModel.reset(new Model(&ctx, id, params.confObjectInit, params.maxSurfels, false));
-    if (!newModel->ok()) return cudaErrorMemoryAllocation;
+    RET_IF(acquireModel(id, params.confObjectInit, &newModel));
     RET_IF(newModel->initFirstRGB());
     spawnOffset_ = 0;
     newModel->maxDepth = seg_max_depth(lastModelData.back());
@@ -93,7 +107,11 @@ cudaError_t CoFusion::segmentAndManageModels() {
     if (m.superPixelCount <= 0 && m.id != 0) {
       for (size_t j = 0; j < models.size(); ++j)
         if (models[j].get() == owners[k]) {
-          inactiveModels.push_back(std::move(models[j]));
+          // the data stays (archive), the buffers serve the next spawn
+          std::unique_ptr<ArchivedModel> a(new ArchivedModel());
+          RET_IF(models[j]->archive(a.get()));
+          inactiveModels.push_back(std::move(a));
+          spareModels.push_back(std::move(models[j]));
           models.erase(models.begin() + j);
           lastDeactivated++;
           break;
@@ -110,8 +128,8 @@ cudaError_t CoFusion::segmentAndManageModels() {
 }
 
 cudaError_t CoFusion::spawnObjectModel(unsigned id, const float* initialPose) {
-  std::unique_ptr<Model> m(new Model(&ctx, id, params.confObjectInit, params.maxSurfels, false));
-  if (!m->ok()) return cudaErrorMemoryAllocation;
+  std::unique_ptr<Model> m;
+  RET_IF(acquireModel(id, params.confObjectInit, &m));
   RET_IF(models[0]->syncPose());
   const float* src = initialPose ? initialPose : models[0]->pose;
   memcpy(m->pose, src, sizeof(m->pose));
@@ -244,6 +262,13 @@ cudaError_t CoFusion::processFrameEx(const FrameInput& in_, const float* inPose,
   RET_IF(ctx.uploadFrameRaw(in.rgb, in.flipColors, in.depth, in.depth16, in.depthScale, in.mask, device_ptrs,
                             shard.active() || !ctx.owns_stream));
   RET_IF(ctx.preprocess(params.depthCutoff));
+  if (params.enableMultipleModels && segmentation && tick_ > 1 && !(inPose && !bootstrap)) {
+    // the super-pixels of this frame, ahead of time on the frame-side stream: they overlap the previous frame's
+    // surfel kernels (or share the SMs with the tracker, whose CTAs leave most issue slots idle)
+    RET_IF(segmentation->slic(ctx.rgb, ctx.preStream));
+    RET_IF(cudaEventRecord(ctx.evOrder2, ctx.preStream));
+    segmentation->slicAheadOf = ctx.rgb;
+  }
   if (tick_ == 1) {
     if (processGlobalModel) {
       RET_IF(models[0]->initialise(tick_, params.maxDepthProcessed));
@@ -400,21 +425,21 @@ void quaternion_of(const float* T, float* q) {  // Eigen::Quaternionf(Matrix3f):
 }
 }  // namespace
 
-cudaError_t CoFusion::modelPoseLog(Model* m, std::vector<int64_t>* ts, std::vector<float>* p7) {
+cudaError_t CoFusion::poseLogEntries(bool isCamera, const std::vector<int64_t>& lts, const std::vector<int>& lframe,
+                                     const std::vector<float>& lhost, std::vector<int64_t>* ts, std::vector<float>* p7) {
   Model* g = models[0].get();
   RET_IF(g->fetchPoseLog());
-  RET_IF(m->fetchPoseLog());
-  const size_t n = m->poseLogTs.size();
-  if (ts) *ts = m->poseLogTs;
+  const size_t n = lts.size();
+  if (ts) *ts = lts;
   if (p7) {
     p7->resize(n * 7);
     for (size_t k = 0; k < n; ++k) {
-      const float* P = m->poseLogHost.data() + k * 12;
+      const float* P = lhost.data() + k * 12;
       float T[12];
-      if (m == g) {
+      if (isCamera) {
         memcpy(T, P, sizeof(T));
       } else {  // object -> world = cameraPose * modelPose^-1 of the same frame
-        const int f = m->poseLogFrame[k];
+        const int f = lframe[k];
         float inv[12];
         rigid_inverse(P, inv);
         rigid_mul(g->poseLogHost.data() + (size_t)f * 12, inv, T);
@@ -429,18 +454,20 @@ cudaError_t CoFusion::modelPoseLog(Model* m, std::vector<int64_t>* ts, std::vect
   return cudaSuccess;
 }
 
+cudaError_t CoFusion::modelPoseLog(Model* m, std::vector<int64_t>* ts, std::vector<float>* p7) {
+  RET_IF(m->fetchPoseLog());
+  return poseLogEntries(m == models[0].get(), m->poseLogTs, m->poseLogFrame, m->poseLogHost, ts, p7);
+}
+
 cudaError_t CoFusion::poseLog(size_t i, std::vector<int64_t>* ts, std::vector<float>* p7) {
   if (i >= models.size()) return cudaErrorInvalidValue;
   return modelPoseLog(models[i].get(), ts, p7);
 }
 
 cudaError_t CoFusion::exportPoses(const char* dir) {  // CoFusion.cpp:758-783
-  auto one = [&](Model* m) -> cudaError_t {
-    std::vector<int64_t> ts;
-    std::vector<float> p;
-    RET_IF(modelPoseLog(m, &ts, &p));
+  auto write = [&](unsigned id, const std::vector<int64_t>& ts, const std::vector<float>& p) -> cudaError_t {
     if (ts.empty()) return cudaSuccess;  // Model::isLoggingPoses
-    const std::string fn = std::string(dir) + "/poses-" + std::to_string(m->id) + ".txt";
+    const std::string fn = std::string(dir) + "/poses-" + std::to_string(id) + ".txt";
     FILE* f = fopen(fn.c_str(), "w");
     if (!f) return cudaErrorInvalidValue;
     for (size_t k = 0; k < ts.size(); ++k) {
@@ -451,8 +478,16 @@ cudaError_t CoFusion::exportPoses(const char* dir) {  // CoFusion.cpp:758-783
     fclose(f);
     return cudaSuccess;
   };
-  for (auto& m : models) RET_IF(one(m.get()));
-  for (auto& m : inactiveModels) RET_IF(one(m.get()));
+  std::vector<int64_t> ts;
+  std::vector<float> p;
+  for (auto& m : models) {
+    RET_IF(modelPoseLog(m.get(), &ts, &p));
+    RET_IF(write(m->id, ts, p));
+  }
+  for (auto& a : inactiveModels) {
+    RET_IF(poseLogEntries(false, a->poseLogTs, a->poseLogFrame, a->poseLogHost, &ts, &p));
+    RET_IF(write(a->id, ts, p));
+  }
   return cudaSuccess;
 }
 

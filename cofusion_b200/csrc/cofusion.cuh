@@ -86,7 +86,9 @@ class CoFusion {
   Context ctx;
   CoFusionParams params;
   std::vector<std::unique_ptr<Model>> models;
-  std::vector<std::unique_ptr<Model>> inactiveModels;  // CoFusion::inactivateModel keeps the data
+  std::vector<std::unique_ptr<ArchivedModel>> inactiveModels;  // CoFusion::inactivateModel keeps the data
+  std::vector<std::unique_ptr<Model>> spareModels;  // buffers of lost models (and one made ahead), reused by the next spawn
+  cudaError_t acquireModel(unsigned id, float conf, std::unique_ptr<Model>* out);
   // tracking statistics of model i after the last processFrame (waits for that frame's tracker)
   cudaError_t stats(size_t i, TrackStats* out) {
     if (i >= models.size()) return cudaErrorInvalidValue;
@@ -108,6 +110,8 @@ class CoFusion {
   unsigned char takeNextModelID();       // getNextModelID(true)
   cudaError_t logPoses(int64_t timestamp);
   cudaError_t modelPoseLog(Model* m, std::vector<int64_t>* ts, std::vector<float>* p7);
+  cudaError_t poseLogEntries(bool isCamera, const std::vector<int64_t>& lts, const std::vector<int>& lframe,
+                             const std::vector<float>& lhost, std::vector<int64_t>* ts, std::vector<float>* p7);
   bool poseLogging_ = false;
   int logFrames_ = 0;  // frames logged so far (index into the camera model's log)
   int tick_ = 1;

@@ -60,6 +60,9 @@ constexpr int kMaxHalo = 4;           // model window = tile + halo pixels on ev
 struct MLevel {  // per model, per level
   const float *vmap_g_prev, *nmap_g_prev, *lastDepth, *nextDepth;
   const unsigned char *lastImage, *cand;
+  // extents of the model in this level's image, or null (= everywhere): [minx, miny, -maxx, -maxy] of the photometric
+  // candidates, then the same of the valid model vertices (written by rgb_prepare_tiled_kernel with atomicMin)
+  const int* box;
   const CUtensorMap *tm_d1, *tm_cand, *tm_pv, *tm_pn, *tm_ld, *tm_li;  // camera model (m == 0) only
 };
 struct MParams {
@@ -128,6 +131,7 @@ struct TFixed {  // fixed head of the dynamic shared memory
   unsigned long long bar_frame[3], bar_win;
   int cntw[kMaxM][kNW], sigw[kMaxM][kNW];
   int tot[kMaxM][2];
+  int box[kMaxM][8];  // this level: candidates [minx, miny, maxx, maxy], valid model vertices [minx, miny, maxx, maxy]
   float tmpErr[kMaxM];
   int winacc[3];
   int win_x0, win_y0;
@@ -315,10 +319,13 @@ __device__ __forceinline__ void xaccumulate_se3(float (&acc)[32], const float (&
 template <bool FS, bool MS>
 __device__ __forceinline__ bool residual_pixel(const LvCtx& c, const MLevel& L, const RgbWarp& Wp, float maxDepthDelta,
                                                int lx, int ly, int x, int y, const unsigned char* nextImage, int& u0,
-                                               int& v0, float& diff, float& d0) {
+                                               int& v0, float& diff, float& d0, const int* box) {
   extern __shared__ __align__(128) unsigned char dyn_smem_raw[];
   bool cand;
   float d1;
+  // an object model fills a few percent of the image: outside the extent of its candidates the gate is 0, known
+  // without the (long-latency, per-pixel serial) global load
+  if (!MS && (x < box[0] || y < box[1] || x > box[2] || y > box[3])) return false;
   if (MS) {
     cand = SM_U8(c.oCAND)[ly * c.pb + lx + c.shb] != 0;
     d1 = SM_F32(c.oD1)[ly * c.pf + lx + c.shf];
@@ -357,13 +364,16 @@ __device__ __noinline__ void phase1(int lvl, int m) {
   const unsigned char* nextImage = p.F[lvl].nextImage;
   int cnt = 0, sig = 0;
   int k = 0;
-  for (PixIt it = pix_begin(c); it.i < c.npx; pix_next(c, it), ++k) {
+  // a tile the model's candidates do not reach has nothing to enumerate
+  const int* bc = sm.box[m];
+  const bool none = !MS && (c.x0 > bc[2] || c.x0 + c.tw <= bc[0] || c.y0 > bc[3] || c.y0 + c.th <= bc[1]);
+  for (PixIt it = pix_begin(c); !none && it.i < c.npx; pix_next(c, it), ++k) {
     const int x = c.x0 + it.lx, y = c.y0 + it.ly;
     int u0, v0;
     float diff, d0;
     unsigned zero = kNoCorr;
     if (x < c.W && y < c.H &&
-        residual_pixel<FS, MS>(c, L, Wp, p.maxDepthDelta, it.lx, it.ly, x, y, nextImage, u0, v0, diff, d0)) {
+        residual_pixel<FS, MS>(c, L, Wp, p.maxDepthDelta, it.lx, it.ly, x, y, nextImage, u0, v0, diff, d0, sm.box[m])) {
       cnt += 1;
       sig += (int)__fmul_rn(diff, diff);  // float -> int truncation, reduce.cu:851
       if (MS) {
@@ -460,10 +470,16 @@ __device__ __noinline__ void phase2(int lvl, int m, float* error_map, int buf) {
       vp = make_float3(SM_F32(c.oPV)[j], SM_F32(c.oPV)[c.wplane + j], SM_F32(c.oPV)[2 * c.wplane + j]);
       np = make_float3(SM_F32(c.oPN)[j], SM_F32(c.oPN)[c.wplane + j], SM_F32(c.oPN)[2 * c.wplane + j]);
     } else {
+      // An object model predicts a few percent of the image; everywhere else its vertex map is NaN.
+      // A NaN in the x plane makes dist NaN whatever the other five planes hold -- and outside the extent of
+      // the valid vertices it is NaN without looking.
+      const int* bv = sm.box[m] + 4;
+      if (ux < bv[0] || uy < bv[1] || ux > bv[2] || uy > bv[3]) {
+        if (err) *err = 0.0f;
+        continue;
+      }
       const int j = uy * c.W + ux;
       vp.x = __ldg(L.vmap_g_prev + j);
-      // An object model predicts a few percent of the image; everywhere else its vertex map is NaN.
-      // A NaN in the x plane makes dist NaN whatever the other five planes hold.
       if (isnan(vp.x)) {
         if (err) *err = 0.0f;
         continue;
@@ -524,7 +540,9 @@ __device__ __noinline__ void phase3(int lvl, int m, float sigma, int buf) {
   for (int i = 0; i < 32; ++i) acc[i] = 0.f;
   bool any = false;
   int k = 0;
-  for (PixIt it = pix_begin(c); it.i < c.npx; pix_next(c, it), ++k) {
+  const int* bc = sm.box[m];
+  const bool none = !MS && (c.x0 > bc[2] || c.x0 + c.tw <= bc[0] || c.y0 > bc[3] || c.y0 + c.th <= bc[1]);
+  for (PixIt it = pix_begin(c); !none && it.i < c.npx; pix_next(c, it), ++k) {
     if (MS) {  // the correspondences of phase 1 never left the SM
       const unsigned zero = SM_U32(c.oCorrZ)[k * kT + threadIdx.x];
       if (zero == kNoCorr) continue;
@@ -537,7 +555,8 @@ __device__ __noinline__ void phase3(int lvl, int m, float sigma, int buf) {
       int u0, v0;
       float diff, d0;
       if (x >= c.W || y >= c.H) continue;
-      if (!residual_pixel<FS, false>(c, p.M[m].L[lvl], sm.S[m].warp, p.maxDepthDelta, it.lx, it.ly, x, y, F.nextImage, u0, v0, diff, d0))
+      if (!residual_pixel<FS, false>(c, p.M[m].L[lvl], sm.S[m].warp, p.maxDepthDelta, it.lx, it.ly, x, y, F.nextImage, u0, v0, diff, d0,
+                                     sm.box[m]))
         continue;
       any = true;
       const int si = it.ly * c.ps + it.lx + c.shs;
@@ -982,6 +1001,13 @@ __device__ __forceinline__ void issue_frame_tma(int lvl) {  // one thread
 __device__ __noinline__ void level_begin(int lvl, unsigned& win_phase) {
   TSMEM();
   const FLevel& F = p.F[lvl];
+  if ((int)threadIdx.x < p.nmodels * 8) {  // model extents of this level (visible after the barriers below)
+    const int m = threadIdx.x >> 3, k = threadIdx.x & 7;
+    const int* b = p.M[m].L[lvl].box;
+    int v = (k & 2) ? ((k & 1) ? F.h - 1 : F.w - 1) : 0;
+    if (b) v = (k & 2) ? -__ldg(b + k) : __ldg(b + k);
+    sm.box[m][k] = v;
+  }
   if (!F.staged) {
     if (threadIdx.x == 0) make_lvctx(lvl);
     __syncthreads();
@@ -1290,6 +1316,8 @@ struct PrepLevel {
   unsigned char* cand;
   int w, h;
   float minScale;
+  const float* vx;  // x plane of the model's global vertex map (extent of the valid vertices), with `box`
+  int* box;         // 8 ints, preset to a large value, or null (camera model: no extents kept)
 };
 struct PrepParams {
   PrepLevel L[3];
@@ -1310,6 +1338,19 @@ __global__ void rgb_prepare_tiled_kernel(const PrepParams pp) {
     if (q < n) {
       int y = q / L.w, x = q - y * L.w;
       rgb_prepare_pixel(L.img, L.w, L.h, L.nextDepth, L.minScale, L.dx, L.dy, L.cand, x, y);
+      if (L.box) {  // extents [minx, miny, -maxx, -maxy]: candidates, valid vertices
+        const bool cf = L.cand[q] != 0, vf = !isnan(__ldg(L.vx + q));
+        const int big = 0x7f7f7f7f;
+        if (__any_sync(__activemask(), cf || vf)) {
+          const unsigned am = __activemask();
+          int v[8] = {cf ? x : big, cf ? y : big, cf ? -x : big, cf ? -y : big, vf ? x : big, vf ? y : big, vf ? -x : big, vf ? -y : big};
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int r = __reduce_min_sync(am, v[k]);
+            if (r != big && (threadIdx.x & 31) == (__ffs(am) - 1)) atomicMin(L.box + k, r);
+          }
+        }
+      }
       return;
     }
     q -= n;
@@ -1533,13 +1574,18 @@ size_t RGBDOdometry::tiledScratchBytes() { return kSyncBytes + 256; }
 
 bool RGBDOdometry::canBatch(int n) const { return n >= 1 && n <= kMaxM && mode_ == 0 && width < 2048 && height < 2048; }
 
-cudaError_t RGBDOdometry::enqueuePrepare(cudaStream_t s, void* sync_words, int nmodels) {
+cudaError_t RGBDOdometry::enqueuePrepare(cudaStream_t s, void* sync_words, int nmodels, bool extents) {
   PrepParams pp;
   int total = 0;
+  if (extents) {
+    if (!d_box_) RET_IF(cudaMalloc((void**)&d_box_, 24 * sizeof(int)));
+    RET_IF(cudaMemsetAsync(d_box_, 0x7f, 24 * sizeof(int), s));  // atomicMin targets
+  }
   for (int i = 0; i < NUM_PYRS; ++i) {
     const int w = width >> i, h = height >> i;
     pp.L[i] = PrepLevel{nextImage[i], (next_is_last_ ? lastDepth[i] : nextDepth[i]), nextdIdx[i], nextdIdy[i], rgbCand[i], w, h,
-                        (float)(pow(minimumGradientMagnitudes[i], 2.0) / pow(sobelScale, 2.0))};
+                        (float)(pow(minimumGradientMagnitudes[i], 2.0) / pow(sobelScale, 2.0)), vmaps_g_prev_[i],
+                        extents ? d_box_ + 8 * i : nullptr};
     total += w * h;
   }
   pp.sync_words = (unsigned long long*)sync_words;
@@ -1577,7 +1623,7 @@ cudaError_t RGBDOdometry::trackTiled(RGBDOdometry* const* od, int n, float (*tra
       RET_IF(cudaMemcpyAsync(o.d_pose_in, h_in, 12 * sizeof(float), cudaMemcpyHostToDevice, s));
     }
     // Sobel images + candidate gates of this model (a caller that spreads the models over streams has done it)
-    if (!prepared) RET_IF(o.enqueuePrepare(s, m == 0 ? scratch : nullptr, n));
+    if (!prepared) RET_IF(o.enqueuePrepare(s, m == 0 ? scratch : nullptr, n, m > 0));
     MParams& M = p.M[m];
     for (int i = 0; i < NUM_PYRS; ++i) {
       MLevel& L = M.L[i];
@@ -1587,6 +1633,7 @@ cudaError_t RGBDOdometry::trackTiled(RGBDOdometry* const* od, int n, float (*tra
       L.nextDepth = o.next_is_last_ ? o.lastDepth[i] : o.nextDepth[i];
       L.lastImage = o.lastImage[i];
       L.cand = o.rgbCand[i];
+      L.box = m > 0 ? o.d_box_ + 8 * i : nullptr;  // object models: see enqueuePrepare
       if (m == 0) {
         const CUtensorMap* tm = ts.d_maps + i * TiledState::TM_COUNT;
         L.tm_d1 = tm + (o.next_is_last_ ? TiledState::TM_D1_LAST : TiledState::TM_D1_NEXT);

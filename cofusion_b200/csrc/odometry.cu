@@ -18,9 +18,10 @@ namespace cfb {
 
 namespace {
 template <class T>
-bool dalloc(T** p, size_t n) {
-  return cudaMalloc((void**)p, n * sizeof(T)) == cudaSuccess &&
-         cudaMemset(*p, 0, n * sizeof(T)) == cudaSuccess;
+bool dalloc(T** p, size_t n, std::vector<std::pair<void*, size_t>>* reg) {
+  if (cudaMalloc((void**)p, n * sizeof(T)) != cudaSuccess || cudaMemset(*p, 0, n * sizeof(T)) != cudaSuccess) return false;
+  reg->push_back({(void*)*p, n * sizeof(T)});
+  return true;
 }
 }  // namespace
 
@@ -38,17 +39,26 @@ RGBDOdometry::RGBDOdometry(int w, int h, float cx, float cy, float fx, float fy,
   bool good = true;
   for (int i = 0; i < NUM_PYRS; ++i) {
     size_t n = (size_t)(w >> i) * (h >> i);
-    good = good && dalloc(&vmaps_g_prev_[i], n * 3) && dalloc(&nmaps_g_prev_[i], n * 3) &&
-           dalloc(&vmaps_curr_[i], n * 3) && dalloc(&nmaps_curr_[i], n * 3) && dalloc(&lastDepth[i], n) &&
-           dalloc(&nextDepth[i], n) && dalloc(&pointClouds[i], n * 3) && dalloc(&lastImage[i], n) &&
-           dalloc(&nextImage[i], n) && dalloc(&lastNextImage[i], n) && dalloc(&nextdIdx[i], n) &&
-           dalloc(&nextdIdy[i], n) && dalloc(&corresImg[i], n) && dalloc(&rgbCand[i], n);
+    good = good && dalloc(&vmaps_g_prev_[i], n * 3, &zeroed_) && dalloc(&nmaps_g_prev_[i], n * 3, &zeroed_) &&
+           dalloc(&vmaps_curr_[i], n * 3, &zeroed_) && dalloc(&nmaps_curr_[i], n * 3, &zeroed_) && dalloc(&lastDepth[i], n, &zeroed_) &&
+           dalloc(&nextDepth[i], n, &zeroed_) && dalloc(&pointClouds[i], n * 3, &zeroed_) && dalloc(&lastImage[i], n, &zeroed_) &&
+           dalloc(&nextImage[i], n, &zeroed_) && dalloc(&lastNextImage[i], n, &zeroed_) && dalloc(&nextdIdx[i], n, &zeroed_) &&
+           dalloc(&nextdIdy[i], n, &zeroed_) && dalloc(&corresImg[i], n, &zeroed_) && dalloc(&rgbCand[i], n, &zeroed_);
   }
-  good = good && dalloc(&vmaps_tmp, (size_t)w * h * 4) && dalloc(&scratch, 1) && dalloc(&gn, 1) &&
-         dalloc(&d_pose, 1) && dalloc(&d_warp, 1) && dalloc(&d_pose_in, 16) &&
-         dalloc((unsigned**)&grid_sync_, 256);
+  good = good && dalloc(&vmaps_tmp, (size_t)w * h * 4, &zeroed_) && dalloc(&scratch, 1, &zeroed_) && dalloc(&gn, 1, &zeroed_) &&
+         dalloc(&d_pose, 1, &zeroed_) && dalloc(&d_warp, 1, &zeroed_) && dalloc(&d_pose_in, 16, &zeroed_) &&
+         dalloc((unsigned**)&grid_sync_, 256, &zeroed_);
   good = good && cudaMallocHost(&h_pinned, 4096) == cudaSuccess;
   ok_ = good;
+}
+
+// Back to the state of a freshly constructed object (a pooled Model is handed to a new object id): every device
+// buffer the constructor zeroed is zeroed again on `s`; plans, graphs and tensor maps (tied to the buffers) stay.
+cudaError_t RGBDOdometry::recycle(cudaStream_t s) {
+  for (auto& z : zeroed_) RET_IF(cudaMemsetAsync(z.first, 0, z.second, s));
+  memset(&stats_, 0, sizeof(stats_));
+  next_is_last_ = false;
+  return cudaSuccess;
 }
 
 RGBDOdometry::~RGBDOdometry() {
@@ -72,6 +82,7 @@ RGBDOdometry::~RGBDOdometry() {
   cudaFree(d_pose_in);
   cudaFree(grid_sync_);
   cudaFree(tiled_scratch_);
+  cudaFree(d_box_);
   destroyTiled();
   if (ev_k0_) cudaEventDestroy(ev_k0_);
   if (ev_k1_) cudaEventDestroy(ev_k1_);

@@ -12,6 +12,7 @@
 //                mode 0 = ONE persistent cooperative kernel over shared-memory tiles (gn_tiled.cu, default),
 //                mode 1 = one fused kernel per step, captured in a CUDA graph (gn_device.cu).
 #pragma once
+#include <utility>
 #include <vector>
 
 #include "cfb_common.cuh"
@@ -99,8 +100,10 @@ class RGBDOdometry {
   // device views (tests / map_view): which as in oracle orc_odom_view
   const void* view(int which, int level, size_t* pitch) const;
 
+ cudaError_t recycle(cudaStream_t s);  // see odometry.cu
  // Sobel images + photometric candidate gates, 3 levels, 1 launch (+ clears the barrier words `acnt`)
-  cudaError_t enqueuePrepare(cudaStream_t s, void* sync_words = nullptr, int nmodels = 1);
+  // extents: also record the extents of the model's candidates / valid vertices per level (object models)
+  cudaError_t enqueuePrepare(cudaStream_t s, void* sync_words = nullptr, int nmodels = 1, bool extents = false);
 
  private:
   cudaError_t populateRGBDData(const unsigned char* img, size_t pitch, int channels, float* const* destDepths,
@@ -113,8 +116,10 @@ class RGBDOdometry {
                                 size_t err_pitch, cudaStream_t s);
   cudaError_t prepareTiled(int nmodels);
   void destroyTiled();
+  std::vector<std::pair<void*, size_t>> zeroed_;  // device buffers the constructor zero-initialised
   TiledState* tiled_ = nullptr;
   void* tiled_scratch_ = nullptr;  // single-model launches
+  int* d_box_ = nullptr;           // model extents, 3 levels x 8 ints (enqueuePrepare)
 
   bool ok_ = false;
   int width, height;

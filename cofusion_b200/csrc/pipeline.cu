@@ -18,8 +18,10 @@ namespace cfb {
 
 namespace {
 template <class T>
-bool dalloc(T** p, size_t n) {
-  return cudaMalloc((void**)p, n * sizeof(T)) == cudaSuccess && cudaMemset(*p, 0, n * sizeof(T)) == cudaSuccess;
+bool dalloc(T** p, size_t n, std::vector<std::pair<void*, size_t>>* reg = nullptr) {
+  if (cudaMalloc((void**)p, n * sizeof(T)) != cudaSuccess || cudaMemset(*p, 0, n * sizeof(T)) != cudaSuccess) return false;
+  if (reg) reg->push_back({(void*)*p, n * sizeof(T)});
+  return true;
 }
 }  // namespace
 
@@ -37,6 +39,7 @@ Context::Context(int dev, int w, int h, float fx, float fy, float cx, float cy)
            cudaEventCreateWithFlags(&evPre[k], cudaEventDisableTiming) == cudaSuccess;
   }
   good = good && cudaEventCreateWithFlags(&evOrder, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&evOrder2, cudaEventDisableTiming) == cudaSuccess &&
          cudaStreamCreateWithFlags(&preStream, cudaStreamNonBlocking) == cudaSuccess;
   rgb = rgbBuf[0];
   depthRaw = depthBuf[0];
@@ -76,6 +79,7 @@ Context::~Context() {
   }
   if (evFork) cudaEventDestroy(evFork);
   if (evOrder) cudaEventDestroy(evOrder);
+  if (evOrder2) cudaEventDestroy(evOrder2);
   if (preStream) cudaStreamDestroy(preStream);
   cudaFree(mask);
   cudaFreeHost(h_mask);
@@ -259,21 +263,21 @@ Model::Model(Context* c, unsigned id_, float conf, unsigned maxSurfels, bool ena
   work = c->stream;
   for (int i = 0; i < 16; ++i) pose[i] = lastPose[i] = (i % 5 == 0) ? 1.f : 0.f;
   const size_t n = (size_t)c->W * c->H;
-  bool good = dalloc(&predVertex, n * 4) && dalloc(&predNormal, n * 4) && dalloc(&predImage, n * 4) &&
-              dalloc(&icpError, n);
+  bool good = dalloc(&predVertex, n * 4, &zeroed_) && dalloc(&predNormal, n * 4, &zeroed_) && dalloc(&predImage, n * 4, &zeroed_) &&
+              dalloc(&icpError, n, &zeroed_);
   const size_t scanCap = (size_t)maxSurfels + n;
-  good = good && dalloc(&buf[0], maxSurfels) && dalloc(&buf[1], maxSurfels) && dalloc(&unstable, n) &&
-         dalloc(&candStaging, n) && dalloc(&candBest, n) && dalloc(&winner, maxSurfels) && dalloc(&keys, n) &&
-         dalloc(&indexMaps.index, n) && dalloc(&indexMaps.vertConf, n) && dalloc(&indexMaps.colorTime, n) &&
-         dalloc(&indexMaps.normRad, n) && dalloc(&splat.image, n) && dalloc(&splat.vertexConf, n) &&
-         dalloc(&splat.normalRad, n) && dalloc(&splat.time, n) && dalloc(&fill.image, n) && dalloc(&fill.vertex, n) &&
-         dalloc(&fill.normal, n) && dalloc(&scan.flags, scanCap) && dalloc(&scan.ranks, scanCap) &&
-         dalloc(&scan.blockSums, 2 * (scanCap / 2048 + 4)) && dalloc(&counters, 1);
+  good = good && dalloc(&buf[0], maxSurfels, &zeroed_) && dalloc(&buf[1], maxSurfels, &zeroed_) && dalloc(&unstable, n, &zeroed_) &&
+         dalloc(&candStaging, n, &zeroed_) && dalloc(&candBest, n, &zeroed_) && dalloc(&winner, maxSurfels, &zeroed_) && dalloc(&keys, n, &zeroed_) &&
+         dalloc(&indexMaps.index, n, &zeroed_) && dalloc(&indexMaps.vertConf, n, &zeroed_) && dalloc(&indexMaps.colorTime, n, &zeroed_) &&
+         dalloc(&indexMaps.normRad, n, &zeroed_) && dalloc(&splat.image, n, &zeroed_) && dalloc(&splat.vertexConf, n, &zeroed_) &&
+         dalloc(&splat.normalRad, n, &zeroed_) && dalloc(&splat.time, n, &zeroed_) && dalloc(&fill.image, n, &zeroed_) && dalloc(&fill.vertex, n, &zeroed_) &&
+         dalloc(&fill.normal, n, &zeroed_) && dalloc(&scan.flags, scanCap, &zeroed_) && dalloc(&scan.ranks, scanCap, &zeroed_) &&
+         dalloc(&scan.blockSums, 2 * (scanCap / 2048 + 4), &zeroed_) && dalloc(&counters, 1, &zeroed_);
   scan.capacity = scanCap;
   scan.host = new ScanHostState();
   good = good && cudaMallocHost(&h_counters, sizeof(MapCounters)) == cudaSuccess;
   if (good) memset(h_counters, 0, sizeof(MapCounters));
-  good = good && dalloc(&dpose, 1) && cudaMallocHost(&h_readback, sizeof(PoseReadback)) == cudaSuccess &&
+  good = good && dalloc(&dpose, 1, &zeroed_) && cudaMallocHost(&h_readback, sizeof(PoseReadback)) == cudaSuccess &&
          cudaEventCreateWithFlags(&evPose, cudaEventDisableTiming) == cudaSuccess;
   ok_ = good;
   if (good) ok_ = uploadPose() == cudaSuccess;
@@ -315,6 +319,55 @@ Model::~Model() {
   cudaFreeHost(h_readback);
   if (evPose) cudaEventDestroy(evPose);
 }
+
+// A pooled model starts over under a new id (CoFusion::spawnObjectModel constructs one, CoFusion.cpp:588-597: some
+// 75 allocations and 400 MB of page mapping per spawn): every buffer the constructor zeroed is zeroed again on the
+// stream, the host state goes back to its initial values.  Requires the model's earlier work to be enqueued on
+// (or joined into) the context's stream.
+cudaError_t Model::recycle(unsigned id_, float conf) {
+  id = id_;
+  confidenceThreshold = conf;
+  maxDepth = FLT_MAX;
+  usePrediction = false;
+  target = 0;
+  renderSource = 1;
+  count_ub = 0;
+  cleanTick = 0;
+  poseStale = false;
+  for (int i = 0; i < 16; ++i) pose[i] = lastPose[i] = (i % 5 == 0) ? 1.f : 0.f;
+  poseLogTs.clear();
+  poseLogFrame.clear();
+  poseLogHost.clear();
+  RET_IF(cudaStreamSynchronize(work));  // h_counters / h_readback are targets of asynchronous copies
+  memset(h_counters, 0, sizeof(MapCounters));
+  for (auto& z : zeroed_) RET_IF(cudaMemsetAsync(z.first, 0, z.second, work));
+  *scan.host = ScanHostState();  // the ticket counter and the status words are zero again
+  RET_IF(odom.recycle(work));
+  return uploadPose();
+}
+
+// What CoFusion::inactivateModel keeps of a lost model (CoFusion.cpp:620-626): its map (the live surfels, in a
+// buffer of their size), pose, threshold and pose log.  Synchronises.
+cudaError_t Model::archive(ArchivedModel* out) {
+  RET_IF(syncPose());
+  RET_IF(fetchPoseLog());
+  out->id = id;
+  out->confidenceThreshold = confidenceThreshold;
+  memcpy(out->pose, pose, sizeof(pose));
+  out->poseLogTs = poseLogTs;
+  out->poseLogFrame = poseLogFrame;
+  out->poseLogHost = poseLogHost;
+  unsigned n = 0;
+  RET_IF(lastCount(&n));
+  out->count = n;
+  if (n) {
+    RET_IF(cudaMalloc((void**)&out->surfels, (size_t)n * sizeof(Surfel)));
+    RET_IF(cudaMemcpyAsync(out->surfels, buf[target], (size_t)n * sizeof(Surfel), cudaMemcpyDeviceToDevice, work));
+    RET_IF(cudaStreamSynchronize(work));
+  }
+  return cudaSuccess;
+}
+ArchivedModel::~ArchivedModel() { cudaFree(surfels); }
 
 // Run this model's next calls on its own stream, ordered after `after` (an event on the context's stream); join()
 // makes the context's stream wait for them.  The per-model stages of a frame are independent
@@ -624,7 +677,7 @@ cudaError_t trackModels(Context* ctx, Model* const* models, int n, const TrackPa
     for (int k = 0; k < nb; ++k) {
       Model* m = models[i + k];
       RET_IF(m->prepareTracking(tp, async));
-      if (spread) RET_IF(m->odom.enqueuePrepare(m->work, k == 0 ? ctx->batchScratch : nullptr, nb));
+      if (spread) RET_IF(m->odom.enqueuePrepare(m->work, k == 0 ? ctx->batchScratch : nullptr, nb, k > 0));
       od[k] = &m->odom;
       pd[k] = m->dpose;
       err[k] = m->icpError;

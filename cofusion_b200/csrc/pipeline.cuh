@@ -58,7 +58,7 @@ class Context {
   // models produce: it runs on preStream into double buffers, so that frame t+1's 80 us of filtering overlap the
   // many small surfel kernels of frame t, which leave most SMs idle.  `stream` joins at evPre.
   cudaStream_t preStream = nullptr;
-  cudaEvent_t evInputs[2] = {nullptr, nullptr}, evPre[2] = {nullptr, nullptr}, evOrder = nullptr;
+  cudaEvent_t evInputs[2] = {nullptr, nullptr}, evPre[2] = {nullptr, nullptr}, evOrder = nullptr, evOrder2 = nullptr;
   float* depthFilteredBuf[2] = {nullptr, nullptr};
   float* depthPyrBuf[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
   float* depthFiltered = nullptr;   // level 0 of the pyramid of the CURRENT frame
@@ -93,6 +93,17 @@ struct TrackParams {  // arguments of Model::performTracking (Model.h:128-129)
   int pyramid, fastOdom, so3;
   float maxDepthProcessed;
   int force_host_loop;
+};
+
+struct ArchivedModel {  // see Model::archive
+  unsigned id = 0, count = 0;
+  Surfel* surfels = nullptr;  // device, `count` records
+  float pose[16];
+  float confidenceThreshold = 0.f;
+  std::vector<int64_t> poseLogTs;
+  std::vector<int> poseLogFrame;
+  std::vector<float> poseLogHost;
+  ~ArchivedModel();
 };
 
 class Model {
@@ -138,6 +149,8 @@ class Model {
   const PoseRef poseRef() const { return PoseRef(&dpose->pose); }
   const PoseRef invRef() const { return PoseRef(&dpose->inv); }
 
+  cudaError_t recycle(unsigned id, float confidenceThreshold);  // pooled model -> fresh model (see pipeline.cu)
+  cudaError_t archive(ArchivedModel* out);
   cudaError_t fork(cudaEvent_t after);  // per-model stream (see pipeline.cu)
   cudaError_t join();
   cudaStream_t work = nullptr;      // the stream this model's calls are enqueued on (the context's unless forked)
@@ -190,6 +203,7 @@ class Model {
   unsigned count_ub = 0;             // host-side upper bound of counters->count
 
  private:
+  std::vector<std::pair<void*, size_t>> zeroed_;  // device buffers the constructor zero-initialised
   bool ok_ = false;
 };
 

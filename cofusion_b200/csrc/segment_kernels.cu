@@ -872,7 +872,7 @@ cudaError_t Segmentation::enqueue(const uint8_t* rgb, const float* depth, int nu
                                   const float* const* icpError, const float* const* vertConf4,
                                   unsigned char nextModelID, bool allowNew, const SegParams& prm, uint8_t* fullSeg,
                                   cudaStream_t s) {
-  RET_IF(slic(rgb, s));
+  if (slicAheadOf != rgb) RET_IF(slic(rgb, s));
   SegState st;
   st.W = W;
   st.H = H;
@@ -924,12 +924,12 @@ struct GraphKey {  // every argument baked into the captured launches
   const void *rgb, *depth, *fullSeg;
   const void* maps[2 * SegLimits::kMaxModels];
   unsigned char ids[SegLimits::kMaxModels + 1];
-  int numModels, allowNew;
+  int numModels, allowNew, slicAhead;
   SegParams prm;
 };
 bool same_key(const GraphKey& a, const GraphKey& b) {
   if (a.rgb != b.rgb || a.depth != b.depth || a.fullSeg != b.fullSeg || a.numModels != b.numModels ||
-      a.allowNew != b.allowNew || memcmp(&a.prm, &b.prm, sizeof(SegParams)) != 0)
+      a.allowNew != b.allowNew || a.slicAhead != b.slicAhead || memcmp(&a.prm, &b.prm, sizeof(SegParams)) != 0)
     return false;
   for (int m = 0; m < a.numModels; ++m)
     if (a.maps[2 * m] != b.maps[2 * m] || a.maps[2 * m + 1] != b.maps[2 * m + 1] || a.ids[m] != b.ids[m]) return false;
@@ -954,6 +954,7 @@ cudaError_t Segmentation::performSegmentationCRF(const uint8_t* rgb, const float
     k.fullSeg = fullSeg;
     k.numModels = numModels;
     k.allowNew = allowNew ? 1 : 0;
+    k.slicAhead = slicAheadOf == rgb ? 1 : 0;
     k.prm = prm;
     for (int m = 0; m < numModels; ++m) {
       k.maps[2 * m] = icpError[m];
@@ -989,6 +990,7 @@ cudaError_t Segmentation::performSegmentationCRF(const uint8_t* rgb, const float
   }
   if (!launched)
     RET_IF(enqueue(rgb, depth, numModels, modelIds, icpError, vertConf4, nextModelID, allowNew, prm, fullSeg, s));
+  slicAheadOf = nullptr;
   RET_IF(cudaStreamSynchronize(s));
   const SegResultHeader* hh = (const SegResultHeader*)h_out;
   const SegModelData* hm = (const SegModelData*)((const char*)h_out + sizeof(SegResultHeader));

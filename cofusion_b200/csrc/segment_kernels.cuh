@@ -54,6 +54,10 @@ class Segmentation {
   int W, H, mx, my, N;
   int launches = 0;      // kernels launched by the last performSegmentationCRF
   bool useGraph = true;  // replay the launch sequence as a CUDA graph on capturable streams
+  // The super-pixels depend on the frame alone: a caller may run slic() ahead (on another stream, ordered before
+  // performSegmentationCRF by an event) and set this to the image it ran on; the next performSegmentationCRF on
+  // that image then skips its own SLIC pass and clears the field.
+  const uint8_t* slicAheadOf = nullptr;
   // device scratch (public: the tests read labels / unary / lowMap through the C ABI)
   int* labels = nullptr;
   float* centers = nullptr;  // [2][N][5] ping-pong

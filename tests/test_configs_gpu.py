@@ -111,6 +111,42 @@ def test_config2_four_objects_closed_loop():
     assert exact_frames >= 8 and max_models >= 3, (exact_frames, max_models, first_div)
 
 
+def test_pooled_models_equal_fresh_models(monkeypatch):
+    """A lost model's buffers serve the next spawn (Model::recycle).  The closed loop must not see the difference:
+    same model lists, masks and poses, bit for bit, as with a newly constructed Model per spawn."""
+    import cofusion_b200 as cfb
+    W, H = 640, 480
+    frames = list(synth.room_sequence(32, W, H, synth.K_DEFAULT, noise=True, n_boxes=4, box_speed=1.0, seed=1234))
+
+    def run():
+        p = cfb.CoFusionParams.default(1 << 20)
+        p.enableMultipleModels = 1
+        cf = cfb.CoFusion(W, H, synth.K_DEFAULT, p)
+        out, spawns, losses = [], 0, 0
+        for t in range(170):
+            k = t % 62
+            _, rgb, d, _, _ = frames[k if k < 32 else 62 - k]
+            cf.process_frame(np.ascontiguousarray(rgb), np.ascontiguousarray(d))
+            ids = [cf.model(i).info()[0] for i in range(cf.num_models)]
+            if t > 0:
+                _, _, spawn, lost = cf.last_segmentation()
+                spawns += int(spawn >= 0)
+                losses += int(lost)
+            out.append((ids, cf.ctx_view_mask().copy(), [cf.model(i).pose.copy() for i in range(cf.num_models)]))
+        return out, spawns, losses
+
+    pooled, spawns, losses = run()
+    monkeypatch.setenv("CFB_NO_MODEL_POOL", "1")
+    fresh, spawns2, losses2 = run()
+    assert (spawns, losses) == (spawns2, losses2)
+    assert spawns >= 2 and losses >= 1, (spawns, losses)  # the sequence must exercise a recycled model
+    for t, (a, b) in enumerate(zip(pooled, fresh)):
+        assert a[0] == b[0], (t, a[0], b[0])
+        assert np.array_equal(a[1], b[1]), t
+        for pa, pb in zip(a[2], b[2]):
+            assert np.array_equal(pa, pb), t
+
+
 # ------------------------------------------------------------------------------------------ configs[4]
 HI_W, HI_H = 1280, 960
 

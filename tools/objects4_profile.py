@@ -17,6 +17,7 @@ def main():
     import bench
     W, H = bench.W, bench.H
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+    pipelined = len(sys.argv) > 2 and sys.argv[2] == "pipelined"  # no drain between frames (as the bench runs)
     n_render = 32
     seq = list(synth.room_sequence(n_render, W, H, synth.K_DEFAULT, noise=True, n_boxes=4, box_speed=1.0, seed=1234))
     dev = [(torch.from_numpy(np.ascontiguousarray(r)).cuda(), torch.from_numpy(np.ascontiguousarray(d)).cuda()) for _, r, d, _, _ in seq]
@@ -24,6 +25,17 @@ def main():
     p.enableMultipleModels = 1
     cf = cfb.CoFusion(W, H, synth.K_DEFAULT, p, device=0)
     rows = []
+    if pipelined:
+        t0 = time.perf_counter()
+        for t in range(n):
+            cf.process_frame(*dev[bench.frame_index(t, n_render)])
+            if t % 20 == 19:
+                torch.cuda.synchronize()
+                t1 = time.perf_counter()
+                print("frames %3d-%3d: %.3f ms/frame, %d models, %.1f launches/frame" % (
+                    t - 19, t, (t1 - t0) * 1e3 / 20, cf.num_models, cf.ctx.take_launch_count() / 20))
+                t0 = time.perf_counter()
+        return
     for t in range(n):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
