@@ -266,14 +266,12 @@ def main():
                     torch.from_numpy(np.ascontiguousarray(ids.astype(np.uint8))).pin_memory() if world > 1 else None)
             host.append(trip)
             devf.append(tuple(None if x is None else x.cuda() for x in trip))
-    uid = [cfb.nccl_unique_id() if (world > 1 and rank == 0) else None]
-    if world > 1:
-        dist.broadcast_object_list(uid, src=0)
-
     def build():
         params = cfb.CoFusionParams.default(1 << 21)
         cf = cfb.CoFusion(W, H, K, params, device=local)
         if world > 1:
+            uid = [cfb.nccl_unique_id() if rank == 0 else None]  # one id per communicator
+            dist.broadcast_object_list(uid, src=0)
             cf.shard_init(rank, world, uid[0])  # collective: the library's own NCCL communicator
         cfb.lib().cfb_model_odometry.restype = cfb.C.c_void_p
         return cf
@@ -285,10 +283,13 @@ def main():
         else:
             cf.process_frame(None, None, None)
         if world > 1 and t == 1:
-            # frame 1: every rank spawns the object model it owns from the renderer's labels (FrameData::mask path)
+            # frame 1: every rank spawns the object model it owns from the renderer's labels (FrameData::mask path).
+            # A new model starts at the camera pose (CoFusion.cpp:593), which only the camera model's rank tracks.
+            cam = torch.from_numpy(cf.model(0).pose.reshape(16).copy()).cuda() if rank == 0 else torch.empty(16, device="cuda")
+            dist.broadcast(cam, src=0)
             for mdl in sharding.models_of_rank(n_models, rank, world):
                 if mdl > 0:
-                    cf.spawn_object_model(mdl)
+                    cf.spawn_object_model(mdl, cam.cpu().numpy())
 
     keep = []
 

@@ -786,6 +786,11 @@ int cfb_cofusion_set_batched_tracking(cfb_cofusion* f, int on) {
   f->f.batchedTracking = on != 0;
   return 0;
 }
+int cfb_cofusion_set_debug_trace(cfb_cofusion* f, void* dev_u64) {
+  REQUIRE(f && !f->f.models.empty(), "cofusion_set_debug_trace");
+  f->f.models[0]->odom.setDebugTrace(dev_u64);
+  return 0;
+}
 cfb_segmentation* cfb_cofusion_segmentation(cfb_cofusion* f) {
   if (!f || !f->f.segmentation) return nullptr;
   if (!f->seg_handle) f->seg_handle = new cfb_segmentation(f->f.segmentation.get());

@@ -71,6 +71,8 @@ struct MParams {
   GNState* g;
   const float* pose_in;
   float* err;
+  unsigned* corrZ;  // object models: photometric correspondences of the iteration, [kPP][grid][kT] (see phase1_obj)
+  float* corrD;
   PoseDev* pd;  // optional device pose block: refreshed by the epilogue, so the frame needs no host round trip
 };
 struct FLevel {  // frame side + tile plan of one level
@@ -153,6 +155,11 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+// per-CTA stamps of iteration 12 (a level-0 iteration): slots 256 + 8 * cta + e, e = 0..4
+#define DBG_CTA(q, e)                                                                              \
+  do {                                                                                             \
+    if (p.dbg && (q) == 12 && threadIdx.x == 0) p.dbg[256 + 8 * blockIdx.x + (e)] = gtime();       \
+  } while (0)
 #define DBG_MARK(slot)                                                       \
   do {                                                                       \
     if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[(slot)] = gtime(); \
@@ -563,6 +570,208 @@ __device__ __noinline__ void phase3(int lvl, int m, float sigma, int buf) {
       const short sdx = FS ? SM_S16(c.oDX)[si] : __ldg(F.dIdx + y * c.W + x);
       const short sdy = FS ? SM_S16(c.oDY)[si] : __ldg(F.dIdy + y * c.W + x);
       rgb_row(c, sigma, p.sobelScale, u0, v0, d0, diff, sdx, sdy, acc);
+    }
+  }
+  store_warp_row(buf, any, acc);
+}
+
+// ------------------------------------------------------------------------- object models on staged levels
+// The shared memory of a CTA holds the frame tiles and the CAMERA model's window; the maps of an object model
+// (m >= 1) stay in global memory.  Written pixel by pixel, a thread's gathers form a chain of dependent L2 round
+// trips (gate -> depth -> matched depth / intensity; vertex x -> five more planes), times its four pixels: the CTAs
+// whose tiles hold the object took twice as long as the rest, and the whole grid waits for them at every sum.
+// These variants run every ROUND of loads for all of the thread's pixels before the first use (2 + 1 + 2 round
+// trips per iteration instead of 32) and hand the correspondences of phase 1 to phase 3 through a coalesced
+// global array.  Per pixel the operations, their order and roundings are those of residual_pixel / phase2 /
+// phase3: the sums are bit-identical.
+__device__ __noinline__ void phase1_obj(int lvl, int m) {
+  TSMEM();
+  const LvCtx& c = sm.lv;
+  const MLevel& L = p.M[m].L[lvl];
+  const RgbWarp& Wp = sm.S[m].warp;
+  int cnt = 0, sig = 0;
+  const int* bc = sm.box[m];
+  const bool none = c.x0 > bc[2] || c.x0 + c.tw <= bc[0] || c.y0 > bc[3] || c.y0 + c.th <= bc[1];
+  if (!none) {
+    const size_t kstride = (size_t)gridDim.x * kT;
+    unsigned* cz = p.M[m].corrZ + (size_t)blockIdx.x * kT + threadIdx.x;
+    float* cd = p.M[m].corrD + (size_t)blockIdx.x * kT + threadIdx.x;
+    int xs[kPP], ys[kPP];
+    unsigned char cand[kPP];
+    float d1[kPP];
+    PixIt it = pix_begin(c);
+#pragma unroll
+    for (int k = 0; k < kPP; ++k) {  // round 1: gate and depth of every pixel
+      const int x = c.x0 + it.lx, y = c.y0 + it.ly;
+      const bool live = it.i < c.npx && x < c.W && y < c.H && !(x < bc[0] || y < bc[1] || x > bc[2] || y > bc[3]);
+      xs[k] = x;
+      ys[k] = live ? y : -1;
+      cand[k] = live ? __ldg(L.cand + y * c.W + x) : (unsigned char)0;
+      d1[k] = live ? __ldg(L.nextDepth + y * c.W + x) : 0.f;
+      pix_next(c, it);
+    }
+    int j[kPP], u0[kPP], v0[kPP];
+    float td1[kPP];
+    const float* kk = Wp.krkinv.m;
+#pragma unroll
+    for (int k = 0; k < kPP; ++k) {
+      j[k] = -1;
+      u0[k] = v0[k] = 0;
+      td1[k] = 0.f;
+      if (cand[k] != 0) {
+        const float fx_ = (float)xs[k], fy_ = (float)ys[k];
+        td1[k] = __fmaf_rn(d1[k], __fadd_rn(__fmaf_rn(kk[7], fy_, __fmul_rn(kk[6], fx_)), kk[8]), Wp.kt[2]);
+        u0[k] = __float2int_rn(__fdiv_rn(__fmaf_rn(d1[k], __fadd_rn(__fmaf_rn(kk[1], fy_, __fmul_rn(kk[0], fx_)), kk[2]), Wp.kt[0]), td1[k]));
+        v0[k] = __float2int_rn(__fdiv_rn(__fmaf_rn(d1[k], __fadd_rn(__fmaf_rn(kk[4], fy_, __fmul_rn(kk[3], fx_)), kk[5]), Wp.kt[1]), td1[k]));
+        if (u0[k] >= 0 && v0[k] >= 0 && u0[k] < c.W && v0[k] < c.H) j[k] = v0[k] * c.W + u0[k];
+      }
+    }
+    float d0[kPP];
+    unsigned char li[kPP];
+#pragma unroll
+    for (int k = 0; k < kPP; ++k) {  // round 2: the matched points
+      d0[k] = j[k] >= 0 ? __ldg(L.lastDepth + j[k]) : 0.f;
+      li[k] = j[k] >= 0 ? __ldg(L.lastImage + j[k]) : (unsigned char)0;
+    }
+#pragma unroll
+    for (int k = 0; k < kPP; ++k) {
+      unsigned zero = kNoCorr;
+      if (j[k] >= 0 && d0[k] > 0 && fabsf(__fsub_rn(td1[k], d0[k])) <= p.maxDepthDelta && li[k] != 0) {
+        const unsigned char ni = SM_U8(c.oIMG)[(ys[k] - c.y0) * c.pb + (xs[k] - c.x0) + c.shb];
+        const float diff = __fsub_rn((float)ni, (float)li[k]);
+        cnt += 1;
+        sig += (int)__fmul_rn(diff, diff);  // float -> int truncation, reduce.cu:851
+        zero = pack_corr(u0[k], v0[k], diff);
+        cd[k * kstride] = d0[k];
+      }
+      if (k * kT + (int)threadIdx.x < c.npx) cz[k * kstride] = zero;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    sig += __shfl_xor_sync(0xffffffffu, sig, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sm.cntw[m][threadIdx.x >> 5] = cnt;
+    sm.sigw[m][threadIdx.x >> 5] = sig;
+  }
+}
+
+__device__ __noinline__ void phase2_obj(int lvl, int m, float* error_map, int buf) {
+  TSMEM();
+  const LvCtx& c = sm.lv;
+  const MLevel& L = p.M[m].L[lvl];
+  const IcpPose& P = sm.S[m].pose;
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+  const float3 tcurr = make_float3(P.tcurr[0], P.tcurr[1], P.tcurr[2]);
+  const float3 tprev = make_float3(P.tprev[0], P.tprev[1], P.tprev[2]);
+  const int HW = c.W * c.H;
+  const int* bv = sm.box[m] + 4;
+  int j[kPP];
+  {
+    PixIt it = pix_begin(c);
+#pragma unroll
+    for (int k = 0; k < kPP; ++k) {  // where each pixel lands in the model's maps (-1: nowhere)
+      j[k] = -1;
+      const int x = c.x0 + it.lx, y = c.y0 + it.ly;
+      if (it.i < c.npx && x < c.W && y < c.H) {
+        const int fi = it.ly * c.pf + it.lx + c.shf;
+        float3 vcurr;
+        vcurr.x = SM_F32(c.oV)[fi];
+        if (!isnan(vcurr.x)) {
+          vcurr.y = SM_F32(c.oV)[c.fplane + fi];
+          vcurr.z = SM_F32(c.oV)[2 * c.fplane + fi];
+          const float3 vcurr_g = xadd(xmul(P.Rcurr, vcurr), tcurr);
+          const float3 vcurr_cp = xmul(P.Rprev_inv, xsub(vcurr_g, tprev));
+          const int ux = __float2int_rn(__fadd_rn(__fdiv_rn(__fmul_rn(vcurr_cp.x, c.fx), vcurr_cp.z), c.cx));
+          const int uy = __float2int_rn(__fadd_rn(__fdiv_rn(__fmul_rn(vcurr_cp.y, c.fy), vcurr_cp.z), c.cy));
+          if (!(ux < 0 || uy < 0 || ux >= c.W || uy >= c.H || vcurr_cp.z < 0) &&
+              !(ux < bv[0] || uy < bv[1] || ux > bv[2] || uy > bv[3]))
+            j[k] = uy * c.W + ux;
+        }
+      }
+      pix_next(c, it);
+    }
+  }
+  float vx[kPP];
+#pragma unroll
+  for (int k = 0; k < kPP; ++k) vx[k] = j[k] >= 0 ? __ldg(L.vmap_g_prev + j[k]) : qnan();  // round 1
+  float q[kPP][5];
+#pragma unroll
+  for (int k = 0; k < kPP; ++k) {  // round 2: the other five planes, only where the object is
+    const bool have = !isnan(vx[k]);
+    q[k][0] = have ? __ldg(L.vmap_g_prev + HW + j[k]) : 0.f;
+    q[k][1] = have ? __ldg(L.vmap_g_prev + 2 * HW + j[k]) : 0.f;
+    q[k][2] = have ? __ldg(L.nmap_g_prev + j[k]) : 0.f;
+    q[k][3] = have ? __ldg(L.nmap_g_prev + HW + j[k]) : 0.f;
+    q[k][4] = have ? __ldg(L.nmap_g_prev + 2 * HW + j[k]) : 0.f;
+  }
+  bool any = false;
+  PixIt it = pix_begin(c);
+#pragma unroll
+  for (int k = 0; k < kPP; ++k) {
+    const int x = c.x0 + it.lx, y = c.y0 + it.ly;
+    if (it.i < c.npx && x < c.W && y < c.H) {
+      float* const err = error_map ? row_ptr(error_map, p.err_pitch, y) + x : nullptr;
+      if (j[k] < 0 || isnan(vx[k])) {
+        if (err) *err = 0.0f;
+      } else {
+        const int fi = it.ly * c.pf + it.lx + c.shf;
+        const float3 vcurr = make_float3(SM_F32(c.oV)[fi], SM_F32(c.oV)[c.fplane + fi], SM_F32(c.oV)[2 * c.fplane + fi]);
+        const float3 vcurr_g = xadd(xmul(P.Rcurr, vcurr), tcurr);
+        const float3 vcurr_cp = xmul(P.Rprev_inv, xsub(vcurr_g, tprev));
+        const float3 vp = make_float3(vx[k], q[k][0], q[k][1]);
+        const float3 np = make_float3(q[k][2], q[k][3], q[k][4]);
+        const float3 ncurr = make_float3(SM_F32(c.oN)[fi], SM_F32(c.oN)[c.fplane + fi], SM_F32(c.oN)[2 * c.fplane + fi]);
+        const float3 ncurr_g = xmul(P.Rcurr, ncurr);
+        const float dist = xnorm(xsub(vp, vcurr_g));
+        const float sine = xnorm(xcross(ncurr_g, np));
+        if (err) *err = isfinite(dist) ? dist : 0.0f;
+        if (sine < p.angleThres && dist <= p.distThres && !isnan(ncurr.x) && !isnan(np.x)) {
+          any = true;
+          icp_found_row(P, tprev, vcurr_cp, vp, np, acc);
+        }
+      }
+    }
+    pix_next(c, it);
+  }
+  store_warp_row(buf, any, acc);
+}
+
+__device__ __noinline__ void phase3_obj(int lvl, int m, float sigma, int buf) {
+  TSMEM();
+  const LvCtx& c = sm.lv;
+  float acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+  bool any = false;
+  const int* bc = sm.box[m];
+  const bool none = c.x0 > bc[2] || c.x0 + c.tw <= bc[0] || c.y0 > bc[3] || c.y0 + c.th <= bc[1];
+  if (!none) {
+    const size_t kstride = (size_t)gridDim.x * kT;
+    const unsigned* cz = p.M[m].corrZ + (size_t)blockIdx.x * kT + threadIdx.x;
+    const float* cd = p.M[m].corrD + (size_t)blockIdx.x * kT + threadIdx.x;
+    unsigned z[kPP];
+    float d0[kPP];
+#pragma unroll
+    for (int k = 0; k < kPP; ++k) {  // written by this thread in phase 1 (plain loads: the read-only path may be stale)
+      const bool live = k * kT + (int)threadIdx.x < c.npx;
+      z[k] = live ? cz[k * kstride] : kNoCorr;
+      d0[k] = live ? cd[k * kstride] : 0.f;
+    }
+    PixIt it = pix_begin(c);
+#pragma unroll
+    for (int k = 0; k < kPP; ++k) {
+      if (z[k] != kNoCorr) {
+        any = true;
+        const int si = it.ly * c.ps + it.lx + c.shs;
+        rgb_row(c, sigma, p.sobelScale, (int)(z[k] & 0x7ffu), (int)((z[k] >> 11) & 0x7ffu), d0[k], (float)((int)(z[k] >> 22) - 256),
+                SM_S16(c.oDX)[si], SM_S16(c.oDY)[si], acc);
+      }
+      pix_next(c, it);
     }
   }
   store_warp_row(buf, any, acc);
@@ -1118,13 +1327,14 @@ __device__ __noinline__ void run_level(int lvl, int q0, int nit, unsigned round0
     const unsigned round = round0 + it;
     const bool last_of_l0 = (lvl == 0 && it + 1 == nit);
     DBG_MARK(8 + q * 8 + 0);
+    DBG_CTA(q, 0);
 
     // -------- phase 1: photometric correspondences of every model, then arrive at barrier A
     for (int m = 0; m < NM; ++m) {
       if (FS && m == 0)
         phase1<true, true>(lvl, m);
       else if (FS)
-        phase1<true, false>(lvl, m);
+        phase1_obj(lvl, m);
       else
         phase1<false, false>(lvl, m);
     }
@@ -1138,6 +1348,7 @@ __device__ __noinline__ void run_level(int lvl, int q0, int nit, unsigned round0
       red_add_u64(&p.acnt[round * kMaxM + threadIdx.x], 1ull | ((unsigned long long)cc << 8) | ((unsigned long long)ss << 32));
     }
     DBG_MARK(8 + q * 8 + 1);
+    DBG_CTA(q, 1);
 
     // -------- phase 2: ICP rows (independent of the counts: hides barrier A)
     for (int m = 0; m < NM; ++m, wbuf ^= 1) {
@@ -1145,13 +1356,14 @@ __device__ __noinline__ void run_level(int lvl, int q0, int nit, unsigned round0
       if (FS && m == 0)
         phase2<true, true>(lvl, m, err, wbuf);
       else if (FS)
-        phase2<true, false>(lvl, m, err, wbuf);
+        phase2_obj(lvl, m, err, wbuf);
       else
         phase2<false, false>(lvl, m, err, wbuf);
       __syncthreads();
       fold_warp_rows(wbuf, m, 0, 29);
     }
     DBG_MARK(8 + q * 8 + 2);
+    DBG_CTA(q, 2);
     if ((int)threadIdx.x < NM) {  // wait for barrier A: all G arrivals carry the global count / sigma
       unsigned long long v;
       do {
@@ -1171,7 +1383,7 @@ __device__ __noinline__ void run_level(int lvl, int q0, int nit, unsigned round0
       if (FS && m == 0)
         phase3<true, true>(lvl, m, sigma, wbuf);
       else if (FS)
-        phase3<true, false>(lvl, m, sigma, wbuf);
+        phase3_obj(lvl, m, sigma, wbuf);
       else
         phase3<false, false>(lvl, m, sigma, wbuf);
       __syncthreads();
@@ -1180,12 +1392,14 @@ __device__ __noinline__ void run_level(int lvl, int q0, int nit, unsigned round0
     }
     __syncthreads();
     DBG_MARK(8 + q * 8 + 4);
+    DBG_CTA(q, 3);
 
     // -------- add this CTA's sums to the grid accumulators, read the totals, solve
     if ((int)threadIdx.x < NM * kSums) publish_sums<kSums>(round);
     DBG_MARK(8 + q * 8 + 5);
     collect_sums<kSums>(round, NM * kSums);
     DBG_MARK(8 + q * 8 + 6);
+    DBG_CTA(q, 4);
     const int is_last = (q + 1 == sm.nsched);
     if ((int)warp < NM) {
       const int m = (int)warp;
@@ -1650,6 +1864,18 @@ cudaError_t RGBDOdometry::trackTiled(RGBDOdometry* const* od, int n, float (*tra
     M.pd = pd ? pd[m] : nullptr;
     M.pose_in = M.pd ? M.pd->tr : o.d_pose_in;
     M.err = err ? err[m] : nullptr;
+    if (m > 0) {  // correspondences handed from phase 1 to phase 3 (phase1_obj)
+      const size_t words = (size_t)kPP * ts.gx * ts.gy * kT;
+      if (o.corr_words_ < words) {
+        cudaFree(o.d_corr_);
+        o.d_corr_ = nullptr;
+        RET_IF(cudaMalloc(&o.d_corr_, words * 8));
+        RET_IF(cudaMemsetAsync(o.d_corr_, 0, words * 8, s));
+        o.corr_words_ = words;
+      }
+      M.corrZ = (unsigned*)o.d_corr_;
+      M.corrD = (float*)o.d_corr_ + words;
+    }
   }
   for (int i = 0; i < NUM_PYRS; ++i) {
     FLevel& F = p.F[i];

@@ -83,6 +83,7 @@ RGBDOdometry::~RGBDOdometry() {
   cudaFree(grid_sync_);
   cudaFree(tiled_scratch_);
   cudaFree(d_box_);
+  cudaFree(d_corr_);
   destroyTiled();
   if (ev_k0_) cudaEventDestroy(ev_k0_);
   if (ev_k1_) cudaEventDestroy(ev_k1_);

@@ -120,6 +120,8 @@ class RGBDOdometry {
   TiledState* tiled_ = nullptr;
   void* tiled_scratch_ = nullptr;  // single-model launches
   int* d_box_ = nullptr;           // model extents, 3 levels x 8 ints (enqueuePrepare)
+  void* d_corr_ = nullptr;         // object model: per-iteration correspondences (trackTiled)
+  size_t corr_words_ = 0;
 
   bool ok_ = false;
   int width, height;

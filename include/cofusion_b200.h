@@ -151,7 +151,7 @@ int cfb_odom_set_mode(cfb_odom* o, int mode);
  * cfb_odom_kernel_timing returns the accumulated milliseconds and launch count (optionally resets). */
 int cfb_odom_enable_kernel_timing(cfb_odom* o, int on);
 int cfb_odom_kernel_timing(cfb_odom* o, double* sum_ms, int* launches, int reset);
-/* Profiling aid: device buffer of >= 256 uint64 that receives a %globaltimer trace of the
+/* Profiling aid: device buffer of >= 2048 uint64 that receives a %globaltimer trace of the
  * persistent kernel's phases (NULL disables). */
 int cfb_odom_set_debug_trace(cfb_odom* o, void* dev_u64);
 /* device views of the internal pyramids. which: 0 vmap_curr 1 nmap_curr 2 vmap_g_prev 3 nmap_g_prev
@@ -365,6 +365,8 @@ int cfb_cofusion_num_inactive_models(cfb_cofusion* f);
  * 0: one launch per model, as the reference's `for (auto model : models) performTracking` loop.
  * Results are bit-identical either way. */
 int cfb_cofusion_set_batched_tracking(cfb_cofusion* f, int on);
+/* tools only: >= 2048 u64 of device memory receiving a %globaltimer phase trace of the frame's tracker launch */
+int cfb_cofusion_set_debug_trace(cfb_cofusion* f, void* dev_u64);
 cfb_segmentation* cfb_cofusion_segmentation(cfb_cofusion* f); /* borrowed; NULL when segmentation is off */
 
 #ifdef __cplusplus

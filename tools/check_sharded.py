@@ -37,9 +37,12 @@ for t in range(frames):
     else:
         cf.process_frame(None, None, None)
     if t == 1:
+        # a new model starts at the camera pose (CoFusion.cpp:593), which only the camera model's rank tracks
+        cam = torch.from_numpy(cf.model(0).pose.reshape(16).copy()).cuda() if rank == 0 else torch.empty(16, device="cuda")
+        dist.broadcast(cam, src=0)
         for m in sharding.models_of_rank(n_models, rank, world):
             if m > 0:
-                cf.spawn_object_model(m)
+                cf.spawn_object_model(m, cam.cpu().numpy())
         if rank == 0:
             for m in range(1, n_models):
                 ref.spawn_object_model(m)

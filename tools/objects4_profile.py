@@ -25,6 +25,32 @@ def main():
     p.enableMultipleModels = 1
     cf = cfb.CoFusion(W, H, synth.K_DEFAULT, p, device=0)
     rows = []
+    if len(sys.argv) > 2 and sys.argv[2] == "trace":  # phase trace of the tracker launch once two models are live
+        import ctypes as C
+        dbg = torch.zeros(2048, dtype=torch.int64, device="cuda")
+        cfb.check(cfb.lib().cfb_cofusion_set_debug_trace(cf._h, C.c_void_p(dbg.data_ptr())))
+        for t in range(n):
+            cf.process_frame(*dev[bench.frame_index(t, n_render)])
+            torch.cuda.synchronize()
+            if cf.num_models >= 2 and t % 10 == 9:
+                q = dbg.cpu().numpy().astype(np.int64)
+                print("frame %d, %d models: barrier0 %.1f us, so3 %.1f us, gn %.1f us" % (
+                    t, cf.num_models, (q[1] - q[0]) / 1e3, (q[2] - q[1]) / 1e3, (q[3] - q[2]) / 1e3))
+                G = 144
+                st = q[256:256 + 8 * G].reshape(G, 8)[:, :5]
+                if st.min() > 0:
+                    d = (st - st[:, :1].min()) / 1e3
+                    order = np.argsort(d[:, 3])
+                    print("  iteration 12, per CTA (us since the first CTA started it): start, after residual, after icp, after rgb rows, after collect")
+                    for b in list(order[:3]) + list(order[-8:]):
+                        print("    cta %3d (tile %2d,%2d): %s" % (b, b % 8, b // 8, " ".join("%6.2f" % v for v in d[b])))
+                for it in (0, 5, 9, 10, 14, 15, 18):
+                    b = 8 + it * 8
+                    nxt = q[b + 8] if it < 18 else q[3]
+                    print("  it %2d: residual+arriveA %.2f  icp %.2f  waitA %.2f  rgbrows %.2f  publish %.2f  collect %.2f  solve %.2f  | total %.2f" % (
+                        it, (q[b+1]-q[b])/1e3, (q[b+2]-q[b+1])/1e3, (q[b+3]-q[b+2])/1e3, (q[b+4]-q[b+3])/1e3, (q[b+5]-q[b+4])/1e3,
+                        (q[b+6]-q[b+5])/1e3, (q[b+7]-q[b+6])/1e3, (nxt-q[b])/1e3))
+        return
     if pipelined:
         t0 = time.perf_counter()
         for t in range(n):

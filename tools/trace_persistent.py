@@ -8,7 +8,7 @@ from test_tracker_gpu import _cuda_odometry
 W = int(sys.argv[1]) if len(sys.argv) > 1 else 640
 case = scenes.room_pair(W, W * 3 // 4)
 co = _cuda_odometry(gu, case)
-dbg = torch.zeros(256, dtype=torch.int64, device="cuda")
+dbg = torch.zeros(2048, dtype=torch.int64, device="cuda")
 cfb.check(cfb.lib().cfb_odom_set_debug_trace(co._h, C.c_void_p(dbg.data_ptr())))
 for _ in range(3):
     co.track(case["T0"])
