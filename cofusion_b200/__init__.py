@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcofusion_b200.so")
+LIB_PATH = os.environ.get("CFB_LIB_PATH") or os.path.join(_HERE, "libcofusion_b200.so")  # (override: A/B builds in tools)
 _lib = None
 
 c_float_p = C.POINTER(C.c_float)

@@ -1,5 +1,6 @@
 // cabi.cu -- extern "C" boundary of libcofusion_b200.so (declarations: include/cofusion_b200.h).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -13,6 +14,12 @@
 #include "tracker_kernels.cuh"
 
 namespace cfb {
+static thread_local bool g_pdl_frame = true;
+bool pdl_enabled() {  // cfb_common.cuh
+  static const bool on = getenv("CFB_NO_PDL") == nullptr;
+  return on && g_pdl_frame;
+}
+void pdl_set(bool on) { g_pdl_frame = on; }
 static thread_local char g_err[512] = "";
 int set_error(cudaError_t e, const char* what, const char* file, int line) {
   snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file,

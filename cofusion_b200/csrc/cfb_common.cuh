@@ -69,6 +69,43 @@ __device__ __forceinline__ float3 mul(const Mat33& m, float3 a) {
                      m.m[6] * a.x + m.m[7] * a.y + m.m[8] * a.z);
 }
 
+// ---- programmatic dependent launch (PDL).  A frame is a chain of ~25 small kernels on one stream; between two
+// of them the GPU idles for the few microseconds the next launch takes to start.  Every kernel of the chain begins
+// with pdl_prologue(): it lets the NEXT kernel of the stream start launching right away (its CTAs become resident
+// and park at their own griddepcontrol.wait) and then waits until the PREVIOUS kernel has completed and its writes
+// are visible.  Data dependencies are untouched -- nothing is read or written before the wait -- only the launch
+// latency moves off the critical path.  Launched without the attribute (or on older parts) both are no-ops.
+__device__ __forceinline__ void pdl_prologue() {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 900
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+bool pdl_enabled();  // false when CFB_NO_PDL is set (cabi.cu) or switched off for the calling thread's frame
+// Early-launched kernels park on the SMs until their predecessor ends.  On ONE stream that is free; with several
+// streams in flight (a frame with object models, segmentation) the parked CTAs take the slots another stream's
+// kernel could run in -- measured: 899 -> 711 frames/s on the 4-object scene.  CoFusion switches it per frame.
+void pdl_set(bool on);
+#define CFB_PDL(e)                      \
+  do {                                  \
+    cudaError_t e__ = (e);              \
+    if (e__ != cudaSuccess) return e__; \
+  } while (0)
+template <class... P, class... A>
+inline cudaError_t launch_pdl(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
 template <class T>
 __device__ __forceinline__ T* row_ptr(T* base, size_t pitch_bytes, int y) {
   return (T*)((char*)base + (size_t)y * pitch_bytes);

@@ -38,6 +38,7 @@ constexpr int BR = 6;
 constexpr int BROWS = 1;
 __global__ void __launch_bounds__(256) bilateral_kernel(const float* __restrict__ depth, size_t dpitch, int W, int H,
                                                         float maxD, float* __restrict__ out, size_t opitch) {
+  pdl_prologue();
   __shared__ float tile[8 * BROWS + 2 * BR][32 + 2 * BR + 1];
   const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8 * BROWS;
   for (int ty = threadIdx.y; ty < 8 * BROWS + 2 * BR; ty += 8)
@@ -344,6 +345,7 @@ struct ModelPyrOut {
 __global__ void model_pyramid_kernel(const float4* __restrict__ v4, const float4* __restrict__ n4, int W, int H,
                                      Mat33 R, float3 t, const float* __restrict__ pose34_dev, float cutoffRGB,
                                      ModelPyrOut o) {
+  pdl_prologue();
   const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y * blockDim.y + threadIdx.y;
   const int W2 = W / 4, H2 = H / 4, W1 = W / 2, H1 = H / 2;
   if (X >= W2 || Y >= H2) return;
@@ -424,6 +426,7 @@ struct FrameMapsArgs {
   float cutoff;
 };
 __global__ void frame_maps_kernel(const FrameMapsArgs a) {
+  pdl_prologue();
   int p = blockIdx.x * blockDim.x + threadIdx.x;
 #pragma unroll
   for (int l = 0; l < 3; ++l) {
@@ -462,6 +465,7 @@ __global__ void frame_maps_kernel(const FrameMapsArgs a) {
 // imageBGRToIntensity for two images (model prediction RGBA8, frame RGB8) in one launch
 __global__ void intensity2_kernel(const unsigned char* __restrict__ a, int cha, unsigned char* __restrict__ da,
                                   const unsigned char* __restrict__ b, int chb, unsigned char* __restrict__ db, int n) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned char* p = blockIdx.y ? (b + (size_t)i * chb) : (a + (size_t)i * cha);
@@ -541,6 +545,7 @@ __device__ __forceinline__ float u8_quantise(float q) {  // pyr_down_uchar_kerne
 }
 
 __global__ void __launch_bounds__(256) pyramid2_kernel(const PyrJobs jobs) {
+  pdl_prologue();
   __shared__ float t0[P0H][P0W + 1];
   __shared__ float t1[P1H][P1W + 1];
   const PyrJob job = jobs.j[blockIdx.z];
@@ -599,6 +604,7 @@ __global__ void __launch_bounds__(256) pyramid2_kernel(const PyrJobs jobs) {
 // does it in f32; Core/FrameData.h:38-41: flipColors swaps the first and third channel)
 __global__ void ingest_kernel(const uint8_t* __restrict__ img, const uint16_t* __restrict__ d16, float scale, int flip,
                               uint8_t* __restrict__ rgb, float* __restrict__ depth, int n) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   if (d16) depth[i] = __fmul_rn((float)__ldg(d16 + i), scale);
@@ -611,7 +617,7 @@ __global__ void ingest_kernel(const uint8_t* __restrict__ img, const uint16_t* _
 }
 cudaError_t launch_ingest(const uint8_t* img, const uint16_t* d16, float scale, int flip, uint8_t* rgb, float* depth, int n,
                           cudaStream_t s) {
-  ingest_kernel<<<(n + 255) / 256, 256, 0, s>>>(img, d16, scale, flip, rgb, depth, n);
+  CFB_PDL(launch_pdl(ingest_kernel, (n + 255) / 256, 256, 0, s, img, d16, scale, flip, rgb, depth, n));
   return cudaGetLastError();
 }
 
@@ -624,13 +630,13 @@ cudaError_t launch_pyramid2(int njobs, const void* const* src, void* const* l1, 
   jobs.sw = sw;
   jobs.sh = sh;
   const dim3 g((sw / 4 + P2W - 1) / P2W, (sh / 4 + P2H - 1) / P2H, njobs);
-  pyramid2_kernel<<<g, dim3(32, 8), 0, s>>>(jobs);
+  CFB_PDL(launch_pdl(pyramid2_kernel, g, dim3(32, 8), 0, s, jobs));
   return cudaGetLastError();
 }
 
 cudaError_t launch_bilateral(const float* depth, size_t dpitch, int W, int H, float maxD, float* out,
                              size_t opitch, cudaStream_t s) {
-  bilateral_kernel<<<dim3((W + 31) / 32, (H + 8 * BROWS - 1) / (8 * BROWS)), kBlock, 0, s>>>(depth, dpitch, W, H, maxD, out, opitch);
+  CFB_PDL(launch_pdl(bilateral_kernel, dim3((W + 31) / 32, (H + 8 * BROWS - 1) / (8 * BROWS)), kBlock, 0, s, depth, dpitch, W, H, maxD, out, opitch));
   return cudaGetLastError();
 }
 cudaError_t launch_pyr_down_gauss_f(const float* src, size_t spitch, int sw, int sh, float* dst,
@@ -711,8 +717,8 @@ cudaError_t launch_model_pyramid(const float* v4, const float* n4, int W, int H,
   }
   o.depth0 = depth0;
   const dim3 b(32, 4);
-  model_pyramid_kernel<<<grid2d(W / 4, H / 4, b), b, 0, s>>>((const float4*)v4, (const float4*)n4, W, H, R,
-                                                            make_float3(t[0], t[1], t[2]), pose34_dev, cutoffRGB, o);
+  CFB_PDL(launch_pdl(model_pyramid_kernel, grid2d(W / 4, H / 4, b), b, 0, s, (const float4*)v4, (const float4*)n4, W, H, R,
+                                                            make_float3(t[0], t[1], t[2]), pose34_dev, cutoffRGB, o));
   return cudaGetLastError();
 }
 cudaError_t launch_frame_maps(const float* const depth[3], int W, int H, Intr K, float cutoff, float* const v[3],
@@ -733,12 +739,12 @@ cudaError_t launch_frame_maps(const float* const depth[3], int W, int H, Intr K,
     total += a.w[l] * a.h[l];
   }
   a.cutoff = cutoff;
-  frame_maps_kernel<<<(total + 255) / 256, 256, 0, s>>>(a);
+  CFB_PDL(launch_pdl(frame_maps_kernel, (total + 255) / 256, 256, 0, s, a));
   return cudaGetLastError();
 }
 cudaError_t launch_intensity2(const unsigned char* a, int cha, unsigned char* da, const unsigned char* b, int chb,
                               unsigned char* db, int n, cudaStream_t s) {
-  intensity2_kernel<<<dim3((n + 255) / 256, 2), 256, 0, s>>>(a, cha, da, b, chb, db, n);
+  CFB_PDL(launch_pdl(intensity2_kernel, dim3((n + 255) / 256, 2), 256, 0, s, a, cha, da, b, chb, db, n));
   return cudaGetLastError();
 }
 cudaError_t launch_pyr_down_uchar2(const unsigned char* sa, unsigned char* da, const unsigned char* sb,

@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(256) scan_lookback_kernel(const uint8_t* __res
                                                            unsigned n_extra, unsigned long long* status, unsigned* ticket,
                                                            unsigned ticket_base, unsigned epoch, uint32_t* __restrict__ ranks,
                                                            unsigned* total, unsigned ntiles) {
+  pdl_prologue();
   __shared__ unsigned s_tile, s_prefix, ws[8];
   if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
   __syncthreads();
@@ -224,7 +225,7 @@ cudaError_t scan_flags(ScanScratch sc, unsigned n_ub, const unsigned* n_dev, uns
   unsigned* ticket = reinterpret_cast<unsigned*>(sc.blockSums);
   ScanHostState& h = *sc.host;
   h.epoch += 1;
-  scan_lookback_kernel<<<nb, 256, 0, s>>>(sc.flags, n_ub, n_dev, n_extra, status, ticket, h.ticketBase, h.epoch, sc.ranks, total, nb);
+  CFB_PDL(launch_pdl(scan_lookback_kernel, nb, 256, 0, s, sc.flags, n_ub, n_dev, n_extra, status, ticket, h.ticketBase, h.epoch, sc.ranks, total, nb));
   h.ticketBase += nb;
   return cudaGetLastError();
 }
@@ -282,6 +283,7 @@ __global__ void set_count_kernel(MapCounters* c, unsigned capacity) {
 __global__ void index_project_kernel(SurfelGeom g, const Surfel* __restrict__ surfels, unsigned n_ub,
                                      const MapCounters* __restrict__ ctr, PoseRef t_inv_ref, int time, float maxDepth,
                                      int timeDelta, unsigned long long* __restrict__ keys) {
+  pdl_prologue();
   const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= n_ub || id >= ctr->count) return;
   const Pose34 t_inv = resolve_pose(t_inv_ref);
@@ -302,6 +304,7 @@ __global__ void index_project_kernel(SurfelGeom g, const Surfel* __restrict__ su
 }
 __global__ void index_resolve_kernel(SurfelGeom g, const Surfel* __restrict__ surfels, PoseRef t_inv_ref,
                                      const unsigned long long* __restrict__ keys, IndexMaps out) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.W * g.H) return;
   const Pose34 t_inv = resolve_pose(t_inv_ref);
@@ -333,6 +336,7 @@ __global__ void fuse_associate_kernel(SurfelGeom g, PoseRef pose_ref, int time, 
                                       unsigned maskID, IndexMaps idx, uint32_t* __restrict__ winner,
                                       Surfel* __restrict__ cand, uint32_t* __restrict__ candBest,
                                       uint8_t* __restrict__ flags, int par, int W2, int H2) {
+  pdl_prologue();
   const int a = blockIdx.x * blockDim.x + threadIdx.x;  // eligible column index (fast: coalesced image reads)
   const int b = blockIdx.y * blockDim.y + threadIdx.y;  // eligible row index
   if (a >= W2 || b >= H2) return;
@@ -415,6 +419,7 @@ __global__ void fuse_associate_kernel(SurfelGeom g, PoseRef pose_ref, int time, 
 // data.geom: every emitted vertex is appended to newUnstableBuffer in draw order
 __global__ void fuse_append_kernel(unsigned n, const uint8_t* __restrict__ flags, const uint32_t* __restrict__ ranks,
                                    const Surfel* __restrict__ cand, Surfel* __restrict__ unstable, MapCounters* ctr) {
+  pdl_prologue();
   unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e == 0) ctr->unstableCount = ctr->scanTotal;
   if (e >= n || !flags[e]) return;
@@ -424,6 +429,7 @@ __global__ void fuse_append_kernel(unsigned n, const uint8_t* __restrict__ flags
 __global__ void fuse_update_kernel(unsigned n, int time, const uint8_t* __restrict__ flags,
                                    const uint32_t* __restrict__ candBest, const uint32_t* __restrict__ winner,
                                    const Surfel* __restrict__ cand, Surfel* __restrict__ surfels) {
+  pdl_prologue();
   unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n || flags[e] != 1) return;
   const uint32_t id = candBest[e];
@@ -451,6 +457,7 @@ __global__ void fuse_update_kernel(unsigned n, int time, const uint8_t* __restri
   store_surfel(surfels + id, o);
 }
 __global__ void fill_u32_kernel(uint32_t* p, unsigned n_ub, const unsigned* n_dev, uint32_t v) {
+  pdl_prologue();
   unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_ub && i < *n_dev) p[i] = v;
 }
@@ -463,6 +470,7 @@ __global__ void clean_evaluate_kernel(SurfelGeom g, Surfel* __restrict__ src, Su
                                       float confThreshold, int timeDelta, const float* __restrict__ depthFiltered,
                                       const uint8_t* __restrict__ mask, unsigned maskID, float outlierCoeff,
                                       IndexMaps idx, uint8_t* __restrict__ flags) {
+  pdl_prologue();
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned count = ctr->count, total = count + ctr->unstableCount;
   if (i >= n_ub) return;
@@ -591,6 +599,7 @@ __global__ void clean_scatter_kernel(const Surfel* __restrict__ src, const Surfe
                                      Surfel* __restrict__ dst, unsigned n_ub, unsigned capacity,
                                      const MapCounters* __restrict__ ctr, const uint8_t* __restrict__ flags,
                                      const uint32_t* __restrict__ ranks) {
+  pdl_prologue();
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned count = ctr->count, total = count + ctr->unstableCount;
   if (i >= n_ub || i >= total || !flags[i]) return;
@@ -600,6 +609,7 @@ __global__ void clean_scatter_kernel(const Surfel* __restrict__ src, const Surfe
   store_surfel(dst + r, load_surfel(rec));
 }
 __global__ void clean_finish_kernel(MapCounters* ctr, unsigned capacity, int time) {
+  pdl_prologue();
   ctr->count = min(ctr->scanTotal, capacity);
   ctr->unstableCount = 0;
   ctr->cleanTick = (unsigned)time;
@@ -664,6 +674,7 @@ __global__ void splat_raster_kernel(SurfelGeom g, const Surfel* __restrict__ sur
                                     const MapCounters* __restrict__ ctr, PoseRef t_inv_ref, float maxDepth,
                                     float confThreshold, int time, int maxTime, int timeDelta,
                                     unsigned long long* __restrict__ keys) {
+  pdl_prologue();
   const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= n_ub || id >= ctr->count) return;
   const Pose34 t_inv = resolve_pose(t_inv_ref);
@@ -690,6 +701,7 @@ __global__ void splat_raster_kernel(SurfelGeom g, const Surfel* __restrict__ sur
 __global__ void splat_resolve_kernel(SurfelGeom g, const Surfel* __restrict__ surfels, PoseRef t_inv_ref, float maxDepth,
                                      float confThreshold, int time, int maxTime, int timeDelta,
                                      const unsigned long long* __restrict__ keys, SplatMaps out) {
+  pdl_prologue();
   const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
   if (px >= g.W || py >= g.H) return;
   const Pose34 t_inv = resolve_pose(t_inv_ref);
@@ -719,6 +731,7 @@ __global__ void splat_resolve_kernel(SurfelGeom g, const Surfel* __restrict__ su
 // ------------------------------------------------------------------------------- a15 fill-in
 __global__ void fill_in_kernel(SurfelGeom g, SplatMaps splat, const uint8_t* __restrict__ rgb,
                                const float* __restrict__ depth, int pt_geom, int pt_rgb, FillMaps out) {
+  pdl_prologue();
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= g.W || y >= g.H) return;
   const int W = g.W, H = g.H, i = y * W + x;
@@ -749,6 +762,7 @@ __global__ void fill_in_kernel(SurfelGeom g, SplatMaps splat, const uint8_t* __r
 }
 // CoFusion::requiresFillIn (CoFusion.cpp:547-565)
 __global__ void requires_fill_in_kernel(SurfelGeom g, const uchar4* __restrict__ image, float ratio, MapCounters* ctr) {
+  pdl_prologue();
   const int cons = 20, lw = g.W / cons, lh = g.H / cons;
   __shared__ int total;
   if (threadIdx.x == 0) total = 0;
@@ -770,6 +784,7 @@ __global__ void requires_fill_in_kernel(SurfelGeom g, const uchar4* __restrict__
 __global__ void select_prediction_kernel(unsigned n, const MapCounters* __restrict__ ctr, int fill_image_always,
                                          SplatMaps splat, FillMaps fill, float4* __restrict__ v,
                                          float4* __restrict__ nrm, uchar4* __restrict__ img) {
+  pdl_prologue();
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const bool doFill = ctr->fillInRequired != 0;
@@ -811,9 +826,9 @@ cudaError_t launch_predict_indices(const SurfelGeom& g, const Surfel* surfels, u
   const unsigned n = (unsigned)g.W * g.H;
   RET_IF(cudaMemsetAsync(keys, 0xFF, (size_t)n * 8, s));
   if (count_ub)
-    index_project_kernel<<<cdiv(count_ub, 256), 256, 0, s>>>(g, surfels, count_ub, ctr, t_inv, time, maxDepth,
-                                                             timeDelta, keys);
-  index_resolve_kernel<<<cdiv(n, 256), 256, 0, s>>>(g, surfels, t_inv, keys, out);
+    CFB_PDL(launch_pdl(index_project_kernel, cdiv(count_ub, 256), 256, 0, s, g, surfels, count_ub, ctr, t_inv, time, maxDepth,
+                                                             timeDelta, keys));
+  CFB_PDL(launch_pdl(index_resolve_kernel, cdiv(n, 256), 256, 0, s, g, surfels, t_inv, keys, out));
   return cudaGetLastError();
 }
 
@@ -825,13 +840,13 @@ cudaError_t launch_fuse(const SurfelGeom& g, Surfel* surfels, unsigned count_ub,
   const int par = ((time % 2) + 2) % 2;
   const int W2 = (g.W - par + 1) / 2, H2 = (g.H - par + 1) / 2;
   const unsigned ne = (unsigned)W2 * H2;
-  if (count_ub) fill_u32_kernel<<<cdiv(count_ub, 256), 256, 0, s>>>(winner, count_ub, &ctr->count, 0xffffffffu);
+  if (count_ub) CFB_PDL(launch_pdl(fill_u32_kernel, cdiv(count_ub, 256), 256, 0, s, winner, count_ub, &ctr->count, 0xffffffffu));
   const dim3 b(32, 8), gr(cdiv(W2, 32), cdiv(H2, 8));
-  fuse_associate_kernel<<<gr, b, 0, s>>>(g, pose, time, rgb, mask, depthRaw, depthFiltered, maxDepth, weighting, maskID,
-                                         idx, winner, cand, candBest, sc.flags, par, W2, H2);
+  CFB_PDL(launch_pdl(fuse_associate_kernel, gr, b, 0, s, g, pose, time, rgb, mask, depthRaw, depthFiltered, maxDepth, weighting, maskID,
+                                         idx, winner, cand, candBest, sc.flags, par, W2, H2));
   RET_IF(scan_flags(sc, ne, nullptr, 0, &ctr->scanTotal, s));
-  fuse_append_kernel<<<cdiv(ne, 256), 256, 0, s>>>(ne, sc.flags, sc.ranks, cand, unstable, ctr);
-  fuse_update_kernel<<<cdiv(ne, 256), 256, 0, s>>>(ne, time, sc.flags, candBest, winner, cand, surfels);
+  CFB_PDL(launch_pdl(fuse_append_kernel, cdiv(ne, 256), 256, 0, s, ne, sc.flags, sc.ranks, cand, unstable, ctr));
+  CFB_PDL(launch_pdl(fuse_update_kernel, cdiv(ne, 256), 256, 0, s, ne, time, sc.flags, candBest, winner, cand, surfels));
   return cudaGetLastError();
 }
 
@@ -841,15 +856,15 @@ cudaError_t launch_clean(const SurfelGeom& g, Surfel* src, Surfel* unstable, Sur
                          unsigned maskID, float outlierCoeff, IndexMaps idx, ScanScratch sc, cudaStream_t s) {
   const unsigned n_ub = count_ub + cand_ub;
   if (n_ub) {
-    clean_evaluate_kernel<<<cdiv(n_ub, 128), 128, 0, s>>>(g, src, unstable, n_ub, ctr, t_inv, time, confThreshold,
+    CFB_PDL(launch_pdl(clean_evaluate_kernel, cdiv(n_ub, 128), 128, 0, s, g, src, unstable, n_ub, ctr, t_inv, time, confThreshold,
                                                           timeDelta, depthFiltered, mask, maskID, outlierCoeff, idx,
-                                                          sc.flags);
+                                                          sc.flags));
     RET_IF(scan_flags(sc, n_ub, &ctr->count, cand_ub, &ctr->scanTotal, s));
-    clean_scatter_kernel<<<cdiv(n_ub, 256), 256, 0, s>>>(src, unstable, dst, n_ub, capacity, ctr, sc.flags, sc.ranks);
+    CFB_PDL(launch_pdl(clean_scatter_kernel, cdiv(n_ub, 256), 256, 0, s, src, unstable, dst, n_ub, capacity, ctr, sc.flags, sc.ranks));
   } else {
     RET_IF(cudaMemsetAsync(&ctr->scanTotal, 0, sizeof(unsigned), s));
   }
-  clean_finish_kernel<<<1, 1, 0, s>>>(ctr, capacity, time);
+  CFB_PDL(launch_pdl(clean_finish_kernel, 1, 1, 0, s, ctr, capacity, time));
   return cudaGetLastError();
 }
 
@@ -859,10 +874,10 @@ cudaError_t launch_combined_predict(const SurfelGeom& g, const Surfel* surfels, 
   const unsigned n = (unsigned)g.W * g.H;
   RET_IF(cudaMemsetAsync(keys, 0xFF, (size_t)n * 8, s));
   if (count_ub)
-    splat_raster_kernel<<<cdiv(count_ub, 128), 128, 0, s>>>(g, surfels, count_ub, ctr, t_inv, maxDepth, confThreshold,
-                                                            time, maxTime, timeDelta, keys);
+    CFB_PDL(launch_pdl(splat_raster_kernel, cdiv(count_ub, 128), 128, 0, s, g, surfels, count_ub, ctr, t_inv, maxDepth, confThreshold,
+                                                            time, maxTime, timeDelta, keys));
   const dim3 b(32, 8), gr(cdiv(g.W, 32), cdiv(g.H, 8));
-  splat_resolve_kernel<<<gr, b, 0, s>>>(g, surfels, t_inv, maxDepth, confThreshold, time, maxTime, timeDelta, keys, out);
+  CFB_PDL(launch_pdl(splat_resolve_kernel, gr, b, 0, s, g, surfels, t_inv, maxDepth, confThreshold, time, maxTime, timeDelta, keys, out));
   return cudaGetLastError();
 }
 
@@ -870,16 +885,16 @@ cudaError_t launch_select_prediction(const SurfelGeom& g, const MapCounters* ctr
                                      SplatMaps splat, FillMaps fill, float* v4, float* n4, uint8_t* img,
                                      cudaStream_t s) {
   const unsigned n = (unsigned)g.W * g.H;
-  select_prediction_kernel<<<cdiv(n, 256), 256, 0, s>>>(n, ctr, fill_image_always, splat, fill, (float4*)v4,
-                                                        (float4*)n4, (uchar4*)img);
+  CFB_PDL(launch_pdl(select_prediction_kernel, cdiv(n, 256), 256, 0, s, n, ctr, fill_image_always, splat, fill, (float4*)v4,
+                                                        (float4*)n4, (uchar4*)img));
   return cudaGetLastError();
 }
 
 cudaError_t launch_fill_in(const SurfelGeom& g, SplatMaps splat, const uint8_t* rgb, const float* depthFiltered,
                            int pt_geom, int pt_rgb, FillMaps out, MapCounters* ctr, float ratio, cudaStream_t s) {
   const dim3 b(32, 8), gr(cdiv(g.W, 32), cdiv(g.H, 8));
-  requires_fill_in_kernel<<<1, 256, 0, s>>>(g, splat.image, ratio, ctr);
-  fill_in_kernel<<<gr, b, 0, s>>>(g, splat, rgb, depthFiltered, pt_geom, pt_rgb, out);
+  CFB_PDL(launch_pdl(requires_fill_in_kernel, 1, 256, 0, s, g, splat.image, ratio, ctr));
+  CFB_PDL(launch_pdl(fill_in_kernel, gr, b, 0, s, g, splat, rgb, depthFiltered, pt_geom, pt_rgb, out));
   return cudaGetLastError();
 }
 
