@@ -429,7 +429,7 @@ int cfb_ctx_view(cfb_ctx* c, int which, const void** dev_ptr, size_t* pitch) {
     case 2: *dev_ptr = x.depthFiltered; *pitch = (size_t)x.W * 4; break;
     case 3: *dev_ptr = x.depthPyr[1]; *pitch = (size_t)(x.W / 2) * 4; break;
     case 4: *dev_ptr = x.depthPyr[2]; *pitch = (size_t)(x.W / 4) * 4; break;
-    case 5: *dev_ptr = x.mask; *pitch = (size_t)x.W; break;
+    case 5: *dev_ptr = x.mask; *pitch = (size_t)x.W; x.maskIsZero = false; break;  // (the caller may write through it)
     default: return set_error_msg(2, "ctx_view: unknown view");
   }
   return 0;

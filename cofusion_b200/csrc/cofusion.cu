@@ -79,6 +79,7 @@ cudaError_t CoFusion::segmentAndManageModels() {
   int cnt = 0;
   bool hasNew = false;
   if (segmentation->slicAheadOf == ctx.rgb) RET_IF(cudaStreamWaitEvent(ctx.stream, ctx.evOrder2, 0));
+  ctx.maskIsZero = false;  // the segmentation writes the label image
   RET_IF(segmentation->performSegmentationCRF(ctx.rgb, ctx.depthRaw, n, ids, icp, conf, nextID_, allowNew, params.seg,
                                               ctx.mask, lastModelData.data(), &cnt, &hasNew, ctx.stream));
   ctx.launches += segmentation->launches;

@@ -785,10 +785,20 @@ __device__ __noinline__ void phase3_obj(int lvl, int m, float sigma, int buf) {
 // word also counts its contributions.  Integer addition commutes: the grid total does not depend on the
 // order in which the CTAs arrive.
 template <int NS>
-__device__ __forceinline__ void publish_sums(unsigned round) {
+__device__ __forceinline__ void publish_sums(unsigned round, bool fold_rows) {
   TSMEM();
   const int t = threadIdx.x, m = t / NS, j = t - m * NS;
-  double d = (double)SM_F32(p.o_blk)[m * 64 + j];
+  float sum;
+  if (fold_rows) {  // one model: the ICP rows are in buffer 0, the RGB rows in buffer 1; folded here, in warp order
+    const int set = j >= 29 ? 1 : 0;
+    const float* r = SM_F32(p.o_wrow) + (size_t)set * kNW * 32 + (j - 29 * set);
+    sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < kNW; ++w) sum += r[w * 32];
+  } else {
+    sum = SM_F32(p.o_blk)[m * 64 + j];
+  }
+  double d = (double)sum;
   if (!(fabs(d) < 9.0e15)) d = 0.0;  // non-finite (or absurd) partial: contributes nothing but still counts
   const long long hi = (long long)(d * (1.0 / 256.0));
   const long long lo = __double2ll_rn((d - (double)hi * 256.0) * 549755813888.0 /* 2^39 */);
@@ -1322,7 +1332,7 @@ __device__ __noinline__ void level_begin(int lvl, unsigned& win_phase) {
 template <bool GENERAL, bool DBGT>
 __device__ __noinline__ void run_level(int lvl, int q0, int nit, unsigned round0) {
   TSMEM();
-  const int NM = p.nmodels, G = gridDim.x;
+  const int NM = GENERAL ? p.nmodels : 1, G = gridDim.x;  // the lean kernel: loops over one model fold away
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool FS = p.F[lvl].staged != 0;
   int wbuf = 0;
@@ -1363,8 +1373,10 @@ __device__ __noinline__ void run_level(int lvl, int q0, int nit, unsigned round0
         phase2_obj(lvl, m, err, wbuf);
       else if (GENERAL)
         phase2<false, false>(lvl, m, err, wbuf);
-      __syncthreads();
-      fold_warp_rows(wbuf, m, 0, 29);
+      if (GENERAL) {  // (one model: both sets of rows are folded by the publishing threads, see publish_sums)
+        __syncthreads();
+        fold_warp_rows(wbuf, m, 0, 29);
+      }
     }
     DBG_MARK(8 + q * 8 + 2);
     DBG_CTA(q, 2);
@@ -1391,15 +1403,15 @@ __device__ __noinline__ void run_level(int lvl, int q0, int nit, unsigned round0
       else if (GENERAL)
         phase3<false, false>(lvl, m, sigma, wbuf);
       __syncthreads();
-      fold_warp_rows(wbuf, m, 1, 29);
+      if (GENERAL) fold_warp_rows(wbuf, m, 1, 29);
       wbuf ^= 1;
     }
-    __syncthreads();
+    if (GENERAL) __syncthreads();
     DBG_MARK(8 + q * 8 + 4);
     DBG_CTA(q, 3);
 
     // -------- add this CTA's sums to the grid accumulators, read the totals, solve
-    if ((int)threadIdx.x < NM * kSums) publish_sums<kSums>(round);
+    if ((int)threadIdx.x < NM * kSums) publish_sums<kSums>(round, !GENERAL);
     DBG_MARK(8 + q * 8 + 5);
     collect_sums<kSums>(round, NM * kSums);
     DBG_MARK(8 + q * 8 + 6);
@@ -1416,9 +1428,10 @@ __device__ __noinline__ void run_level(int lvl, int q0, int nit, unsigned round0
 }
 
 // SO(3) pre-alignment of every model on level 2 (RGBDOdometry.cpp:239-310); returns the rounds used
+template <bool GENERAL>
 __device__ __noinline__ unsigned run_so3() {
   TSMEM();
-  const int NM = p.nmodels;
+  const int NM = GENERAL ? p.nmodels : 1;
   const FLevel& F = p.F[2];
   const int x0 = (blockIdx.x % p.gx) * F.tw, y0 = (blockIdx.x / p.gx) * F.th;
   const unsigned warp = threadIdx.x >> 5;
@@ -1449,7 +1462,7 @@ __device__ __noinline__ unsigned run_so3() {
       wbuf ^= 1;
     }
     __syncthreads();
-    if ((int)threadIdx.x < NM * 11) publish_sums<11>(round);
+    if ((int)threadIdx.x < NM * 11) publish_sums<11>(round, false);
     collect_sums<11>(round, NM * 11);
     if ((int)warp < NM && !sm.S[warp].so3_done) so3_update_warp((int)warp, it);
     __syncthreads();
@@ -1484,7 +1497,7 @@ __global__ void __launch_bounds__(kT, 1) gn_tiled_kernel(const TParams kp) {
   }
   __syncthreads();
   const TParams& p = sm.prm;
-  const int NM = p.nmodels;
+  const int NM = GENERAL ? p.nmodels : 1;
   const unsigned warp = threadIdx.x >> 5;
   DBG_MARK(0);
   // every level's frame tiles are requested now; the finer levels land while the coarser ones iterate
@@ -1498,7 +1511,7 @@ __global__ void __launch_bounds__(kT, 1) gn_tiled_kernel(const TParams kp) {
   __syncthreads();
   DBG_MARK(1);
   unsigned round = 0;
-  if (p.use_so3) round = run_so3();
+  if (p.use_so3) round = run_so3<GENERAL>();
   DBG_MARK(2);
   // ---- Gauss-Newton iterations, coarse to fine (RGBDOdometry.cpp:331-461)
   unsigned win_phase = 0;
@@ -1524,8 +1537,11 @@ __global__ void __launch_bounds__(kT, 1) gn_tiled_kernel(const TParams kp) {
     }
   // pose, inverse, previous pose and fusion weight for the fuse / clean / predict kernels of this frame
   // (pose_math.cuh: the same expressions as the host's, bit for bit)
-  if (blockIdx.x == 0 && (int)threadIdx.x < NM && p.M[threadIdx.x].pd)
+  if (blockIdx.x == 0 && (int)threadIdx.x < NM && p.M[threadIdx.x].pd) {
     pose_block_update(p.M[threadIdx.x].pd, sm.S[threadIdx.x].out_trans, sm.S[threadIdx.x].out_rot);
+    // the statistics follow the block (Model::PoseReadback): the host fetches both with one copy
+    *reinterpret_cast<TrackStats*>(p.M[threadIdx.x].pd + 1) = sm.S[threadIdx.x].stats;
+  }
   DBG_MARK(3);
 }
 

@@ -145,9 +145,11 @@ cudaError_t Context::uploadFrame(const uint8_t* rgb_h, const float* depth_h, con
       m = h_mask;
     }
     RET_IF(cudaMemcpyAsync(mask, m, n, cudaMemcpyHostToDevice, stream));
+    maskIsZero = false;
   } else if (!keepMask) {
     // static scene: everything is background (CoFusion.cpp:190-197)
-    RET_IF(cudaMemsetAsync(mask, 0, n, stream));
+    if (!maskIsZero) RET_IF(cudaMemsetAsync(mask, 0, n, stream));  // (still zero from the last frame otherwise)
+    maskIsZero = true;
   }
   return cudaSuccess;
 }
@@ -207,6 +209,7 @@ cudaError_t Context::uploadFrameRaw(const uint8_t* img, bool flip, const float* 
   if (mask_p) {
     if (device_ptrs) {
       RET_IF(cudaMemcpyAsync(mask, mask_p, n, cudaMemcpyDeviceToDevice, stream));
+      maskIsZero = false;
     } else {
       const uint8_t* m = mask_p;
       if (!pinned(mask_p)) {
@@ -216,9 +219,11 @@ cudaError_t Context::uploadFrameRaw(const uint8_t* img, bool flip, const float* 
         m = h_mask;
       }
       RET_IF(cudaMemcpyAsync(mask, m, n, cudaMemcpyHostToDevice, stream));
+      maskIsZero = false;
     }
   } else if (!keepMask) {
-    RET_IF(cudaMemsetAsync(mask, 0, n, stream));
+    if (!maskIsZero) RET_IF(cudaMemsetAsync(mask, 0, n, stream));  // (still zero from the last frame otherwise)
+    maskIsZero = true;
   }
   return cudaSuccess;
 }
@@ -230,10 +235,13 @@ cudaError_t Context::setFrameDevice(const uint8_t* rgb_d, const float* depth_d, 
   RET_IF(cudaMemcpyAsync(depthRaw, depth_d, n * 4, cudaMemcpyDeviceToDevice, preStream));
   RET_IF(cudaEventRecord(evInputs[cur], preStream));
   RET_IF(cudaStreamWaitEvent(stream, evInputs[cur], 0));
-  if (mask_d)
+  if (mask_d) {
     RET_IF(cudaMemcpyAsync(mask, mask_d, n, cudaMemcpyDeviceToDevice, stream));
-  else if (!keepMask)
-    RET_IF(cudaMemsetAsync(mask, 0, n, stream));
+    maskIsZero = false;
+  } else if (!keepMask) {
+    if (!maskIsZero) RET_IF(cudaMemsetAsync(mask, 0, n, stream));  // (still zero from the last frame otherwise)
+    maskIsZero = true;
+  }
   return cudaSuccess;
 }
 
@@ -275,9 +283,12 @@ Model::Model(Context* c, unsigned id_, float conf, unsigned maxSurfels, bool ena
          dalloc(&scan.blockSums, 2 * (scanCap / 2048 + 4), &zeroed_) && dalloc(&counters, 1, &zeroed_);
   scan.capacity = scanCap;
   scan.host = new ScanHostState();
+  // the projection passes take atomic minima into `keys`; the resolve passes leave it all ones again
+  good = good && cudaMemset(keys, 0xFF, n * sizeof(unsigned long long)) == cudaSuccess;
   good = good && cudaMallocHost(&h_counters, sizeof(MapCounters)) == cudaSuccess;
   if (good) memset(h_counters, 0, sizeof(MapCounters));
-  good = good && dalloc(&dpose, 1, &zeroed_) && cudaMallocHost(&h_readback, sizeof(PoseReadback)) == cudaSuccess &&
+  // the pose block is followed by the tracker statistics of the frame: one read-back copy fetches both
+  good = good && dalloc((PoseReadback**)&dpose, 1, &zeroed_) && cudaMallocHost(&h_readback, sizeof(PoseReadback)) == cudaSuccess &&
          cudaEventCreateWithFlags(&evPose, cudaEventDisableTiming) == cudaSuccess;
   ok_ = good;
   if (good) ok_ = uploadPose() == cudaSuccess;
@@ -342,6 +353,7 @@ cudaError_t Model::recycle(unsigned id_, float conf) {
   memset(h_counters, 0, sizeof(MapCounters));
   for (auto& z : zeroed_) RET_IF(cudaMemsetAsync(z.first, 0, z.second, work));
   *scan.host = ScanHostState();  // the ticket counter and the status words are zero again
+  RET_IF(cudaMemsetAsync(keys, 0xFF, (size_t)ctx->W * ctx->H * sizeof(unsigned long long), work));
   RET_IF(odom.recycle(work));
   return uploadPose();
 }
@@ -435,8 +447,7 @@ cudaError_t Model::uploadPose() {
 }
 
 cudaError_t Model::enqueuePoseReadback() {
-  RET_IF(cudaMemcpyAsync(&h_readback->block, dpose, sizeof(PoseDev), cudaMemcpyDeviceToHost, work));
-  RET_IF(cudaMemcpyAsync(&h_readback->stats, odom.statsDevice(), sizeof(TrackStats), cudaMemcpyDeviceToHost, work));
+  RET_IF(cudaMemcpyAsync(h_readback, dpose, sizeof(PoseReadback), cudaMemcpyDeviceToHost, work));  // block + statistics
   RET_IF(cudaEventRecord(evPose, work));
   poseStale = true;
   return cudaSuccess;
@@ -551,7 +562,7 @@ cudaError_t Model::clean(int time, int timeDelta, float /*depthCutoff*/, float o
   renderSource = t;
   unsigned ub = count_ub + cand_ub;
   count_ub = ub < capacity ? ub : capacity;
-  ctx->launches += 4;
+  ctx->launches += 3;  // evaluate, scan, scatter (+ closing of the pass)
   // refresh the host-side bound with the exact count whenever the stream is next synchronised
   RET_IF(cudaMemcpyAsync(h_counters, counters, sizeof(MapCounters), cudaMemcpyDeviceToHost, work));
   return cudaSuccess;
@@ -566,7 +577,7 @@ cudaError_t Model::combinedPredict(float depthCutoff, int time, int maxTime, int
 
 cudaError_t Model::performFillIn(bool frameToFrameRGB, bool lost) {
   if (!allowsFillIn) return cudaSuccess;
-  ctx->launches += 2;
+  ctx->launches += 1;
   return launch_fill_in(geom(), splat, ctx->rgb, ctx->depthFiltered, lost ? 1 : 0, (lost || frameToFrameRGB) ? 1 : 0,
                         fill, counters, 0.75f, work);
 }
@@ -588,7 +599,7 @@ cudaError_t Model::downloadMap(float* dst, size_t cap, unsigned* count_out) {
 cudaError_t Model::uploadMap(const float* src, unsigned count) {
   if (count > capacity) count = capacity;
   RET_IF(cudaMemcpyAsync(buf[target], src, (size_t)count * sizeof(Surfel), cudaMemcpyHostToDevice, work));
-  MapCounters c = {count, 0, 0, 0, 0};
+  MapCounters c = {count, 0, 0, 0, 0, 0, 0, 0};
   *h_counters = c;
   RET_IF(cudaMemcpyAsync(counters, h_counters, sizeof(MapCounters), cudaMemcpyHostToDevice, work));
   RET_IF(cudaStreamSynchronize(work));

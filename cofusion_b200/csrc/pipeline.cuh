@@ -64,6 +64,7 @@ class Context {
   float* depthFiltered = nullptr;   // level 0 of the pyramid of the CURRENT frame
   float* depthPyr[3] = {nullptr, nullptr, nullptr};
   uint8_t* mask = nullptr;          // label image (model ids)
+  bool maskIsZero = false;          // the label image is known to be all background (skips the per-frame clear)
   uint16_t* d16Buf[2] = {nullptr, nullptr};    // raw depth of the ingest path (allocated on first use)
   uint16_t* h_d16Buf[2] = {nullptr, nullptr};
   uint8_t* rawImgBuf[2] = {nullptr, nullptr};  // image before the channel swap

@@ -303,12 +303,13 @@ __global__ void index_project_kernel(SurfelGeom g, const Surfel* __restrict__ su
   atomicMin(&keys[py * g.W + px], key);
 }
 __global__ void index_resolve_kernel(SurfelGeom g, const Surfel* __restrict__ surfels, PoseRef t_inv_ref,
-                                     const unsigned long long* __restrict__ keys, IndexMaps out) {
+                                     unsigned long long* __restrict__ keys, IndexMaps out) {
   pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.W * g.H) return;
   const Pose34 t_inv = resolve_pose(t_inv_ref);
   const unsigned long long k = keys[i];
+  keys[i] = ~0ull;  // the buffer is left as the next projection pass expects it (no memset between passes)
   if (k == ~0ull) {
     out.index[i] = 0;
     const float4 z = make_float4(0, 0, 0, 0);
@@ -596,17 +597,30 @@ __global__ void clean_evaluate_kernel(SurfelGeom g, Surfel* __restrict__ src, Su
   }
 }
 __global__ void clean_scatter_kernel(const Surfel* __restrict__ src, const Surfel* __restrict__ unstable,
-                                     Surfel* __restrict__ dst, unsigned n_ub, unsigned capacity,
-                                     const MapCounters* __restrict__ ctr, const uint8_t* __restrict__ flags,
-                                     const uint32_t* __restrict__ ranks) {
+                                     Surfel* __restrict__ dst, unsigned n_ub, unsigned capacity, MapCounters* ctr,
+                                     const uint8_t* __restrict__ flags, const uint32_t* __restrict__ ranks, int time) {
   pdl_prologue();
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned count = ctr->count, total = count + ctr->unstableCount;
-  if (i >= n_ub || i >= total || !flags[i]) return;
-  const unsigned r = ranks[i];
-  if (r >= capacity) return;
-  const Surfel* rec = (i < count) ? (src + i) : (unstable + (i - count));
-  store_surfel(dst + r, load_surfel(rec));
+  if (i < n_ub && i < total && flags[i]) {
+    const unsigned r = ranks[i];
+    if (r < capacity) {
+      const Surfel* rec = (i < count) ? (src + i) : (unstable + (i - count));
+      store_surfel(dst + r, load_surfel(rec));
+    }
+  }
+  // the last block to get here closes the pass (what a one-thread launch did before): every block has read the
+  // counters by then
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&ctr->cleanTicket, 1u) == gridDim.x - 1) {
+      ctr->count = min(ctr->scanTotal, capacity);
+      ctr->unstableCount = 0;
+      ctr->cleanTick = (unsigned)time;
+      ctr->cleanTicket = 0;
+    }
+  }
 }
 __global__ void clean_finish_kernel(MapCounters* ctr, unsigned capacity, int time) {
   pdl_prologue();
@@ -700,13 +714,14 @@ __global__ void splat_raster_kernel(SurfelGeom g, const Surfel* __restrict__ sur
 }
 __global__ void splat_resolve_kernel(SurfelGeom g, const Surfel* __restrict__ surfels, PoseRef t_inv_ref, float maxDepth,
                                      float confThreshold, int time, int maxTime, int timeDelta,
-                                     const unsigned long long* __restrict__ keys, SplatMaps out) {
+                                     unsigned long long* __restrict__ keys, SplatMaps out) {
   pdl_prologue();
   const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
   if (px >= g.W || py >= g.H) return;
   const Pose34 t_inv = resolve_pose(t_inv_ref);
   const int i = py * g.W + px;
   const unsigned long long k = keys[i];
+  keys[i] = ~0ull;  // the buffer is left as the next projection pass expects it (no memset between passes)
   if (k == ~0ull) {
     out.image[i] = make_uchar4(0, 0, 0, 0);
     out.vertexConf[i] = make_float4(0, 0, 0, 0);
@@ -729,11 +744,9 @@ __global__ void splat_resolve_kernel(SurfelGeom g, const Surfel* __restrict__ su
 }
 
 // ------------------------------------------------------------------------------- a15 fill-in
-__global__ void fill_in_kernel(SurfelGeom g, SplatMaps splat, const uint8_t* __restrict__ rgb,
-                               const float* __restrict__ depth, int pt_geom, int pt_rgb, FillMaps out) {
-  pdl_prologue();
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= g.W || y >= g.H) return;
+__device__ __forceinline__ void fill_in_pixel(const SurfelGeom& g, const SplatMaps& splat, const uint8_t* __restrict__ rgb,
+                                              const float* __restrict__ depth, int pt_geom, int pt_rgb, const FillMaps& out,
+                                              int x, int y, int* s_cnt) {
   const int W = g.W, H = g.H, i = y * W + x;
   const float inv_fx = 1.0f / g.fx, inv_fy = 1.0f / g.fy;  // FillIn.cpp:73-74
   const float4 sv = splat.vertexConf[i];
@@ -759,24 +772,38 @@ __global__ void fill_in_kernel(SurfelGeom g, SplatMaps splat, const uint8_t* __r
     out.image[i] = make_uchar4(rgb[i * 3], rgb[i * 3 + 1], rgb[i * 3 + 2], 255);
   else
     out.image[i] = si;
-}
-// CoFusion::requiresFillIn (CoFusion.cpp:547-565)
-__global__ void requires_fill_in_kernel(SurfelGeom g, const uchar4* __restrict__ image, float ratio, MapCounters* ctr) {
-  pdl_prologue();
-  const int cons = 20, lw = g.W / cons, lh = g.H / cons;
-  __shared__ int total;
-  if (threadIdx.x == 0) total = 0;
-  __syncthreads();
-  int sum = 0;
-  for (int q = threadIdx.x; q < lw * lh; q += blockDim.x) {
-    const int i = q % lw, j = q / lw;
-    const int sx = texel(((float)i + 0.5f) / (float)lw, g.W), sy = texel(((float)j + 0.5f) / (float)lh, g.H);
-    const uchar4 p = image[sy * g.W + sx];
-    sum += (p.x > 0 && p.y > 0 && p.z > 0) ? 1 : 0;
+  {  // is this pixel one of requiresFillIn's samples?  (sample q of a row of lw sits at texel((q + 0.5) / lw))
+    const int cons = 20, lw = W / cons, lh = H / cons;
+    if (lw > 0 && lh > 0) {
+      const int qi = min(x * lw / W, lw - 1), qj = min(y * lh / H, lh - 1);
+      if (texel(((float)qi + 0.5f) / (float)lw, W) == x && texel(((float)qj + 0.5f) / (float)lh, H) == y &&
+          si.x > 0 && si.y > 0 && si.z > 0)
+        atomicAdd(s_cnt, 1);
+    }
   }
-  atomicAdd(&total, sum);
+}
+// CoFusion::requiresFillIn (CoFusion.cpp:547-565) rides along: the 20-pixel sample grid of the splat image is counted
+// by the threads that own those pixels, the last block forms the ratio (a 1-CTA launch before).
+__global__ void fill_in_kernel(SurfelGeom g, SplatMaps splat, const uint8_t* __restrict__ rgb,
+                               const float* __restrict__ depth, int pt_geom, int pt_rgb, FillMaps out, MapCounters* ctr,
+                               float ratio) {
+  pdl_prologue();
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0 && threadIdx.y == 0) s_cnt = 0;
   __syncthreads();
-  if (threadIdx.x == 0) ctr->fillInRequired = ((float)total / (float)(lh * lw) < ratio) ? 1u : 0u;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x < g.W && y < g.H) fill_in_pixel(g, splat, rgb, depth, pt_geom, pt_rgb, out, x, y, &s_cnt);
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    if (s_cnt) atomicAdd(&ctr->fillSamples, (unsigned)s_cnt);
+    __threadfence();
+    if (atomicAdd(&ctr->fillTicket, 1u) == gridDim.x * gridDim.y - 1) {
+      const int cons = 20, lw = g.W / cons, lh = g.H / cons;
+      const unsigned total = atomicExch(&ctr->fillSamples, 0u);
+      ctr->fillInRequired = ((float)total / (float)(lh * lw) < ratio) ? 1u : 0u;
+      ctr->fillTicket = 0;
+    }
+  }
 }
 
 // Model::initICP (Model.cpp:350-367) chooses between the splat prediction and the fill-in images
@@ -824,7 +851,7 @@ cudaError_t launch_predict_indices(const SurfelGeom& g, const Surfel* surfels, u
                                    const MapCounters* ctr, const PoseRef& t_inv, int time, float maxDepth,
                                    int timeDelta, unsigned long long* keys, IndexMaps out, cudaStream_t s) {
   const unsigned n = (unsigned)g.W * g.H;
-  RET_IF(cudaMemsetAsync(keys, 0xFF, (size_t)n * 8, s));
+  // keys: all ones on entry (Model construction, then every resolve pass restores it)
   if (count_ub)
     CFB_PDL(launch_pdl(index_project_kernel, cdiv(count_ub, 256), 256, 0, s, g, surfels, count_ub, ctr, t_inv, time, maxDepth,
                                                              timeDelta, keys));
@@ -860,19 +887,17 @@ cudaError_t launch_clean(const SurfelGeom& g, Surfel* src, Surfel* unstable, Sur
                                                           timeDelta, depthFiltered, mask, maskID, outlierCoeff, idx,
                                                           sc.flags));
     RET_IF(scan_flags(sc, n_ub, &ctr->count, cand_ub, &ctr->scanTotal, s));
-    CFB_PDL(launch_pdl(clean_scatter_kernel, cdiv(n_ub, 256), 256, 0, s, src, unstable, dst, n_ub, capacity, ctr, sc.flags, sc.ranks));
+    CFB_PDL(launch_pdl(clean_scatter_kernel, cdiv(n_ub, 256), 256, 0, s, src, unstable, dst, n_ub, capacity, ctr, sc.flags, sc.ranks, time));
   } else {
     RET_IF(cudaMemsetAsync(&ctr->scanTotal, 0, sizeof(unsigned), s));
+    CFB_PDL(launch_pdl(clean_finish_kernel, 1, 1, 0, s, ctr, capacity, time));
   }
-  CFB_PDL(launch_pdl(clean_finish_kernel, 1, 1, 0, s, ctr, capacity, time));
   return cudaGetLastError();
 }
 
 cudaError_t launch_combined_predict(const SurfelGeom& g, const Surfel* surfels, unsigned count_ub, MapCounters* ctr,
                                     const PoseRef& t_inv, float maxDepth, float confThreshold, int time, int maxTime,
                                     int timeDelta, unsigned long long* keys, SplatMaps out, cudaStream_t s) {
-  const unsigned n = (unsigned)g.W * g.H;
-  RET_IF(cudaMemsetAsync(keys, 0xFF, (size_t)n * 8, s));
   if (count_ub)
     CFB_PDL(launch_pdl(splat_raster_kernel, cdiv(count_ub, 128), 128, 0, s, g, surfels, count_ub, ctr, t_inv, maxDepth, confThreshold,
                                                             time, maxTime, timeDelta, keys));
@@ -893,8 +918,7 @@ cudaError_t launch_select_prediction(const SurfelGeom& g, const MapCounters* ctr
 cudaError_t launch_fill_in(const SurfelGeom& g, SplatMaps splat, const uint8_t* rgb, const float* depthFiltered,
                            int pt_geom, int pt_rgb, FillMaps out, MapCounters* ctr, float ratio, cudaStream_t s) {
   const dim3 b(32, 8), gr(cdiv(g.W, 32), cdiv(g.H, 8));
-  CFB_PDL(launch_pdl(requires_fill_in_kernel, 1, 256, 0, s, g, splat.image, ratio, ctr));
-  CFB_PDL(launch_pdl(fill_in_kernel, gr, b, 0, s, g, splat, rgb, depthFiltered, pt_geom, pt_rgb, out));
+  CFB_PDL(launch_pdl(fill_in_kernel, gr, b, 0, s, g, splat, rgb, depthFiltered, pt_geom, pt_rgb, out, ctr, ratio));
   return cudaGetLastError();
 }
 

@@ -55,6 +55,8 @@ struct MapCounters {
   unsigned scanTotal;      // scratch: result of the last flag scan
   unsigned fillInRequired; // CoFusion::requiresFillIn of the last prediction
   unsigned cleanTick;      // `time` of the clean() that produced `count` (lets the host bound the count without a sync)
+  unsigned cleanTicket;    // scratch: blocks of the last clean_scatter that have finished (the last one closes the pass)
+  unsigned fillSamples, fillTicket;  // scratch of the requiresFillIn count inside fill_in_kernel
 };
 
 struct IndexMaps {  // ModelProjection sparse targets (ModelProjection.cpp:72-76)
