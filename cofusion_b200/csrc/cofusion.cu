@@ -186,6 +186,58 @@ struct Timeline {
   }
 };
 Timeline g_tl;
+
+// Finer device timeline (tools only, CFB_TIMELINE=2): events on the pipeline stream between the stages of a
+// single-model frame; the mean device time of every section over 200 frames goes to stderr.
+struct FineTimeline {
+  static constexpr int kMax = 12, kRing = 64;  // the host may run dozens of frames ahead of the device
+  bool on = false, init = false;
+  cudaEvent_t ev[kRing][kMax];
+  const char* name[kMax];
+  int n[kRing] = {0};
+  double sum[kMax] = {0}, gap = 0;
+  int frames = 0, cur = 0;
+  void begin() {
+    if (!init) {
+      init = true;
+      const char* e = getenv("CFB_TIMELINE");
+      on = e && atoi(e) == 2;
+      if (on)
+        for (int a = 0; a < kRing; ++a)
+          for (int b = 0; b < kMax; ++b) cudaEventCreate(&ev[a][b]);
+    }
+    if (!on) return;
+    cur = (cur + 1) % kRing;
+    n[cur] = 0;
+  }
+  void mark(cudaStream_t s, const char* what) {
+    if (!on || n[cur] >= kMax) return;
+    name[n[cur]] = what;
+    cudaEventRecord(ev[cur][n[cur]++], s);
+  }
+  void end() {
+    if (!on) return;
+    const int old = (cur + 1) % kRing, nxt = (cur + 2) % kRing;  // the oldest frames of the ring
+    if (n[old] < 2 || n[nxt] < 1 || cudaEventQuery(ev[nxt][0]) != cudaSuccess) return;
+    float ms;
+    for (int k = 0; k + 1 < n[old]; ++k)
+      if (cudaEventElapsedTime(&ms, ev[old][k], ev[old][k + 1]) == cudaSuccess) sum[k] += ms;
+    if (cudaEventElapsedTime(&ms, ev[old][n[old] - 1], ev[nxt][0]) == cudaSuccess) gap += ms;
+    if (++frames == 200) {
+      fprintf(stderr, "[cfb timeline2, us]");
+      double tot = 0;
+      for (int k = 0; k + 1 < n[old]; ++k) {
+        fprintf(stderr, " %s->%s %.1f |", name[k], name[k + 1], sum[k] * 5.0);
+        tot += sum[k];
+        sum[k] = 0;
+      }
+      fprintf(stderr, " to next frame %.1f | frame %.1f\n", gap * 5.0, (tot + gap) * 5.0);
+      gap = 0;
+      frames = 0;
+    }
+  }
+};
+FineTimeline g_ft;
 }  // namespace
 
 cudaError_t CoFusion::processFrame(const uint8_t* rgb, const float* depth, const uint8_t* mask, bool device_ptrs,
@@ -246,7 +298,7 @@ cudaError_t CoFusion::processFrameEx(const FrameInput& in_, const float* inPose,
   Timeline& tl = g_tl;
   if (!tl.init) {
     tl.init = true;
-    tl.on = getenv("CFB_TIMELINE") != nullptr;
+    tl.on = getenv("CFB_TIMELINE") != nullptr && atoi(getenv("CFB_TIMELINE")) == 1;
     if (tl.on)
       for (int a = 0; a < 2; ++a)
         for (int b = 0; b < 4; ++b) cudaEventCreate(&tl.ev[a][b]);
@@ -258,6 +310,12 @@ cudaError_t CoFusion::processFrameEx(const FrameInput& in_, const float* inPose,
     cudaEventRecord(tl.ev[tl.cur][k], ctx.stream);
   };
   mark(0);
+  g_ft.begin();
+  g_ft.mark(ctx.stream, "start");
+  {  // see cfb_common.cuh (CFB_PDL_ALL: tools, keeps it on for multi-stream frames too)
+    static const bool all = getenv("CFB_PDL_ALL") != nullptr;
+    pdl_set(all || (models.size() == 1 && !params.enableMultipleModels));
+  }
   // device inputs produced on the pipeline stream itself (the broadcast of the sharded path, a caller's own stream)
   // are ordered after it; otherwise the frame side starts right away, next to the previous frame's tail
   RET_IF(ctx.uploadFrameRaw(in.rgb, in.flipColors, in.depth, in.depth16, in.depthScale, in.mask, device_ptrs,
@@ -305,6 +363,7 @@ cudaError_t CoFusion::processFrameEx(const FrameInput& in_, const float* inPose,
     tp.maxDepthProcessed = params.maxDepthProcessed;
     tp.force_host_loop = 0;
     mark(1);
+    g_ft.mark(ctx.stream, "frame-side");
     {
       std::vector<Model*> ms = processed();
       if (ms.empty()) {
@@ -316,6 +375,7 @@ cudaError_t CoFusion::processFrameEx(const FrameInput& in_, const float* inPose,
       }
     }
     mark(2);
+    g_ft.mark(ctx.stream, "tracked");
     if (bootstrap) {  // globalModel->overridePose(globalModel->getPose() * inPose) (CoFusion.cpp:219-222)
       Model* g = models[0].get();
       RET_IF(g->syncPose());
@@ -339,12 +399,18 @@ cudaError_t CoFusion::processFrameEx(const FrameInput& in_, const float* inPose,
       const std::vector<Model*> act = processed();
       RET_IF(forkModels(act));
       for (Model* m : act) RET_IF(m->predictIndices(tick_, params.maxDepthProcessed, params.timeDelta));
+      g_ft.mark(ctx.stream, "indices");
       for (Model* m : act) RET_IF(m->fuse(tick_, params.maxDepthProcessed, weightMultiplier));
+      g_ft.mark(ctx.stream, "fused");
       for (Model* m : act) RET_IF(m->predictIndices(tick_, params.maxDepthProcessed, params.timeDelta));
+      g_ft.mark(ctx.stream, "indices2");
       for (Model* m : act) RET_IF(m->clean(tick_, params.timeDelta, params.maxDepthProcessed, params.outlierCoefficient));
+      g_ft.mark(ctx.stream, "cleaned");
     }
   }
   RET_IF(predict());
+  g_ft.mark(ctx.stream, "predicted");
+  g_ft.end();
   for (auto& m : models) RET_IF(m->join());
   tick_++;
   if (poseLogging_) RET_IF(logPoses(in.timestamp));
