@@ -273,12 +273,31 @@ int cfb_so3_step(const uint8_t* lastImage, const uint8_t* nextImage, size_t ip, 
 }
 
 /* ------------------------------------------------------------------------------ RGBDOdometry */
+// Every entry that enqueues work runs under the device of its handle (two instances on different GPUs in one
+// process, or a caller that changed the current device, must not launch on the wrong one); the caller's current
+// device is restored on return.
+struct DevScope {
+  int prev = -1, dev;
+  explicit DevScope(int d) : dev(d) {
+    if (d >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != d) cudaSetDevice(d); else prev = -1;
+  }
+  ~DevScope() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+static int current_device() {
+  int d = -1;
+  return cudaGetDevice(&d) == cudaSuccess ? d : -1;
+}
+
 struct cfb_odom {
   RGBDOdometry* p;  // owned unless `borrowed`
   bool borrowed;
+  int device;
   RGBDOdometry& impl_ref() { return *p; }
 };
 #define impl impl_ref()
+extern "C++" inline int device_of(const cfb_odom* h) { return h ? h->device : -1; }
 
 int cfb_odom_create(int width, int height, float cx, float cy, float fx, float fy, float distThresh,
                     float angleThresh, cfb_odom** out) {
@@ -291,7 +310,7 @@ int cfb_odom_create(int width, int height, float cx, float cy, float fx, float f
     delete r;
     return set_error_msg(4, "odom_create: device allocation failed");
   }
-  *out = new cfb_odom{r, false};
+  *out = new cfb_odom{r, false, current_device()};
   return 0;
 }
 void cfb_odom_destroy(cfb_odom* o) {
@@ -303,27 +322,32 @@ void cfb_odom_destroy(cfb_odom* o) {
 int cfb_odom_init_icp(cfb_odom* o, const float* const depth_pyr[3], const size_t pitch[3], float cutoff,
                       void* stream) {
   REQUIRE(o && depth_pyr && pitch, "odom_init_icp");
+  DevScope dev_scope__(device_of(o));
   CK(o->impl.initICP(depth_pyr, pitch, cutoff, ST(stream)));
   return 0;
 }
 int cfb_odom_init_icp_model(cfb_odom* o, const float* v4, const float* n4, float cutoff, const float pose[16],
                             void* stream) {
   REQUIRE(o && v4 && n4 && pose, "odom_init_icp_model");
+  DevScope dev_scope__(device_of(o));
   CK(o->impl.initICPModel(v4, n4, cutoff, pose, ST(stream)));
   return 0;
 }
 int cfb_odom_init_rgb_model(cfb_odom* o, const uint8_t* img, size_t pitch, int channels, void* stream) {
   REQUIRE(o && img && (channels == 3 || channels == 4), "odom_init_rgb_model");
+  DevScope dev_scope__(device_of(o));
   CK(o->impl.initRGBModel(img, pitch, channels, ST(stream)));
   return 0;
 }
 int cfb_odom_init_rgb(cfb_odom* o, const uint8_t* img, size_t pitch, int channels, void* stream) {
   REQUIRE(o && img && (channels == 3 || channels == 4), "odom_init_rgb");
+  DevScope dev_scope__(device_of(o));
   CK(o->impl.initRGB(img, pitch, channels, ST(stream)));
   return 0;
 }
 int cfb_odom_init_first_rgb(cfb_odom* o, const uint8_t* img, size_t pitch, int channels, void* stream) {
   REQUIRE(o && img && (channels == 3 || channels == 4), "odom_init_first_rgb");
+  DevScope dev_scope__(device_of(o));
   CK(o->impl.initFirstRGB(img, pitch, channels, ST(stream)));
   return 0;
 }
@@ -332,6 +356,7 @@ int cfb_odom_get_incremental_transformation(cfb_odom* o, float trans[3], float r
                                             size_t err_pitch, int force_host_loop, cfb_track_stats* stats_out,
                                             void* stream) {
   REQUIRE(o && trans && rot, "odom_get_incremental_transformation");
+  DevScope dev_scope__(device_of(o));
   CK(o->impl.getIncrementalTransformation(trans, rot, rgbOnly != 0, icpWeight, pyramid != 0, fastOdom != 0,
                                           so3 != 0, err, err_pitch, force_host_loop != 0, ST(stream)));
   if (stats_out) memcpy(stats_out, &o->impl.stats(), sizeof(cfb_track_stats));
@@ -339,26 +364,31 @@ int cfb_odom_get_incremental_transformation(cfb_odom* o, float trans[3], float r
 }
 int cfb_odom_set_mode(cfb_odom* o, int mode) {
   REQUIRE(o && (mode == 0 || mode == 1), "odom_set_mode");
+  DevScope dev_scope__(device_of(o));
   o->impl.setMode(mode);
   return 0;
 }
 int cfb_odom_enable_kernel_timing(cfb_odom* o, int on) {
   REQUIRE(o, "odom_enable_kernel_timing");
+  DevScope dev_scope__(device_of(o));
   o->impl.enableKernelTiming(on != 0);
   return 0;
 }
 int cfb_odom_kernel_timing(cfb_odom* o, double* sum_ms, int* launches, int reset) {
   REQUIRE(o, "odom_kernel_timing");
+  DevScope dev_scope__(device_of(o));
   o->impl.kernelTiming(sum_ms, launches, reset != 0);
   return 0;
 }
 int cfb_odom_set_debug_trace(cfb_odom* o, void* dev_u64) {
   REQUIRE(o, "odom_set_debug_trace");
+  DevScope dev_scope__(device_of(o));
   o->impl.setDebugTrace(dev_u64);
   return 0;
 }
 int cfb_odom_view(cfb_odom* o, int which, int level, const void** dev_ptr, size_t* pitch) {
   REQUIRE(o && dev_ptr && pitch && level >= 0 && level < 3, "odom_view");
+  DevScope dev_scope__(device_of(o));
   *dev_ptr = o->impl.view(which, level, pitch);
   return *dev_ptr ? 0 : set_error_msg(2, "odom_view: unknown view");
 }
@@ -379,10 +409,13 @@ struct cfb_model {
   Model& m;
   cfb_odom odom_handle;
   cfb_model(Context* c, unsigned id, float conf, unsigned maxSurfels, bool fillIn)
-      : owned(new Model(c, id, conf, maxSurfels, fillIn)), m(*owned), odom_handle{&owned->odom, true} {}
-  explicit cfb_model(Model* b) : owned(nullptr), m(*b), odom_handle{&b->odom, true} {}
+      : owned(new Model(c, id, conf, maxSurfels, fillIn)), m(*owned), odom_handle{&owned->odom, true, c->device} {}
+  explicit cfb_model(Model* b) : owned(nullptr), m(*b), odom_handle{&b->odom, true, b->ctx->device} {}
   ~cfb_model() { delete owned; }
 };
+extern "C++" inline int device_of(const cfb_ctx* h) { return h ? h->c.device : -1; }
+extern "C++" inline int device_of(const cfb_model* h) { return h ? h->m.ctx->device : -1; }
+
 
 int cfb_ctx_create(int device, int W, int H, float fx, float fy, float cx, float cy, cfb_ctx** out) {
   REQUIRE(out && W >= 32 && H >= 32 && (W % 8) == 0 && (H % 4) == 0,
@@ -402,26 +435,31 @@ void cfb_ctx_destroy(cfb_ctx* c) { delete c; }
 void* cfb_ctx_stream(cfb_ctx* c) { return c ? (void*)c->c.stream : nullptr; }
 int cfb_ctx_upload_frame(cfb_ctx* c, const uint8_t* rgb, const float* depth, const uint8_t* mask) {
   REQUIRE(c && rgb && depth, "ctx_upload_frame");
+  DevScope dev_scope__(device_of(c));
   CK(c->c.uploadFrame(rgb, depth, mask));
   return 0;
 }
 int cfb_ctx_set_frame_device(cfb_ctx* c, const uint8_t* rgb, const float* depth, const uint8_t* mask) {
   REQUIRE(c && rgb && depth, "ctx_set_frame_device");
+  DevScope dev_scope__(device_of(c));
   CK(c->c.setFrameDevice(rgb, depth, mask, true));
   return 0;
 }
 int cfb_ctx_preprocess(cfb_ctx* c, float depthCutoff) {
   REQUIRE(c, "ctx_preprocess");
+  DevScope dev_scope__(device_of(c));
   CK(c->c.preprocess(depthCutoff));
   return 0;
 }
 int cfb_ctx_sync(cfb_ctx* c) {
   REQUIRE(c, "ctx_sync");
+  DevScope dev_scope__(device_of(c));
   CK(c->c.sync());
   return 0;
 }
 int cfb_ctx_view(cfb_ctx* c, int which, const void** dev_ptr, size_t* pitch) {
   REQUIRE(c && dev_ptr && pitch, "ctx_view");
+  DevScope dev_scope__(device_of(c));
   Context& x = c->c;
   switch (which) {
     case 0: *dev_ptr = x.rgb; *pitch = (size_t)x.W * 3; break;
@@ -444,6 +482,7 @@ int cfb_ctx_take_launch_count(cfb_ctx* c) {
 int cfb_model_create(cfb_ctx* c, unsigned id, float conf, unsigned max_surfels, int enable_fill_in,
                      cfb_model** out) {
   REQUIRE(c && out && max_surfels > 0 && id < 256, "model_create");
+  DevScope dev_scope__(device_of(c));
   *out = nullptr;
   cfb_model* m = new (std::nothrow) cfb_model(&c->c, id, conf, max_surfels, enable_fill_in != 0);
 
@@ -457,12 +496,14 @@ int cfb_model_create(cfb_ctx* c, unsigned id, float conf, unsigned max_surfels, 
 void cfb_model_destroy(cfb_model* m) { delete m; }
 int cfb_model_get_pose(cfb_model* m, float pose[16]) {
   REQUIRE(m && pose, "model_get_pose");
+  DevScope dev_scope__(device_of(m));
   CK(m->m.syncPose());
   memcpy(pose, m->m.pose, sizeof(float) * 16);
   return 0;
 }
 int cfb_model_override_pose(cfb_model* m, const float pose[16]) {
   REQUIRE(m && pose, "model_override_pose");
+  DevScope dev_scope__(device_of(m));
   CK(m->m.syncPose());
   memcpy(m->m.pose, pose, sizeof(float) * 16);
   memcpy(m->m.lastPose, pose, sizeof(float) * 16);
@@ -471,6 +512,7 @@ int cfb_model_override_pose(cfb_model* m, const float pose[16]) {
 }
 int cfb_model_set_pose_keep_last(cfb_model* m, const float pose[16]) {
   REQUIRE(m && pose, "model_set_pose_keep_last");
+  DevScope dev_scope__(device_of(m));
   CK(m->m.syncPose());
   memcpy(m->m.pose, pose, sizeof(float) * 16);
   CK(m->m.uploadPose());
@@ -479,17 +521,20 @@ int cfb_model_set_pose_keep_last(cfb_model* m, const float pose[16]) {
 int cfb_model_set_prediction(cfb_model* m, const float* v4, const float* n4, const uint8_t* img, int channels,
                              int device_ptrs) {
   REQUIRE(m && v4 && n4 && img && (channels == 3 || channels == 4), "model_set_prediction");
+  DevScope dev_scope__(device_of(m));
   CK(m->m.setPrediction(v4, n4, img, channels, device_ptrs != 0));
   return 0;
 }
 int cfb_model_init_first_rgb(cfb_model* m) {
   REQUIRE(m, "model_init_first_rgb");
+  DevScope dev_scope__(device_of(m));
   CK(m->m.initFirstRGB());
   return 0;
 }
 int cfb_model_perform_tracking(cfb_model* m, const cfb_track_params* p, float pose_out[16],
                                cfb_track_stats* stats_out) {
   REQUIRE(m && p, "model_perform_tracking");
+  DevScope dev_scope__(device_of(m));
   TrackParams tp;
   static_assert(sizeof(TrackParams) == sizeof(cfb_track_params), "track params layout");
   memcpy(&tp, p, sizeof(tp));
@@ -500,11 +545,13 @@ int cfb_model_perform_tracking(cfb_model* m, const cfb_track_params* p, float po
 }
 int cfb_model_set_confidence_threshold(cfb_model* m, float v) {
   REQUIRE(m, "model_set_confidence_threshold");
+  DevScope dev_scope__(device_of(m));
   m->m.confidenceThreshold = v;
   return 0;
 }
 int cfb_model_get_info(cfb_model* m, unsigned* id, float* confThresh, float* maxDepth) {
   REQUIRE(m, "model_get_info");
+  DevScope dev_scope__(device_of(m));
   if (id) *id = m->m.id;
   if (confThresh) *confThresh = m->m.confidenceThreshold;
   if (maxDepth) *maxDepth = m->m.maxDepth;
@@ -512,36 +559,43 @@ int cfb_model_get_info(cfb_model* m, unsigned* id, float* confThresh, float* max
 }
 int cfb_model_set_max_depth(cfb_model* m, float d) {
   REQUIRE(m, "model_set_max_depth");
+  DevScope dev_scope__(device_of(m));
   m->m.maxDepth = d;
   return 0;
 }
 int cfb_model_initialise(cfb_model* m, int time, float maxDepthProcessed) {
   REQUIRE(m, "model_initialise");
+  DevScope dev_scope__(device_of(m));
   CK(m->m.initialise(time, maxDepthProcessed));
   return 0;
 }
 int cfb_model_predict_indices(cfb_model* m, int time, float depthCutoff, int timeDelta) {
   REQUIRE(m, "model_predict_indices");
+  DevScope dev_scope__(device_of(m));
   CK(m->m.predictIndices(time, depthCutoff, timeDelta));
   return 0;
 }
 int cfb_model_fuse(cfb_model* m, int time, float depthCutoff, float weightMultiplier) {
   REQUIRE(m, "model_fuse");
+  DevScope dev_scope__(device_of(m));
   CK(m->m.fuse(time, depthCutoff, weightMultiplier));
   return 0;
 }
 int cfb_model_clean(cfb_model* m, int time, int timeDelta, float depthCutoff, float outlierCoefficient) {
   REQUIRE(m, "model_clean");
+  DevScope dev_scope__(device_of(m));
   CK(m->m.clean(time, timeDelta, depthCutoff, outlierCoefficient));
   return 0;
 }
 int cfb_model_combined_predict(cfb_model* m, float depthCutoff, int time, int maxTime, int timeDelta) {
   REQUIRE(m, "model_combined_predict");
+  DevScope dev_scope__(device_of(m));
   CK(m->m.combinedPredict(depthCutoff, time, maxTime, timeDelta));
   return 0;
 }
 int cfb_model_perform_fill_in(cfb_model* m, int frameToFrameRGB, int lost) {
   REQUIRE(m, "model_perform_fill_in");
+  DevScope dev_scope__(device_of(m));
   CK(m->m.performFillIn(frameToFrameRGB != 0, lost != 0));
   return 0;
 }
@@ -551,22 +605,26 @@ float cfb_model_compute_fusion_weight(cfb_model* m, float weightMultiplier) {
 }
 int cfb_model_download_map(cfb_model* m, float* dst, size_t cap, unsigned* count_out) {
   REQUIRE(m, "model_download_map");
+  DevScope dev_scope__(device_of(m));
   CK(m->m.downloadMap(dst, cap, count_out));
   return 0;
 }
 int cfb_model_upload_map(cfb_model* m, const float* src, unsigned count) {
   REQUIRE(m && (src || !count), "model_upload_map");
+  DevScope dev_scope__(device_of(m));
   CK(m->m.uploadMap(src, count));
   return 0;
 }
 int cfb_model_last_count(cfb_model* m, unsigned* count_out) {
   REQUIRE(m && count_out, "model_last_count");
+  DevScope dev_scope__(device_of(m));
   CK(m->m.lastCount(count_out));
   return 0;
 }
 cfb_odom* cfb_model_odometry(cfb_model* m) { return m ? &m->odom_handle : nullptr; }
 int cfb_model_view(cfb_model* m, int which, const void** dev_ptr, size_t* pitch) {
   REQUIRE(m && dev_ptr && pitch, "model_view");
+  DevScope dev_scope__(device_of(m));
   const size_t W = (size_t)m->m.ctx->W;
   switch (which) {
     case 0: *dev_ptr = m->m.predVertex; *pitch = W * 16; break;
@@ -596,10 +654,12 @@ struct cfb_segmentation {
   Segmentation* owned;
   Segmentation& s;
   int lastLabels = 0, lastModels = 0;
+  int device = current_device();
   cfb_segmentation(int W, int H) : owned(new Segmentation(W, H)), s(*owned) {}
   explicit cfb_segmentation(Segmentation* b) : owned(nullptr), s(*b) {}
   ~cfb_segmentation() { delete owned; }
 };
+extern "C++" inline int device_of(const cfb_segmentation* h) { return h ? h->device : -1; }
 void cfb_seg_default_params(cfb_seg_params* p) {
   static_assert(sizeof(cfb_seg_params) == sizeof(SegParams), "seg params layout");
   static_assert(sizeof(cfb_model_data) == sizeof(SegModelData), "model data layout");
@@ -623,6 +683,7 @@ int cfb_segmentation_create(int device, int W, int H, cfb_segmentation** out) {
 void cfb_segmentation_destroy(cfb_segmentation* s) { delete s; }
 int cfb_segmentation_slic(cfb_segmentation* s, const uint8_t* rgb, void* stream) {
   REQUIRE(s && rgb, "segmentation_slic");
+  DevScope dev_scope__(device_of(s));
   CK(s->s.slic(rgb, ST(stream)));
   return 0;
 }
@@ -634,6 +695,7 @@ int cfb_segmentation_perform_crf(cfb_segmentation* s, const uint8_t* rgb, const 
   REQUIRE(s && rgb && depth && modelIds && icpError && vertConf4 && prm && fullSeg && md_out && md_count &&
               hasNewLabel && numModels >= 1 && numModels <= CFB_SEG_MAX_MODELS,
           "segmentation_perform_crf");
+  DevScope dev_scope__(device_of(s));
   SegParams p;
   memcpy(&p, prm, sizeof(p));
   bool hn = false;
@@ -646,6 +708,7 @@ int cfb_segmentation_perform_crf(cfb_segmentation* s, const uint8_t* rgb, const 
 }
 int cfb_segmentation_view(cfb_segmentation* s, int which, const void** dev_ptr, size_t* bytes) {
   REQUIRE(s && dev_ptr && bytes, "segmentation_view");
+  DevScope dev_scope__(device_of(s));
   const Segmentation& g = s->s;
   const size_t N = g.N;
   switch (which) {
@@ -665,14 +728,18 @@ struct cfb_cofusion {
   CoFusion f;
   cfb_ctx ctx_handle;
   std::vector<cfb_model*> model_handles;
+  std::vector<cfb_model*> retired_handles;  // of models that left the active list: kept (callers may still hold them)
   cfb_cofusion(int d, int w, int h, float fx, float fy, float cx, float cy, const CoFusionParams& p)
       : f(d, w, h, fx, fy, cx, cy, p), ctx_handle(&f.ctx) {}
   ~cfb_cofusion() {
     for (auto* h : model_handles) delete h;
+    for (auto* h : retired_handles) delete h;
     delete seg_handle;
   }
   cfb_segmentation* seg_handle = nullptr;
-  void sync_handles() {  // handle[i] wraps model(i); handles of deactivated models are dropped
+  // handle[i] wraps model(i).  The handle of a model that left the active list stays valid memory until the
+  // cfb_cofusion is destroyed (its Model object lives on in the pool); it then refers to whatever that object holds.
+  void sync_handles() {
     std::vector<cfb_model*> next;
     for (size_t i = 0; i < f.numModels(); ++i) {
       cfb_model* h = nullptr;
@@ -683,10 +750,13 @@ struct cfb_cofusion {
         }
       next.push_back(h ? h : new cfb_model(f.model(i)));
     }
-    for (auto* old : model_handles) delete old;
+    for (auto* old : model_handles)
+      if (old) retired_handles.push_back(old);
     model_handles.swap(next);
   }
 };
+
+extern "C++" inline int device_of(const cfb_cofusion* h) { return h ? h->f.ctx.device : -1; }
 
 void cfb_cofusion_default_params(cfb_cofusion_params* p) {
   if (!p) return;
@@ -718,6 +788,7 @@ void cfb_cofusion_destroy(cfb_cofusion* f) { delete f; }
 int cfb_cofusion_process_frame(cfb_cofusion* f, const uint8_t* rgb, const float* depth, const uint8_t* mask,
                                int device_ptrs, float weightMultiplier) {
   REQUIRE(f && ((rgb && depth) || (f->f.shard.active() && f->f.shard.rank() != 0)), "cofusion_process_frame");
+  DevScope dev_scope__(device_of(f));
   CK(f->f.processFrame(rgb, depth, mask, device_ptrs != 0, weightMultiplier));
   if (f->f.params.enableMultipleModels) f->sync_handles();
   return 0;
@@ -725,6 +796,7 @@ int cfb_cofusion_process_frame(cfb_cofusion* f, const uint8_t* rgb, const float*
 int cfb_cofusion_process_frame_ex(cfb_cofusion* f, const cfb_frame* fr, const float* inPose16, float weightMultiplier,
                                   int bootstrap) {
   REQUIRE(f && fr && (!bootstrap || inPose16), "cofusion_process_frame_ex");
+  DevScope dev_scope__(device_of(f));
   REQUIRE((f->f.shard.active() && f->f.shard.rank() != 0) || (fr->rgb && (fr->depth || fr->depth_u16)), "cofusion_process_frame_ex: frame");
   FrameInput in;
   in.rgb = fr->rgb;
@@ -747,17 +819,20 @@ int cfb_nccl_unique_id(unsigned char id[128]) {
 }
 int cfb_cofusion_shard_init(cfb_cofusion* f, int rank, int world, const unsigned char id[128]) {
   REQUIRE(f && id, "cofusion_shard_init");
+  DevScope dev_scope__(device_of(f));
   const char* err = "";
   if (f->f.shardInit(rank, world, id, &err) != cudaSuccess) return set_error_msg(5, err);
   return 0;
 }
 int cfb_cofusion_enable_pose_logging(cfb_cofusion* f, int on) {
   REQUIRE(f, "cofusion_enable_pose_logging");
+  DevScope dev_scope__(device_of(f));
   f->f.enablePoseLogging(on != 0);
   return 0;
 }
 int cfb_cofusion_pose_log(cfb_cofusion* f, int index, int64_t* ts, float* pose7, int capacity, int* n) {
   REQUIRE(f && n && index >= 0 && (size_t)index < f->f.numModels(), "cofusion_pose_log");
+  DevScope dev_scope__(device_of(f));
   std::vector<int64_t> t;
   std::vector<float> p;
   CK(f->f.poseLog((size_t)index, &t, &p));
@@ -769,17 +844,20 @@ int cfb_cofusion_pose_log(cfb_cofusion* f, int index, int64_t* ts, float* pose7,
 }
 int cfb_cofusion_export_poses(cfb_cofusion* f, const char* dir) {
   REQUIRE(f && dir, "cofusion_export_poses");
+  DevScope dev_scope__(device_of(f));
   CK(f->f.exportPoses(dir));
   return 0;
 }
 int cfb_cofusion_save_ply(cfb_cofusion* f, const char* dir) {
   REQUIRE(f && dir, "cofusion_save_ply");
+  DevScope dev_scope__(device_of(f));
   CK(f->f.savePly(dir));
   return 0;
 }
 int cfb_cofusion_last_segmentation(cfb_cofusion* f, cfb_model_data* md_out, int* md_count, int* hasNewLabel,
                                    int* spawned_id, int* deactivated) {
   REQUIRE(f && md_count, "cofusion_last_segmentation");
+  DevScope dev_scope__(device_of(f));
   *md_count = (int)f->f.lastModelData.size();
   if (md_out && *md_count) memcpy(md_out, f->f.lastModelData.data(), sizeof(cfb_model_data) * *md_count);
   if (hasNewLabel) *hasNewLabel = f->f.lastHasNewLabel ? 1 : 0;
@@ -790,11 +868,13 @@ int cfb_cofusion_last_segmentation(cfb_cofusion* f, cfb_model_data* md_out, int*
 int cfb_cofusion_num_inactive_models(cfb_cofusion* f) { return f ? (int)f->f.inactiveModels.size() : 0; }
 int cfb_cofusion_set_batched_tracking(cfb_cofusion* f, int on) {
   REQUIRE(f, "cofusion_set_batched_tracking");
+  DevScope dev_scope__(device_of(f));
   f->f.batchedTracking = on != 0;
   return 0;
 }
 int cfb_cofusion_set_debug_trace(cfb_cofusion* f, void* dev_u64) {
   REQUIRE(f && !f->f.models.empty(), "cofusion_set_debug_trace");
+  DevScope dev_scope__(device_of(f));
   f->f.models[0]->odom.setDebugTrace(dev_u64);
   return 0;
 }
@@ -805,6 +885,7 @@ cfb_segmentation* cfb_cofusion_segmentation(cfb_cofusion* f) {
 }
 int cfb_cofusion_spawn_object_model(cfb_cofusion* f, unsigned id, const float* initialPose16) {
   REQUIRE(f && id > 0 && id < 256, "cofusion_spawn_object_model");
+  DevScope dev_scope__(device_of(f));
   CK(f->f.spawnObjectModel(id, initialPose16));
   f->sync_handles();
   return 0;
@@ -818,6 +899,7 @@ cfb_model* cfb_cofusion_model(cfb_cofusion* f, int index) {
 cfb_ctx* cfb_cofusion_ctx(cfb_cofusion* f) { return f ? &f->ctx_handle : nullptr; }
 int cfb_cofusion_last_stats(cfb_cofusion* f, int index, cfb_track_stats* out) {
   REQUIRE(f && out && index >= 0 && (size_t)index < f->f.numModels(), "cofusion_last_stats");
+  DevScope dev_scope__(device_of(f));
   TrackStats st;
   CK(f->f.stats((size_t)index, &st));
   memcpy(out, &st, sizeof(cfb_track_stats));

@@ -156,15 +156,17 @@ int grid_for(int N, int per_thread) {
 
 }  // namespace
 
-int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+int num_sms() {  // of the CURRENT device (the ABI entries run under the device of their handle)
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!cache[dev]) {
+    int n = 0;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    cache[dev] = n > 0 ? n : 148;
   }
-  return n;
+  return cache[dev];
 }
 
 cudaError_t launch_icp_step(const IcpArgs& a, const IcpPose* d_pose, StepScratch* sc, cudaStream_t s) {
