@@ -344,11 +344,12 @@ def main():
     ms, launches, (kms, kn), nsurf, mine = timed(devf, sampler)
     ms_e2e, _, _, _, _ = timed(host)
     if rank != 0:
+        # done: the reductions inside timed() were the last collectives.  Leave without a rank-by-rank tear-down of
+        # the communicators (rank 0 still has its report to assemble and must not be waited for)
         torch.cuda.synchronize()
-        keep.clear()
-        dist.barrier()
-        dist.destroy_process_group()
-        return
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
     value = sharding.aggregate_value(n_models, args.steps, ms)
     e2e = sharding.aggregate_value(n_models, args.steps, ms_e2e)
@@ -416,10 +417,13 @@ def main():
     }
     print(json.dumps(line), flush=True)
     torch.cuda.synchronize()
-    keep.clear()
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # every rank has finished its timed loops (the max-over-ranks reductions above are collective): leave
+        # without tearing communicators down rank by rank -- a rank that is slow to exit must not hold the others
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+    keep.clear()
 
 
 if __name__ == "__main__":

@@ -14,6 +14,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool ok() const { return GetUniqueId && CommInitRank && CommDestroy && Broadcast && GetErrorString; }
@@ -32,6 +33,7 @@ NcclApi& nccl() {
       api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
       api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
       api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+      api.CommAbort = (decltype(api.CommAbort))dlsym(api.handle, "ncclCommAbort");
       api.Broadcast = (decltype(api.Broadcast))dlsym(api.handle, "ncclBroadcast");
       api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
     }
@@ -99,8 +101,13 @@ int FrameShard::init(int rank, int world, const unsigned char id[128], size_t pa
 }
 
 FrameShard::~FrameShard() {
+  // every broadcast this rank issued has completed: release the communicator without waiting for the peers
+  // (ncclCommDestroy finalises collectively and was seen to hang at the end of a 4-rank run; abort is local)
   if (stream_) cudaStreamSynchronize(stream_);
-  if (comm_ && nccl().CommDestroy) nccl().CommDestroy((ncclComm_t)comm_);
+  if (comm_ && nccl().CommAbort)
+    nccl().CommAbort((ncclComm_t)comm_);
+  else if (comm_ && nccl().CommDestroy)
+    nccl().CommDestroy((ncclComm_t)comm_);
   for (int k = 0; k < 2; ++k) {
     cudaFree(buf_[k]);
     if (evDone_[k]) cudaEventDestroy(evDone_[k]);
