@@ -102,6 +102,7 @@ struct TParams {
   size_t err_pitch;
   float distThres, angleThres, maxDepthDelta, sobelScale, icpWeight;
   int use_so3;
+  int direct_poll;  // the reading threads wait on their own words (no one-thread hint stage before them)
   int iters[3];
   unsigned o_wrow, o_blk, o_out, o_corr;
   unsigned long long* dbg;
@@ -813,12 +814,14 @@ template <int NS>
 __device__ __forceinline__ void collect_sums(unsigned round, int nactive_threads) {
   TSMEM();
   const unsigned G = gridDim.x;
-  if (threadIdx.x == 0) {
-    const unsigned long long* w0 = p.xacc + (size_t)round * p.nmodels * kXWords * kXStride;
-    while ((unsigned)(ld_u64_relaxed(w0) & 0xffull) != G) {
+  if (!p.direct_poll) {
+    if (threadIdx.x == 0) {
+      const unsigned long long* w0 = p.xacc + (size_t)round * p.nmodels * kXWords * kXStride;
+      while ((unsigned)(ld_u64_relaxed(w0) & 0xffull) != G) {
+      }
     }
+    __syncthreads();
   }
-  __syncthreads();
   const int t = threadIdx.x;
   if (t < nactive_threads) {
     const int m = t / NS, j = t - m * NS;
@@ -1353,13 +1356,12 @@ __device__ __noinline__ void run_level(int lvl, int q0, int nit, unsigned round0
         phase1<false, false>(lvl, m);
     }
     __syncthreads();
-    if ((int)threadIdx.x < NM) {  // integer sums commute exactly; the payload rides on the arrival itself
-      unsigned cc = 0, ss = 0;
-      for (int w = 0; w < kNW; ++w) {
-        cc += (unsigned)sm.cntw[threadIdx.x][w];
-        ss += (unsigned)sm.sigw[threadIdx.x][w];
-      }
-      red_add_u64(&p.acnt[round * kMaxM + threadIdx.x], 1ull | ((unsigned long long)cc << 8) | ((unsigned long long)ss << 32));
+    if ((int)warp < NM) {  // integer sums commute exactly; the payload rides on the arrival itself (warp m: model m)
+      unsigned cc = lane < kNW ? (unsigned)sm.cntw[warp][lane] : 0u, ss = lane < kNW ? (unsigned)sm.sigw[warp][lane] : 0u;
+      cc = __reduce_add_sync(0xffffffffu, cc);
+      ss = __reduce_add_sync(0xffffffffu, ss);
+      if (lane == 0)
+        red_add_u64(&p.acnt[round * kMaxM + warp], 1ull | ((unsigned long long)cc << 8) | ((unsigned long long)ss << 32));
     }
     DBG_MARK(8 + q * 8 + 1);
     DBG_CTA(q, 1);
@@ -1929,6 +1931,11 @@ cudaError_t RGBDOdometry::trackTiled(RGBDOdometry* const* od, int n, float (*tra
   p.sobelScale = f.sobelScale;
   p.icpWeight = icpWeight;
   p.use_so3 = so3 ? 1 : 0;
+  {
+    // default on: 0.286 -> 0.280 ms per launch (one L2 round trip less per iteration); CFB_TILED_DIRECT=0 for A/B
+    static const int direct = getenv("CFB_TILED_DIRECT") ? atoi(getenv("CFB_TILED_DIRECT")) : 1;
+    p.direct_poll = direct;
+  }
   p.iters[0] = fastOdom ? 3 : 10;
   p.iters[1] = pyramid ? 5 : 0;
   p.iters[2] = pyramid ? 4 : 0;
