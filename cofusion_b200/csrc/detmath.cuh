@@ -17,7 +17,15 @@ __host__ __device__ __forceinline__ float det_expf(float x) {
   // selected at the end (same values as `if (!(x >= -87)) return x != x ? x : 0; if (x > 88) x = 88;`)
   const float x_in = x;
   x = fminf(fmaxf(x, -87.0f), 88.0f);
+#ifdef __CUDA_ARCH__
+  // rint and the float -> int conversion both issue on the quarter-rate conversion pipe, and this function runs 169
+  // times per pixel of the bilateral filter.  Adding 1.5 * 2^23 rounds to the nearest integer, ties to even -- exactly
+  // rintf for |v| < 2^22 -- and the integer is then the difference of the bit patterns.  Same n, same result.
+  const float tmagic = __fadd_rn(__fmul_rn(x, 1.44269504088896341f), 12582912.0f);
+  const float n = __fadd_rn(tmagic, -12582912.0f);
+#else
   const float n = rintf(x * 1.44269504088896341f);
+#endif
   float r = fmaf(n, -0.693359375f, x);
   r = fmaf(n, 2.12194440e-4f, r);
   float p = 1.9875691500E-4f;
@@ -27,7 +35,11 @@ __host__ __device__ __forceinline__ float det_expf(float x) {
   p = fmaf(p, r, 1.6666665459E-1f);
   p = fmaf(p, r, 5.0000001201E-1f);
   const float y = fmaf(p, r * r, r) + 1.0f;
+#ifdef __CUDA_ARCH__
+  const int e = __float_as_int(tmagic) - 0x4B400000;  // in [-126, 127]
+#else
   const int e = (int)n;  // in [-126, 127]
+#endif
   union {
     unsigned u;
     float f;
@@ -45,9 +57,10 @@ __device__ __forceinline__ float2 det_expf2_nonpos(float2 x) {
   const float2 x_in = x;
   x.x = fmaxf(x.x, -87.0f);
   x.y = fmaxf(x.y, -87.0f);
-  float2 n = __fmul2_rn(x, make_float2(1.44269504088896341f, 1.44269504088896341f));
-  n.x = rintf(n.x);
-  n.y = rintf(n.y);
+  // n = rint(x * log2 e) by the magic-number addition (see det_expf): packed adds instead of two conversions
+  const float2 tm = make_float2(__fadd_rn(__fmul_rn(x.x, 1.44269504088896341f), 12582912.0f),
+                                __fadd_rn(__fmul_rn(x.y, 1.44269504088896341f), 12582912.0f));
+  const float2 n = make_float2(__fadd_rn(tm.x, -12582912.0f), __fadd_rn(tm.y, -12582912.0f));
   float2 r = __ffma2_rn(n, make_float2(-0.693359375f, -0.693359375f), x);
   r = __ffma2_rn(n, make_float2(2.12194440e-4f, 2.12194440e-4f), r);
   float2 p = make_float2(1.9875691500E-4f, 1.9875691500E-4f);
@@ -58,8 +71,8 @@ __device__ __forceinline__ float2 det_expf2_nonpos(float2 x) {
   p = __ffma2_rn(p, r, make_float2(5.0000001201E-1f, 5.0000001201E-1f));
   const float2 y = __fadd2_rn(__ffma2_rn(p, __fmul2_rn(r, r), r), make_float2(1.0f, 1.0f));
   float2 sc;
-  sc.x = __int_as_float(((int)n.x + 127) << 23);
-  sc.y = __int_as_float(((int)n.y + 127) << 23);
+  sc.x = __int_as_float((__float_as_int(tm.x) - 0x4B400000 + 127) << 23);
+  sc.y = __int_as_float((__float_as_int(tm.y) - 0x4B400000 + 127) << 23);
   float2 v = __fmul2_rn(y, sc);
   v.x = (x_in.x >= -87.0f) ? v.x : ((x_in.x != x_in.x) ? x_in.x : 0.0f);
   v.y = (x_in.y >= -87.0f) ? v.y : ((x_in.y != x_in.y) ? x_in.y : 0.0f);
