@@ -375,6 +375,8 @@ cudaError_t CoFusion::processFrameEx(const FrameInput& in_, const float* inPose,
       }
     }
     mark(2);
+    RET_IF(cudaEventRecord(ctx.evTracked, ctx.stream));  // the next frame's frame side starts behind the tracker
+    ctx.trackedRecorded = true;
     g_ft.mark(ctx.stream, "tracked");
     if (bootstrap) {  // globalModel->overridePose(globalModel->getPose() * inPose) (CoFusion.cpp:219-222)
       Model* g = models[0].get();

@@ -1477,6 +1477,8 @@ template <bool GENERAL, bool DBGT>
 __global__ void __launch_bounds__(kT, 1) gn_tiled_kernel(const TParams kp) {
   extern __shared__ __align__(128) unsigned char dyn_smem_raw[];
   TFixed& sm = *reinterpret_cast<TFixed*>(dyn_smem_raw);
+  // launched as a programmatic dependent (plain launch, CFB_TILED_PLAIN): wait for the kernel before; a no-op otherwise
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   {  // parameters -> shared memory (the phase functions are not inlined)
     const int* src = reinterpret_cast<const int*>(&kp);
     int* dst = reinterpret_cast<int*>(&sm.prm);
@@ -1956,7 +1958,25 @@ cudaError_t RGBDOdometry::trackTiled(RGBDOdometry* const* od, int n, float (*tra
   }
   void* args[] = {(void*)&p};
   if (f.time_kernel_) RET_IF(cudaEventRecord(f.ev_k0_, s));
-  RET_IF(cudaLaunchCooperativeKernel(kernels[variant], dim3(ts.gx * ts.gy), dim3(kT), args, ts.smem_bytes, s));
+  // The grid barrier is the kernel's own (atomics); a cooperative launch only adds the guarantee that all CTAs are
+  // co-resident, which one CTA per SM on an otherwise draining GPU has anyway.  CFB_TILED_PLAIN=1 (experiment): plain
+  // launch with the programmatic-dependency attribute, so that the launch latency hides behind the prepare kernel.
+  static const bool plain = getenv("CFB_TILED_PLAIN") != nullptr;
+  if (plain) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ts.gx * ts.gy);
+    cfg.blockDim = dim3(kT);
+    cfg.dynamicSmemBytes = ts.smem_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    RET_IF(cudaLaunchKernelExC(&cfg, kernels[variant], args));
+  } else {
+    RET_IF(cudaLaunchCooperativeKernel(kernels[variant], dim3(ts.gx * ts.gy), dim3(kT), args, ts.smem_bytes, s));
+  }
   if (f.time_kernel_) {
     RET_IF(cudaEventRecord(f.ev_k1_, s));
     f.ev_pending_ = true;

@@ -1,6 +1,8 @@
 // pipeline.cu -- cfb::Context / cfb::Model (see pipeline.cuh).
 #include "pipeline.cuh"
 
+#include <stdlib.h>
+
 #include <float.h>
 #include <math.h>
 #include <string.h>
@@ -39,6 +41,7 @@ Context::Context(int dev, int w, int h, float fx, float fy, float cx, float cy)
            cudaEventCreateWithFlags(&evPre[k], cudaEventDisableTiming) == cudaSuccess;
   }
   good = good && cudaEventCreateWithFlags(&evOrder, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&evTracked, cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&evOrder2, cudaEventDisableTiming) == cudaSuccess &&
          cudaStreamCreateWithFlags(&preStream, cudaStreamNonBlocking) == cudaSuccess;
   rgb = rgbBuf[0];
@@ -79,6 +82,7 @@ Context::~Context() {
   }
   if (evFork) cudaEventDestroy(evFork);
   if (evOrder) cudaEventDestroy(evOrder);
+  if (evTracked) cudaEventDestroy(evTracked);
   if (evOrder2) cudaEventDestroy(evOrder2);
   if (preStream) cudaStreamDestroy(preStream);
   cudaFree(mask);
@@ -100,6 +104,10 @@ cudaError_t Context::beginFrame(bool inputs_follow_stream) {
   for (int i = 0; i < 3; ++i) depthPyr[i] = depthPyrBuf[cur][i];
   RET_IF(cudaStreamWaitEvent(copyStream, evBufferFree[cur], 0));
   RET_IF(cudaStreamWaitEvent(preStream, evBufferFree[cur], 0));
+  {
+    static const bool early = getenv("CFB_PRE_EARLY") != nullptr;  // A/B switch (tools): do not wait for the tracker
+    if (trackedRecorded && !early) RET_IF(cudaStreamWaitEvent(preStream, evTracked, 0));
+  }
   if (inputs_follow_stream) {
     RET_IF(cudaEventRecord(evOrder, stream));
     RET_IF(cudaStreamWaitEvent(preStream, evOrder, 0));

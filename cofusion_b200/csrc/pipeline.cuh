@@ -59,6 +59,11 @@ class Context {
   // many small surfel kernels of frame t, which leave most SMs idle.  `stream` joins at evPre.
   cudaStream_t preStream = nullptr;
   cudaEvent_t evInputs[2] = {nullptr, nullptr}, evPre[2] = {nullptr, nullptr}, evOrder = nullptr, evOrder2 = nullptr;
+  // recorded after the tracker launch of a frame: the frame side of the NEXT frame starts behind it.  The tracker
+  // needs every SM (one CTA each, all of the shared memory); a bilateral filter in flight at that moment holds it
+  // up, while the surfel kernels after the tracker leave room for it.
+  cudaEvent_t evTracked = nullptr;
+  bool trackedRecorded = false;
   float* depthFilteredBuf[2] = {nullptr, nullptr};
   float* depthPyrBuf[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
   float* depthFiltered = nullptr;   // level 0 of the pyramid of the CURRENT frame
