@@ -24,4 +24,22 @@ _, rgb, d, _, _ = seq[-1]
 full, mds, hn = seg.perform_crf(torch.from_numpy(np.ascontiguousarray(rgb)).cuda(), torch.from_numpy(np.ascontiguousarray(d)).cuda(),
                                 [m.info()[0] for m in ms], [m.view_ptr(3) for m in ms], [m.view_ptr(9) for m in ms], 3, True)
 torch.cuda.synchronize()
+# the closed loop of tests/test_configs_gpu.py::test_config2 (640x480, spawns from frame 4, a loss within 12 frames):
+# the segmentation decides spawn / loss -> pooled models (recycle), per-model streams, object-model tracker phases
+W2, H2, K2 = 640, 480, synth.K_DEFAULT
+p = cfb.CoFusionParams.default(1 << 19)
+p.confGlobalInit = 1.5
+p.enableMultipleModels = 1
+p.modelSpawnOffset = 2
+p.seg.unaryWeightError = 150.0
+p.seg.unaryThresholdNew = 3.5
+cl = cfb.CoFusion(W2, H2, K2, p)
+ids_seen, lost = set(), 0
+for t, (_, rgb, d, _, _) in enumerate(synth.room_sequence(14, W2, H2, K2, noise=True, n_boxes=4, box_speed=4.0, box_start=3)):
+    cl.process_frame(np.ascontiguousarray(rgb), np.ascontiguousarray(d))
+    ids_seen.update(cl.model(i).info()[0] for i in range(cl.num_models))
+    if t > 0:
+        lost += cl.last_segmentation()[3]
+torch.cuda.synchronize()
+print("closed loop: models seen", sorted(ids_seen), "live", cl.num_models, "lost", lost, "inactive", cl.num_inactive_models)
 print("sanitize_smoke done: models", len(ms), "labels", len(mds), "surfels", [m.last_count() for m in ms])
