@@ -312,10 +312,7 @@ cudaError_t CoFusion::processFrameEx(const FrameInput& in_, const float* inPose,
   mark(0);
   g_ft.begin();
   g_ft.mark(ctx.stream, "start");
-  {  // see cfb_common.cuh (CFB_PDL_ALL: tools, keeps it on for multi-stream frames too)
-    static const bool all = getenv("CFB_PDL_ALL") != nullptr;
-    pdl_set(all || (models.size() == 1 && !params.enableMultipleModels));
-  }
+  pdl_set(models.size() == 1 && !params.enableMultipleModels);  // see cfb_common.cuh
   // device inputs produced on the pipeline stream itself (the broadcast of the sharded path, a caller's own stream)
   // are ordered after it; otherwise the frame side starts right away, next to the previous frame's tail
   RET_IF(ctx.uploadFrameRaw(in.rgb, in.flipColors, in.depth, in.depth16, in.depthScale, in.mask, device_ptrs,

@@ -102,7 +102,6 @@ struct TParams {
   size_t err_pitch;
   float distThres, angleThres, maxDepthDelta, sobelScale, icpWeight;
   int use_so3;
-  int direct_poll;  // the reading threads wait on their own words (no one-thread hint stage before them)
   int iters[3];
   unsigned o_wrow, o_blk, o_out, o_corr;
   unsigned long long* dbg;
@@ -808,20 +807,13 @@ __device__ __forceinline__ void publish_sums(unsigned round, bool fold_rows) {
   red_add_u64(x + kXStride, ((unsigned long long)lo << 8) + 1ull);
 }
 
-// one thread waits until word 0 of model 0 shows every CTA (a hint, no fence anywhere); then thread t < nm * NS
-// reads its two words -- again if one of them does not count G contributions yet -- into outd[m][j] (double)
+// thread t < nm * NS reads its two words -- again while one of them does not count G contributions yet -- into
+// outd[m][j] (double).  No fence anywhere: a word is complete when its low byte says so.  (A one-thread wait on word 0
+// in front of the readers, as a hint, cost one L2 round trip per iteration: 0.286 -> 0.280 ms per launch without it.)
 template <int NS>
 __device__ __forceinline__ void collect_sums(unsigned round, int nactive_threads) {
   TSMEM();
   const unsigned G = gridDim.x;
-  if (!p.direct_poll) {
-    if (threadIdx.x == 0) {
-      const unsigned long long* w0 = p.xacc + (size_t)round * p.nmodels * kXWords * kXStride;
-      while ((unsigned)(ld_u64_relaxed(w0) & 0xffull) != G) {
-      }
-    }
-    __syncthreads();
-  }
   const int t = threadIdx.x;
   if (t < nactive_threads) {
     const int m = t / NS, j = t - m * NS;
@@ -1477,8 +1469,6 @@ template <bool GENERAL, bool DBGT>
 __global__ void __launch_bounds__(kT, 1) gn_tiled_kernel(const TParams kp) {
   extern __shared__ __align__(128) unsigned char dyn_smem_raw[];
   TFixed& sm = *reinterpret_cast<TFixed*>(dyn_smem_raw);
-  // launched as a programmatic dependent (plain launch, CFB_TILED_PLAIN): wait for the kernel before; a no-op otherwise
-  asm volatile("griddepcontrol.wait;" ::: "memory");
   {  // parameters -> shared memory (the phase functions are not inlined)
     const int* src = reinterpret_cast<const int*>(&kp);
     int* dst = reinterpret_cast<int*>(&sm.prm);
@@ -1933,11 +1923,6 @@ cudaError_t RGBDOdometry::trackTiled(RGBDOdometry* const* od, int n, float (*tra
   p.sobelScale = f.sobelScale;
   p.icpWeight = icpWeight;
   p.use_so3 = so3 ? 1 : 0;
-  {
-    // default on: 0.286 -> 0.280 ms per launch (one L2 round trip less per iteration); CFB_TILED_DIRECT=0 for A/B
-    static const int direct = getenv("CFB_TILED_DIRECT") ? atoi(getenv("CFB_TILED_DIRECT")) : 1;
-    p.direct_poll = direct;
-  }
   p.iters[0] = fastOdom ? 3 : 10;
   p.iters[1] = pyramid ? 5 : 0;
   p.iters[2] = pyramid ? 4 : 0;
@@ -1958,25 +1943,8 @@ cudaError_t RGBDOdometry::trackTiled(RGBDOdometry* const* od, int n, float (*tra
   }
   void* args[] = {(void*)&p};
   if (f.time_kernel_) RET_IF(cudaEventRecord(f.ev_k0_, s));
-  // The grid barrier is the kernel's own (atomics); a cooperative launch only adds the guarantee that all CTAs are
-  // co-resident, which one CTA per SM on an otherwise draining GPU has anyway.  CFB_TILED_PLAIN=1 (experiment): plain
-  // launch with the programmatic-dependency attribute, so that the launch latency hides behind the prepare kernel.
-  static const bool plain = getenv("CFB_TILED_PLAIN") != nullptr;
-  if (plain) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(ts.gx * ts.gy);
-    cfg.blockDim = dim3(kT);
-    cfg.dynamicSmemBytes = ts.smem_bytes;
-    cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    RET_IF(cudaLaunchKernelExC(&cfg, kernels[variant], args));
-  } else {
-    RET_IF(cudaLaunchCooperativeKernel(kernels[variant], dim3(ts.gx * ts.gy), dim3(kT), args, ts.smem_bytes, s));
-  }
+  // (a plain launch with the programmatic-dependency attribute instead of the cooperative one was measured: no gain)
+  RET_IF(cudaLaunchCooperativeKernel(kernels[variant], dim3(ts.gx * ts.gy), dim3(kT), args, ts.smem_bytes, s));
   if (f.time_kernel_) {
     RET_IF(cudaEventRecord(f.ev_k1_, s));
     f.ev_pending_ = true;

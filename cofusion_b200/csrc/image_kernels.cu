@@ -36,10 +36,10 @@ constexpr int BR = 6;
 // Rows per thread.  Measured on B200 (VGA): 1 row/thread 78 us (1200 CTAs on 1184 resident slots: the
 // last 16 run as a short second wave), 3 rows/thread 160 us -- the kernel lives on occupancy (64
 // warps/SM hide the exp() dependency chains), so the single-row shape stays.
-// TR = rows of a tile (8 threads in y: a tile of 9 rows gives warp 0 a second row).  A 640x480 frame is 1200 tiles of
-// 32x8 on 1184 resident CTA slots (148 SMs x 8): the last 16 tiles run as a second, nearly empty wave.  With 9-row
-// tiles the frame is 1080 CTAs, one wave.
-template <int TR>
+// A 640x480 frame is 1200 tiles of 32x8 on 1184 resident CTA slots (148 SMs x 8): the last 16 tiles run as a second,
+// nearly empty wave.  9-row tiles (1080 CTAs, one wave, warp 0 takes a second row) were measured: no faster
+// (0.620 vs 0.618 ms per frame) -- the kernels of the other stream fill that tail anyway.
+constexpr int TR = 8;
 __global__ void __launch_bounds__(256) bilateral_kernel(const float* __restrict__ depth, size_t dpitch, int W, int H,
                                                         float maxD, float* __restrict__ out, size_t opitch) {
   pdl_prologue();
@@ -640,14 +640,7 @@ cudaError_t launch_pyramid2(int njobs, const void* const* src, void* const* l1, 
 
 cudaError_t launch_bilateral(const float* depth, size_t dpitch, int W, int H, float maxD, float* out,
                              size_t opitch, cudaStream_t s) {
-  // 8-row tiles: 1200 CTAs at 640x480 on 1184 resident slots.  The 9-row shape (1080 CTAs, one wave) was measured
-  // and is no faster (0.620 vs 0.618 ms per frame: other streams' kernels fill the tail of the second wave anyway).
-  static const bool nine = getenv("CFB_BILATERAL_ROWS") && atoi(getenv("CFB_BILATERAL_ROWS")) == 9;  // A/B switch (tools)
-  const int gx = (W + 31) / 32;
-  if (nine)
-    CFB_PDL(launch_pdl(bilateral_kernel<9>, dim3(gx, (H + 8) / 9), kBlock, 0, s, depth, dpitch, W, H, maxD, out, opitch));
-  else
-    CFB_PDL(launch_pdl(bilateral_kernel<8>, dim3(gx, (H + 7) / 8), kBlock, 0, s, depth, dpitch, W, H, maxD, out, opitch));
+  CFB_PDL(launch_pdl(bilateral_kernel, dim3((W + 31) / 32, (H + TR - 1) / TR), kBlock, 0, s, depth, dpitch, W, H, maxD, out, opitch));
   return cudaGetLastError();
 }
 cudaError_t launch_pyr_down_gauss_f(const float* src, size_t spitch, int sw, int sh, float* dst,

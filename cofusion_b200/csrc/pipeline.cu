@@ -105,10 +105,9 @@ cudaError_t Context::beginFrame(bool inputs_follow_stream) {
   RET_IF(cudaStreamWaitEvent(copyStream, evBufferFree[cur], 0));
   RET_IF(cudaStreamWaitEvent(preStream, evBufferFree[cur], 0));
   {
-    static const bool early = getenv("CFB_PRE_EARLY") != nullptr;  // A/B switch (tools): do not wait for the tracker
     // (with the segmentation in the loop the frame has a host synchronisation in its middle and the early start wins:
     //  933 vs 903 frames/s on the 4-object scene; without it 0.625 vs 0.633 ms per frame the other way round)
-    if (trackedRecorded && !early && !keepMask) RET_IF(cudaStreamWaitEvent(preStream, evTracked, 0));
+    if (trackedRecorded && !keepMask) RET_IF(cudaStreamWaitEvent(preStream, evTracked, 0));
   }
   if (inputs_follow_stream) {
     RET_IF(cudaEventRecord(evOrder, stream));

@@ -305,13 +305,13 @@ __global__ void index_project_kernel(SurfelGeom g, const Surfel* __restrict__ su
   atomicMin(&keys[py * g.W + px], key);
 }
 __global__ void index_resolve_kernel(SurfelGeom g, const Surfel* __restrict__ surfels, PoseRef t_inv_ref,
-                                     unsigned long long* __restrict__ keys, IndexMaps out, int reset_keys) {
+                                     unsigned long long* __restrict__ keys, IndexMaps out) {
   pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.W * g.H) return;
   const Pose34 t_inv = resolve_pose(t_inv_ref);
   const unsigned long long k = keys[i];
-  if (reset_keys) keys[i] = ~0ull;  // the buffer is left as the next projection pass expects it (no memset between passes)
+  keys[i] = ~0ull;  // the buffer is left as the next projection pass expects it (no memset between passes)
   if (k == ~0ull) {
     out.index[i] = 0;
     const float4 z = make_float4(0, 0, 0, 0);
@@ -716,14 +716,14 @@ __global__ void splat_raster_kernel(SurfelGeom g, const Surfel* __restrict__ sur
 }
 __global__ void splat_resolve_kernel(SurfelGeom g, const Surfel* __restrict__ surfels, PoseRef t_inv_ref, float maxDepth,
                                      float confThreshold, int time, int maxTime, int timeDelta,
-                                     unsigned long long* __restrict__ keys, SplatMaps out, int reset_keys) {
+                                     unsigned long long* __restrict__ keys, SplatMaps out) {
   pdl_prologue();
   const int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
   if (px >= g.W || py >= g.H) return;
   const Pose34 t_inv = resolve_pose(t_inv_ref);
   const int i = py * g.W + px;
   const unsigned long long k = keys[i];
-  if (reset_keys) keys[i] = ~0ull;  // the buffer is left as the next projection pass expects it (no memset between passes)
+  keys[i] = ~0ull;  // the buffer is left as the next projection pass expects it (no memset between passes)
   if (k == ~0ull) {
     out.image[i] = make_uchar4(0, 0, 0, 0);
     out.vertexConf[i] = make_float4(0, 0, 0, 0);
@@ -854,12 +854,10 @@ cudaError_t launch_predict_indices(const SurfelGeom& g, const Surfel* surfels, u
                                    int timeDelta, unsigned long long* keys, IndexMaps out, cudaStream_t s) {
   const unsigned n = (unsigned)g.W * g.H;
   // keys: all ones on entry (Model construction, then every resolve pass restores it)
-  static const bool memset_keys = getenv("CFB_KEYS_MEMSET") != nullptr;  // A/B switch (tools)
-  if (memset_keys) RET_IF(cudaMemsetAsync(keys, 0xFF, (size_t)n * 8, s));
   if (count_ub)
     CFB_PDL(launch_pdl(index_project_kernel, cdiv(count_ub, 256), 256, 0, s, g, surfels, count_ub, ctr, t_inv, time, maxDepth,
                                                              timeDelta, keys));
-  CFB_PDL(launch_pdl(index_resolve_kernel, cdiv(n, 256), 256, 0, s, g, surfels, t_inv, keys, out, memset_keys ? 0 : 1));
+  CFB_PDL(launch_pdl(index_resolve_kernel, cdiv(n, 256), 256, 0, s, g, surfels, t_inv, keys, out));
   return cudaGetLastError();
 }
 
@@ -902,13 +900,11 @@ cudaError_t launch_clean(const SurfelGeom& g, Surfel* src, Surfel* unstable, Sur
 cudaError_t launch_combined_predict(const SurfelGeom& g, const Surfel* surfels, unsigned count_ub, MapCounters* ctr,
                                     const PoseRef& t_inv, float maxDepth, float confThreshold, int time, int maxTime,
                                     int timeDelta, unsigned long long* keys, SplatMaps out, cudaStream_t s) {
-  static const bool memset_keys = getenv("CFB_KEYS_MEMSET") != nullptr;
-  if (memset_keys) RET_IF(cudaMemsetAsync(keys, 0xFF, (size_t)g.W * g.H * 8, s));
   if (count_ub)
     CFB_PDL(launch_pdl(splat_raster_kernel, cdiv(count_ub, 128), 128, 0, s, g, surfels, count_ub, ctr, t_inv, maxDepth, confThreshold,
                                                             time, maxTime, timeDelta, keys));
   const dim3 b(32, 8), gr(cdiv(g.W, 32), cdiv(g.H, 8));
-  CFB_PDL(launch_pdl(splat_resolve_kernel, gr, b, 0, s, g, surfels, t_inv, maxDepth, confThreshold, time, maxTime, timeDelta, keys, out, memset_keys ? 0 : 1));
+  CFB_PDL(launch_pdl(splat_resolve_kernel, gr, b, 0, s, g, surfels, t_inv, maxDepth, confThreshold, time, maxTime, timeDelta, keys, out));
   return cudaGetLastError();
 }
 
