@@ -24,6 +24,9 @@ _, rgb, d, _, _ = seq[-1]
 full, mds, hn = seg.perform_crf(torch.from_numpy(np.ascontiguousarray(rgb)).cuda(), torch.from_numpy(np.ascontiguousarray(d)).cuda(),
                                 [m.info()[0] for m in ms], [m.view_ptr(3) for m in ms], [m.view_ptr(9) for m in ms], 3, True)
 torch.cuda.synchronize()
+if os.environ.get("SANITIZE_PART") == "1":  # racecheck / synccheck are slow: the small part only
+    print("sanitize_smoke part 1 done: models", len(ms), "labels", len(mds), "surfels", [m.last_count() for m in ms])
+    sys.exit(0)
 # the closed loop of tests/test_configs_gpu.py::test_config2 (640x480, spawns from frame 4, a loss within 12 frames):
 # the segmentation decides spawn / loss -> pooled models (recycle), per-model streams, object-model tracker phases
 W2, H2, K2 = 640, 480, synth.K_DEFAULT
