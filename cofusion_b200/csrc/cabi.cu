@@ -626,10 +626,11 @@ int cfb_model_view(cfb_model* m, int which, const void** dev_ptr, size_t* pitch)
   REQUIRE(m && dev_ptr && pitch, "model_view");
   DevScope dev_scope__(device_of(m));
   const size_t W = (size_t)m->m.ctx->W;
+  const bool direct = m->m.usePrediction && !m->m.allowsFillIn;  // object models track against the splat maps themselves
   switch (which) {
-    case 0: *dev_ptr = m->m.predVertex; *pitch = W * 16; break;
-    case 1: *dev_ptr = m->m.predNormal; *pitch = W * 16; break;
-    case 2: *dev_ptr = m->m.predImage; *pitch = W * 4; break;
+    case 0: *dev_ptr = direct ? (const void*)m->m.splat.vertexConf : m->m.predVertex; *pitch = W * 16; break;
+    case 1: *dev_ptr = direct ? (const void*)m->m.splat.normalRad : m->m.predNormal; *pitch = W * 16; break;
+    case 2: *dev_ptr = direct ? (const void*)m->m.splat.image : m->m.predImage; *pitch = W * 4; break;
     case 3: *dev_ptr = m->m.icpError; *pitch = W * 4; break;
     case 4: *dev_ptr = m->m.indexMaps.index; *pitch = W * 4; break;
     case 5: *dev_ptr = m->m.indexMaps.vertConf; *pitch = W * 16; break;

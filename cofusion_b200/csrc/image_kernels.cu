@@ -428,6 +428,10 @@ struct FrameMapsArgs {
   int w[3], h[3];
   float fx_inv[3], fy_inv[3], cx[3], cy[3];
   float cutoff;
+  // optional: imageBGRToIntensity of up to two images of ni pixels rides along (the tracker's grey images)
+  const unsigned char* img[2];
+  unsigned char* grey[2];
+  int ch[2], ni;
 };
 __global__ void frame_maps_kernel(const FrameMapsArgs a) {
   pdl_prologue();
@@ -463,6 +467,18 @@ __global__ void frame_maps_kernel(const FrameMapsArgs a) {
       return;
     }
     p -= n;
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (p < a.ni) {
+      if (a.img[k]) {
+        const unsigned char* q = a.img[k] + (size_t)p * a.ch[k];
+        const float s = __fmaf_rn((float)q[2], 0.587f, __fmaf_rn((float)q[1], 0.299f, __fmul_rn((float)q[0], 0.114f)));
+        a.grey[k][p] = (unsigned char)(int)s;
+      }
+      return;
+    }
+    p -= a.ni;
   }
 }
 
@@ -726,9 +742,17 @@ cudaError_t launch_model_pyramid(const float* v4, const float* n4, int W, int H,
   return cudaGetLastError();
 }
 cudaError_t launch_frame_maps(const float* const depth[3], int W, int H, Intr K, float cutoff, float* const v[3],
-                              float* const n[3], cudaStream_t s) {
+                              float* const n[3], cudaStream_t s, const unsigned char* imgA, int chA, unsigned char* greyA,
+                              const unsigned char* imgB, int chB, unsigned char* greyB) {
   FrameMapsArgs a;
   int total = 0;
+  a.img[0] = imgA;
+  a.img[1] = imgB;
+  a.grey[0] = greyA;
+  a.grey[1] = greyB;
+  a.ch[0] = chA;
+  a.ch[1] = chB;
+  a.ni = (imgA || imgB) ? W * H : 0;
   for (int l = 0; l < 3; ++l) {
     const Intr k = K.level(l);
     a.depth[l] = depth[l];
@@ -743,6 +767,7 @@ cudaError_t launch_frame_maps(const float* const depth[3], int W, int H, Intr K,
     total += a.w[l] * a.h[l];
   }
   a.cutoff = cutoff;
+  total += 2 * a.ni;
   CFB_PDL(launch_pdl(frame_maps_kernel, (total + 255) / 256, 256, 0, s, a));
   return cudaGetLastError();
 }

@@ -44,7 +44,9 @@ cudaError_t launch_model_pyramid(const float* v4, const float* n4, int W, int H,
                                  float cutoffRGB, float* const v[3], float* const n[3], float* depth0,
                                  cudaStream_t s, const float* pose34_dev = nullptr /* device 3x4 pose overrides R, t */);
 cudaError_t launch_frame_maps(const float* const depth[3], int W, int H, Intr K, float cutoff, float* const v[3],
-                              float* const n[3], cudaStream_t s);
+                              float* const n[3], cudaStream_t s, const unsigned char* imgA = nullptr, int chA = 0,
+                              unsigned char* greyA = nullptr, const unsigned char* imgB = nullptr, int chB = 0,
+                              unsigned char* greyB = nullptr);
 cudaError_t launch_intensity2(const unsigned char* a, int cha, unsigned char* da, const unsigned char* b, int chb,
                               unsigned char* db, int n, cudaStream_t s);
 cudaError_t launch_pyr_down_uchar2(const unsigned char* sa, unsigned char* da, const unsigned char* sb,

@@ -203,8 +203,9 @@ cudaError_t RGBDOdometry::initAll(const float* v4, const float* n4, const unsign
   // lastDepth; the device loop reads lastDepth for both instead of building a second copy
   next_is_last_ = true;
   // frame side
-  RET_IF(launch_frame_maps(depthPyr, width, height, intr, depthCutoff, vmaps_curr_, nmaps_curr_, s));
-  RET_IF(launch_intensity2(modelImg, modelCh, lastImage[0], frameImg, frameCh, nextImage[0], width * height, s));
+  // + both grey images (model prediction, frame) in the same launch
+  RET_IF(launch_frame_maps(depthPyr, width, height, intr, depthCutoff, vmaps_curr_, nmaps_curr_, s, modelImg, modelCh, lastImage[0],
+                           frameImg, frameCh, nextImage[0]));
   {  // lastDepth + both grey images, both levels each, in ONE launch
     const void* src[3] = {lastDepth[0], lastImage[0], nextImage[0]};
     void* l1[3] = {lastDepth[1], lastImage[1], nextImage[1]};

@@ -294,6 +294,8 @@ Model::Model(Context* c, unsigned id_, float conf, unsigned maxSurfels, bool ena
   scan.host = new ScanHostState();
   // the projection passes take atomic minima into `keys`; the resolve passes leave it all ones again
   good = good && cudaMemset(keys, 0xFF, n * sizeof(unsigned long long)) == cudaSuccess;
+  // likewise `winner` (atomic minima of candidate ordinals): the winners of a fuse restore their entries
+  good = good && cudaMemset(winner, 0xFF, (size_t)maxSurfels * sizeof(uint32_t)) == cudaSuccess;
   good = good && cudaMallocHost(&h_counters, sizeof(MapCounters)) == cudaSuccess;
   if (good) memset(h_counters, 0, sizeof(MapCounters));
   // the pose block is followed by the tracker statistics of the frame: one read-back copy fetches both
@@ -363,6 +365,7 @@ cudaError_t Model::recycle(unsigned id_, float conf) {
   for (auto& z : zeroed_) RET_IF(cudaMemsetAsync(z.first, 0, z.second, work));
   *scan.host = ScanHostState();  // the ticket counter and the status words are zero again
   RET_IF(cudaMemsetAsync(keys, 0xFF, (size_t)ctx->W * ctx->H * sizeof(unsigned long long), work));
+  RET_IF(cudaMemsetAsync(winner, 0xFF, (size_t)capacity * sizeof(uint32_t), work));
   RET_IF(odom.recycle(work));
   return uploadPose();
 }
@@ -554,7 +557,7 @@ cudaError_t Model::predictIndices(int time, float depthCutoff, int timeDelta) {
 
 cudaError_t Model::fuse(int time, float depthCutoff, float weightMultiplier) {
   const float md = depthCutoff < maxDepth ? depthCutoff : maxDepth;  // Model.cpp:443
-  ctx->launches += 5;
+  ctx->launches += 3;  // associate, scan, apply
   return launch_fuse(geom(), buf[target], count_ub, counters, poseRef(), time, ctx->rgb, ctx->mask, ctx->depthRaw,
                      ctx->depthFiltered, md, WeightRef(&dpose->weightBase, weightMultiplier), id, indexMaps, winner,
                      candStaging, candBest, unstable, scan, work);
@@ -624,6 +627,8 @@ cudaError_t Model::prepareTracking(const TrackParams& tp, bool devicePose) {
     memcpy(lastPose, pose, sizeof(pose));
   }  // otherwise the tracker's epilogue moves pose -> last inside the device block
   cudaStream_t s = work;
+  const float *pv = predVertex, *pn = predNormal;
+  const uint8_t* pi = predImage;
   if (usePrediction) {
     // Model::initICP (Model.cpp:350-367): splat prediction, or the fill-in images when
     // CoFusion::requiresFillIn says so -- selected on the device (no host wait)
@@ -631,18 +636,16 @@ cudaError_t Model::prepareTracking(const TrackParams& tp, bool devicePose) {
       RET_IF(launch_select_prediction(geom(), counters, tp.frameToFrameRGB ? 1 : 0, splat, fill, predVertex, predNormal,
                                       predImage, s));
       ctx->launches += 1;
-    } else {
-      const size_t n = (size_t)ctx->W * ctx->H;
-      RET_IF(cudaMemcpyAsync(predVertex, splat.vertexConf, n * 16, cudaMemcpyDeviceToDevice, s));
-      RET_IF(cudaMemcpyAsync(predNormal, splat.normalRad, n * 16, cudaMemcpyDeviceToDevice, s));
-      RET_IF(cudaMemcpyAsync(predImage, splat.image, n * 4, cudaMemcpyDeviceToDevice, s));
+    } else {  // an object model tracks against its splat prediction as it is (no copy)
+      pv = (const float*)splat.vertexConf;
+      pn = (const float*)splat.normalRad;
+      pi = (const uint8_t*)splat.image;
     }
   }
   // Model::initICP (Model.cpp:350-367): model pyramids first, then the frame's (fused launches)
   const float* pyr[3] = {ctx->depthPyr[0], ctx->depthPyr[1], ctx->depthPyr[2]};
-  RET_IF(odom.initAll(predVertex, predNormal, predImage, 4, pyr, ctx->rgb, 3, tp.maxDepthProcessed, pose, s,
-                      devicePose ? dpose->pose.m : nullptr));
-  ctx->launches += 4;  // model pyramid, frame maps, grey, all pyramids (lastDepth + both grey images, both levels)
+  RET_IF(odom.initAll(pv, pn, pi, 4, pyr, ctx->rgb, 3, tp.maxDepthProcessed, pose, s, devicePose ? dpose->pose.m : nullptr));
+  ctx->launches += 3;  // model pyramid, frame maps + grey images, all pyramids (lastDepth + both grey images, both levels)
   return cudaSuccess;
 }
 

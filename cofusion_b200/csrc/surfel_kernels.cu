@@ -419,25 +419,23 @@ __global__ void fuse_associate_kernel(SurfelGeom g, PoseRef pose_ref, int time, 
   }
   store_surfel(cand + e, c);
 }
-// data.geom: every emitted vertex is appended to newUnstableBuffer in draw order
-__global__ void fuse_append_kernel(unsigned n, const uint8_t* __restrict__ flags, const uint32_t* __restrict__ ranks,
-                                   const Surfel* __restrict__ cand, Surfel* __restrict__ unstable, MapCounters* ctr) {
+// After the scan: every candidate (flag 1 = associated, 2 = new) joins the unstable list at its rank (data.geom), and
+// the winning pixel of each touched surfel updates it in place (update.vert).  One launch for both; the winner also
+// puts its surfel's entry of `winner` back to all ones, so the array needs no clearing pass before the next fuse
+// (a losing candidate that reads the entry after that still sees "not me").
+__global__ void fuse_apply_kernel(unsigned n, int time, const uint8_t* __restrict__ flags, const uint32_t* __restrict__ ranks,
+                                  const uint32_t* __restrict__ candBest, uint32_t* __restrict__ winner,
+                                  const Surfel* __restrict__ cand, Surfel* __restrict__ unstable, Surfel* __restrict__ surfels,
+                                  MapCounters* ctr) {
   pdl_prologue();
   unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e == 0) ctr->unstableCount = ctr->scanTotal;
   if (e >= n || !flags[e]) return;
-  store_surfel(unstable + ranks[e], load_surfel(cand + e));
-}
-// update.vert for the winning pixel of each touched surfel, in place
-__global__ void fuse_update_kernel(unsigned n, int time, const uint8_t* __restrict__ flags,
-                                   const uint32_t* __restrict__ candBest, const uint32_t* __restrict__ winner,
-                                   const Surfel* __restrict__ cand, Surfel* __restrict__ surfels) {
-  pdl_prologue();
-  unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n || flags[e] != 1) return;
+  const Surfel nw = load_surfel(cand + e);
+  store_surfel(unstable + ranks[e], nw);
+  if (flags[e] != 1) return;
   const uint32_t id = candBest[e];
   if (winner[id] != e) return;
-  const Surfel nw = load_surfel(cand + e);
   Surfel o = load_surfel(surfels + id);
   const float c_k = o.pos.w, a = nw.pos.w, ftime = (float)time;
   if (nw.nrm.w < (1.0f + 0.5f) * o.nrm.w) {
@@ -458,11 +456,7 @@ __global__ void fuse_update_kernel(unsigned n, int time, const uint8_t* __restri
     o.col.w = ftime;
   }
   store_surfel(surfels + id, o);
-}
-__global__ void fill_u32_kernel(uint32_t* p, unsigned n_ub, const unsigned* n_dev, uint32_t v) {
-  pdl_prologue();
-  unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_ub && i < *n_dev) p[i] = v;
+  winner[id] = 0xffffffffu;
 }
 
 // ------------------------------------------------------------------------------- a17 clean
@@ -869,13 +863,12 @@ cudaError_t launch_fuse(const SurfelGeom& g, Surfel* surfels, unsigned count_ub,
   const int par = ((time % 2) + 2) % 2;
   const int W2 = (g.W - par + 1) / 2, H2 = (g.H - par + 1) / 2;
   const unsigned ne = (unsigned)W2 * H2;
-  if (count_ub) CFB_PDL(launch_pdl(fill_u32_kernel, cdiv(count_ub, 256), 256, 0, s, winner, count_ub, &ctr->count, 0xffffffffu));
+  // `winner` is all ones on entry (Model construction; the winners of the last fuse restored their entries)
   const dim3 b(32, 8), gr(cdiv(W2, 32), cdiv(H2, 8));
   CFB_PDL(launch_pdl(fuse_associate_kernel, gr, b, 0, s, g, pose, time, rgb, mask, depthRaw, depthFiltered, maxDepth, weighting, maskID,
                                          idx, winner, cand, candBest, sc.flags, par, W2, H2));
   RET_IF(scan_flags(sc, ne, nullptr, 0, &ctr->scanTotal, s));
-  CFB_PDL(launch_pdl(fuse_append_kernel, cdiv(ne, 256), 256, 0, s, ne, sc.flags, sc.ranks, cand, unstable, ctr));
-  CFB_PDL(launch_pdl(fuse_update_kernel, cdiv(ne, 256), 256, 0, s, ne, time, sc.flags, candBest, winner, cand, surfels));
+  CFB_PDL(launch_pdl(fuse_apply_kernel, cdiv(ne, 256), 256, 0, s, ne, time, sc.flags, sc.ranks, candBest, winner, cand, unstable, surfels, ctr));
   return cudaGetLastError();
 }
 
