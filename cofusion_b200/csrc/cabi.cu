@@ -626,7 +626,7 @@ int cfb_model_view(cfb_model* m, int which, const void** dev_ptr, size_t* pitch)
   REQUIRE(m && dev_ptr && pitch, "model_view");
   DevScope dev_scope__(device_of(m));
   const size_t W = (size_t)m->m.ctx->W;
-  const bool direct = m->m.usePrediction && !m->m.allowsFillIn;  // object models track against the splat maps themselves
+  const bool direct = m->m.usePrediction;  // the tracker reads the splat maps themselves (views 0-2: an installed prediction)
   switch (which) {
     case 0: *dev_ptr = direct ? (const void*)m->m.splat.vertexConf : m->m.predVertex; *pitch = W * 16; break;
     case 1: *dev_ptr = direct ? (const void*)m->m.splat.normalRad : m->m.predNormal; *pitch = W * 16; break;

@@ -1938,8 +1938,11 @@ cudaError_t RGBDOdometry::trackTiled(RGBDOdometry* const* od, int n, float (*tra
   const void* kernels[4] = {(const void*)gn_tiled_kernel<false, false>, (const void*)gn_tiled_kernel<true, false>,
                             (const void*)gn_tiled_kernel<false, true>, (const void*)gn_tiled_kernel<true, true>};
   if (!(ts.attr_set & (1 << variant))) {
-    RET_IF(cudaFuncSetAttribute(kernels[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts.smem_bytes));
-    ts.attr_set |= 1 << variant;
+    // all four at once: setting the attribute also loads the kernel (lazy module loading), so the first frame with a
+    // second model does not pay for loading the general instantiation
+    for (int v = 0; v < 4; ++v)
+      RET_IF(cudaFuncSetAttribute(kernels[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts.smem_bytes));
+    ts.attr_set = 15;
   }
   void* args[] = {(void*)&p};
   if (f.time_kernel_) RET_IF(cudaEventRecord(f.ev_k0_, s));

@@ -348,8 +348,13 @@ struct ModelPyrOut {
 };
 __global__ void model_pyramid_kernel(const float4* __restrict__ v4, const float4* __restrict__ n4, int W, int H,
                                      Mat33 R, float3 t, const float* __restrict__ pose34_dev, float cutoffRGB,
-                                     ModelPyrOut o) {
+                                     ModelPyrOut o, const float4* __restrict__ v4_alt, const float4* __restrict__ n4_alt,
+                                     const unsigned* __restrict__ sel) {
   pdl_prologue();
+  if (sel && *sel != 0) {  // fill-in images instead of the splat prediction (see PredAlt)
+    v4 = v4_alt;
+    n4 = n4_alt;
+  }
   const int X = blockIdx.x * blockDim.x + threadIdx.x, Y = blockIdx.y * blockDim.y + threadIdx.y;
   const int W2 = W / 4, H2 = H / 4, W1 = W / 2, H1 = H / 2;
   if (X >= W2 || Y >= H2) return;
@@ -432,6 +437,9 @@ struct FrameMapsArgs {
   const unsigned char* img[2];
   unsigned char* grey[2];
   int ch[2], ni;
+  const unsigned char* imgA_alt;  // image 0 comes from here when *selA != 0 or always (see PredAlt)
+  const unsigned* selA;
+  int altA_always;
 };
 __global__ void frame_maps_kernel(const FrameMapsArgs a) {
   pdl_prologue();
@@ -472,7 +480,9 @@ __global__ void frame_maps_kernel(const FrameMapsArgs a) {
   for (int k = 0; k < 2; ++k) {
     if (p < a.ni) {
       if (a.img[k]) {
-        const unsigned char* q = a.img[k] + (size_t)p * a.ch[k];
+        const unsigned char* base = a.img[k];
+        if (k == 0 && a.imgA_alt && (a.altA_always || (a.selA && *a.selA != 0))) base = a.imgA_alt;
+        const unsigned char* q = base + (size_t)p * a.ch[k];
         const float s = __fmaf_rn((float)q[2], 0.587f, __fmaf_rn((float)q[1], 0.299f, __fmul_rn((float)q[0], 0.114f)));
         a.grey[k][p] = (unsigned char)(int)s;
       }
@@ -729,7 +739,7 @@ cudaError_t launch_project_to_point_cloud(const float* depth, size_t dpitch, int
 
 cudaError_t launch_model_pyramid(const float* v4, const float* n4, int W, int H, const Mat33& R, const float t[3],
                                  float cutoffRGB, float* const v[3], float* const n[3], float* depth0,
-                                 cudaStream_t s, const float* pose34_dev) {
+                                 cudaStream_t s, const float* pose34_dev, const PredAlt* alt) {
   ModelPyrOut o;
   for (int i = 0; i < 3; ++i) {
     o.v[i] = v[i];
@@ -738,13 +748,17 @@ cudaError_t launch_model_pyramid(const float* v4, const float* n4, int W, int H,
   o.depth0 = depth0;
   const dim3 b(32, 4);
   CFB_PDL(launch_pdl(model_pyramid_kernel, grid2d(W / 4, H / 4, b), b, 0, s, (const float4*)v4, (const float4*)n4, W, H, R,
-                                                            make_float3(t[0], t[1], t[2]), pose34_dev, cutoffRGB, o));
+                                                            make_float3(t[0], t[1], t[2]), pose34_dev, cutoffRGB, o,
+                     (const float4*)(alt ? alt->v4 : nullptr), (const float4*)(alt ? alt->n4 : nullptr), alt ? alt->sel : nullptr));
   return cudaGetLastError();
 }
 cudaError_t launch_frame_maps(const float* const depth[3], int W, int H, Intr K, float cutoff, float* const v[3],
                               float* const n[3], cudaStream_t s, const unsigned char* imgA, int chA, unsigned char* greyA,
-                              const unsigned char* imgB, int chB, unsigned char* greyB) {
+                              const unsigned char* imgB, int chB, unsigned char* greyB, const PredAlt* altA) {
   FrameMapsArgs a;
+  a.imgA_alt = altA ? altA->img : nullptr;
+  a.selA = altA ? altA->sel : nullptr;
+  a.altA_always = altA ? altA->img_always : 0;
   int total = 0;
   a.img[0] = imgA;
   a.img[1] = imgB;

@@ -40,13 +40,22 @@ cudaError_t launch_project_to_point_cloud(const float* depth, size_t dpitch, int
                                           size_t cpitch, cudaStream_t s);
 
 // ---- fused builders for Model::performTracking (same arithmetic, fewer launches; unpitched buffers)
+// Model::initICP's choice between the splat prediction and the fill-in images (Model.cpp:350-367,
+// CoFusion::requiresFillIn), taken where the maps are READ: *sel != 0 -> the alternative vertex / normal maps;
+// *sel != 0 or img_always -> the alternative image.  All null: no choice to make.
+struct PredAlt {
+  const float *v4 = nullptr, *n4 = nullptr;
+  const unsigned char* img = nullptr;
+  const unsigned* sel = nullptr;
+  int img_always = 0;
+};
 cudaError_t launch_model_pyramid(const float* v4, const float* n4, int W, int H, const Mat33& R, const float t[3],
                                  float cutoffRGB, float* const v[3], float* const n[3], float* depth0,
-                                 cudaStream_t s, const float* pose34_dev = nullptr /* device 3x4 pose overrides R, t */);
+                                 cudaStream_t s, const float* pose34_dev = nullptr, const PredAlt* alt = nullptr);
 cudaError_t launch_frame_maps(const float* const depth[3], int W, int H, Intr K, float cutoff, float* const v[3],
                               float* const n[3], cudaStream_t s, const unsigned char* imgA = nullptr, int chA = 0,
                               unsigned char* greyA = nullptr, const unsigned char* imgB = nullptr, int chB = 0,
-                              unsigned char* greyB = nullptr);
+                              unsigned char* greyB = nullptr, const PredAlt* altA = nullptr);
 cudaError_t launch_intensity2(const unsigned char* a, int cha, unsigned char* da, const unsigned char* b, int chb,
                               unsigned char* db, int n, cudaStream_t s);
 cudaError_t launch_pyr_down_uchar2(const unsigned char* sa, unsigned char* da, const unsigned char* sb,

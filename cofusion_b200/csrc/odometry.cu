@@ -49,6 +49,11 @@ RGBDOdometry::RGBDOdometry(int w, int h, float cx, float cy, float fx, float fy,
          dalloc(&d_pose, 1, &zeroed_) && dalloc(&d_warp, 1, &zeroed_) && dalloc(&d_pose_in, 16, &zeroed_) &&
          dalloc((unsigned**)&grid_sync_, 256, &zeroed_);
   good = good && cudaMallocHost(&h_pinned, 4096) == cudaSuccess;
+  // what the tracker needs of an OBJECT model (extents, correspondences of an iteration): here rather than inside
+  // the first multi-model frame.  Sized for the largest grid the tile planner makes (one CTA per SM, <= 160).
+  corr_words_ = (size_t)4 * 160 * 576;
+  good = good && dalloc((int**)&d_box_, 24, &zeroed_) && cudaMalloc(&d_corr_, corr_words_ * 8) == cudaSuccess &&
+         cudaMemset(d_corr_, 0, corr_words_ * 8) == cudaSuccess;
   ok_ = good;
 }
 
@@ -188,7 +193,8 @@ cudaError_t RGBDOdometry::initFirstRGB(const unsigned char* img, size_t pitch, i
 
 cudaError_t RGBDOdometry::initAll(const float* v4, const float* n4, const unsigned char* modelImg, int modelCh,
                                   const float* const depthPyr[NUM_PYRS], const unsigned char* frameImg, int frameCh,
-                                  float depthCutoff, const float pose[16], cudaStream_t s, const float* pose34_dev) {
+                                  float depthCutoff, const float pose[16], cudaStream_t s, const float* pose34_dev,
+                                  const PredAlt* alt) {
   if ((width % 4) || (height % 4)) return cudaErrorInvalidValue;
   Mat33 R;
   float t[3];
@@ -198,14 +204,14 @@ cudaError_t RGBDOdometry::initAll(const float* v4, const float* n4, const unsign
   }
   // model side: global-frame vertex/normal pyramid + lastDepth level 0
   RET_IF(launch_model_pyramid(v4, n4, width, height, R, t, maxDepthRGB, vmaps_g_prev_, nmaps_g_prev_, lastDepth[0], s,
-                              pose34_dev));
+                              pose34_dev, alt));
   // quirk kept: initRGB derives nextDepth from the same model prediction (vmaps_tmp) -> it IS
   // lastDepth; the device loop reads lastDepth for both instead of building a second copy
   next_is_last_ = true;
   // frame side
   // + both grey images (model prediction, frame) in the same launch
   RET_IF(launch_frame_maps(depthPyr, width, height, intr, depthCutoff, vmaps_curr_, nmaps_curr_, s, modelImg, modelCh, lastImage[0],
-                           frameImg, frameCh, nextImage[0]));
+                           frameImg, frameCh, nextImage[0], alt));
   {  // lastDepth + both grey images, both levels each, in ONE launch
     const void* src[3] = {lastDepth[0], lastImage[0], nextImage[0]};
     void* l1[3] = {lastDepth[1], lastImage[1], nextImage[1]};

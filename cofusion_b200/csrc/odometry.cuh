@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "cfb_common.cuh"
+#include "image_kernels.cuh"
 #include "tracker_kernels.cuh"
 
 namespace cfb {
@@ -71,7 +72,8 @@ class RGBDOdometry {
   cudaError_t initAll(const float* v4, const float* n4, const unsigned char* modelImg, int modelCh,
                       const float* const depthPyr[NUM_PYRS], const unsigned char* frameImg, int frameCh,
                       float depthCutoff, const float pose[16], cudaStream_t s,
-                      const float* pose34_dev = nullptr /* device 3x4 pose: overrides `pose` without a host copy */);
+                      const float* pose34_dev = nullptr /* device 3x4 pose: overrides `pose` without a host copy */,
+                      const PredAlt* alt = nullptr /* fill-in alternative of the model prediction, chosen on the device */);
 
   // RGBDOdometry.cpp:217-477. trans[3], rot[9] (row-major) in/out on the host.
   // icp_error_map: optional device f32 W*H (pitch bytes) written on the last level-0 iteration.

@@ -301,6 +301,10 @@ Model::Model(Context* c, unsigned id_, float conf, unsigned maxSurfels, bool ena
   // the pose block is followed by the tracker statistics of the frame: one read-back copy fetches both
   good = good && dalloc((PoseReadback**)&dpose, 1, &zeroed_) && cudaMallocHost(&h_readback, sizeof(PoseReadback)) == cudaSuccess &&
          cudaEventCreateWithFlags(&evPose, cudaEventDisableTiming) == cudaSuccess;
+  // the per-model stream of multi-model frames exists from the start (its creation inside a frame was measured at
+  // up to tens of milliseconds the first time)
+  good = good && cudaStreamCreateWithFlags(&mstream, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&evJoin, cudaEventDisableTiming) == cudaSuccess;
   ok_ = good;
   if (good) ok_ = uploadPose() == cudaSuccess;
 }
@@ -629,22 +633,26 @@ cudaError_t Model::prepareTracking(const TrackParams& tp, bool devicePose) {
   cudaStream_t s = work;
   const float *pv = predVertex, *pn = predNormal;
   const uint8_t* pi = predImage;
+  PredAlt alt;
   if (usePrediction) {
-    // Model::initICP (Model.cpp:350-367): splat prediction, or the fill-in images when
-    // CoFusion::requiresFillIn says so -- selected on the device (no host wait)
+    // Model::initICP (Model.cpp:350-367): the tracker reads the splat prediction as it is (no copy) -- or, for the
+    // camera model, the fill-in images when CoFusion::requiresFillIn says so: the pyramid builders read through that
+    // choice (a device flag, no host wait, no selection pass)
+    pv = (const float*)splat.vertexConf;
+    pn = (const float*)splat.normalRad;
+    pi = (const uint8_t*)splat.image;
     if (allowsFillIn) {
-      RET_IF(launch_select_prediction(geom(), counters, tp.frameToFrameRGB ? 1 : 0, splat, fill, predVertex, predNormal,
-                                      predImage, s));
-      ctx->launches += 1;
-    } else {  // an object model tracks against its splat prediction as it is (no copy)
-      pv = (const float*)splat.vertexConf;
-      pn = (const float*)splat.normalRad;
-      pi = (const uint8_t*)splat.image;
+      alt.v4 = (const float*)fill.vertex;
+      alt.n4 = (const float*)fill.normal;
+      alt.img = (const unsigned char*)fill.image;
+      alt.sel = &counters->fillInRequired;
+      alt.img_always = tp.frameToFrameRGB ? 1 : 0;
     }
   }
   // Model::initICP (Model.cpp:350-367): model pyramids first, then the frame's (fused launches)
   const float* pyr[3] = {ctx->depthPyr[0], ctx->depthPyr[1], ctx->depthPyr[2]};
-  RET_IF(odom.initAll(pv, pn, pi, 4, pyr, ctx->rgb, 3, tp.maxDepthProcessed, pose, s, devicePose ? dpose->pose.m : nullptr));
+  RET_IF(odom.initAll(pv, pn, pi, 4, pyr, ctx->rgb, 3, tp.maxDepthProcessed, pose, s, devicePose ? dpose->pose.m : nullptr,
+                      alt.sel ? &alt : nullptr));
   ctx->launches += 3;  // model pyramid, frame maps + grey images, all pyramids (lastDepth + both grey images, both levels)
   return cudaSuccess;
 }

@@ -802,20 +802,6 @@ __global__ void fill_in_kernel(SurfelGeom g, SplatMaps splat, const uint8_t* __r
   }
 }
 
-// Model::initICP (Model.cpp:350-367) chooses between the splat prediction and the fill-in images
-// from CoFusion::requiresFillIn; the choice is made on the device so the host never waits for it.
-__global__ void select_prediction_kernel(unsigned n, const MapCounters* __restrict__ ctr, int fill_image_always,
-                                         SplatMaps splat, FillMaps fill, float4* __restrict__ v,
-                                         float4* __restrict__ nrm, uchar4* __restrict__ img) {
-  pdl_prologue();
-  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const bool doFill = ctr->fillInRequired != 0;
-  v[i] = doFill ? fill.vertex[i] : splat.vertexConf[i];
-  nrm[i] = doFill ? fill.normal[i] : splat.normalRad[i];
-  img[i] = (doFill || fill_image_always) ? fill.image[i] : splat.image[i];
-}
-
 inline unsigned cdiv(unsigned a, unsigned b) { return (a + b - 1) / b; }
 
 }  // namespace
@@ -901,14 +887,6 @@ cudaError_t launch_combined_predict(const SurfelGeom& g, const Surfel* surfels, 
   return cudaGetLastError();
 }
 
-cudaError_t launch_select_prediction(const SurfelGeom& g, const MapCounters* ctr, int fill_image_always,
-                                     SplatMaps splat, FillMaps fill, float* v4, float* n4, uint8_t* img,
-                                     cudaStream_t s) {
-  const unsigned n = (unsigned)g.W * g.H;
-  CFB_PDL(launch_pdl(select_prediction_kernel, cdiv(n, 256), 256, 0, s, n, ctr, fill_image_always, splat, fill, (float4*)v4,
-                                                        (float4*)n4, (uchar4*)img));
-  return cudaGetLastError();
-}
 
 cudaError_t launch_fill_in(const SurfelGeom& g, SplatMaps splat, const uint8_t* rgb, const float* depthFiltered,
                            int pt_geom, int pt_rgb, FillMaps out, MapCounters* ctr, float ratio, cudaStream_t s) {

@@ -115,9 +115,4 @@ cudaError_t launch_fill_in(const SurfelGeom& g, SplatMaps splat, const uint8_t* 
                            int passthrough_geom, int passthrough_rgb, FillMaps out, MapCounters* counters,
                            float ratio, cudaStream_t s);
 
-// Model::initICP's source selection (Model.cpp:354-360), decided on the device
-cudaError_t launch_select_prediction(const SurfelGeom& g, const MapCounters* counters, int fill_image_always,
-                                     SplatMaps splat, FillMaps fill, float* v4, float* n4, uint8_t* img,
-                                     cudaStream_t s);
-
 }  // namespace cfb
