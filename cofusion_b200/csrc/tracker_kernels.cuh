@@ -15,7 +15,7 @@ struct StepScratch {
   int rgb_sigma;
   int pad1[30];
   float result[32];          // packed sums of the last step (29 SE3 / 11 SO3 used)
-  float partials[kMaxBlocks * 32];
+  float partials[kMaxBlocks * 32];  // ONE row of 32 partial sums per block: grid_for() caps every grid at kMaxBlocks
 };
 
 // Pose block read by the ICP kernel from device memory (so the device-resident GN loop can update
